@@ -1,0 +1,155 @@
+/*
+ * include/ncm_sd_gpu.h -- C ABI of the B200 (sm_100a) density-estimation path that sits
+ * under NumCosmo's NcmStatsDist vtable (libncm_sd_gpu.so).
+ *
+ * Plain C: opaque context, doubles, row-major matrices with explicit leading dimensions,
+ * int status returns (0 = ok; the host glue turns non-zero into g_error, the reference's
+ * only error channel).  No GLib and no torch types.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the
+ * NumCosmo source tree, v0.27.0).  There is NO CPU fallback behind any of them: without a
+ * CUDA device ncm_sd_gpu_ctx_new fails with NCM_SD_GPU_ENODEV.
+ */
+#ifndef NCM_SD_GPU_H
+#define NCM_SD_GPU_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ncm_sd_gpu_ctx ncm_sd_gpu_ctx;
+
+enum
+{
+  NCM_SD_GPU_OK      = 0,
+  NCM_SD_GPU_EINVAL  = 1, /* bad argument / call order */
+  NCM_SD_GPU_ENODEV  = 2, /* no usable CUDA device */
+  NCM_SD_GPU_ECUDA   = 3, /* CUDA runtime error, see ncm_sd_gpu_last_error */
+  NCM_SD_GPU_ENOTPD  = 4, /* NNLS: normal matrix not positive definite even after the diagonal retry */
+  NCM_SD_GPU_ENCCL   = 5, /* NCCL error */
+  NCM_SD_GPU_ENOMEM  = 6
+};
+
+enum { NCM_SD_GPU_KERNEL_GAUSS = 0, NCM_SD_GPU_KERNEL_ST = 1 };
+enum { NCM_SD_GPU_KDE = 0, NCM_SD_GPU_VKDE = 1 };
+
+#define NCM_SD_GPU_MAX_DIM 32
+
+/* ---- context ---------------------------------------------------------------------- */
+
+/* One context per (process, device): owns the stream, the device buffers and (optionally)
+ * an NCCL communicator.  Plays the role of the per-object scratch the reference keeps in
+ * NcmMemoryPool (ncm_stats_dist_kde.c:128-147, ncm_stats_dist_vkde.c:121-141). */
+int ncm_sd_gpu_ctx_new (ncm_sd_gpu_ctx **ctx, int device);
+int ncm_sd_gpu_ctx_free (ncm_sd_gpu_ctx *ctx);
+const char *ncm_sd_gpu_last_error (const ncm_sd_gpu_ctx *ctx);
+int ncm_sd_gpu_device_count (void);
+/* cudaStream_t the context launches on (as void*), for callers that own device buffers. */
+void *ncm_sd_gpu_stream (ncm_sd_gpu_ctx *ctx);
+int ncm_sd_gpu_synchronize (ncm_sd_gpu_ctx *ctx);
+
+/* ---- kernel + bandwidth -------------------------------------------------------------
+ * ncm_stats_dist_kernel_gauss_new / ncm_stats_dist_kernel_st_new
+ * (ncm_stats_dist_kernel_gauss.c:357-373, ncm_stats_dist_kernel_st.c:416-435). */
+int ncm_sd_gpu_set_kernel (ncm_sd_gpu_ctx *ctx, int kind, double nu, int d);
+
+/* ---- centres ------------------------------------------------------------------------
+ * KDE: result of _ncm_stats_dist_kde_prepare_kernel (ncm_stats_dist_kde.c:378-490):
+ *   invUsample [n_obs x d] = sample . U^-1 (rows 0..n_kernels-1 are the kernel centres),
+ *   U [d x d] upper Cholesky factor of the covariance, lnnorm = kernel_lnnorm (no d ln h). */
+int ncm_sd_gpu_upload_kde (ncm_sd_gpu_ctx *ctx, int n_obs, int n_kernels, const double *invUsample, int ld,
+                           const double *U, int ldu, double lnnorm);
+/* VKDE: result of _ncm_stats_dist_vkde_build_cov_array_kdtree (ncm_stats_dist_vkde.c:362-496):
+ *   sample [n_obs x d] raw points, U_all [n_kernels x d x d] upper factors (dense, row-major),
+ *   lnnorms [n_kernels] (no d ln h). */
+int ncm_sd_gpu_upload_vkde (ncm_sd_gpu_ctx *ctx, int n_obs, int n_kernels, const double *sample, int ld,
+                            const double *U_all, const double *lnnorms);
+/* weights + bandwidth: self->weights / self->href of NcmStatsDistPrivate
+ * (ncm_stats_dist_private.h:39-76), set by _ncm_stats_dist_prepare (ncm_stats_dist.c:753-767). */
+int ncm_sd_gpu_set_weights (ncm_sd_gpu_ctx *ctx, int n_kernels, const double *weights, double href);
+int ncm_sd_gpu_set_href (ncm_sd_gpu_ctx *ctx, double href);
+int ncm_sd_gpu_get_weights (ncm_sd_gpu_ctx *ctx, int n_kernels, double *weights);
+
+/* ---- batched evaluation (the new "eval_vec") -----------------------------------------
+ * q calls of ncm_stats_dist_eval_m2lnp / ncm_stats_dist_eval (ncm_stats_dist.c:1527-1554 ->
+ * ncm_stats_dist_kde.c:596-681, ncm_stats_dist_vkde.c:631-723, kernels'
+ * eval_sum0/sum1_gamma_lambda).  X [q x d] host, out [q] host. */
+int ncm_sd_gpu_eval_m2lnp (ncm_sd_gpu_ctx *ctx, int q, const double *X, int ldx, double *m2lnp_out);
+int ncm_sd_gpu_eval (ncm_sd_gpu_ctx *ctx, int q, const double *X, int ldx, double *p_out);
+/* same with device-resident buffers (dX [q x d] ld = ldx, dOut [q]); asynchronous on the ctx stream */
+int ncm_sd_gpu_eval_m2lnp_dev (ncm_sd_gpu_ctx *ctx, int q, const double *dX, int ldx, double *dOut);
+
+/* ---- interpolation matrix -------------------------------------------------------------
+ * klass->compute_IM followed by the 1/f_i row scaling of _ncm_stats_dist_compute_IM_full
+ * (ncm_stats_dist.c:791-804; ncm_stats_dist_kde.c:492-557; ncm_stats_dist_vkde.c:517-606).
+ * Rows = the n_obs uploaded points, columns = the n_kernels centres; row_scale[n_obs]
+ * (= 1/f_i) may be NULL.  The matrix stays resident on the device for ncm_sd_gpu_nnls_solve;
+ * it is copied to IM_host [n_obs x n_kernels, ld = n_kernels] only if IM_host != NULL. */
+int ncm_sd_gpu_compute_IM (ncm_sd_gpu_ctx *ctx, const double *row_scale, double *IM_host);
+
+/* ---- NNLS ------------------------------------------------------------------------------
+ * ncm_nnls_solve with NCM_NNLS_UMETHOD_NORMAL on the resident IM and f = 1
+ * (ncm_nnls.c:767-871; NcmISet logic ncm_iset.c:853-1077).  x_out [n_kernels].
+ * The un-normalised solution also replaces the resident weights (call set_weights after the
+ * host applied the shrink normalisation of ncm_stats_dist.c:1087-1093). */
+typedef struct ncm_sd_gpu_nnls_stats
+{
+  int n_chol;    /* Cholesky factorisations */
+  int n_retry;   /* factorisations that needed the regularised retry */
+  int n_outer;   /* accepted outer iterations */
+  int n_passive; /* final passive-set size */
+} ncm_sd_gpu_nnls_stats;
+
+int ncm_sd_gpu_nnls_solve (ncm_sd_gpu_ctx *ctx, double reltol, double *x_out, double *rnorm_out, ncm_sd_gpu_nnls_stats *stats);
+/* generic entry (used by the NNLS parity tests): A [nrows x ncols] host row-major, f [nrows] host */
+int ncm_sd_gpu_nnls_solve_host (ncm_sd_gpu_ctx *ctx, int nrows, int ncols, const double *A, int lda, const double *f,
+                                double reltol, double *x_out, double *rnorm_out, ncm_sd_gpu_nnls_stats *stats);
+
+/* ---- proposal sampling -------------------------------------------------------------------
+ * The affine map of kernel->sample (ncm_stats_dist_kernel_gauss.c:335-355,
+ * ncm_stats_dist_kernel_st.c:388-414): X_out[r] = centre[kidx[r]] + scale[r] * U_{kidx[r]}^T (href * Z[r]),
+ * with the standard normals Z [q x d] (and scale = sqrt(nu / chi2_nu) for ST, NULL for Gauss)
+ * drawn by the caller's RNG in reference order. */
+int ncm_sd_gpu_sample_apply (ncm_sd_gpu_ctx *ctx, int q, const int *kidx, const double *Z, int ldz, const double *scale,
+                             double *X_out, int ldx);
+/* counter-based (Philox4x32-10) throughput mode, one stream per proposal row; NOT stream-
+ * compatible with the reference RNG (hard part a). */
+int ncm_sd_gpu_sample_philox (ncm_sd_gpu_ctx *ctx, int q, unsigned long long seed, unsigned long long offset,
+                              double *X_out, int ldx, int *kidx_out);
+
+/* ---- multi-GPU ------------------------------------------------------------------------------
+ * One process per GPU.  Query rows and IM row blocks are sharded by the caller (each rank
+ * uploads the same centres and its own rows); the only exchange is the all-reduce of the NNLS
+ * normal equations (M = IM^T IM, b = IM^T 1) and of A^T r / |r|^2 per outer iteration. */
+int ncm_sd_gpu_comm_unique_id (char id_out[128]);
+int ncm_sd_gpu_comm_init (ncm_sd_gpu_ctx *ctx, int nranks, int rank, const char id[128]);
+/* restrict compute_IM to observation rows [row0, row0 + nrows) on this rank */
+int ncm_sd_gpu_set_row_shard (ncm_sd_gpu_ctx *ctx, int row0, int nrows);
+
+/* ---- instrumentation ------------------------------------------------------------------------- */
+enum
+{
+  NCM_SD_GPU_T_EVAL = 0,  /* eval kernels */
+  NCM_SD_GPU_T_IM,        /* IM kernel */
+  NCM_SD_GPU_T_SYRK,      /* normal equations */
+  NCM_SD_GPU_T_CHOL,      /* Cholesky + triangular solves */
+  NCM_SD_GPU_T_NNLS_MISC, /* gathers, residuals, gradients */
+  NCM_SD_GPU_T_H2D,
+  NCM_SD_GPU_T_D2H,
+  NCM_SD_GPU_T_LEN
+};
+/* device time (CUDA events on the ctx stream) accumulated per stage, milliseconds, and the
+ * number of kernels launched since the last reset */
+int ncm_sd_gpu_get_timers (ncm_sd_gpu_ctx *ctx, double ms[NCM_SD_GPU_T_LEN], long long *n_launches);
+int ncm_sd_gpu_reset_timers (ncm_sd_gpu_ctx *ctx);
+int ncm_sd_gpu_enable_timers (ncm_sd_gpu_ctx *ctx, int enable);
+
+/* plain FP64 building blocks exported for tests and microbenchmarks (device pointers) */
+int ncm_sd_gpu_dsyrk_ata_dev (ncm_sd_gpu_ctx *ctx, int nrows, int ncols, const double *dA, int lda, double *dM, int ldm);
+int ncm_sd_gpu_dpotrf_upper_dev (ncm_sd_gpu_ctx *ctx, int n, double *dM, int ldm, int *info_host);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* NCM_SD_GPU_H */

@@ -1,0 +1,129 @@
+// Shared device/host helpers of libncm_sd_gpu (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cmath>
+
+#define NCM_WARP 32
+#define NCM_NEG_BIG (-1.0e300)   // running-max seed: finite, so (t - m) never evaluates inf - inf
+
+// ---- shared-memory / mbarrier / bulk-copy (TMA 1-D) primitives ------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
+// global -> shared bulk async copy (UBLKCP), completion counted in bytes on an mbarrier.
+// dst/src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---- cp.async (LDGSTS) 16-byte -----------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src_gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async16_zfill(void *dst_smem, const void *src_gmem, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// ---- FP64 tensor core: DMMA.8x8x4 -----------------------------------------------------------------
+// A (8x4, row): lane l holds A[l/4][l%4];  B (4x8, col): lane l holds B[l%4][l/4];
+// C (8x8): lane l holds C[l/4][2*(l%4) + {0,1}].
+__device__ __forceinline__ void dmma884(double &c0, double &c1, const double a, const double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// ---- log-sum-exp state -----------------------------------------------------------------------------
+// (m, s): log-sum = m + log(s), s counts the arg-max term as 1 (the reference returns
+// gamma = m and lambda = s - 1, ncm_stats_dist_kernel_gauss.c:246-289).
+struct Lse {
+  double m, s;
+};
+
+__device__ __forceinline__ void lse_init(Lse &a) {
+  a.m = NCM_NEG_BIG;
+  a.s = 0.0;
+}
+
+__device__ __forceinline__ void lse_push(Lse &a, const double t) {
+  const double d = t - a.m;
+  const double e = exp(-fabs(d));
+  if (d > 0.0) {
+    a.s = fma(a.s, e, 1.0);
+    a.m = t;
+  } else {
+    a.s += e;
+  }
+}
+
+__device__ __forceinline__ void lse_merge(Lse &a, const double m2, const double s2) {
+  const double d = m2 - a.m;
+  const double e = exp(-fabs(d));
+  if (d > 0.0) {
+    a.s = fma(a.s, e, s2);
+    a.m = m2;
+  } else {
+    a.s = fma(s2, e, a.s);
+  }
+}
+
+__device__ __forceinline__ void lse_warp_reduce_xor(Lse &a, const int width) {
+  for (int off = width >> 1; off > 0; off >>= 1) {
+    const double m2 = __shfl_xor_sync(0xffffffffu, a.m, off);
+    const double s2 = __shfl_xor_sync(0xffffffffu, a.s, off);
+    lse_merge(a, m2, s2);
+  }
+}
+
+// kernel function in the log domain: ln Kbar(chi2)   (Appendix C of SURVEY.md)
+//   Gauss: -chi2/2 ; ST: kappa * log1p(chi2 / nu), kappa = -(nu + d)/2
+struct KernParams {
+  int kind;        // 0 Gauss, 1 ST
+  double nu;
+  double kappa;    // -(nu + d) / 2
+  double inv_nu;
+};
+
+__device__ __forceinline__ double kern_lnK(const KernParams &kp, const double chi2) {
+  return kp.kind == 0 ? -0.5 * chi2 : kp.kappa * log1p(chi2 * kp.inv_nu);
+}
+// Kbar(chi2) as the reference evaluates it (eval_unnorm): exp(-chi2/2) or pow(1 + chi2/nu, kappa)
+__device__ __forceinline__ double kern_K(const KernParams &kp, const double chi2) {
+  return kp.kind == 0 ? exp(-0.5 * chi2) : pow(1.0 + chi2 * kp.inv_nu, kp.kappa);
+}

@@ -1,0 +1,132 @@
+// Internal context of libncm_sd_gpu: stream, device buffers, timers.
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+#include "../../include/ncm_sd_gpu.h"
+#include "common.cuh"
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  // grow-only device allocation; returns false on failure
+  bool reserve(size_t bytes);
+  void release();
+  template <typename T>
+  T *as() const { return static_cast<T *>(p); }
+};
+
+struct PinBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  bool reserve(size_t bytes);
+  void release();
+  template <typename T>
+  T *as() const { return static_cast<T *>(p); }
+};
+
+struct ncm_sd_gpu_ctx {
+  int device = 0;
+  int n_sm = 148;
+  cudaStream_t stream = nullptr;
+  std::string err;
+
+  // kernel
+  int kind = 0;
+  double nu = 3.0;
+  int d = 0;
+  int dp = 0;   // VKDE template dimension (d padded to the next instantiated size)
+
+  // model
+  int type = -1;   // NCM_SD_GPU_KDE / VKDE
+  int n_obs = 0, n_kernels = 0;
+  double href = 1.0;
+  double lnnorm = 0.0;       // KDE common lnnorm
+  int row0 = 0, nrows = 0;   // IM row shard on this rank
+  bool have_weights = false;
+
+  // VKDE buffers
+  DevBuf sample;     // [n_obs x d] raw points (row-major, ld = d)
+  DevBuf vrec;       // [n_kernels x vrec_len] packed records: theta[dp], Lp[dp(dp+1)/2] (diag = 1/U_kk)
+  int vrec_len = 0;
+  DevBuf lnu;        // [n_kernels] per-kernel lnnorm (VKDE) -- without d ln h
+  DevBuf cterm;      // [n_kernels] ln w_i - lnu_i
+  DevBuf weights;    // [n_kernels]
+  DevBuf Ufull;      // VKDE: [n_kernels x d x d] dense factors (sample_apply) ; KDE: [d x d]
+
+  // KDE buffers
+  int kp = 0;        // padded K of the augmented GEMM
+  DevBuf zc;         // [n_obs x d] whitened centred points
+  DevBuf zmean;      // [d]
+  DevBuf bfrag;      // fragment-major B operand of the kernels [n_kernels/8][kp/4][32]
+  DevBuf kde_U;      // [d x d]
+
+  // queries / outputs / partials
+  DevBuf qX, qOut, qA, part;
+  PinBuf pinX, pinOut;
+
+  // IM + NNLS
+  DevBuf IM;         // [nrows_local x n_kernels]
+  DevBuf rowscale;   // [n_obs]
+  DevBuf M, MU, nn_b, nn_x, nn_r, nn_g, nn_tmp, nn_idx, nn_f;
+  PinBuf pin_nn;
+
+  // NCCL
+  void *nccl_comm = nullptr;
+  int nranks = 1, rank = 0;
+
+  // timers
+  bool timers_on = false;
+  double t_ms[NCM_SD_GPU_T_LEN] = {0};
+  long long n_launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+  int fail(int code, const std::string &msg) {
+    err = msg;
+    return code;
+  }
+};
+
+#define NCM_CUDA_OK(ctx, call)                                                                                     \
+  do {                                                                                                             \
+    cudaError_t e__ = (call);                                                                                      \
+    if (e__ != cudaSuccess)                                                                                        \
+      return (ctx)->fail(NCM_SD_GPU_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + ":" + \
+                                               std::to_string(__LINE__) + ")");                                   \
+  } while (0)
+
+struct StageTimer {
+  ncm_sd_gpu_ctx *c;
+  int stage;
+  StageTimer(ncm_sd_gpu_ctx *ctx, int st) : c(ctx), stage(st) {
+    if (c->timers_on) cudaEventRecord(c->ev0, c->stream);
+  }
+  ~StageTimer() {
+    if (c->timers_on) {
+      cudaEventRecord(c->ev1, c->stream);
+      cudaEventSynchronize(c->ev1);
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+      c->t_ms[stage] += ms;
+    }
+  }
+};
+
+// ---- kernels' host launchers (defined in the .cu files) --------------------------------------------
+int vkde_pad_dim(int d);
+int vkde_pack(ncm_sd_gpu_ctx *c, const double *dU_all /* n x d x d */);
+int vkde_eval_launch(ncm_sd_gpu_ctx *c, int q, const double *dX, int ldx, double *dOut, bool as_density);
+int vkde_im_launch(ncm_sd_gpu_ctx *c, const double *dRowScale);
+
+int kde_prepare(ncm_sd_gpu_ctx *c, const double *dInvU /* n_obs x d */);
+int kde_set_weights(ncm_sd_gpu_ctx *c);
+int kde_eval_launch(ncm_sd_gpu_ctx *c, int q, const double *dX, int ldx, double *dOut, bool as_density);
+int kde_im_launch(ncm_sd_gpu_ctx *c, const double *dRowScale);
+
+int update_cterm(ncm_sd_gpu_ctx *c);
+
+int dsyrk_ata(ncm_sd_gpu_ctx *c, int nrows, int ncols, const double *dA, int lda, double *dM, int ldm);
+int dpotrf_upper(ncm_sd_gpu_ctx *c, int n, double *dM, int ldm, double *dRhs /* optional, solved in place */, int *info_host);
+int nnls_solve_dev(ncm_sd_gpu_ctx *c, int nrows, int ncols, const double *dA, int lda, const double *dF, double reltol, double *x_host,
+                   double *rnorm_host, ncm_sd_gpu_nnls_stats *stats);
+int sample_apply_launch(ncm_sd_gpu_ctx *c, int q, const int *dIdx, const double *dZ, int ldz, const double *dScale, double *dX, int ldx);

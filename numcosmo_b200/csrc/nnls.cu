@@ -1,0 +1,403 @@
+// NNLS driver: block-pivoting active-set method on the normal equations, device linear algebra,
+// host index-set decisions.
+//
+// Replaces ncm_nnls_solve with NCM_NNLS_UMETHOD_NORMAL (ncm_nnls.c:767-871):
+//   M = A^T A (upper), b = A^T f                         ncm_nnls.c:791-792
+//   _ncm_nnls_solve_feasible                             ncm_nnls.c:728-751
+//   residuals / mgrad                                    ncm_nnls.c:710-726
+//   outer loop with add_frac halving                     ncm_nnls.c:825-868
+// and the NcmISet operations it relies on (ncm_iset.c:853-1077): the passive set is always
+// handled in ascending index order, "invalid" means x_i < 1e-300, the most negative
+// max_remove entries are evicted, and the largest add_frac share of the positive gradient
+// entries is admitted.  Which systems get solved decides the final passive set, so this
+// logic mirrors the reference decision by decision; only the arithmetic runs on the device.
+//
+// Deviation (documented in DESIGN.md): when a passive-set matrix is not numerically positive
+// definite the reference falls back to LAPACK dsysv and then dgels (ncm_nnls.c:573-638); here the
+// factorisation is retried with a relative diagonal shift (1e-13, 1e-11, 1e-9) and counted in
+// stats->n_retry.  Such systems are conditioned far beyond the 1e-10 parity bar either way.
+#include <algorithm>
+#include <cstring>
+#include <dlfcn.h>
+#include <vector>
+#include "ctx.h"
+#include "nccl_shim.h"
+
+int dsyrk_ata_general(ncm_sd_gpu_ctx *c, int K, int n, const double *dP, int ldp, double *dC, int ldc, double alpha, double beta);
+int dpotrf_upper_solve(ncm_sd_gpu_ctx *c, int n, double *dM, int ldm, double *dRhs, double *dDinv, int *dInfo, int *info_host);
+int gemv_t(ncm_sd_gpu_ctx *c, const double *dA, int lda, int nrows, int ncols, const double *dv, double *dOut, DevBuf &tmp);
+int residual(ncm_sd_gpu_ctx *c, const double *dA, int lda, int nrows, int ncols, const double *dx, const double *df, double *dr,
+             double *d_ss_part, int *nblocks_out);
+
+// ---- NCCL through dlopen (nccl_shim.h) ----------------------------------------------------------------
+NcclApi &nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried   = true;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (h != nullptr) {
+      api.GetUniqueId    = (decltype(api.GetUniqueId)) dlsym(h, "ncclGetUniqueId");
+      api.CommInitRank   = (decltype(api.CommInitRank)) dlsym(h, "ncclCommInitRank");
+      api.AllReduce      = (decltype(api.AllReduce)) dlsym(h, "ncclAllReduce");
+      api.CommDestroy    = (decltype(api.CommDestroy)) dlsym(h, "ncclCommDestroy");
+      api.GetErrorString = (decltype(api.GetErrorString)) dlsym(h, "ncclGetErrorString");
+      api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.CommDestroy && api.GetErrorString;
+    }
+  }
+  return api;
+}
+
+static int allreduce_sum(ncm_sd_gpu_ctx *c, double *dbuf, size_t count) {
+  if (c->nranks <= 1) return NCM_SD_GPU_OK;
+  NcclApi &api   = nccl_api();
+  ncclResult_t r = api.AllReduce(dbuf, dbuf, count, ncclDouble, ncclSum, (ncclComm_t) c->nccl_comm, c->stream);
+  if (r != ncclSuccess) return c->fail(NCM_SD_GPU_ENCCL, std::string("ncclAllReduce: ") + api.GetErrorString(r));
+  return NCM_SD_GPU_OK;
+}
+
+namespace {
+
+__global__ void gather_sym_kernel(const double *__restrict__ M, int ldm, const int *__restrict__ idx, int np, double *__restrict__ S, int lds,
+                                  const double *__restrict__ b, double *__restrict__ rhs, double shift) {
+  // S[i][j] = M[idx[i]][idx[j]] for j >= i (idx ascending => source is in the upper triangle)
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y;
+  if (i >= np || j >= np) return;
+  if (j >= i) {
+    double v = M[(size_t) idx[i] * ldm + idx[j]];
+    if (i == j) v += shift;
+    S[(size_t) i * lds + j] = v;
+  }
+  if (i == 0) rhs[j] = b[idx[j]];
+}
+
+__global__ void copy_upper_kernel(const double *__restrict__ M, int ldm, int n, double *__restrict__ S, int lds, const double *__restrict__ b,
+                                  double *__restrict__ rhs, double shift) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y;
+  if (i >= n || j >= n) return;
+  if (j >= i) {
+    double v = M[(size_t) i * ldm + j];
+    if (i == j) v += shift;
+    S[(size_t) i * lds + j] = v;
+  }
+  if (i == 0) rhs[j] = b[j];
+}
+
+__global__ void sum_parts_kernel(const double *__restrict__ part, int n, double *__restrict__ out) {
+  __shared__ double sh[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += part[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if (threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = sh[0];
+}
+
+__global__ void diag_mean_kernel(const double *__restrict__ M, int ldm, int n, double *__restrict__ out) {
+  __shared__ double sh[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += M[(size_t) i * ldm + i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if (threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = sh[0] / n;
+}
+
+// GSL sort/subsetind_source.c semantics (first-come wins on ties), as NcmISet uses them
+void sort_smallest_index(std::vector<int> &p, int k, const std::vector<double> &src, int n) {
+  p.assign(k, 0);
+  if (k == 0 || n == 0) return;
+  int j         = 1;
+  double xbound = src[0];
+  p[0]          = 0;
+  for (int i = 1; i < n; i++) {
+    const double xi = src[i];
+    if (j < k)
+      j++;
+    else if (xi >= xbound)
+      continue;
+    int i1;
+    for (i1 = j - 1; i1 > 0; i1--) {
+      if (xi > src[p[i1 - 1]]) break;
+      p[i1] = p[i1 - 1];
+    }
+    p[i1]  = i;
+    xbound = src[p[j - 1]];
+  }
+}
+
+void sort_largest_index(std::vector<int> &p, int k, const std::vector<double> &src, int n) {
+  p.assign(k, 0);
+  if (k == 0 || n == 0) return;
+  int j         = 1;
+  double xbound = src[0];
+  p[0]          = 0;
+  for (int i = 1; i < n; i++) {
+    const double xi = src[i];
+    if (j < k)
+      j++;
+    else if (xi <= xbound)
+      continue;
+    int i1;
+    for (i1 = j - 1; i1 > 0; i1--) {
+      if (xi < src[p[i1 - 1]]) break;
+      p[i1] = p[i1 - 1];
+    }
+    p[i1]  = i;
+    xbound = src[p[j - 1]];
+  }
+}
+
+struct NnlsWork {
+  ncm_sd_gpu_ctx *c;
+  int nrows, n, lda, ldm;
+  const double *dA, *dF;
+  double *dM, *dMU, *db, *drhs, *dx, *dr, *dr_try, *dg, *ddinv, *dss, *dscal;
+  int *didx, *dinfo;
+  double *h_buf;   // pinned: n doubles + 8
+  int *h_idx;      // pinned: n ints
+  double diag_mean = 0.0;
+  ncm_sd_gpu_nnls_stats *st;
+};
+
+// solve M[P,P] x_P = b[P]; result in h_buf[0..np)
+int solve_unconstrained(NnlsWork &w, const std::vector<int> &P) {
+  ncm_sd_gpu_ctx *c = w.c;
+  const int np      = (int) P.size();
+  if (np == 0) return NCM_SD_GPU_OK;
+  static const double shifts[4] = {0.0, 1.0e-13, 1.0e-11, 1.0e-9};
+  for (int attempt = 0; attempt < 4; ++attempt) {
+    const double shift = shifts[attempt] * w.diag_mean;
+    {
+      StageTimer t(c, NCM_SD_GPU_T_NNLS_MISC);
+      if (np == w.n) {
+        dim3 grid((np + 255) / 256, np);
+        copy_upper_kernel<<<grid, 256, 0, c->stream>>>(w.dM, w.ldm, np, w.dMU, w.ldm, w.db, w.drhs, shift);
+      } else {
+        std::memcpy(w.h_idx, P.data(), sizeof(int) * np);
+        NCM_CUDA_OK(c, cudaMemcpyAsync(w.didx, w.h_idx, sizeof(int) * np, cudaMemcpyHostToDevice, c->stream));
+        dim3 grid((np + 255) / 256, np);
+        gather_sym_kernel<<<grid, 256, 0, c->stream>>>(w.dM, w.ldm, w.didx, np, w.dMU, w.ldm, w.db, w.drhs, shift);
+      }
+      c->n_launches++;
+    }
+    int info = 0;
+    {
+      StageTimer t(c, NCM_SD_GPU_T_CHOL);
+      int rc = dpotrf_upper_solve(c, np, w.dMU, w.ldm, w.drhs, w.ddinv, w.dinfo, &info);
+      if (rc != NCM_SD_GPU_OK) return rc;
+    }
+    if (w.st) w.st->n_chol++;
+    if (info == 0) {
+      NCM_CUDA_OK(c, cudaMemcpyAsync(w.h_buf, w.drhs, sizeof(double) * np, cudaMemcpyDeviceToHost, c->stream));
+      NCM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+      return NCM_SD_GPU_OK;
+    }
+    if (w.st) w.st->n_retry++;
+  }
+  return c->fail(NCM_SD_GPU_ENOTPD, "nnls: passive-set normal matrix is not positive definite");
+}
+
+// ncm_nnls.c:728-751
+int solve_feasible(NnlsWork &w, std::vector<int> &P, std::vector<double> &x, int max_remove) {
+  std::vector<int> invalid, ptmp;
+  std::vector<double> vals;
+  while (true) {
+    int rc = solve_unconstrained(w, P);
+    if (rc != NCM_SD_GPU_OK) return rc;
+    std::fill(x.begin(), x.end(), 0.0);
+    for (size_t j = 0; j < P.size(); ++j) x[P[j]] = w.h_buf[j];
+    invalid.clear();
+    for (int i : P)
+      if (x[i] < 1.0e-300) invalid.push_back(i);
+    if (invalid.empty()) return NCM_SD_GPU_OK;
+    // ncm_iset_remove_smallest_subset, ncm_iset.c:920-985
+    const int rsize = (int) invalid.size();
+    std::vector<char> drop(w.n, 0);
+    if (max_remove >= rsize) {
+      for (int i : invalid) drop[i] = 1;
+    } else {
+      vals.resize(rsize);
+      for (int j = 0; j < rsize; ++j) vals[j] = x[invalid[j]];
+      sort_smallest_index(ptmp, max_remove, vals, rsize);
+      for (int j = 0; j < max_remove; ++j) drop[invalid[ptmp[j]]] = 1;
+    }
+    std::vector<int> Pn;
+    Pn.reserve(P.size());
+    for (int i : P)
+      if (!drop[i]) Pn.push_back(i);
+    P.swap(Pn);
+  }
+}
+
+// rnorm of x (host) -> residual vector left in dr_out
+int compute_residuals(NnlsWork &w, const std::vector<double> &x, double *dr_out, double *rnorm) {
+  ncm_sd_gpu_ctx *c = w.c;
+  StageTimer t(c, NCM_SD_GPU_T_NNLS_MISC);
+  std::memcpy(w.h_buf, x.data(), sizeof(double) * w.n);
+  NCM_CUDA_OK(c, cudaMemcpyAsync(w.dx, w.h_buf, sizeof(double) * w.n, cudaMemcpyHostToDevice, c->stream));
+  int nb = 0;
+  int rc = residual(c, w.dA, w.lda, w.nrows, w.n, w.dx, w.dF, dr_out, w.dss, &nb);
+  if (rc != NCM_SD_GPU_OK) return rc;
+  sum_parts_kernel<<<1, 256, 0, c->stream>>>(w.dss, nb, w.dscal);
+  c->n_launches++;
+  rc = allreduce_sum(c, w.dscal, 1);
+  if (rc != NCM_SD_GPU_OK) return rc;
+  NCM_CUDA_OK(c, cudaMemcpyAsync(w.h_buf + w.n, w.dscal, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  NCM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  *rnorm = sqrt(w.h_buf[w.n]);
+  return NCM_SD_GPU_OK;
+}
+
+int compute_mgrad(NnlsWork &w, const double *dr_in, std::vector<double> &g) {
+  ncm_sd_gpu_ctx *c = w.c;
+  StageTimer t(c, NCM_SD_GPU_T_NNLS_MISC);
+  int rc = gemv_t(c, w.dA, w.lda, w.nrows, w.n, dr_in, w.dg, c->nn_tmp);
+  if (rc != NCM_SD_GPU_OK) return rc;
+  rc = allreduce_sum(c, w.dg, w.n);
+  if (rc != NCM_SD_GPU_OK) return rc;
+  NCM_CUDA_OK(c, cudaMemcpyAsync(w.h_buf, w.dg, sizeof(double) * w.n, cudaMemcpyDeviceToHost, c->stream));
+  NCM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  g.assign(w.h_buf, w.h_buf + w.n);
+  return NCM_SD_GPU_OK;
+}
+
+// ncm_iset_add_largest_subset, ncm_iset.c:994-1077
+int add_largest_subset(std::vector<int> &P, int n, const std::vector<double> &v, double min, double add_frac) {
+  const int csize = n - (int) P.size();
+  if (csize == 0) return 0;
+  std::vector<double> vc;
+  std::vector<int> ic;
+  std::vector<char> in(n, 0);
+  for (int i : P) in[i] = 1;
+  for (int j = 0; j < n; ++j) {
+    if (!in[j] && v[j] > min) {
+      vc.push_back(v[j]);
+      ic.push_back(j);
+    }
+  }
+  const int k = (int) vc.size();
+  double a    = k * add_frac;
+  if (a < 1.0) a = 1.0;
+  if ((double) k < a) a = (double) k;
+  const int adds = (int) a;
+  if (adds > 0) {
+    std::vector<int> p;
+    sort_largest_index(p, adds, vc, k);
+    for (int j = 0; j < adds; ++j) P.push_back(ic[p[j]]);
+    std::sort(P.begin(), P.end());
+  }
+  return adds;
+}
+
+}   // namespace
+
+int nnls_solve_dev(ncm_sd_gpu_ctx *c, int nrows, int ncols, const double *dA, int lda, const double *dF, double reltol, double *x_host,
+                   double *rnorm_host, ncm_sd_gpu_nnls_stats *stats) {
+  const int n   = ncols;
+  const int ldm = (n + 7) & ~7;
+  if (stats) std::memset(stats, 0, sizeof(*stats));
+  const size_t mm = (size_t) n * ldm * sizeof(double);
+  if (!c->M.reserve(mm) || !c->MU.reserve(mm) || !c->nn_b.reserve((size_t) (4 * n + 64) * sizeof(double)) ||
+      !c->nn_x.reserve((size_t) (2 * n + 16) * sizeof(double)) || !c->nn_r.reserve((size_t) (2 * nrows + 16) * sizeof(double)) ||
+      !c->nn_g.reserve((size_t) (nrows / 8 + n + 64) * sizeof(double)) || !c->nn_idx.reserve((size_t) (n + 16) * sizeof(int)) ||
+      !c->pin_nn.reserve((size_t) (n + 16) * sizeof(double) + (size_t) (n + 16) * sizeof(int)))
+    return c->fail(NCM_SD_GPU_ENOMEM, "nnls: out of memory");
+
+  NnlsWork w;
+  w.c = c; w.nrows = nrows; w.n = n; w.lda = lda; w.ldm = ldm; w.dA = dA; w.dF = dF; w.st = stats;
+  w.dM     = c->M.as<double>();
+  w.dMU    = c->MU.as<double>();
+  w.db     = c->nn_b.as<double>();
+  w.drhs   = w.db + (n + 16);
+  w.ddinv  = w.drhs + (n + 16);
+  w.dscal  = w.ddinv + (n + 16);
+  w.dx     = c->nn_x.as<double>();
+  w.dg     = w.dx + (n + 8);
+  w.dr     = c->nn_r.as<double>();
+  w.dr_try = w.dr + (nrows + 8);
+  w.dss    = c->nn_g.as<double>();
+  w.didx   = c->nn_idx.as<int>();
+  w.dinfo  = w.didx + (n + 8);
+  w.h_buf  = c->pin_nn.as<double>();
+  w.h_idx  = reinterpret_cast<int *>(w.h_buf + (n + 16));
+
+  int rc;
+  {
+    StageTimer t(c, NCM_SD_GPU_T_SYRK);
+    rc = dsyrk_ata_general(c, nrows, n, dA, lda, w.dM, ldm, 1.0, 0.0);
+    if (rc != NCM_SD_GPU_OK) return rc;
+    rc = allreduce_sum(c, w.dM, (size_t) n * ldm);
+    if (rc != NCM_SD_GPU_OK) return rc;
+  }
+  {
+    StageTimer t(c, NCM_SD_GPU_T_NNLS_MISC);
+    rc = gemv_t(c, dA, lda, nrows, n, dF, w.db, c->nn_tmp);
+    if (rc != NCM_SD_GPU_OK) return rc;
+    rc = allreduce_sum(c, w.db, n);
+    if (rc != NCM_SD_GPU_OK) return rc;
+    diag_mean_kernel<<<1, 256, 0, c->stream>>>(w.dM, ldm, n, w.dscal);
+    c->n_launches++;
+    NCM_CUDA_OK(c, cudaMemcpyAsync(w.h_buf, w.dscal, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    NCM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    w.diag_mean = w.h_buf[0];
+  }
+
+  std::vector<int> P(n), P_try;
+  for (int i = 0; i < n; ++i) P[i] = i;
+  std::vector<double> x(n, 0.0), x_try(n, 0.0), mgrad;
+  double rnorm = 0.0;
+
+  rc = solve_feasible(w, P, x, n);
+  if (rc != NCM_SD_GPU_OK) return rc;
+  rc = compute_residuals(w, x, w.dr, &rnorm);
+  if (rc != NCM_SD_GPU_OK) return rc;
+  rc = compute_mgrad(w, w.dr, mgrad);
+  if (rc != NCM_SD_GPU_OK) return rc;
+
+  while (true) {
+    double add_frac = 1.0;
+    bool finish     = false;
+    double lrnorm   = 0.0;
+    while (true) {
+      P_try           = P;
+      const int added = add_largest_subset(P_try, n, mgrad, rnorm * reltol, add_frac);
+      add_frac *= 0.5;
+      if (added == 0) {
+        finish = true;
+        break;
+      }
+      rc = solve_feasible(w, P_try, x_try, added);
+      if (rc != NCM_SD_GPU_OK) return rc;
+      rc = compute_residuals(w, x_try, w.dr_try, &lrnorm);
+      if (rc != NCM_SD_GPU_OK) return rc;
+      if (rnorm - lrnorm > rnorm * reltol) {
+        P = P_try;
+        x = x_try;
+        std::swap(w.dr, w.dr_try);
+        rnorm = lrnorm;
+        if (stats) stats->n_outer++;
+        break;
+      }
+      if (added == 1) {
+        finish = true;
+        break;
+      }
+    }
+    if (finish) break;
+    rc = compute_mgrad(w, w.dr, mgrad);
+    if (rc != NCM_SD_GPU_OK) return rc;
+  }
+  if (stats) stats->n_passive = (int) P.size();
+  std::memcpy(x_host, x.data(), sizeof(double) * n);
+  *rnorm_host = rnorm;
+  return NCM_SD_GPU_OK;
+}

@@ -1,0 +1,305 @@
+// VKDE (per-centre covariance) kernels: batched eval_m2lnp / eval and the interpolation matrix.
+//
+// Replaces _ncm_stats_dist_vkde_eval_weights{,_m2lnp} (ncm_stats_dist_vkde.c:631-723) and
+// _ncm_stats_dist_vkde_compute_IM (ncm_stats_dist_vkde.c:517-606):
+//     chi2_i(x) = | U_i^-T (x - theta_i) |^2 / h^2
+// One thread owns one query point (coordinates in registers); the CTA streams the centres'
+// packed records  { theta_i[DP], L_i = U_i^T packed lower, diagonal stored as 1/U_kk }
+// through shared memory with bulk async copies (cp.async.bulk + mbarrier, double buffered);
+// every lane of a warp reads the same record element (shared-memory broadcast) while doing
+// the forward substitution in registers, then the kernel function and an online
+// log-sum-exp.  The centre range is split across gridDim.y so that small query batches
+// still fill 148 SMs; partial (max, sum) pairs are merged by lse_finalize_kernel.
+#include "ctx.h"
+
+namespace {
+
+template <int DP>
+struct VkdeCfg {
+  static constexpr int REC = (DP + DP * (DP + 1) / 2 + 1) & ~1;   // doubles per record (even => 16 B multiple)
+  static constexpr int CH  = DP <= 8 ? 64 : DP <= 12 ? 32 : DP <= 16 ? 16 : DP <= 24 ? 8 : 4;   // centres per stage
+  static constexpr int TQ  = 128;                                  // queries (= threads) per CTA
+};
+
+// ---- record packing -------------------------------------------------------------------------------
+__global__ void vkde_pack_kernel(const double *__restrict__ sample, const double *__restrict__ U_all, double *__restrict__ rec, int n,
+                                 int d, int dp, int rec_len) {
+  const int i = blockIdx.x;
+  if (i >= n) return;
+  const double *U = U_all + (size_t) i * d * d;
+  double *r       = rec + (size_t) i * rec_len;
+  for (int k = threadIdx.x; k < dp; k += blockDim.x) r[k] = k < d ? sample[(size_t) i * d + k] : 0.0;
+  const int tri = dp * (dp + 1) / 2;
+  for (int t = threadIdx.x; t < tri; t += blockDim.x) {
+    // t = k (k + 1) / 2 + j, j <= k
+    int k = (int) ((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+    while (k * (k + 1) / 2 > t) --k;
+    while ((k + 1) * (k + 2) / 2 <= t) ++k;
+    const int j = t - k * (k + 1) / 2;
+    double v;
+    if (k < d && j < d)
+      v = (j == k) ? 1.0 / U[k * d + k] : U[j * d + k];   // L[k][j] = U[j][k]
+    else
+      v = (j == k) ? 1.0 : 0.0;
+    r[dp + t] = v;
+  }
+  if (threadIdx.x == 0 && dp + tri < rec_len) r[dp + tri] = 0.0;
+}
+
+struct VkdeArgs {
+  const double *X;        // queries [q x ldx]
+  int ldx, q, d;
+  const double *rec;      // packed records
+  const double *cvec;     // eval: ln w_i - lnu_i ; IM: 1 / exp(lnu_i + d ln h)
+  int n;                  // centres
+  int per_split;          // centres per gridDim.y slice (multiple of CH)
+  double inv_h2;
+  KernParams kp;
+  // eval outputs
+  double *part_m, *part_s;   // [gridDim.y x q]
+  // IM outputs
+  double *IM;             // [q x ldim]
+  int ldim;
+  const double *rowscale; // [q] or null
+};
+
+template <int DP, int MODE>   // MODE 0: log-sum-exp partials ; MODE 1: IM entries
+__global__ void __launch_bounds__(VkdeCfg<DP>::TQ) vkde_kernel(const VkdeArgs a) {
+  using Cfg = VkdeCfg<DP>;
+  constexpr int REC = Cfg::REC, CH = Cfg::CH;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *srec      = reinterpret_cast<double *>(smem_raw);             // [2][CH * REC]
+  double *scv       = srec + 2 * CH * REC;                              // [2][CH]
+  uint64_t *bars    = reinterpret_cast<uint64_t *>(scv + 2 * CH);       // [2]
+
+  const int tid = threadIdx.x;
+  const int qi  = blockIdx.x * Cfg::TQ + tid;
+  const bool qv = qi < a.q;
+
+  const int c_begin = blockIdx.y * a.per_split;
+  const int c_end   = min(a.n, c_begin + a.per_split);
+  const int nch     = (c_end - c_begin + CH - 1) / CH;
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  auto issue = [&](int ch) {
+    const int st  = ch & 1;
+    const int c0  = c_begin + ch * CH;
+    const int cnt = min(CH, c_end - c0);
+    const uint32_t b_rec = (uint32_t) (cnt * REC * sizeof(double));
+    const uint32_t b_cv  = (uint32_t) (((cnt + 1) & ~1) * sizeof(double));
+    mbar_arrive_expect_tx(&bars[st], b_rec + b_cv);
+    bulk_g2s(srec + st * CH * REC, a.rec + (size_t) c0 * REC, b_rec, &bars[st]);
+    bulk_g2s(scv + st * CH, a.cvec + c0, b_cv, &bars[st]);
+  };
+
+  if (tid == 0 && nch > 0) issue(0);
+
+  double x[DP];
+#pragma unroll
+  for (int k = 0; k < DP; ++k) x[k] = (qv && k < a.d) ? a.X[(size_t) qi * a.ldx + k] : 0.0;
+
+  Lse acc;
+  lse_init(acc);
+  const double rs = (MODE == 1 && qv && a.rowscale != nullptr) ? a.rowscale[qi] : 1.0;
+
+  for (int ch = 0; ch < nch; ++ch) {
+    if (tid == 0 && ch + 1 < nch) issue(ch + 1);
+    mbar_wait(&bars[ch & 1], (ch >> 1) & 1);
+    const int c0       = c_begin + ch * CH;
+    const int cnt      = min(CH, c_end - c0);
+    const double *base = srec + (ch & 1) * CH * REC;
+    const double *cv   = scv + (ch & 1) * CH;
+
+    for (int c = 0; c < cnt; ++c) {
+      const double *r = base + c * REC;
+      const double *L = r + DP;
+      double y[DP];
+      double chi2 = 0.0;
+#pragma unroll
+      for (int k = 0; k < DP; ++k) {
+        double t = x[k] - r[k];
+#pragma unroll
+        for (int j = 0; j < k; ++j) t = fma(-L[k * (k + 1) / 2 + j], y[j], t);
+        y[k] = t * L[k * (k + 1) / 2 + k];
+        chi2 = fma(y[k], y[k], chi2);
+      }
+      chi2 *= a.inv_h2;
+      if (MODE == 0) {
+        lse_push(acc, kern_lnK(a.kp, chi2) + cv[c]);
+      } else {
+        if (qv) a.IM[(size_t) qi * a.ldim + (c0 + c)] = kern_K(a.kp, chi2) * cv[c] * rs;
+      }
+    }
+    __syncthreads();   // everyone is done with stage (ch & 1) before it is refilled
+  }
+
+  if (MODE == 0 && qv) {
+    a.part_m[(size_t) blockIdx.y * a.q + qi] = acc.m;
+    a.part_s[(size_t) blockIdx.y * a.q + qi] = acc.s;
+  }
+}
+
+template <int DP, int MODE>
+int launch_t(ncm_sd_gpu_ctx *c, const VkdeArgs &a, int n_splits) {
+  using Cfg = VkdeCfg<DP>;
+  const size_t smem = (size_t) (2 * Cfg::CH * Cfg::REC + 2 * Cfg::CH) * sizeof(double) + 2 * sizeof(uint64_t);
+  static bool attr_set = false;
+  if (!attr_set) {
+    NCM_CUDA_OK(c, cudaFuncSetAttribute(vkde_kernel<DP, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    attr_set = true;
+  }
+  dim3 grid((a.q + Cfg::TQ - 1) / Cfg::TQ, n_splits);
+  vkde_kernel<DP, MODE><<<grid, Cfg::TQ, smem, c->stream>>>(a);
+  c->n_launches++;
+  NCM_CUDA_OK(c, cudaGetLastError());
+  return NCM_SD_GPU_OK;
+}
+
+template <int DP>
+int ch_of() { return VkdeCfg<DP>::CH; }
+
+#define VKDE_DISPATCH(DPV, CALL)                 \
+  switch (DPV) {                                 \
+    case 2: { constexpr int DP = 2; CALL; } break;     \
+    case 3: { constexpr int DP = 3; CALL; } break;     \
+    case 4: { constexpr int DP = 4; CALL; } break;     \
+    case 5: { constexpr int DP = 5; CALL; } break;     \
+    case 6: { constexpr int DP = 6; CALL; } break;     \
+    case 7: { constexpr int DP = 7; CALL; } break;     \
+    case 8: { constexpr int DP = 8; CALL; } break;     \
+    case 10: { constexpr int DP = 10; CALL; } break;   \
+    case 12: { constexpr int DP = 12; CALL; } break;   \
+    case 14: { constexpr int DP = 14; CALL; } break;   \
+    case 16: { constexpr int DP = 16; CALL; } break;   \
+    case 20: { constexpr int DP = 20; CALL; } break;   \
+    case 24: { constexpr int DP = 24; CALL; } break;   \
+    case 28: { constexpr int DP = 28; CALL; } break;   \
+    case 32: { constexpr int DP = 32; CALL; } break;   \
+    default: return c->fail(NCM_SD_GPU_EINVAL, "vkde: unsupported padded dimension"); \
+  }
+
+}   // namespace
+
+int vkde_pad_dim(int d) {
+  static const int sizes[] = {2, 3, 4, 5, 6, 7, 8, 10, 12, 14, 16, 20, 24, 28, 32};
+  for (int s : sizes)
+    if (d <= s) return s;
+  return -1;
+}
+
+static int vkde_rec_len(int dp) { return (dp + dp * (dp + 1) / 2 + 1) & ~1; }
+
+static int vkde_ch(ncm_sd_gpu_ctx *c, int dp) {
+  int ch = 0;
+  VKDE_DISPATCH(dp, ch = ch_of<DP>());
+  return ch;
+}
+
+int vkde_pack(ncm_sd_gpu_ctx *c, const double *dU_all) {
+  c->dp       = vkde_pad_dim(c->d);
+  c->vrec_len = vkde_rec_len(c->dp);
+  if (!c->vrec.reserve((size_t) c->n_kernels * c->vrec_len * sizeof(double))) return c->fail(NCM_SD_GPU_ENOMEM, "vkde_pack: out of device memory");
+  vkde_pack_kernel<<<c->n_kernels, 128, 0, c->stream>>>(c->sample.as<double>(), dU_all, c->vrec.as<double>(), c->n_kernels, c->d, c->dp,
+                                                      c->vrec_len);
+  c->n_launches++;
+  NCM_CUDA_OK(c, cudaGetLastError());
+  return NCM_SD_GPU_OK;
+}
+
+// merge the per-split partials:  out = -2 (m + log s + shift)  or  exp(m + log s + shift)
+__global__ void lse_finalize_kernel(const double *__restrict__ pm, const double *__restrict__ ps, const double *__restrict__ row_add, int q,
+                                    int n_splits, double shift, int as_density, double *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= q) return;
+  Lse a;
+  a.m = pm[i];
+  a.s = ps[i];
+  for (int s = 1; s < n_splits; ++s) lse_merge(a, pm[(size_t) s * q + i], ps[(size_t) s * q + i]);
+  const double ln = a.m + log(a.s) + shift + (row_add != nullptr ? row_add[i] : 0.0);
+  out[i]          = as_density ? exp(ln) : -2.0 * ln;
+}
+
+int lse_finalize_launch(ncm_sd_gpu_ctx *c, const double *pm, const double *ps, const double *row_add, int q, int n_splits, double shift,
+                        bool as_density, double *dOut) {
+  lse_finalize_kernel<<<(q + 255) / 256, 256, 0, c->stream>>>(pm, ps, row_add, q, n_splits, shift, as_density ? 1 : 0, dOut);
+  c->n_launches++;
+  NCM_CUDA_OK(c, cudaGetLastError());
+  return NCM_SD_GPU_OK;
+}
+
+static void fill_kp(const ncm_sd_gpu_ctx *c, KernParams &kp) {
+  kp.kind   = c->kind;
+  kp.nu     = c->nu;
+  kp.kappa  = -0.5 * (c->nu + c->d);
+  kp.inv_nu = 1.0 / c->nu;
+}
+
+// choose the number of centre splits so that the grid is about two waves of resident CTAs
+static int pick_splits(const ncm_sd_gpu_ctx *c, int q_tiles, int n, int ch, int ctas_per_sm) {
+  const int target = c->n_sm * ctas_per_sm;
+  int splits       = (target + q_tiles - 1) / q_tiles;
+  const int max_sp = (n + ch - 1) / ch;
+  if (splits > max_sp) splits = max_sp;
+  if (splits < 1) splits = 1;
+  return splits;
+}
+
+int vkde_eval_launch(ncm_sd_gpu_ctx *c, int q, const double *dX, int ldx, double *dOut, bool as_density) {
+  const int dp      = c->dp;
+  const int ch      = vkde_ch(c, dp);
+  const int q_tiles = (q + 127) / 128;
+  int splits        = pick_splits(c, q_tiles, c->n_kernels, ch, 4);
+  int per_split     = ((c->n_kernels + splits - 1) / splits + ch - 1) / ch * ch;
+  splits            = (c->n_kernels + per_split - 1) / per_split;
+  if (!c->part.reserve((size_t) 2 * splits * q * sizeof(double))) return c->fail(NCM_SD_GPU_ENOMEM, "vkde_eval: out of device memory");
+  VkdeArgs a;
+  a.X = dX; a.ldx = ldx; a.q = q; a.d = c->d;
+  a.rec = c->vrec.as<double>(); a.cvec = c->cterm.as<double>();
+  a.n = c->n_kernels; a.per_split = per_split;
+  a.inv_h2 = 1.0 / (c->href * c->href);
+  fill_kp(c, a.kp);
+  a.part_m = c->part.as<double>(); a.part_s = a.part_m + (size_t) splits * q;
+  a.IM = nullptr; a.ldim = 0; a.rowscale = nullptr;
+  int rc = NCM_SD_GPU_OK;
+  VKDE_DISPATCH(dp, rc = (launch_t<DP, 0>(c, a, splits)));
+  if (rc != NCM_SD_GPU_OK) return rc;
+  // m2lnp = -2 (gamma + log1p(lambda) - d ln h), ncm_stats_dist_vkde.c:721
+  return lse_finalize_launch(c, a.part_m, a.part_s, nullptr, q, splits, -c->d * log(c->href), as_density, dOut);
+}
+
+__global__ void vkde_invnorm_kernel(const double *__restrict__ lnu, int n, double dlnh, double *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = 1.0 / exp(lnu[i] + dlnh);   // 1 / norm_i, ncm_stats_dist_vkde.c:601-603
+}
+
+int vkde_im_launch(ncm_sd_gpu_ctx *c, const double *dRowScale) {
+  const int dp = c->dp;
+  const int ch = vkde_ch(c, dp);
+  const int q  = c->nrows;
+  if (!c->nn_tmp.reserve((size_t) (c->n_kernels + 2) * sizeof(double))) return c->fail(NCM_SD_GPU_ENOMEM, "vkde_im: out of device memory");
+  vkde_invnorm_kernel<<<(c->n_kernels + 255) / 256, 256, 0, c->stream>>>(c->lnu.as<double>(), c->n_kernels, c->d * log(c->href),
+                                                                        c->nn_tmp.as<double>());
+  c->n_launches++;
+  const int q_tiles = (q + 127) / 128;
+  int splits        = pick_splits(c, q_tiles, c->n_kernels, ch, 4);
+  int per_split     = ((c->n_kernels + splits - 1) / splits + ch - 1) / ch * ch;
+  splits            = (c->n_kernels + per_split - 1) / per_split;
+  VkdeArgs a;
+  a.X = c->sample.as<double>() + (size_t) c->row0 * c->d; a.ldx = c->d; a.q = q; a.d = c->d;
+  a.rec = c->vrec.as<double>(); a.cvec = c->nn_tmp.as<double>();
+  a.n = c->n_kernels; a.per_split = per_split;
+  a.inv_h2 = 1.0 / (c->href * c->href);
+  fill_kp(c, a.kp);
+  a.part_m = a.part_s = nullptr;
+  a.IM = c->IM.as<double>(); a.ldim = (c->n_kernels + 7) & ~7;
+  a.rowscale = dRowScale != nullptr ? dRowScale + c->row0 : nullptr;
+  int rc = NCM_SD_GPU_OK;
+  VKDE_DISPATCH(dp, rc = (launch_t<DP, 1>(c, a, splits)));
+  return rc;
+}

@@ -111,6 +111,7 @@ void orc_sd_eval_batch (orc_sd *sd, const double *X, int ldx, int q, double *out
 int orc_sd_kernel_choose (orc_sd *sd, orc_rng *rng);
 void orc_sd_sample (orc_sd *sd, double *x, orc_rng *rng);
 
+void orc_sd_set_weights (orc_sd *sd, const double *w);
 int orc_sd_get_dim (const orc_sd *sd);
 int orc_sd_get_sample_size (const orc_sd *sd);
 int orc_sd_get_n_obs (const orc_sd *sd);

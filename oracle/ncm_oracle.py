@@ -95,6 +95,7 @@ def lib():
             "orc_sd_eval_batch": (None, [vp, _dp, i, i, _dp, i]),
             "orc_sd_kernel_choose": (i, [vp, vp]),
             "orc_sd_sample": (None, [vp, _dp, vp]),
+            "orc_sd_set_weights": (None, [vp, _dp]),
             "orc_sd_get_dim": (i, [vp]),
             "orc_sd_get_sample_size": (i, [vp]),
             "orc_sd_get_n_obs": (i, [vp]),
@@ -306,6 +307,11 @@ class StatsDist:
         out = np.zeros(X.shape[0])
         lib().orc_sd_eval_batch(self._h, _p(X), X.shape[1], X.shape[0], _p(out), nthreads)
         return out
+
+    def set_weights(self, w):
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        assert w.size == self.get_n_kernels()
+        lib().orc_sd_set_weights(self._h, _p(w))
 
     def kernel_choose(self, rng: RNG) -> int:
         return lib().orc_sd_kernel_choose(self._h, rng.ptr)

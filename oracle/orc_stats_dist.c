@@ -1226,6 +1226,14 @@ orc_sd_sample (orc_sd *sd, double *x, orc_rng *rng)
   orc_kernel_sample (&sd->kernel, cov_U, sd->d, sd->href, x_i, x, rng);
 }
 
+/* test hook: overwrite self->weights (the reference exposes them through peek_weights, ncm_stats_dist.c:1775-1780) */
+void
+orc_sd_set_weights (orc_sd *sd, const double *w)
+{
+  memcpy (sd->weights, w, sizeof (double) * sd->n_kernels);
+  sd->wcum_ready = 0;
+}
+
 int orc_sd_get_dim (const orc_sd *sd) { return sd->d; }
 int orc_sd_get_sample_size (const orc_sd *sd) { return sd->n_sample; }
 int orc_sd_get_n_obs (const orc_sd *sd) { return sd->n_obs; }
