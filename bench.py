@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py -- APES density-estimation hot path on B200 (see DESIGN.md, section Measurement).
+
+Workload at N = 1 (BASELINE.json configs[1]): APES + VKDE, Gaussian kernel, 10-D multivariate normal
+target (NcmDataGaussCovMVND recipe), 4096 walkers.  One "step" = one whole-ensemble APES iteration
+= 2 half-steps, each: interpolation matrix (N x N pairs, N = W/2 = 2048) + NNLS weight solve +
+batched eval_m2lnp of the 2N transition points against the N centres.  Pairs per step = 6 N^2.
+
+  value   device path with the block's inputs (centres, factors, query points) resident in HBM:
+          IM -> NNLS -> weights -> eval, timed with CUDA events on the context streams.
+  e2e     the same iteration through the reference-facing host API (ncm_b200_esmcmc_run over
+          ncm_stats_dist_* -> C ABI) with HOST buffers: prepare_kernel on the host, uploads, IM, NNLS,
+          host-ordered proposal sampling, batched eval, likelihood + accept; wall clock.
+  --impl reference   the CPU oracle port of the reference's algorithm (OpenMP + OpenBLAS, all host cores).
+
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "kernel_pair_evals_per_s"
+UNIT = "pairs/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="apes_vkde_gauss_mvnd10_w4096",
+                    choices=["apes_vkde_gauss_mvnd10_w4096", "eval_sweep", "prepare_interp"])
+    ap.add_argument("--walkers", type=int, default=4096)
+    ap.add_argument("--dim", type=int, default=10)
+    ap.add_argument("--sweep-q", type=int, default=65536)
+    ap.add_argument("--sweep-n", type=int, default=65536)
+    ap.add_argument("--sd", default="vkde", choices=["kde", "vkde"])
+    ap.add_argument("--kernel", default="gauss", choices=["gauss", "st3", "cauchy"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peaks = {"hbm_gbs": 6650.0, "source": "fallback"}
+    if os.path.exists(p):
+        try:
+            peaks.update(json.load(open(p)))
+            peaks["source"] = "measured"
+        except Exception:
+            pass
+    # FP64 peaks are not in MEASURED_PEAKS.json (bf16 + HBM only): measured on this pool with
+    # tools/microbench (profiles/r01_fp64_peaks.jsonl): cuBLAS DGEMM 8192^3 and a DMMA issue loop.
+    peaks["fp64_dgemm_tflops"] = 35.46
+    peaks["fp64_dmma_tflops"] = 37.1
+    return peaks
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device: int):
+        self.device, self.samples, self._stop, self._t = device, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx.append(float(s[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_problem(W, d, seed=1):
+    """configs[1] inputs: ncm_data_gauss_cov_mvnd_new_full (d, sigma in [2e-2, 5e-2], cor_level 30, mu in [1, 2]) and W walkers drawn
+    from the target."""
+    from oracle import ncm_oracle as O
+    from helpers import mvnd_problem
+
+    mu, cov, X, m2lnL = mvnd_problem(O, d, W, seed)
+    tgt = O.Target(O.TARGET_MVND, d, np.full(d, -50.0), np.full(d, 50.0), mu=mu, cov=cov)
+    return mu, cov, tgt, X, m2lnL
+
+
+def make_problem_b200(S, W, d, seed=1, sigma=(2e-2, 5e-2), cor_level=30.0, mu_range=(1.0, 2.0)):
+    """Same recipe and the same MT19937 stream as make_problem, drawn with the product's own NcmRNG mirror
+    (bit-identical to the oracle's, tests/test_oracle_known_answers.py) so that the GPU arm never touches oracle/."""
+    rng = S.RNG(seed)
+    P = np.zeros((d, d))
+    cm = np.eye(d)
+    for k in range(d - 1):          # ncm_matrix_fill_rand_cor, ncm_matrix.c:1687-1735
+        for i in range(k + 1, d):
+            p = (rng.beta_gen(cor_level, cor_level) - 0.5) * 2.0
+            P[k, i] = p
+            for l in range(k - 1, -1, -1):
+                p = p * np.sqrt((1.0 - P[l, i] ** 2) * (1.0 - P[l, k] ** 2)) + P[l, i] * P[l, k]
+            cm[k, i] = cm[i, k] = p
+    for k in range(d):              # ncm_matrix_fill_rand_cov, :1752-1770
+        s = rng.uniform_gen(sigma[0], sigma[1])
+        cm[:, k] *= s
+        cm[k, :] *= s
+    mu = np.array([rng.uniform_gen(*mu_range) for _ in range(d)])
+    L = np.linalg.cholesky(cm)
+    z = np.array([[rng.gaussian_gen(0.0, 1.0) for _ in range(d)] for _ in range(W)])
+    X = np.ascontiguousarray(mu + z @ L.T)
+    return mu, cm, np.ascontiguousarray(L.T), X, np.einsum("ij,ij->i", z, z)
+
+
+KT = {"gauss": ("GAUSS", 0, 1.0), "st3": ("ST3", 1, 3.0), "cauchy": ("CAUCHY", 1, 1.0)}
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_apes(args, W, d, iters, nthreads):
+    """The reference algorithm on the host cores (oracle port): returns seconds per iteration + stage timers."""
+    from oracle import ncm_oracle as O
+
+    mu, cov, tgt, X, m2lnL = make_problem(W, d)
+    _, okind, nu = KT[args.kernel]
+    O.lib().orc_set_blas_threads(nthreads)
+    os.environ["OMP_NUM_THREADS"] = str(nthreads)
+    ap = O.APES(W, d, O.SD_VKDE, okind, nu, over_smooth=1.0, use_interp=True, use_threads=True)
+    theta, ml = X.copy(), m2lnL.copy()
+    rng = O.RNG(1234)
+    ap.run(tgt, theta, ml, 1, rng, nthreads=nthreads)   # warm-up iteration
+    t0 = time.perf_counter()
+    ap.run(tgt, theta, ml, iters, rng, nthreads=nthreads)
+    dt = (time.perf_counter() - t0) / iters
+    return dt, ap.timers()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    W, d = args.walkers, args.dim
+    ncores = os.cpu_count() or 1
+    N = W // 2
+    pairs = 6.0 * N * N
+    # warm-up happens inside cpu_apes (1 iteration); args.warmup - 1 further untimed iterations are folded into it
+    dt, timers = cpu_apes(args, W, d, max(1, args.steps), ncores)
+    val = pairs / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"APES iteration, VKDE {args.kernel} kernel, {d}-D MVND, {W} walkers (6 N^2 pairs/step, N={N})",
+                   "note": "CPU oracle port of the reference algorithm (the reference itself cannot be built here: no GLib/GSL/meson)"},
+        "walker_steps_per_s": W / dt,
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": ncores, "kind": "port",
+                         "sample": f"{args.steps} full APES iterations at W={W}, d={d} (OpenMP walkers-parallel eval, centre-parallel IM, threaded OpenBLAS NNLS)"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "stage_s_total": {k: float(v) for k, v in timers.items()},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from numcosmo_b200 import capi
+    from numcosmo_b200 import stats_dist as S
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; numcosmo_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = S.lib()
+    lib.ncm_b200_set_device(local_rank)
+
+    W, d = args.walkers, args.dim
+    N = W // 2
+    pairs_step = 6.0 * N * N
+    mu, cov, U_tgt, X, m2lnL = make_problem_b200(S, W, d)
+    ktn, okind, nu = KT[args.kernel]
+    lb, ub = np.full(d, -50.0), np.full(d, 50.0)
+    peaks = load_peaks()
+
+    # ---------------- e2e: host API, host buffers, whole iteration ----------------
+    apes = S.FitESMCMCWalkerAPES(W, d, S.FitESMCMCWalkerAPESMethod.VKDE, getattr(S.FitESMCMCWalkerAPESKType, ktn), 1.0, True)
+    apes.set_use_threads(True)
+    theta, ml = X.copy(), m2lnL.copy()
+    rng = S.RNG(1234)
+    apes.run("mvnd", lb, ub, theta, ml, max(args.warmup, 1), rng, target_args=(mu, U_tgt), record_accept=False)
+    sds = apes.peek_sds()
+    ctxs = [capi.Context.borrowed(lib.ncm_stats_dist_b200_peek_ctx(sd._h)) for sd in sds]
+    for c in ctxs:
+        c.reset_timers()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    acc, _ = apes.run("mvnd", lb, ub, theta, ml, args.steps, rng, target_args=(mu, U_tgt), record_accept=True)
+    torch.cuda.synchronize()
+    e2e_dt = (time.perf_counter() - t0) / args.steps
+    traffic = [c.get_traffic() for c in ctxs]
+    e2e_launches = sum(c.get_timers()[1] for c in ctxs)
+    h2d_step = sum(t[0] for t in traffic) / args.steps
+    d2h_step = sum(t[1] for t in traffic) / args.steps
+    accept_rate = float(acc.mean())
+    # stage breakdown of the e2e path (separate pass with the per-stage CUDA-event timers on)
+    apes.enable_timers(True)
+    for c in ctxs:
+        c.reset_timers()
+    _, stage = apes.run("mvnd", lb, ub, theta, ml, 2, rng, target_args=(mu, U_tgt), record_accept=False)
+    stage = {k: v / 2 for k, v in stage.items()}
+    apes.enable_timers(False)
+
+    # ---------------- value: device-resident half-steps through the C ABI ----------------
+    # The two contexts behind sd0 / sd1 hold the state of a real APES iteration (centres, packed factors,
+    # lnnorms of the other half, uploaded by the last prepare_kernel): block b is updated from them.
+    gctx, dQ, dOut, rowscale, hrefs = [], [], [], [], []
+    for b in range(2):
+        mlc = ml[N:] if b == 0 else ml[:N]
+        c = ctxs[b]
+        c.n_kernels = c.n_obs = N
+        c.d = d
+        href = sds[b].get_href()
+        if world > 1:
+            uid = [capi.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            c.comm_init(world, rank, uid[0])
+            r0 = (N * rank) // world
+            r1 = (N * (rank + 1)) // world
+            c.set_row_shard(r0, r1 - r0)
+        f = np.exp(-0.5 * (mlc - mlc.min()))
+        rowscale.append(1.0 / f)
+        blk = theta[:N] if b == 0 else theta[N:]
+        q_all = np.vstack([blk + 1e-3, blk])            # theta*_k and theta_k of the block: 2N query points
+        q0, q1 = (2 * N * rank) // world, (2 * N * (rank + 1)) // world
+        dQ.append(torch.from_numpy(np.ascontiguousarray(q_all[q0:q1])).cuda())
+        dOut.append(torch.empty(q1 - q0, dtype=torch.float64, device="cuda"))
+        gctx.append(c)
+        hrefs.append(href)
+    streams = [torch.cuda.ExternalStream(c.stream) for c in gctx]
+
+    def half_step(b):
+        c = gctx[b]
+        c.compute_IM(rowscale[b])
+        x, rnorm, st = c.nnls_solve()
+        w = (1.0 - 0.01) * x / x.sum() + 0.01 / N
+        c.set_weights(w, hrefs[b])
+        c.eval_m2lnp_dev(dQ[b].shape[0], dQ[b].data_ptr(), d, dOut[b].data_ptr())
+        return st
+
+    def step():
+        half_step(0)
+        return half_step(1)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    for c in gctx:
+        c.synchronize()
+        c.reset_timers()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(2 * args.steps)]
+    with ClockSampler(local_rank) as clk:
+        for it in range(args.steps):
+            for b in range(2):
+                e0, e1 = ev[2 * it + b]
+                e0.record(streams[b])
+                st = half_step(b)
+                e1.record(streams[b])
+        for c in gctx:
+            c.synchronize()
+    torch.cuda.synchronize()
+    dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+    t_dev = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    dev_ms = float(t_dev.item())
+    ms_per_step = dev_ms / args.steps
+    value = pairs_step / (ms_per_step * 1e-3)
+    launches = sum(c.get_timers()[1] for c in gctx)
+
+    # ---------------- roofline of the dominant kernel (separate pass, per-stage CUDA-event timers on) ----------------
+    for c in gctx:
+        c.enable_timers(True)
+        c.reset_timers()
+    nroof = 3
+    nchol = 0
+    for _ in range(nroof):
+        nchol += half_step(0)["n_chol"] + half_step(1)["n_chol"]
+    tm = {k: 0.0 for k in capi.T_NAMES}
+    for c in gctx:
+        t, _ = c.get_timers()
+        for k in tm:
+            tm[k] += t[k] / nroof
+        c.enable_timers(False)
+    rows_local = N // world
+    syrk_flops = float(rows_local) * N * N                 # n_obs . n_kernels^2, one SYRK launch per half-step
+    syrk_ms = tm["syrk"] / 2.0
+    achieved = syrk_flops / (syrk_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": "ata_kernel (DMMA SYRK M = IM^T IM, n = k = %d)" % N, "achieved": achieved, "peak": peaks["fp64_dgemm_tflops"],
+                "unit": "TFLOP/s", "frac": achieved / peaks["fp64_dgemm_tflops"], "traffic": None,
+                "peak_source": "FP64 is not in MEASURED_PEAKS.json; cuBLAS DGEMM 8192^3 measured on this pool (profiles/r01_fp64_peaks.jsonl)",
+                "step_share_ms": {k: round(v, 4) for k, v in tm.items()}, "chol_solves_per_step": nchol / nroof}
+
+    # ---------------- CPU baseline (rank 0, bounded sample) ----------------
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        ncores = os.cpu_count() or 1
+        cdt, ctm = cpu_apes(args, W, d, 3, ncores)
+        cpu = {"value": pairs_step / cdt, "unit": UNIT, "cores": ncores, "kind": "port",
+               "sample": f"3 full APES iterations at W={W}, d={d} on the host cores (oracle port; 1 warm-up iteration)",
+               "ms_per_step": cdt * 1e3, "walker_steps_per_s": W / cdt}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"APES iteration, VKDE {args.kernel} kernel, {d}-D MVND, {W} walkers (6 N^2 pairs/step, N={N}); "
+                                   "IM rows and query rows sharded over ranks, centres replicated",
+                       "l2_policy": "each half-step streams a fresh 33.5 MB IM + 2 x 33.5 MB normal matrices; the two half-steps alternate contexts, "
+                                    "so no timed kernel re-reads data left by its previous launch (working set per step > 126 MB L2)"},
+            "walker_steps_per_s": W / (ms_per_step * 1e-3),
+            "e2e": {"value": pairs_step / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
+                    "ms_per_step": e2e_dt * 1e3, "walker_steps_per_s": W / e2e_dt, "accept_rate": accept_rate,
+                    "stage_ms_per_step": {k: round(v, 3) for k, v in stage.items()}, "gpu_launches_per_step": e2e_launches / args.steps,
+                    "api": "ncm_b200_esmcmc_run -> ncm_stats_dist_prepare_interp / ncm_stats_dist_eval_m2lnp_array -> C ABI (single GPU per ensemble)"},
+            "gpu_launches": int(launches),
+            "clocks": clk.summary(),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

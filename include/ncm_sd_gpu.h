@@ -142,6 +142,8 @@ enum
  * number of kernels launched since the last reset */
 int ncm_sd_gpu_get_timers (ncm_sd_gpu_ctx *ctx, double ms[NCM_SD_GPU_T_LEN], long long *n_launches);
 int ncm_sd_gpu_reset_timers (ncm_sd_gpu_ctx *ctx);
+/* bytes this context copied host->device / device->host since the last reset_timers */
+int ncm_sd_gpu_get_traffic (ncm_sd_gpu_ctx *ctx, long long *h2d_bytes, long long *d2h_bytes);
 int ncm_sd_gpu_enable_timers (ncm_sd_gpu_ctx *ctx, int enable);
 
 /* plain FP64 building blocks exported for tests and microbenchmarks (device pointers) */

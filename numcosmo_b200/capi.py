@@ -27,7 +27,7 @@ SYMBOLS = (
     "ncm_sd_gpu_set_href", "ncm_sd_gpu_get_weights", "ncm_sd_gpu_eval_m2lnp", "ncm_sd_gpu_eval", "ncm_sd_gpu_eval_m2lnp_dev",
     "ncm_sd_gpu_compute_IM", "ncm_sd_gpu_nnls_solve", "ncm_sd_gpu_nnls_solve_host", "ncm_sd_gpu_sample_apply", "ncm_sd_gpu_sample_philox",
     "ncm_sd_gpu_comm_unique_id", "ncm_sd_gpu_comm_init", "ncm_sd_gpu_set_row_shard", "ncm_sd_gpu_get_timers", "ncm_sd_gpu_reset_timers",
-    "ncm_sd_gpu_enable_timers", "ncm_sd_gpu_dsyrk_ata_dev", "ncm_sd_gpu_dpotrf_upper_dev",
+    "ncm_sd_gpu_enable_timers", "ncm_sd_gpu_get_traffic", "ncm_sd_gpu_dsyrk_ata_dev", "ncm_sd_gpu_dpotrf_upper_dev",
 )
 
 
@@ -87,6 +87,7 @@ def load():
             "ncm_sd_gpu_get_timers": (i, [vp, _dp, C.POINTER(ll)]),
             "ncm_sd_gpu_reset_timers": (i, [vp]),
             "ncm_sd_gpu_enable_timers": (i, [vp, i]),
+            "ncm_sd_gpu_get_traffic": (i, [vp, C.POINTER(ll), C.POINTER(ll)]),
             "ncm_sd_gpu_dsyrk_ata_dev": (i, [vp, i, i, vp, i, vp, i]),
             "ncm_sd_gpu_dpotrf_upper_dev": (i, [vp, i, vp, i, _ip]),
         }
@@ -124,7 +125,8 @@ class Context:
 
     def close(self):
         if getattr(self, "_h", None):
-            load().ncm_sd_gpu_ctx_free(self._h)
+            if getattr(self, "_own", True):
+                load().ncm_sd_gpu_ctx_free(self._h)
             self._h = None
 
     def __del__(self):
@@ -246,6 +248,21 @@ class Context:
         n = C.c_longlong()
         self._ck(load().ncm_sd_gpu_get_timers(self._h, _p(ms), C.byref(n)))
         return dict(zip(T_NAMES, ms.tolist())), n.value
+
+    def get_traffic(self):
+        a, b = C.c_longlong(), C.c_longlong()
+        self._ck(load().ncm_sd_gpu_get_traffic(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    @classmethod
+    def borrowed(cls, handle):
+        """Wrap a context owned by a host-mirror object (ncm_stats_dist_b200_peek_ctx)."""
+        self = cls.__new__(cls)
+        self._h = C.c_void_p(handle)
+        self._own = False
+        self.device = -1
+        self.d = self.n_kernels = self.n_obs = 0
+        return self
 
     def dsyrk_ata_dev(self, nrows, ncols, dA_ptr, lda, dM_ptr, ldm):
         self._ck(load().ncm_sd_gpu_dsyrk_ata_dev(self._h, nrows, ncols, dA_ptr, lda, dM_ptr, ldm))

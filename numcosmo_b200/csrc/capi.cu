@@ -192,8 +192,8 @@ int ncm_sd_gpu_upload_kde(ncm_sd_gpu_ctx *c, int n_obs, int n_kernels, const dou
   if (!c->qX.reserve((size_t) n_obs * d * sizeof(double)) || !c->kde_U.reserve((size_t) d * d * sizeof(double)) ||
       !c->weights.reserve((size_t) (n_kernels + 8) * sizeof(double)))
     return c->fail(NCM_SD_GPU_ENOMEM, "upload_kde: out of device memory");
-  NCM_CUDA_OK(c, cudaMemcpy2DAsync(c->qX.p, d * sizeof(double), invU, ld * sizeof(double), d * sizeof(double), n_obs, cudaMemcpyHostToDevice, c->stream));
-  NCM_CUDA_OK(c, cudaMemcpy2DAsync(c->kde_U.p, d * sizeof(double), U, ldu * sizeof(double), d * sizeof(double), d, cudaMemcpyHostToDevice, c->stream));
+  NCM_CUDA_OK(c, ncm_memcpy2d_async(c,c->qX.p, d * sizeof(double), invU, ld * sizeof(double), d * sizeof(double), n_obs, cudaMemcpyHostToDevice, c->stream));
+  NCM_CUDA_OK(c, ncm_memcpy2d_async(c,c->kde_U.p, d * sizeof(double), U, ldu * sizeof(double), d * sizeof(double), d, cudaMemcpyHostToDevice, c->stream));
   c->type      = NCM_SD_GPU_KDE;
   c->n_obs     = n_obs;
   c->n_kernels = n_kernels;
@@ -218,9 +218,9 @@ int ncm_sd_gpu_upload_vkde(ncm_sd_gpu_ctx *c, int n_obs, int n_kernels, const do
   if (!c->sample.reserve((size_t) n_obs * d * sizeof(double)) || !c->Ufull.reserve((size_t) n_kernels * d * d * sizeof(double)) ||
       !c->lnu.reserve((size_t) (n_kernels + 8) * sizeof(double)) || !c->weights.reserve((size_t) (n_kernels + 8) * sizeof(double)))
     return c->fail(NCM_SD_GPU_ENOMEM, "upload_vkde: out of device memory");
-  NCM_CUDA_OK(c, cudaMemcpy2DAsync(c->sample.p, d * sizeof(double), sample, ld * sizeof(double), d * sizeof(double), n_obs, cudaMemcpyHostToDevice, c->stream));
-  NCM_CUDA_OK(c, cudaMemcpyAsync(c->Ufull.p, U_all, (size_t) n_kernels * d * d * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  NCM_CUDA_OK(c, cudaMemcpyAsync(c->lnu.p, lnnorms, (size_t) n_kernels * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  NCM_CUDA_OK(c, ncm_memcpy2d_async(c,c->sample.p, d * sizeof(double), sample, ld * sizeof(double), d * sizeof(double), n_obs, cudaMemcpyHostToDevice, c->stream));
+  NCM_CUDA_OK(c, ncm_memcpy_async(c,c->Ufull.p, U_all, (size_t) n_kernels * d * d * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  NCM_CUDA_OK(c, ncm_memcpy_async(c,c->lnu.p, lnnorms, (size_t) n_kernels * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   c->type      = NCM_SD_GPU_VKDE;
   c->n_obs     = n_obs;
   c->n_kernels = n_kernels;
@@ -240,7 +240,7 @@ int ncm_sd_gpu_set_weights(ncm_sd_gpu_ctx *c, int n_kernels, const double *weigh
   cudaSetDevice(c->device);
   {
     StageTimer t(c, NCM_SD_GPU_T_H2D);
-    NCM_CUDA_OK(c, cudaMemcpyAsync(c->weights.p, weights, (size_t) n_kernels * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    NCM_CUDA_OK(c, ncm_memcpy_async(c,c->weights.p, weights, (size_t) n_kernels * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   }
   c->href         = href;
   c->have_weights = true;
@@ -263,7 +263,7 @@ int ncm_sd_gpu_get_weights(ncm_sd_gpu_ctx *c, int n_kernels, double *weights) {
   int rc = check_ready(c, true);
   if (rc != NCM_SD_GPU_OK) return rc;
   if (n_kernels != c->n_kernels || weights == nullptr) return c->fail(NCM_SD_GPU_EINVAL, "get_weights: bad arguments");
-  NCM_CUDA_OK(c, cudaMemcpyAsync(weights, c->weights.p, (size_t) n_kernels * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  NCM_CUDA_OK(c, ncm_memcpy_async(c,weights, c->weights.p, (size_t) n_kernels * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   NCM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
   return NCM_SD_GPU_OK;
 }
@@ -288,7 +288,7 @@ static int eval_host(ncm_sd_gpu_ctx *c, int q, const double *X, int ldx, double 
     return c->fail(NCM_SD_GPU_ENOMEM, "eval: out of device memory");
   {
     StageTimer t(c, NCM_SD_GPU_T_H2D);
-    NCM_CUDA_OK(c, cudaMemcpy2DAsync(c->qX.p, d * sizeof(double), X, ldx * sizeof(double), d * sizeof(double), q, cudaMemcpyHostToDevice, c->stream));
+    NCM_CUDA_OK(c, ncm_memcpy2d_async(c,c->qX.p, d * sizeof(double), X, ldx * sizeof(double), d * sizeof(double), q, cudaMemcpyHostToDevice, c->stream));
   }
   {
     StageTimer t(c, NCM_SD_GPU_T_EVAL);
@@ -298,7 +298,7 @@ static int eval_host(ncm_sd_gpu_ctx *c, int q, const double *X, int ldx, double 
   }
   {
     StageTimer t(c, NCM_SD_GPU_T_D2H);
-    NCM_CUDA_OK(c, cudaMemcpyAsync(out, c->qOut.p, (size_t) q * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    NCM_CUDA_OK(c, ncm_memcpy_async(c,out, c->qOut.p, (size_t) q * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     NCM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
   }
   return NCM_SD_GPU_OK;
@@ -325,7 +325,7 @@ int ncm_sd_gpu_compute_IM(ncm_sd_gpu_ctx *c, const double *row_scale, double *IM
     return c->fail(NCM_SD_GPU_ENOMEM, "compute_IM: out of device memory");
   if (row_scale != nullptr) {
     StageTimer t(c, NCM_SD_GPU_T_H2D);
-    NCM_CUDA_OK(c, cudaMemcpyAsync(c->rowscale.p, row_scale, (size_t) c->n_obs * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    NCM_CUDA_OK(c, ncm_memcpy_async(c,c->rowscale.p, row_scale, (size_t) c->n_obs * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   }
   if (c->nrows > 0) {
     StageTimer t(c, NCM_SD_GPU_T_IM);
@@ -335,7 +335,7 @@ int ncm_sd_gpu_compute_IM(ncm_sd_gpu_ctx *c, const double *row_scale, double *IM
   }
   if (IM_host != nullptr && c->nrows > 0) {
     StageTimer t(c, NCM_SD_GPU_T_D2H);
-    NCM_CUDA_OK(c, cudaMemcpy2DAsync(IM_host, (size_t) c->n_kernels * sizeof(double), c->IM.p, (size_t) ldim * sizeof(double),
+    NCM_CUDA_OK(c, ncm_memcpy2d_async(c,IM_host, (size_t) c->n_kernels * sizeof(double), c->IM.p, (size_t) ldim * sizeof(double),
                                      (size_t) c->n_kernels * sizeof(double), c->nrows, cudaMemcpyDeviceToHost, c->stream));
   }
   NCM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
@@ -350,7 +350,7 @@ int ncm_sd_gpu_nnls_solve(ncm_sd_gpu_ctx *c, double reltol, double *x_out, doubl
   const int ldim = (c->n_kernels + 7) & ~7;
   rc = nnls_solve_dev(c, c->nrows, c->n_kernels, c->IM.as<double>(), ldim, nullptr, reltol, x_out, rnorm_out, stats);
   if (rc != NCM_SD_GPU_OK) return rc;
-  NCM_CUDA_OK(c, cudaMemcpyAsync(c->weights.p, x_out, (size_t) c->n_kernels * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  NCM_CUDA_OK(c, ncm_memcpy_async(c,c->weights.p, x_out, (size_t) c->n_kernels * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   NCM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
   return NCM_SD_GPU_OK;
 }
@@ -365,9 +365,9 @@ int ncm_sd_gpu_nnls_solve_host(ncm_sd_gpu_ctx *c, int nrows, int ncols, const do
   if (!c->IM.reserve((size_t) nrows * ldim * sizeof(double)) || !c->nn_f.reserve((size_t) (nrows + 8) * sizeof(double)))
     return c->fail(NCM_SD_GPU_ENOMEM, "nnls_solve_host: out of device memory");
   NCM_CUDA_OK(c, cudaMemsetAsync(c->IM.p, 0, (size_t) nrows * ldim * sizeof(double), c->stream));
-  NCM_CUDA_OK(c, cudaMemcpy2DAsync(c->IM.p, (size_t) ldim * sizeof(double), A, (size_t) lda * sizeof(double), (size_t) ncols * sizeof(double), nrows,
+  NCM_CUDA_OK(c, ncm_memcpy2d_async(c,c->IM.p, (size_t) ldim * sizeof(double), A, (size_t) lda * sizeof(double), (size_t) ncols * sizeof(double), nrows,
                                    cudaMemcpyHostToDevice, c->stream));
-  NCM_CUDA_OK(c, cudaMemcpyAsync(c->nn_f.p, f, (size_t) nrows * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  NCM_CUDA_OK(c, ncm_memcpy_async(c,c->nn_f.p, f, (size_t) nrows * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   return nnls_solve_dev(c, nrows, ncols, c->IM.as<double>(), ldim, c->nn_f.as<double>(), reltol, x_out, rnorm_out, stats);
 }
 
@@ -384,14 +384,14 @@ int ncm_sd_gpu_sample_apply(ncm_sd_gpu_ctx *c, int q, const int *kidx, const dou
   if (!c->qX.reserve(2 * bz + (size_t) q * sizeof(double)) || !c->nn_idx.reserve((size_t) (q + 8) * sizeof(int)))
     return c->fail(NCM_SD_GPU_ENOMEM, "sample_apply: out of device memory");
   double *dZ = c->qX.as<double>(), *dXo = dZ + (size_t) q * d, *dS = dXo + (size_t) q * d;
-  NCM_CUDA_OK(c, cudaMemcpy2DAsync(dZ, d * sizeof(double), Z, ldz * sizeof(double), d * sizeof(double), q, cudaMemcpyHostToDevice, c->stream));
-  NCM_CUDA_OK(c, cudaMemcpyAsync(c->nn_idx.p, kidx, (size_t) q * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-  if (scale != nullptr) NCM_CUDA_OK(c, cudaMemcpyAsync(dS, scale, (size_t) q * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  NCM_CUDA_OK(c, ncm_memcpy2d_async(c,dZ, d * sizeof(double), Z, ldz * sizeof(double), d * sizeof(double), q, cudaMemcpyHostToDevice, c->stream));
+  NCM_CUDA_OK(c, ncm_memcpy_async(c,c->nn_idx.p, kidx, (size_t) q * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  if (scale != nullptr) NCM_CUDA_OK(c, ncm_memcpy_async(c,dS, scale, (size_t) q * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   sample_apply_kernel<<<(q + 127) / 128, 128, 0, c->stream>>>(c->sample.as<double>(), d, c->Ufull.as<double>(), 1, d, c->nn_idx.as<int>(), dZ, d,
                                                             scale != nullptr ? dS : nullptr, c->href, q, dXo, d);
   c->n_launches++;
   NCM_CUDA_OK(c, cudaGetLastError());
-  NCM_CUDA_OK(c, cudaMemcpy2DAsync(X_out, ldx * sizeof(double), dXo, d * sizeof(double), d * sizeof(double), q, cudaMemcpyDeviceToHost, c->stream));
+  NCM_CUDA_OK(c, ncm_memcpy2d_async(c,X_out, ldx * sizeof(double), dXo, d * sizeof(double), d * sizeof(double), q, cudaMemcpyDeviceToHost, c->stream));
   NCM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
   return NCM_SD_GPU_OK;
 }
@@ -407,8 +407,8 @@ int ncm_sd_gpu_sample_philox(ncm_sd_gpu_ctx *c, int q, unsigned long long seed, 
     return c->fail(NCM_SD_GPU_ENOMEM, "sample_philox: out of device memory");
   rc = sample_philox_launch(c, q, seed, offset, c->qX.as<double>(), d, c->nn_idx.as<int>());
   if (rc != NCM_SD_GPU_OK) return rc;
-  NCM_CUDA_OK(c, cudaMemcpy2DAsync(X_out, ldx * sizeof(double), c->qX.p, d * sizeof(double), d * sizeof(double), q, cudaMemcpyDeviceToHost, c->stream));
-  if (kidx_out != nullptr) NCM_CUDA_OK(c, cudaMemcpyAsync(kidx_out, c->nn_idx.p, (size_t) q * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  NCM_CUDA_OK(c, ncm_memcpy2d_async(c,X_out, ldx * sizeof(double), c->qX.p, d * sizeof(double), d * sizeof(double), q, cudaMemcpyDeviceToHost, c->stream));
+  if (kidx_out != nullptr) NCM_CUDA_OK(c, ncm_memcpy_async(c,kidx_out, c->nn_idx.p, (size_t) q * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   NCM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
   return NCM_SD_GPU_OK;
 }
@@ -450,6 +450,13 @@ int ncm_sd_gpu_reset_timers(ncm_sd_gpu_ctx *c) {
   if (c == nullptr) return NCM_SD_GPU_EINVAL;
   std::memset(c->t_ms, 0, sizeof(c->t_ms));
   c->n_launches = 0;
+  c->h2d_bytes = c->d2h_bytes = 0;
+  return NCM_SD_GPU_OK;
+}
+int ncm_sd_gpu_get_traffic(ncm_sd_gpu_ctx *c, long long *h2d_bytes, long long *d2h_bytes) {
+  if (c == nullptr) return NCM_SD_GPU_EINVAL;
+  if (h2d_bytes != nullptr) *h2d_bytes = c->h2d_bytes;
+  if (d2h_bytes != nullptr) *d2h_bytes = c->d2h_bytes;
   return NCM_SD_GPU_OK;
 }
 int ncm_sd_gpu_enable_timers(ncm_sd_gpu_ctx *c, int enable) {

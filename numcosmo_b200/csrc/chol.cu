@@ -191,7 +191,7 @@ int dpotrf_upper_solve(ncm_sd_gpu_ctx *c, int n, double *dM, int ldm, double *dR
   }
   NCM_CUDA_OK(c, cudaGetLastError());
   if (info_host != nullptr) {
-    NCM_CUDA_OK(c, cudaMemcpyAsync(info_host, dInfo, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    NCM_CUDA_OK(c, ncm_memcpy_async(c,info_host, dInfo, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     NCM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
   }
   return NCM_SD_GPU_OK;

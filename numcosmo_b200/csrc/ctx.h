@@ -79,6 +79,7 @@ struct ncm_sd_gpu_ctx {
   bool timers_on = false;
   double t_ms[NCM_SD_GPU_T_LEN] = {0};
   long long n_launches = 0;
+  long long h2d_bytes = 0, d2h_bytes = 0;   // bytes moved over PCIe by this context (ncm_sd_gpu_get_traffic)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
   int fail(int code, const std::string &msg) {
@@ -94,6 +95,19 @@ struct ncm_sd_gpu_ctx {
       return (ctx)->fail(NCM_SD_GPU_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + ":" + \
                                                std::to_string(__LINE__) + ")");                                   \
   } while (0)
+
+// host <-> device copies go through these so that the context can report its PCIe traffic
+inline cudaError_t ncm_memcpy_async(ncm_sd_gpu_ctx *c, void *dst, const void *src, size_t bytes, cudaMemcpyKind kind, cudaStream_t s) {
+  if (kind == cudaMemcpyHostToDevice) c->h2d_bytes += (long long) bytes;
+  if (kind == cudaMemcpyDeviceToHost) c->d2h_bytes += (long long) bytes;
+  return cudaMemcpyAsync(dst, src, bytes, kind, s);
+}
+inline cudaError_t ncm_memcpy2d_async(ncm_sd_gpu_ctx *c, void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height,
+                                      cudaMemcpyKind kind, cudaStream_t s) {
+  if (kind == cudaMemcpyHostToDevice) c->h2d_bytes += (long long) (width * height);
+  if (kind == cudaMemcpyDeviceToHost) c->d2h_bytes += (long long) (width * height);
+  return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, kind, s);
+}
 
 struct StageTimer {
   ncm_sd_gpu_ctx *c;

@@ -183,7 +183,7 @@ int solve_unconstrained(NnlsWork &w, const std::vector<int> &P) {
         copy_upper_kernel<<<grid, 256, 0, c->stream>>>(w.dM, w.ldm, np, w.dMU, w.ldm, w.db, w.drhs, shift);
       } else {
         std::memcpy(w.h_idx, P.data(), sizeof(int) * np);
-        NCM_CUDA_OK(c, cudaMemcpyAsync(w.didx, w.h_idx, sizeof(int) * np, cudaMemcpyHostToDevice, c->stream));
+        NCM_CUDA_OK(c, ncm_memcpy_async(c,w.didx, w.h_idx, sizeof(int) * np, cudaMemcpyHostToDevice, c->stream));
         dim3 grid((np + 255) / 256, np);
         gather_sym_kernel<<<grid, 256, 0, c->stream>>>(w.dM, w.ldm, w.didx, np, w.dMU, w.ldm, w.db, w.drhs, shift);
       }
@@ -197,7 +197,7 @@ int solve_unconstrained(NnlsWork &w, const std::vector<int> &P) {
     }
     if (w.st) w.st->n_chol++;
     if (info == 0) {
-      NCM_CUDA_OK(c, cudaMemcpyAsync(w.h_buf, w.drhs, sizeof(double) * np, cudaMemcpyDeviceToHost, c->stream));
+      NCM_CUDA_OK(c, ncm_memcpy_async(c,w.h_buf, w.drhs, sizeof(double) * np, cudaMemcpyDeviceToHost, c->stream));
       NCM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
       return NCM_SD_GPU_OK;
     }
@@ -243,7 +243,7 @@ int compute_residuals(NnlsWork &w, const std::vector<double> &x, double *dr_out,
   ncm_sd_gpu_ctx *c = w.c;
   StageTimer t(c, NCM_SD_GPU_T_NNLS_MISC);
   std::memcpy(w.h_buf, x.data(), sizeof(double) * w.n);
-  NCM_CUDA_OK(c, cudaMemcpyAsync(w.dx, w.h_buf, sizeof(double) * w.n, cudaMemcpyHostToDevice, c->stream));
+  NCM_CUDA_OK(c, ncm_memcpy_async(c,w.dx, w.h_buf, sizeof(double) * w.n, cudaMemcpyHostToDevice, c->stream));
   int nb = 0;
   int rc = residual(c, w.dA, w.lda, w.nrows, w.n, w.dx, w.dF, dr_out, w.dss, &nb);
   if (rc != NCM_SD_GPU_OK) return rc;
@@ -251,7 +251,7 @@ int compute_residuals(NnlsWork &w, const std::vector<double> &x, double *dr_out,
   c->n_launches++;
   rc = allreduce_sum(c, w.dscal, 1);
   if (rc != NCM_SD_GPU_OK) return rc;
-  NCM_CUDA_OK(c, cudaMemcpyAsync(w.h_buf + w.n, w.dscal, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  NCM_CUDA_OK(c, ncm_memcpy_async(c,w.h_buf + w.n, w.dscal, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   NCM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
   *rnorm = sqrt(w.h_buf[w.n]);
   return NCM_SD_GPU_OK;
@@ -264,7 +264,7 @@ int compute_mgrad(NnlsWork &w, const double *dr_in, std::vector<double> &g) {
   if (rc != NCM_SD_GPU_OK) return rc;
   rc = allreduce_sum(c, w.dg, w.n);
   if (rc != NCM_SD_GPU_OK) return rc;
-  NCM_CUDA_OK(c, cudaMemcpyAsync(w.h_buf, w.dg, sizeof(double) * w.n, cudaMemcpyDeviceToHost, c->stream));
+  NCM_CUDA_OK(c, ncm_memcpy_async(c,w.h_buf, w.dg, sizeof(double) * w.n, cudaMemcpyDeviceToHost, c->stream));
   NCM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
   g.assign(w.h_buf, w.h_buf + w.n);
   return NCM_SD_GPU_OK;
@@ -346,7 +346,7 @@ int nnls_solve_dev(ncm_sd_gpu_ctx *c, int nrows, int ncols, const double *dA, in
     if (rc != NCM_SD_GPU_OK) return rc;
     diag_mean_kernel<<<1, 256, 0, c->stream>>>(w.dM, ldm, n, w.dscal);
     c->n_launches++;
-    NCM_CUDA_OK(c, cudaMemcpyAsync(w.h_buf, w.dscal, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    NCM_CUDA_OK(c, ncm_memcpy_async(c,w.h_buf, w.dscal, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     NCM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
     w.diag_mean = w.h_buf[0];
   }

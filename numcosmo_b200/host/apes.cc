@@ -1,0 +1,406 @@
+// NcmFitESMCMCWalkerAPES mirror + the ESMCMC accept loop around it.
+//
+//   set_sys           ncm_fit_esmcmc_walker_apes.c:509-608  (BOTH methods build NcmStatsDistVKDE objects, :563-572)
+//   prepare_random_walk / random_walk_sample / sample      :646-739
+//   setup             :741-817   + NEW: one batched GPU eval of {theta*_k, theta_k} for the whole block
+//   transition_prob   :819-859   (host: O(d) random-walk mixture on top of the cached density values)
+//   step / prob_norm  :861-919   (step only reads the cache)
+//   run               ncm_fit_esmcmc.c:2136-2148 (jumps), :2151-2232 (run_interval), :2235-2288 (run, ki = 0)
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <vector>
+#include "internal.h"
+
+namespace {
+constexpr double LN2PI     = 1.8378770664093454835606594728112352797227949472755668;
+constexpr double ERF_BOUND = 1.0;
+
+double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// ncm_util.c:645-716
+double log_gaussian_integral(double xl, double xu, double mu, double sigma) {
+  const double zl = (xl - mu) / sigma, zu = (xu - mu) / sigma;
+  if (zl == zu) return -INFINITY;
+  double ul, uu;
+  if (zl < zu) {
+    ul = zl * M_SQRT1_2;
+    uu = zu * M_SQRT1_2;
+  } else {
+    ul = zu * M_SQRT1_2;
+    uu = zl * M_SQRT1_2;
+  }
+  if (ul > ERF_BOUND) return log(fabs(0.5 * (erfc(ul) - erfc(uu))));
+  if (uu < -ERF_BOUND) return log(fabs(0.5 * (erfc(-ul) - erfc(-uu))));
+  if ((uu > ERF_BOUND) && (ul < -ERF_BOUND)) return log1p(-0.5 * (erfc(uu) + erfc(-ul)));
+  return log(fabs(0.5 * (erf(uu) - erf(ul))));
+}
+
+struct RandomWalk {
+  std::vector<double> std, lb, ub;
+};
+}   // namespace
+
+struct _NcmFitESMCMCWalkerAPES {
+  guint size, size_2, nparams;
+  NcmFitESMCMCWalkerAPESMethod method;
+  NcmFitESMCMCWalkerAPESKType k_type;
+  double over_smooth, shrink, random_walk_prob, random_walk_scale, local_frac;
+  gboolean use_interp, use_threads;
+  guint exploration;
+  NcmStatsDist *sd0, *sd1;
+  std::vector<double> thetastar, m2lnp_star, m2lnp_cur, m2lnL_s0, m2lnL_s1, jumps;
+  RandomWalk rw0, rw1;
+  double t_sample_ms, t_eval_ms;
+};
+
+namespace {
+
+void set_sys(NcmFitESMCMCWalkerAPES *a) {
+  ncm_stats_dist_clear(&a->sd0);
+  ncm_stats_dist_clear(&a->sd1);
+  if (a->size % 2 != 0) {
+    ncm_b200_error("_ncm_fit_esmcmc_walker_apes_set_sys: assertion failed (self->size %% 2 == 0)");
+    return;
+  }
+  a->size_2 = a->size / 2;
+  a->m2lnp_star.assign(a->size, 0.0);
+  a->m2lnp_cur.assign(a->size, 0.0);
+  a->m2lnL_s0.assign(a->size_2, 0.0);
+  a->m2lnL_s1.assign(a->size_2, 0.0);
+  a->jumps.assign(a->size, 0.0);
+  a->thetastar.assign((size_t) a->size * a->nparams, 0.0);
+  NcmStatsDistKernel *kernel = nullptr;
+  switch (a->k_type) {
+    case NCM_FIT_ESMCMC_WALKER_APES_KTYPE_CAUCHY: kernel = ncm_stats_dist_kernel_st_new(a->nparams, 1.0); break;
+    case NCM_FIT_ESMCMC_WALKER_APES_KTYPE_ST3: kernel = ncm_stats_dist_kernel_st_new(a->nparams, 3.0); break;
+    default: kernel = ncm_stats_dist_kernel_gauss_new(a->nparams); break;
+  }
+  if (kernel == nullptr) return;
+  // METHOD_KDE and METHOD_VKDE both construct NcmStatsDistVKDE (walker_apes.c:563-572)
+  a->sd0 = ncm_stats_dist_vkde_new(kernel, NCM_STATS_DIST_CV_NONE);
+  a->sd1 = ncm_stats_dist_vkde_new(kernel, NCM_STATS_DIST_CV_NONE);
+  if (a->method == NCM_FIT_ESMCMC_WALKER_APES_METHOD_VKDE) {
+    const guint cov_estimates = (guint) (a->local_frac * a->size_2);
+    if (cov_estimates < 2)
+      ncm_b200_error("Number of walkers per block (%d) is too low for the current dimension (%d).\n\tToo few points (%d) to estimate local covariances.",
+                     a->size_2, a->nparams, cov_estimates);
+  }
+  ncm_stats_dist_kernel_free(kernel);
+  for (NcmStatsDist *sd : {a->sd0, a->sd1}) {
+    ncm_stats_dist_set_over_smooth(sd, a->over_smooth);
+    ncm_stats_dist_set_shrink(sd, a->shrink);
+    ncm_stats_dist_set_use_threads(sd, a->use_threads);
+    ncm_stats_dist_vkde_set_local_frac(sd, a->local_frac);
+  }
+}
+
+bool valid_bounds(const double *lb, const double *ub, const double *x, guint d) {
+  for (guint i = 0; i < d; i++)
+    if ((x[i] < lb[i]) || (x[i] > ub[i])) return false;
+  return true;
+}
+
+void prepare_random_walk(NcmFitESMCMCWalkerAPES *a, NcmStatsDist *sd, RandomWalk &rw, const double *lb, const double *ub) {
+  if (a->random_walk_prob > 0.0) {
+    NcmMatrix *cov = ncm_stats_dist_peek_full_cov(sd);
+    rw.std.resize(a->nparams);
+    rw.lb.assign(lb, lb + a->nparams);
+    rw.ub.assign(ub, ub + a->nparams);
+    for (guint i = 0; i < a->nparams; i++) {
+      const double var = ncm_matrix_get(cov, i, i);
+      if (var <= 0.0) {
+        ncm_b200_error("Invalid covariance matrix: diagonal element %d is non-positive.", i);
+        return;
+      }
+      rw.std[i] = sqrt(var) * 0.25;   // literal 0.25; random_walk_scale is stored but unused (walker_apes.c:684-688)
+    }
+  }
+}
+
+void apes_sample(NcmFitESMCMCWalkerAPES *a, NcmStatsDist *sd, const RandomWalk &rw, const double *lb, const double *ub, const double *theta,
+                 double *thetastar, NcmRNG *rng) {
+  const guint d = a->nparams;
+  NcmVector *ts = ncm_vector_new_data_static(thetastar, d, 1);
+  do {
+    if (a->random_walk_prob != 0.0 && ncm_rng_uniform01_pos_gen(rng) < a->random_walk_prob) {
+      for (guint i = 0; i < d; i++) {
+        double x;
+        do {
+          x = ncm_rng_gaussian_gen(rng, theta[i], rw.std[i]);
+        } while ((x < rw.lb[i]) || (x > rw.ub[i]));
+        thetastar[i] = x;
+      }
+    } else {
+      ncm_stats_dist_sample(sd, ts, rng);
+    }
+  } while (!valid_bounds(lb, ub, thetastar, d));
+  ncm_vector_free(ts);
+}
+
+double transition_prob(NcmFitESMCMCWalkerAPES *a, const RandomWalk &rw, const double *theta, const double *thetastar, double m2lnp_sd) {
+  if (!(a->random_walk_prob > 0.0)) return m2lnp_sd;
+  double m2lnp_rw = 0.0;
+  for (guint i = 0; i < a->nparams; i++) {
+    const double sd      = rw.std[i];
+    const double ln_norm = 0.5 * LN2PI + log(sd) + log_gaussian_integral(rw.lb[i], rw.ub[i], theta[i], sd);
+    const double r       = (thetastar[i] - theta[i]) / sd;
+    m2lnp_rw += r * r + 2.0 * ln_norm;
+  }
+  m2lnp_rw += -2.0 * log(a->random_walk_prob);
+  m2lnp_sd += -2.0 * log1p(-a->random_walk_prob);
+  if (m2lnp_sd < m2lnp_rw) return m2lnp_sd - 2.0 * log1p(exp(-0.5 * (m2lnp_rw - m2lnp_sd)));
+  return m2lnp_rw - 2.0 * log1p(exp(-0.5 * (m2lnp_sd - m2lnp_rw)));
+}
+
+void setup_block(NcmFitESMCMCWalkerAPES *a, int block, const double *lb, const double *ub, const double *theta, const double *m2lnL, guint ki,
+                 guint kf, NcmRNG *rng) {
+  const guint d          = a->nparams;
+  NcmStatsDist *sd       = block == 0 ? a->sd0 : a->sd1;
+  RandomWalk &rw         = block == 0 ? a->rw0 : a->rw1;
+  std::vector<double> &s = block == 0 ? a->m2lnL_s0 : a->m2lnL_s1;
+  const guint c0         = block == 0 ? a->size_2 : 0;   // centres come from the OTHER half
+
+  ncm_stats_dist_reset(sd);
+  for (guint i = 0; i < a->size_2; i++) {
+    s[i]         = m2lnL[c0 + i];
+    NcmVector *v = ncm_vector_new_data_static(const_cast<double *>(&theta[(size_t) (c0 + i) * d]), d, 1);
+    ncm_stats_dist_add_obs(sd, v);
+    ncm_vector_free(v);
+  }
+  if (a->use_interp) {
+    NcmVector *mv = ncm_vector_new_data_static(s.data(), a->size_2, 1);
+    ncm_stats_dist_prepare_interp(sd, mv);
+    ncm_vector_free(mv);
+  } else {
+    ncm_stats_dist_prepare(sd);
+  }
+  if (ncm_b200_error_pending()) return;
+  prepare_random_walk(a, sd, rw, lb, ub);
+
+  double t0 = now_ms();
+  for (guint k = ki; k < kf; k++) apes_sample(a, sd, rw, lb, ub, &theta[(size_t) k * d], &a->thetastar[(size_t) k * d], rng);
+  double t1 = now_ms();
+  a->t_sample_ms += t1 - t0;
+
+  // NEW: both density evaluations of _apes_step (walker_apes.c:872-873) for every walker of the block in ONE call
+  const guint nb = kf - ki;
+  NcmMatrix *Q   = ncm_matrix_new(2 * nb, d);
+  NcmVector *out = ncm_vector_new(2 * nb);
+  memcpy(ncm_matrix_data(Q), &a->thetastar[(size_t) ki * d], sizeof(double) * nb * d);
+  memcpy(ncm_matrix_data(Q) + (size_t) nb * d, &theta[(size_t) ki * d], sizeof(double) * nb * d);
+  ncm_stats_dist_eval_m2lnp_array(sd, Q, out);
+  for (guint k = ki; k < kf; k++) {
+    const double *th = &theta[(size_t) k * d], *ts = &a->thetastar[(size_t) k * d];
+    a->m2lnp_star[k] = transition_prob(a, rw, th, ts, ncm_vector_get(out, k - ki));
+    a->m2lnp_cur[k]  = transition_prob(a, rw, ts, th, ncm_vector_get(out, nb + k - ki));
+  }
+  ncm_matrix_free(Q);
+  ncm_vector_free(out);
+  a->t_eval_ms += now_ms() - t1;
+}
+
+}   // namespace
+
+extern "C" {
+
+NcmFitESMCMCWalkerAPES *ncm_fit_esmcmc_walker_apes_new_full(guint nwalkers, guint nparams, NcmFitESMCMCWalkerAPESMethod method,
+                                                            NcmFitESMCMCWalkerAPESKType k_type, gdouble over_smooth, gboolean use_interp) {
+  NcmFitESMCMCWalkerAPES *a = new NcmFitESMCMCWalkerAPES();
+  a->size             = nwalkers;
+  a->nparams          = nparams;
+  a->method           = method;
+  a->k_type           = k_type;
+  a->over_smooth      = over_smooth;
+  a->shrink           = 0.01;
+  a->random_walk_prob = 0.02;
+  a->random_walk_scale = 1.0;
+  a->local_frac       = 0.05;
+  a->use_interp       = use_interp;
+  a->use_threads      = FALSE;
+  a->exploration      = 0;
+  a->sd0 = a->sd1 = nullptr;
+  a->t_sample_ms = a->t_eval_ms = 0.0;
+  set_sys(a);
+  return a;
+}
+// defaults of the property specs, walker_apes.c:358-475
+NcmFitESMCMCWalkerAPES *ncm_fit_esmcmc_walker_apes_new(guint nwalkers, guint nparams) {
+  return ncm_fit_esmcmc_walker_apes_new_full(nwalkers, nparams, NCM_FIT_ESMCMC_WALKER_APES_METHOD_VKDE, NCM_FIT_ESMCMC_WALKER_APES_KTYPE_CAUCHY,
+                                             1.0, TRUE);
+}
+void ncm_fit_esmcmc_walker_apes_free(NcmFitESMCMCWalkerAPES *a) {
+  if (a == nullptr) return;
+  ncm_stats_dist_clear(&a->sd0);
+  ncm_stats_dist_clear(&a->sd1);
+  delete a;
+}
+void ncm_fit_esmcmc_walker_apes_clear(NcmFitESMCMCWalkerAPES **a) {
+  if (a != nullptr && *a != nullptr) {
+    ncm_fit_esmcmc_walker_apes_free(*a);
+    *a = nullptr;
+  }
+}
+void ncm_fit_esmcmc_walker_apes_set_method(NcmFitESMCMCWalkerAPES *a, NcmFitESMCMCWalkerAPESMethod m) {
+  a->method = m;
+  set_sys(a);
+}
+void ncm_fit_esmcmc_walker_apes_set_k_type(NcmFitESMCMCWalkerAPES *a, NcmFitESMCMCWalkerAPESKType k) {
+  a->k_type = k;
+  set_sys(a);
+}
+void ncm_fit_esmcmc_walker_apes_set_over_smooth(NcmFitESMCMCWalkerAPES *a, const gdouble os) {
+  a->over_smooth = os;
+  ncm_stats_dist_set_over_smooth(a->sd0, os);   // forwarded immediately (walker_apes.c:1162-1166)
+  ncm_stats_dist_set_over_smooth(a->sd1, os);
+}
+void ncm_fit_esmcmc_walker_apes_set_shrink(NcmFitESMCMCWalkerAPES *a, const gdouble s) { a->shrink = s; }   // only stored (:1178-1187)
+void ncm_fit_esmcmc_walker_apes_set_random_walk_prob(NcmFitESMCMCWalkerAPES *a, const gdouble p) { a->random_walk_prob = p; }
+void ncm_fit_esmcmc_walker_apes_set_random_walk_scale(NcmFitESMCMCWalkerAPES *a, const gdouble s) { a->random_walk_scale = s; }
+NcmFitESMCMCWalkerAPESMethod ncm_fit_esmcmc_walker_apes_get_method(NcmFitESMCMCWalkerAPES *a) { return a->method; }
+NcmFitESMCMCWalkerAPESKType ncm_fit_esmcmc_walker_apes_get_k_type(NcmFitESMCMCWalkerAPES *a) { return a->k_type; }
+gdouble ncm_fit_esmcmc_walker_apes_get_over_smooth(NcmFitESMCMCWalkerAPES *a) { return a->over_smooth; }
+gdouble ncm_fit_esmcmc_walker_apes_get_shrink(NcmFitESMCMCWalkerAPES *a) { return a->shrink; }
+gdouble ncm_fit_esmcmc_walker_apes_get_random_walk_prob(NcmFitESMCMCWalkerAPES *a) { return a->random_walk_prob; }
+gdouble ncm_fit_esmcmc_walker_apes_get_random_walk_scale(NcmFitESMCMCWalkerAPES *a) { return a->random_walk_scale; }
+void ncm_fit_esmcmc_walker_apes_use_interp(NcmFitESMCMCWalkerAPES *a, gboolean u) { a->use_interp = u; }
+gboolean ncm_fit_esmcmc_walker_apes_interp(NcmFitESMCMCWalkerAPES *a) { return a->use_interp; }
+void ncm_fit_esmcmc_walker_apes_set_use_threads(NcmFitESMCMCWalkerAPES *a, gboolean u) {
+  a->use_threads = u;
+  ncm_stats_dist_set_use_threads(a->sd0, u);
+  ncm_stats_dist_set_use_threads(a->sd1, u);
+}
+gboolean ncm_fit_esmcmc_walker_apes_get_use_threads(NcmFitESMCMCWalkerAPES *a) { return a->use_threads; }
+void ncm_fit_esmcmc_walker_apes_peek_sds(NcmFitESMCMCWalkerAPES *a, NcmStatsDist **sd0, NcmStatsDist **sd1) {
+  *sd0 = a->sd0;
+  *sd1 = a->sd1;
+}
+void ncm_fit_esmcmc_walker_apes_set_local_frac(NcmFitESMCMCWalkerAPES *a, gdouble lf) {
+  a->local_frac = lf;
+  ncm_stats_dist_vkde_set_local_frac(a->sd0, lf);
+  ncm_stats_dist_vkde_set_local_frac(a->sd1, lf);
+}
+void ncm_fit_esmcmc_walker_apes_set_exploration(NcmFitESMCMCWalkerAPES *a, guint e) { a->exploration = e; }
+
+void ncm_fit_esmcmc_walker_apes_setup(NcmFitESMCMCWalkerAPES *a, const gdouble *lb, const gdouble *ub, const gdouble *theta, const gdouble *m2lnL,
+                                      guint ki, guint kf, NcmRNG *rng) {
+  if (ki < a->size_2) setup_block(a, 0, lb, ub, theta, m2lnL, ki, kf < a->size_2 ? kf : a->size_2, rng);
+  if (kf > a->size_2) setup_block(a, 1, lb, ub, theta, m2lnL, ki > a->size_2 ? ki : a->size_2, kf, rng);
+  if (a->exploration > 0) a->exploration--;
+}
+
+void ncm_fit_esmcmc_walker_apes_step(NcmFitESMCMCWalkerAPES *a, const gdouble *theta, gdouble *thetastar, guint k) {
+  (void) theta;
+  memcpy(thetastar, &a->thetastar[(size_t) k * a->nparams], sizeof(double) * a->nparams);
+  if (!(std::isfinite(a->m2lnp_star[k]) && std::isfinite(a->m2lnp_cur[k])))
+    ncm_b200_error("_ncm_fit_esmcmc_walker_apes_step: assertion failed (gsl_finite (m2lnapes_star) && gsl_finite (m2lnapes_cur))");
+}
+
+gdouble ncm_fit_esmcmc_walker_apes_prob_norm(NcmFitESMCMCWalkerAPES *a, guint k) {
+  if (a->exploration) return 0.0;
+  return -0.5 * (a->m2lnp_cur[k] - a->m2lnp_star[k]);
+}
+const gdouble *ncm_fit_esmcmc_walker_apes_peek_thetastar(NcmFitESMCMCWalkerAPES *a) { return a->thetastar.data(); }
+const gdouble *ncm_fit_esmcmc_walker_apes_peek_m2lnp_star(NcmFitESMCMCWalkerAPES *a) { return a->m2lnp_star.data(); }
+const gdouble *ncm_fit_esmcmc_walker_apes_peek_m2lnp_cur(NcmFitESMCMCWalkerAPES *a) { return a->m2lnp_cur.data(); }
+
+void ncm_b200_esmcmc_run(NcmFitESMCMCWalkerAPES *a, NcmB200M2lnLFunc m2lnL_func, void *user_data, const gdouble *lb, const gdouble *ub,
+                         gdouble *theta, gdouble *m2lnL, guint iters, NcmRNG *rng, unsigned char *accepted, gdouble *timers_ms) {
+  const guint d = a->nparams, W = a->size, W2 = a->size_2;
+  std::vector<double> m2lnL_star(W2), thetastar(d);
+  double t_like = 0.0;
+  const double t_begin = now_ms();
+  a->t_sample_ms = a->t_eval_ms = 0.0;
+  ncm_b200_error_clear();
+  for (guint it = 0; it < iters; it++) {
+    unsigned char *acc = accepted != nullptr ? &accepted[(size_t) it * W] : nullptr;
+    if (acc != nullptr) memset(acc, 0, W);
+    for (guint k = 0; k < W; k++) a->jumps[k] = ncm_rng_uniform01_gen(rng);   // _ncm_fit_esmcmc_get_jumps (0, W)
+    for (int block = 0; block < 2; block++) {
+      const guint ki = block == 0 ? 0 : W2, kf = block == 0 ? W2 : W;
+      ncm_fit_esmcmc_walker_apes_setup(a, lb, ub, theta, m2lnL, ki, kf, rng);
+      if (ncm_b200_error_pending()) return;
+      const double t0 = now_ms();
+      m2lnL_func(&a->thetastar[(size_t) ki * d], kf - ki, d, m2lnL_star.data(), user_data);
+      for (guint k = ki; k < kf; k++) {
+        ncm_fit_esmcmc_walker_apes_step(a, theta, thetastar.data(), k);
+        double prob = 0.0;
+        if (valid_bounds(lb, ub, thetastar.data(), d)) {
+          const double ms = m2lnL_star[k - ki];
+          if (std::isfinite(ms)) {
+            const double lnq   = ncm_fit_esmcmc_walker_apes_prob_norm(a, k);
+            const double m2lnq = -2.0 * lnq;
+            const double m2lnp = ms - m2lnL[k] + m2lnq;
+            prob               = exp(-0.5 * m2lnp);
+            prob               = prob < 1.0 ? prob : 1.0;
+          }
+          if (a->jumps[k] < prob) {
+            memcpy(&theta[(size_t) k * d], thetastar.data(), sizeof(double) * d);
+            m2lnL[k] = ms;
+            if (acc != nullptr) acc[k] = 1;
+          }
+        }
+      }
+      t_like += now_ms() - t0;
+    }
+  }
+  if (timers_ms != nullptr) {
+    double g0[NCM_SD_GPU_T_LEN] = {0}, g1[NCM_SD_GPU_T_LEN] = {0}, h0 = 0.0, h1 = 0.0;
+    long long n0 = 0, n1 = 0;
+    ncm_stats_dist_b200_get_timers(a->sd0, g0, &n0, &h0);
+    ncm_stats_dist_b200_get_timers(a->sd1, g1, &n1, &h1);
+    timers_ms[0] = h0 + h1;
+    timers_ms[1] = g0[NCM_SD_GPU_T_IM] + g1[NCM_SD_GPU_T_IM];
+    timers_ms[2] = g0[NCM_SD_GPU_T_SYRK] + g1[NCM_SD_GPU_T_SYRK] + g0[NCM_SD_GPU_T_CHOL] + g1[NCM_SD_GPU_T_CHOL] + g0[NCM_SD_GPU_T_NNLS_MISC] +
+                   g1[NCM_SD_GPU_T_NNLS_MISC];
+    timers_ms[3] = a->t_sample_ms;
+    timers_ms[4] = a->t_eval_ms;
+    timers_ms[5] = t_like;
+    timers_ms[6] = g0[NCM_SD_GPU_T_H2D] + g1[NCM_SD_GPU_T_H2D] + g0[NCM_SD_GPU_T_D2H] + g1[NCM_SD_GPU_T_D2H];
+    timers_ms[7] = now_ms() - t_begin;
+  }
+}
+
+void ncm_b200_target_rosenbrock(const gdouble *X, guint n, guint nparams, gdouble *m2lnL, void *) {
+  for (guint i = 0; i < n; i++) {
+    const double x1 = X[(size_t) i * nparams], x2 = X[(size_t) i * nparams + 1];
+    const double a = x2 - x1 * x1, b = 1.0 - x1;
+    m2lnL[i]       = (100.0 * (a * a) + (b * b)) * 1.0e-1;
+  }
+}
+
+void ncm_b200_target_funnel(const gdouble *X, guint n, guint nparams, gdouble *m2lnL, void *) {
+  for (guint i = 0; i < n; i++) {
+    const double *x       = &X[(size_t) i * nparams];
+    const double nu       = x[0];
+    const double sigma_nu = exp(0.5 * nu);
+    const guint x_len     = nparams - 1;
+    double v              = x_len * nu + (nu / 3.0) * (nu / 3.0);
+    for (guint j = 0; j < x_len; j++) {
+      const double r = x[1 + j] / sigma_nu;
+      v += r * r;
+    }
+    m2lnL[i] = v;
+  }
+}
+
+void ncm_b200_target_mvnd(const gdouble *X, guint n, guint nparams, gdouble *m2lnL, void *user_data) {
+  const NcmB200MVND *t = (const NcmB200MVND *) user_data;
+  const guint d        = nparams;
+  double v[NCM_SD_GPU_MAX_DIM];
+  for (guint i = 0; i < n; i++) {
+    const double *x = &X[(size_t) i * d];
+    double s        = 0.0;
+    for (guint k = 0; k < d; k++) {
+      double acc = x[k] - t->mu[k];
+      for (guint j = 0; j < k; j++) acc -= t->U[j * d + k] * v[j];
+      v[k] = acc / t->U[k * d + k];
+      s += v[k] * v[k];
+    }
+    m2lnL[i] = s;
+  }
+}
+
+}   // extern "C"

@@ -1,0 +1,82 @@
+// Internal definitions of libncm_stats_dist_b200 (host-side mirror of the reference interface).
+#pragma once
+#include <cstddef>
+#include <string>
+#include <vector>
+#include "../../include/ncm_sd_gpu.h"
+#include "../../include/ncm_stats_dist_b200.h"
+
+struct _NcmVector {
+  double *data;
+  guint len;
+  guint stride;
+  int ref;
+  bool own;
+};
+
+struct _NcmMatrix {
+  double *data;
+  guint nrows, ncols, tda;
+  int ref;
+  bool own;
+};
+
+struct _NcmRNG {
+  unsigned long mt[624];
+  int mti;
+  unsigned long seed;
+};
+
+struct _NcmStatsDistKernel {
+  int kind;   // NCM_SD_GPU_KERNEL_GAUSS / ST
+  guint d;
+  double nu;
+  int ref;
+};
+
+struct _NcmStatsDist {
+  int ref;
+  int type;   // NCM_SD_GPU_KDE / VKDE
+  NcmStatsDistKernel *kernel;
+  guint d;
+  // sample_array: GPtrArray of NcmVector (add_obs dups, ncm_stats_dist.c:1681-1686)
+  std::vector<void *> sample;
+  GPtrArray sample_view;
+  // properties
+  double over_smooth, shrink, split_frac, local_frac;
+  NcmStatsDistCV cv_type;
+  gboolean use_threads, print_fit, use_rot_href;
+  NcmStatsDistKDECovType cov_type;
+  guint nearPD_maxiter;
+  NcmMatrix *cov_fixed;
+  // state (NcmStatsDistPrivate, ncm_stats_dist_private.h:39-76)
+  guint n_obs, n_kernels;
+  double href, min_m2lnp, max_m2lnp, rnorm;
+  NcmVector *weights, *wcum;
+  gboolean wcum_ready;
+  bool prepared;
+  // KDE (NcmStatsDistKDEPrivate)
+  NcmMatrix *cov, *cov_decomp;
+  double kernel_lnnorm;
+  std::vector<double> sample_matrix, invUsample;   // [n_obs x d]
+  // VKDE (NcmStatsDistVKDEPrivate): cov_array as live NcmMatrix objects over one slab
+  std::vector<double> cov_slab;                    // [n_kernels x d x d]
+  std::vector<NcmMatrix *> cov_array;
+  std::vector<double> lnnorms;
+  // GPU
+  ncm_sd_gpu_ctx *gpu;
+  ncm_sd_gpu_nnls_stats nnls_stats;
+  double host_prepare_kernel_ms;
+};
+
+void ncm_b200_error(const char *fmt, ...);
+bool ncm_b200_error_pending();   // true when a handler swallowed an error since the last clear
+void ncm_b200_error_clear();
+
+// dense helpers (host side only works on d x d objects and O(N d^2) preparation)
+int ncm_b200_cholesky_upper(double *a, int n, int ld);                 // A = U^T U in place (upper); 0 or 1-based failing pivot
+int ncm_b200_nearPD_upper(double *a, int n, int maxiter);              // Higham nearPD + Cholesky, ncm_matrix.c:1248-1343
+double ncm_b200_cholesky_lndet(const double *U, int n, int ld);        // ncm_matrix.c:1157-1185
+void ncm_b200_cholesky_decomp_fallback(double *cov_decomp, const double *cov, int d, int maxiter);   // kde.c:344-367
+
+int ncm_b200_default_device();

@@ -58,6 +58,46 @@ struct orc_sd
   double timers[3];
 };
 
+/* The reference environment pins an OpenMP build of OpenBLAS (environment.yml), where BLAS calls made
+ * from inside an OpenMP region run single-threaded.  SciPy's OpenBLAS is a pthreads build: the same
+ * nesting serialises on its global lock.  Around the OpenMP regions the oracle therefore switches
+ * OpenBLAS to one thread and restores the previous count afterwards. */
+static int
+blas_enter_omp (void)
+{
+  const int prev = scipy_openblas_get_num_threads ();
+
+  scipy_openblas_set_num_threads (1);
+
+  return prev;
+}
+
+static void
+blas_leave_omp (int prev)
+{
+  scipy_openblas_set_num_threads (prev);
+}
+
+/* gsl_blas_dtrsv (CblasUpper, CblasTrans, CblasNonUnit, U, x) for the d x d factors of the per-point
+ * evaluation loops, written out as the forward substitution it is.  OpenBLAS takes a global buffer lock
+ * in every level-2 call, which under the walkers-parallel OpenMP loop made these d <= 30 calls ~20x
+ * slower than the arithmetic; inlining gives the CPU baseline its best case.  daxpy / ddot likewise. */
+static inline void
+trsv_upper_trans (const int d, const double *U, const int ld, double *x)
+{
+  int k, j;
+
+  for (k = 0; k < d; k++)
+  {
+    double t = x[k];
+
+    for (j = 0; j < k; j++)
+      t -= U[j * ld + k] * x[j];
+
+    x[k] = t / U[k * ld + k];
+  }
+}
+
 static double
 now_s (void)
 {
@@ -490,6 +530,8 @@ vkde_build_cov_array (orc_sd *sd)
     sd->cov_array_len = n_kernels;
   }
 
+  const int blas_prev = blas_enter_omp ();
+
   #pragma omp parallel if (sd->use_threads)
   {
     orc_stats_vec sv;
@@ -540,6 +582,8 @@ vkde_build_cov_array (orc_sd *sd)
     free (items);
     free (cov);
   }
+
+  blas_leave_omp (blas_prev);
 
   return 0;
 }
@@ -690,6 +734,7 @@ vkde_compute_IM (orc_sd *sd, double *IM)
   const int n_obs        = sd->n_obs;
   const double href2     = sd->href * sd->href;
   const double one_href2 = 1.0 / href2;
+  const int blas_prev = blas_enter_omp ();
   int i;
 
   #pragma omp parallel if (sd->use_threads)
@@ -728,6 +773,8 @@ vkde_compute_IM (orc_sd *sd, double *IM)
 
     free (invUsample_matrix);
   }
+
+  blas_leave_omp (blas_prev);
 
   {
     const double lnnorm_href = d * log (sd->href);
@@ -951,7 +998,7 @@ kde_eval_m2lnp (orc_sd *sd, const double *x, double *v, double *chi2, double *ln
   int i;
 
   memcpy (v, x, sizeof (double) * d);
-  scipy_cblas_dtrsv (OrcRowMajor, OrcUpper, OrcTrans, OrcNonUnit, d, sd->cov_decomp, d, v, 1);
+  trsv_upper_trans (d, sd->cov_decomp, d, v);
 
   for (i = 0; i < sd->n_kernels; i++)
   {
@@ -985,7 +1032,7 @@ kde_eval (orc_sd *sd, const double *x, double *v, double *chi2)
   int i;
 
   memcpy (v, x, sizeof (double) * d);
-  scipy_cblas_dtrsv (OrcRowMajor, OrcUpper, OrcTrans, OrcNonUnit, d, sd->cov_decomp, d, v, 1);
+  trsv_upper_trans (d, sd->cov_decomp, d, v);
 
   for (i = 0; i < sd->n_kernels; i++)
   {
@@ -1023,12 +1070,20 @@ vkde_eval_m2lnp (orc_sd *sd, const double *x, double *delta_x, double *chi2, dou
     const double *cov_decomp_i = &sd->cov_array[(size_t) i * d * d];
     const double *theta_i      = sd->sample[i];
 
-    memcpy (delta_x, x, sizeof (double) * d);
-    scipy_cblas_daxpy (d, -1.0, theta_i, 1, delta_x, 1);
+    {
+      double dot = 0.0;
+      int k;
 
-    scipy_cblas_dtrsv (OrcRowMajor, OrcUpper, OrcTrans, OrcNonUnit, d, cov_decomp_i, d, delta_x, 1);
+      for (k = 0; k < d; k++)
+        delta_x[k] = x[k] - theta_i[k];
 
-    chi2[i] = scipy_cblas_ddot (d, delta_x, 1, delta_x, 1) * one_href2;
+      trsv_upper_trans (d, cov_decomp_i, d, delta_x);
+
+      for (k = 0; k < d; k++)
+        dot += delta_x[k] * delta_x[k];
+
+      chi2[i] = dot * one_href2;
+    }
   }
 
   orc_kernel_eval_sum0_gamma_lambda (&sd->kernel, chi2, sd->weights, sd->lnnorms, lnK, sd->n_kernels, &gamma, &lambda);
@@ -1051,12 +1106,20 @@ vkde_eval (orc_sd *sd, const double *x, double *delta_x, double *chi2)
     const double *cov_decomp_i = &sd->cov_array[(size_t) i * d * d];
     const double *theta_i      = sd->sample[i];
 
-    memcpy (delta_x, x, sizeof (double) * d);
-    scipy_cblas_daxpy (d, -1.0, theta_i, 1, delta_x, 1);
+    {
+      double dot = 0.0;
+      int k;
 
-    scipy_cblas_dtrsv (OrcRowMajor, OrcUpper, OrcTrans, OrcNonUnit, d, cov_decomp_i, d, delta_x, 1);
+      for (k = 0; k < d; k++)
+        delta_x[k] = x[k] - theta_i[k];
 
-    chi2[i] = scipy_cblas_ddot (d, delta_x, 1, delta_x, 1) * one_href2;
+      trsv_upper_trans (d, cov_decomp_i, d, delta_x);
+
+      for (k = 0; k < d; k++)
+        dot += delta_x[k] * delta_x[k];
+
+      chi2[i] = dot * one_href2;
+    }
   }
 
   orc_kernel_eval_unnorm_vec (&sd->kernel, chi2, 1, chi2, 1, sd->n_kernels);
@@ -1117,6 +1180,7 @@ orc_sd_eval (orc_sd *sd, const double *x)
 void
 orc_sd_eval_m2lnp_batch (orc_sd *sd, const double *X, int ldx, int q, double *out, int nthreads)
 {
+  const int blas_prev = blas_enter_omp ();
   int i;
 
   #pragma omp parallel num_threads (nthreads > 0 ? nthreads : 1)
@@ -1139,11 +1203,14 @@ orc_sd_eval_m2lnp_batch (orc_sd *sd, const double *X, int ldx, int q, double *ou
     free (chi2);
     free (lnK);
   }
+
+  blas_leave_omp (blas_prev);
 }
 
 void
 orc_sd_eval_batch (orc_sd *sd, const double *X, int ldx, int q, double *out, int nthreads)
 {
+  const int blas_prev = blas_enter_omp ();
   int i;
 
   #pragma omp parallel num_threads (nthreads > 0 ? nthreads : 1)
@@ -1164,6 +1231,8 @@ orc_sd_eval_batch (orc_sd *sd, const double *X, int ldx, int q, double *out, int
     free (v);
     free (chi2);
   }
+
+  blas_leave_omp (blas_prev);
 }
 
 /* ncm_stats_dist.c:1565-1606 */

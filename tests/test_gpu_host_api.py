@@ -1,0 +1,141 @@
+"""GPU parity through the host mirror of the reference interface (ncm_stats_dist_* / APES names):
+reads like tests/c/ncm/stats/test_ncm_stats_dist.c, checked against the CPU oracle."""
+import numpy as np
+import pytest
+
+from helpers import mvnd_problem, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(oracle, sd_s, k_s, nu, d):
+    from numcosmo_b200 import stats_dist as S
+
+    kern = S.StatsDistKernelGauss(d) if k_s == "gauss" else S.StatsDistKernelST(d, nu)
+    sd = S.StatsDistKDE(kern, S.StatsDistCV.NONE) if sd_s == "kde" else S.StatsDistVKDE(kern, S.StatsDistCV.NONE)
+    o = oracle.StatsDist(oracle.SD_KDE if sd_s == "kde" else oracle.SD_VKDE, oracle.KERNEL_GAUSS if k_s == "gauss" else oracle.KERNEL_ST, d, nu)
+    return sd, o
+
+
+@pytest.mark.parametrize("sd_s,k_s,nu,d,n", [("kde", "gauss", 3.0, 3, 600), ("kde", "st", 3.0, 5, 500), ("vkde", "gauss", 3.0, 10, 800),
+                                               ("vkde", "st", 1.0, 2, 400), ("vkde", "st", 3.0, 20, 900)])
+def test_prepare_interp_eval_accessors(oracle, sd_s, k_s, nu, d, n):
+    sd, o = _mk(oracle, sd_s, k_s, nu, d)
+    mu, cov, X, m2lnL = mvnd_problem(oracle, d, n, seed=300 + d)
+    for x in X:
+        sd.add_obs(x)
+    o.add_obs_matrix(X)
+    o.set_use_threads(True)
+    sd.set_use_threads(True)
+    sd.prepare_interp(m2lnL)
+    assert o.prepare_interp(m2lnL) == 0
+    assert sd.get_n_kernels() == n and sd.get_sample_size() == n
+    assert abs(sd.get_href() / o.get_href() - 1) < 1e-14
+    # accessors (test_ncm_stats_dist.c:998-1117): factors, lnnorm, weights
+    for i in (0, n // 2, n - 1):
+        assert np.max(np.abs(np.triu(sd.peek_cov_decomp(i)) - np.triu(o.peek_cov_decomp(i)))) < 1e-11 * np.abs(o.peek_cov_decomp(i)).max()
+        assert abs(sd.get_lnnorm(i) - o.get_lnnorm(i)) < 1e-10
+    w, wo = sd.peek_weights(), o.peek_weights()
+    assert abs(w.sum() - 1.0) < 1e-12
+    st, so = sd.nnls_stats(), o.nnls_stats()
+    if st["n_passive"] == so["n_passive"] and st["n_retry"] == 0:
+        assert np.max(np.abs(w - wo)) / wo.max() < 1e-6
+    assert abs(sd.get_rnorm() - o.get_rnorm()) <= 1e-8 * max(o.get_rnorm(), 1e-20) + 1e-18
+    # densities: single-point API and the new batched entry
+    Q = np.vstack([X[:40] + 0.002, mu + 2.0 * (X[40:80] - mu)])
+    exp = o.eval_m2lnp_batch(Q, 4)
+    got = sd.eval_m2lnp_array(Q)
+    assert rel_err(got, exp) < 1e-6
+    for j in (0, 11, 79):
+        assert abs(sd.eval_m2lnp(Q[j]) - got[j]) <= 1e-12 * abs(got[j])
+        assert abs(sd.eval(Q[j]) / np.exp(-0.5 * got[j]) - 1) < 1e-10
+    # get_Ki consistency (test_ncm_stats_dist.c:1040-1117): cov_i = href^2 U^T U, n_i = exp(lnnorm), w_i = weight
+    y, cv, n_i, w_i = sd.get_Ki(3)
+    U = np.triu(sd.peek_cov_decomp(3))
+    assert np.allclose(y, X[3]) and np.allclose(cv, sd.get_href() ** 2 * U.T @ U, rtol=1e-12, atol=0)
+    assert abs(n_i / np.exp(sd.get_lnnorm(3)) - 1) < 1e-13 and w_i == w[3]
+
+
+def test_prepare_without_interp_and_sampling_stream(oracle):
+    from numcosmo_b200 import stats_dist as S
+
+    d, n = 4, 500
+    for k_s, nu in (("gauss", 3.0), ("st", 3.0)):
+        sd, o = _mk(oracle, "vkde", k_s, nu, d)
+        mu, cov, X, _ = mvnd_problem(oracle, d, n, seed=17)
+        for x in X:
+            sd.add_obs(x)
+        o.add_obs_matrix(X)
+        sd.prepare()
+        assert o.prepare() == 0
+        assert np.allclose(sd.peek_weights(), 1.0 / n)
+        Q = X[:100] * 1.001
+        assert rel_err(sd.eval_m2lnp_array(Q), o.eval_m2lnp_batch(Q, 2)) < 1e-10
+        # identical proposal stream for a fixed seed (host RNG in reference order)
+        r1, r2 = S.RNG(1234), oracle.RNG(1234)
+        for _ in range(200):
+            a, b = sd.sample(r1), o.sample(r2)
+            assert np.max(np.abs(a - b)) <= 1e-13 * np.abs(b).max()
+        assert r1.gen_ulong() == r2.get()
+
+
+def test_errors_match_reference_messages(oracle):
+    from numcosmo_b200 import stats_dist as S
+
+    kern = S.StatsDistKernelGauss(3)
+    sd = S.StatsDistKDE(kern, S.StatsDistCV.NONE)
+    for i in range(3):
+        sd.add_obs(np.arange(3.0) + i)
+    with pytest.raises(S.NcmError, match="the sample is too small"):
+        sd.prepare()
+    sd2 = S.StatsDistVKDE(kern, S.StatsDistCV.NONE)
+    rs = np.random.default_rng(0)
+    for i in range(30):
+        sd2.add_obs(rs.standard_normal(3))
+    with pytest.raises(S.NcmError, match="Too few observations"):
+        sd2.prepare()   # local_frac * n_obs = 1.5 < 2
+
+
+@pytest.mark.parametrize("target,k_type,d,W", [("mvnd", "gauss", 5, 500), ("rosenbrock", "st3", 2, 200), ("funnel", "cauchy", 4, 400), ("mvnd", "st3", 10, 1000)])
+def test_apes_identical_accepted_sequence(oracle, target, k_type, d, W):
+    """Fixed RNG stream -> identical accept/reject sequence and walker positions as the CPU oracle
+    (pattern of tests/c/ncm/fit/test_ncm_fit_esmcmc.c:888-971 parity/serial_vs_threaded)."""
+    from numcosmo_b200 import stats_dist as S
+
+    kmap = {"gauss": (S.FitESMCMCWalkerAPESKType.GAUSS, oracle.KERNEL_GAUSS, 1.0), "st3": (S.FitESMCMCWalkerAPESKType.ST3, oracle.KERNEL_ST, 3.0),
+            "cauchy": (S.FitESMCMCWalkerAPESKType.CAUCHY, oracle.KERNEL_ST, 1.0)}
+    kt, ok, nu = kmap[k_type]
+    rs = np.random.default_rng(42)
+    if target == "mvnd":
+        mu, cov, X, m2lnL = mvnd_problem(oracle, d, W, seed=77)
+        lb, ub = np.full(d, -50.0), np.full(d, 50.0)
+        tgt = oracle.Target(oracle.TARGET_MVND, d, lb, ub, mu=mu, cov=cov)
+        targs = (mu, tgt.U)
+        theta = X.copy()
+    elif target == "rosenbrock":
+        lb, ub = np.array([-200.0, -400.0]), np.array([200.0, 800.0])
+        tgt = oracle.Target(oracle.TARGET_ROSENBROCK, d, lb, ub)
+        targs = None
+        theta = np.ascontiguousarray(rs.standard_normal((W, d)) * [1.0, 2.0] + [0.5, 1.0])
+    else:
+        lb, ub = np.array([-1000.0] + [-1e6] * (d - 1)), np.array([1000.0] + [1e6] * (d - 1))
+        tgt = oracle.Target(oracle.TARGET_FUNNEL, d, lb, ub)
+        targs = None
+        nu_ = rs.standard_normal(W) * 1.5
+        theta = np.ascontiguousarray(np.column_stack([nu_] + [rs.standard_normal(W) * np.exp(0.5 * nu_) for _ in range(d - 1)]))
+    m2lnL0 = np.array([tgt.m2lnL(x) for x in theta])
+    iters = 6
+    # CPU oracle
+    th_o, ml_o = theta.copy(), m2lnL0.copy()
+    ao = oracle.APES(W, d, oracle.SD_VKDE, ok, nu, over_smooth=1.0, use_interp=True, use_threads=True)
+    acc_o = ao.run(tgt, th_o, ml_o, iters, oracle.RNG(2024), nthreads=4)
+    # GPU path
+    th_g, ml_g = theta.copy(), m2lnL0.copy()
+    ag = S.FitESMCMCWalkerAPES(W, d, S.FitESMCMCWalkerAPESMethod.VKDE, kt, 1.0, True)
+    ag.set_use_threads(True)
+    acc_g, timers = ag.run(target, lb, ub, th_g, ml_g, iters, S.RNG(2024), target_args=targs)
+    diff = np.argwhere(acc_o != acc_g)
+    assert diff.size == 0, f"first divergence at (iter, walker) = {diff[0]}"
+    assert acc_g.mean() > 0.05, acc_g.mean()
+    assert np.max(np.abs(th_g - th_o)) <= 1e-9 * np.abs(th_o).max()
+    assert rel_err(ag.peek_m2lnp_star(), ao.peek_m2lnp_star()) < 1e-6
