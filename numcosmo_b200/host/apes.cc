@@ -314,6 +314,10 @@ void ncm_b200_esmcmc_run(NcmFitESMCMCWalkerAPES *a, NcmB200M2lnLFunc m2lnL_func,
   const double t_begin = now_ms();
   a->t_sample_ms = a->t_eval_ms = 0.0;
   ncm_b200_error_clear();
+  double s0[NCM_SD_GPU_T_LEN] = {0}, s1[NCM_SD_GPU_T_LEN] = {0}, sh0 = 0.0, sh1 = 0.0;
+  long long sn0 = 0, sn1 = 0;
+  ncm_stats_dist_b200_get_timers(a->sd0, s0, &sn0, &sh0);   // snapshot: the context timers are cumulative
+  ncm_stats_dist_b200_get_timers(a->sd1, s1, &sn1, &sh1);
   for (guint it = 0; it < iters; it++) {
     unsigned char *acc = accepted != nullptr ? &accepted[(size_t) it * W] : nullptr;
     if (acc != nullptr) memset(acc, 0, W);
@@ -351,6 +355,12 @@ void ncm_b200_esmcmc_run(NcmFitESMCMCWalkerAPES *a, NcmB200M2lnLFunc m2lnL_func,
     long long n0 = 0, n1 = 0;
     ncm_stats_dist_b200_get_timers(a->sd0, g0, &n0, &h0);
     ncm_stats_dist_b200_get_timers(a->sd1, g1, &n1, &h1);
+    for (int i = 0; i < NCM_SD_GPU_T_LEN; i++) {
+      g0[i] -= s0[i];
+      g1[i] -= s1[i];
+    }
+    h0 -= sh0;
+    h1 -= sh1;
     timers_ms[0] = h0 + h1;
     timers_ms[1] = g0[NCM_SD_GPU_T_IM] + g1[NCM_SD_GPU_T_IM];
     timers_ms[2] = g0[NCM_SD_GPU_T_SYRK] + g1[NCM_SD_GPU_T_SYRK] + g0[NCM_SD_GPU_T_CHOL] + g1[NCM_SD_GPU_T_CHOL] + g0[NCM_SD_GPU_T_NNLS_MISC] +

@@ -1,0 +1,50 @@
+"""FP64 building blocks exported by the C ABI (DMMA SYRK, blocked Cholesky) against numpy."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("m,n", [(64, 64), (300, 130), (1000, 257), (128, 1024), (2048, 2048)])
+def test_dsyrk_ata(gpu_ctx, m, n):
+    import torch
+
+    rs = np.random.default_rng(m + n)
+    A = rs.standard_normal((m, n))
+    lda = (n + 7) // 8 * 8
+    dA = torch.zeros((m, lda), dtype=torch.float64, device="cuda")
+    dA[:, :n] = torch.from_numpy(A).cuda()
+    dM = torch.zeros((n, lda), dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    gpu_ctx.dsyrk_ata_dev(m, n, dA.data_ptr(), lda, dM.data_ptr(), lda)
+    gpu_ctx.synchronize()
+    M = dM.cpu().numpy()[:, :n]
+    ref = A.T @ A
+    iu = np.triu_indices(n)
+    assert np.max(np.abs(M[iu] - ref[iu])) < 1e-12 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("n", [1, 5, 64, 65, 200, 1000, 2048])
+def test_dpotrf_upper(gpu_ctx, n):
+    import torch
+
+    rs = np.random.default_rng(n)
+    B = rs.standard_normal((n + 10, n))
+    S = B.T @ B + 0.1 * np.eye(n)
+    ld = (n + 7) // 8 * 8
+    dM = torch.zeros((n, ld), dtype=torch.float64, device="cuda")
+    dM[:, :n] = torch.from_numpy(np.triu(S)).cuda()
+    torch.cuda.synchronize()
+    info = gpu_ctx.dpotrf_upper_dev(n, dM.data_ptr(), ld)
+    assert info == 0
+    U = np.triu(dM.cpu().numpy()[:, :n])
+    Uref = np.linalg.cholesky(S).T
+    assert np.max(np.abs(U - Uref)) < 1e-10 * np.abs(Uref).max()
+    # not positive definite -> 1-based index of the failing pivot
+    S2 = S.copy()
+    k = n // 2
+    S2[k, k] = -1.0
+    dM[:, :n] = torch.from_numpy(np.triu(S2)).cuda()
+    torch.cuda.synchronize()
+    info = gpu_ctx.dpotrf_upper_dev(n, dM.data_ptr(), ld)
+    assert info == k + 1

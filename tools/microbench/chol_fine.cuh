@@ -40,7 +40,7 @@ constexpr int DS = NB + 2;   // row pitch of the shared block: columns 0..63, rh
 // its column against it and writes it back; then all 256 threads apply the rank-8 update to the rest.
 __global__ void __launch_bounds__(256) chol_diag_kernel(double *__restrict__ M, int ldm, int n, int k0, double *__restrict__ rhs,
                                                         double *__restrict__ dinv, int *__restrict__ info) {
-  __shared__ __align__(16) double S[NB][DS];
+  __shared__ double S[NB][DS];
   __shared__ double sDinv[NB];
   __shared__ int sBad;
   const int tid = threadIdx.x;
@@ -49,31 +49,15 @@ __global__ void __launch_bounds__(256) chol_diag_kernel(double *__restrict__ M, 
   NCM_PROBE(0);
   {
     // 256 threads x 16 independent loads: row = tid / 4, columns (tid % 4) * 16 .. + 15
-    if (nb == NB) {
-      // full block: 8 independent 16-byte loads per thread, a warp reads one 512-byte row per instruction
-      // (the lower triangle is loaded and ignored)
-      double2 v[8];
+    const int r = tid >> 2, cb = (tid & 3) * 16;
+    double v[16];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int chunk = q * 256 + tid;   // 32 chunks of 16 B per row
-        v[q] = *reinterpret_cast<const double2 *>(M + (size_t) (k0 + (chunk >> 5)) * ldm + k0 + (chunk & 31) * 2);
-      }
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int chunk = q * 256 + tid;
-        *reinterpret_cast<double2 *>(&S[chunk >> 5][(chunk & 31) * 2]) = v[q];
-      }
-    } else {
-      const int r = tid >> 2, cb = (tid & 3) * 16;
-      double v[16];
-#pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        const int cidx = cb + q;
-        v[q] = (r < nb && cidx < nb && cidx >= r) ? M[(size_t) (k0 + r) * ldm + k0 + cidx] : ((r == cidx && r >= nb) ? 1.0 : 0.0);
-      }
-#pragma unroll
-      for (int q = 0; q < 16; ++q) S[r][cb + q] = v[q];
+    for (int q = 0; q < 16; ++q) {
+      const int cidx = cb + q;
+      v[q] = (r < nb && cidx < nb && cidx >= r) ? M[(size_t) (k0 + r) * ldm + k0 + cidx] : ((r == cidx && r >= nb) ? 1.0 : 0.0);
     }
+#pragma unroll
+    for (int q = 0; q < 16; ++q) S[r][cb + q] = v[q];
     if (tid < NB) S[tid][NB] = (tid < nb && rhs != nullptr) ? rhs[k0 + tid] : 0.0;
   }
   __syncthreads();
@@ -82,14 +66,11 @@ __global__ void __launch_bounds__(256) chol_diag_kernel(double *__restrict__ M, 
 #pragma unroll 1
   for (int kb = 0; kb < NB / 8; ++kb) {
     const int b0    = 8 * kb;
-    const int ncols = NB - b0 + 1;                    // remaining columns + rhs
-    const bool solver = tid >= 8 && tid < ncols;      // threads 8 .. ncols-1: one remaining column (or the rhs) each
-    const bool writer = tid >= 224 && tid < 232;      // an otherwise idle warp writes the factored sub-block back
-    // Divergent if/else paths cost ~100 cycles per reconvergence point here, so both roles run the same
-    // straight-line code and only their stores are predicated.
-    if (solver || writer) {
-      const int ci = (tid == ncols - 1) ? NB : (solver ? b0 + tid : b0);
-      // 8 x 8 diagonal sub-block (upper) in registers; every thread reads the same addresses (broadcast)
+    const int ncols = NB - b0 + 1;   // remaining columns + rhs
+    if (kb == 0 && tid == 8) g_probe[39] = clock64();
+    if (tid < ncols) {
+      const int ci = (tid == ncols - 1) ? NB : b0 + tid;
+      // 8 x 8 diagonal sub-block (upper) in registers; all threads read the same addresses (broadcast)
       double dgl[8][8];
 #pragma unroll
       for (int r = 0; r < 8; ++r)
@@ -98,13 +79,14 @@ __global__ void __launch_bounds__(256) chol_diag_kernel(double *__restrict__ M, 
       double col[8];
 #pragma unroll
       for (int r = 0; r < 8; ++r) col[r] = S[b0 + r][ci];
+      if (kb == 0 && tid == 8) g_probe[40] = clock64();
       double inv[8];
       int bad = 0;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         double piv = dgl[j][j];
         if (!(piv > 0.0)) {
-          bad = (bad == 0) ? k0 + b0 + j + 1 : bad;
+          if (bad == 0) bad = k0 + b0 + j + 1;
           piv = 1.0;
         }
         inv[j]    = rsqrt(piv);
@@ -116,81 +98,75 @@ __global__ void __launch_bounds__(256) chol_diag_kernel(double *__restrict__ M, 
 #pragma unroll
           for (int q = r; q < 8; ++q) dgl[r][q] = fma(-dgl[j][r], dgl[j][q], dgl[r][q]);
       }
-      // x = D^-T s_c  (the writer threads run it on a dummy column and discard it)
-      double x[8];
+      if (kb == 0 && tid == 8) g_probe[41] = clock64();
+      if (tid < 8) {
+        // columns of the sub-block itself: thread q writes column q of the factor
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        double t = col[r];
+        for (int r = 0; r < 8; ++r)
 #pragma unroll
-        for (int s = 0; s < r; ++s) t = fma(-dgl[s][r], x[s], t);
-        x[r] = t * inv[r];
-      }
-      const int wq = tid - 224;   // writer: column wq of the factor
+          for (int q = r; q < 8; ++q)
+            if (q == tid) S[b0 + r][b0 + q] = dgl[r][q];
+        if (tid == 0) {
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        double v = x[r];
-        if (writer) {
-#pragma unroll
-          for (int q = r; q < 8; ++q) v = (q == wq) ? dgl[r][q] : v;
+          for (int j = 0; j < 8; ++j) sDinv[b0 + j] = inv[j];
+          if (bad != 0 && sBad == 0) sBad = bad;
         }
-        const int cc = writer ? b0 + wq : ci;
-        if (solver || (writer && wq >= r)) S[b0 + r][cc] = v;
-      }
-      if (writer && wq == 0) {
+      } else {
+        // x = D^-T s_c
+        double x[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) sDinv[b0 + j] = inv[j];
-        if (bad != 0 && sBad == 0) sBad = bad;
+        for (int r = 0; r < 8; ++r) {
+          double t = col[r];
+#pragma unroll
+          for (int s = 0; s < r; ++s) t = fma(-dgl[s][r], x[s], t);
+          x[r] = t * inv[r];
+        }
+        if (kb == 0 && tid == 8) g_probe[42] = clock64();
+#pragma unroll
+        for (int r = 0; r < 8; ++r) S[b0 + r][ci] = x[r];
+        if (kb == 0 && tid == 8) g_probe[43] = clock64();
       }
     }
+    if (kb == 0 && tid == 8) g_probe[44] = clock64();
     __syncthreads();
+    if (kb == 0 && tid == 8) g_probe[45] = clock64();
     NCM_PROBE(2 + 2 * kb);
-    // rank-8 update of the remaining upper triangle and of the rhs column: 16 x 16 threads, cyclic 4 x 4 tiles,
-    // straight-line with predicated stores
+    // rank-8 update of the remaining upper triangle and of the rhs column: 16 x 16 threads, cyclic 4 x 4 tiles
     {
       const int base = b0 + 8;
       const int ty = tid >> 4, tx = tid & 15;
       if (base < NB) {
-        double xr[4][8], xc[4][8], xh[8];
+        double xr[4][8], xc[4][8];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int r = min(base + ty + 16 * i, NB - 1);
-          const int c = min(base + tx + 16 * i, NB - 1);
+          const int r = base + ty + 16 * i;
+          const int c = base + tx + 16 * i;
 #pragma unroll
           for (int s = 0; s < 8; ++s) {
-            xr[i][s] = S[b0 + s][r];
-            xc[i][s] = S[b0 + s][c];
+            xr[i][s] = (r < NB) ? S[b0 + s][r] : 0.0;
+            xc[i][s] = (c < NB) ? S[b0 + s][c] : 0.0;
           }
         }
 #pragma unroll
-        for (int s = 0; s < 8; ++s) xh[s] = S[b0 + s][NB];
-        // all 20 accumulators are loaded before any store, so the 8-deep FMA chains overlap
-        double acc[4][5];
-#pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int rc = min(base + ty + 16 * i, NB - 1);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = S[rc][min(base + tx + 16 * j, NB - 1)];
-          acc[i][4] = S[rc][NB];
-        }
-#pragma unroll
-        for (int s = 0; s < 8; ++s)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = fma(-xr[i][s], xc[j][s], acc[i][j]);
-            acc[i][4] = fma(-xr[i][s], xh[s], acc[i][4]);
-          }
-        // (operand rows b0 .. b0+7 are not written in this phase and every thread owns its (r, c) entries)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r   = base + ty + 16 * i;
-          const bool rv = r < NB;
+          const int r = base + ty + 16 * i;
+          if (r >= NB) continue;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int c = base + tx + 16 * j;
-            if (rv && c < NB && c >= r) S[r][c] = acc[i][j];
+            if (c < NB && c >= r) {
+              double acc = S[r][c];
+#pragma unroll
+              for (int s = 0; s < 8; ++s) acc = fma(-xr[i][s], xc[j][s], acc);
+              S[r][c] = acc;
+            }
           }
-          if (rv && tx == 0) S[r][NB] = acc[i][4];
+          if (tx == 0) {
+            double acc = S[r][NB];
+#pragma unroll
+            for (int s = 0; s < 8; ++s) acc = fma(-xr[i][s], S[b0 + s][NB], acc);
+            S[r][NB] = acc;
+          }
         }
       }
     }
@@ -201,16 +177,10 @@ __global__ void __launch_bounds__(256) chol_diag_kernel(double *__restrict__ M, 
   {
     const int r = tid >> 2, cb = (tid & 3) * 16;
     if (r < nb) {
-      double *dst = M + (size_t) (k0 + r) * ldm + k0 + cb;
 #pragma unroll
-      for (int q = 0; q < 16; q += 2) {
+      for (int q = 0; q < 16; ++q) {
         const int cidx = cb + q;
-        if (cidx >= r && cidx + 1 < nb)
-          *reinterpret_cast<double2 *>(dst + q) = make_double2(S[r][cidx], S[r][cidx + 1]);
-        else {
-          if (cidx < nb && cidx >= r) dst[q] = S[r][cidx];
-          if (cidx + 1 < nb && cidx + 1 >= r) dst[q + 1] = S[r][cidx + 1];
-        }
+        if (cidx < nb && cidx >= r) M[(size_t) (k0 + r) * ldm + k0 + cidx] = S[r][cidx];
       }
     }
   }
@@ -229,26 +199,20 @@ __global__ void __launch_bounds__(128) chol_panel_kernel(double *__restrict__ M,
   __shared__ double sD[NB];
   __shared__ double sY[NB];
   const int tid = threadIdx.x;
-  NCM_PROBE(49);
   {
-    // 128 threads x 16 independent 16-byte loads; a warp reads one 512-byte row per instruction (coalesced)
+    // 128 threads x 16 independent 16-byte loads: row = tid / 2, columns (tid % 2) * 32 .. + 31
+    const int s = tid >> 1, cb = (tid & 1) * 32;
+    const double2 *src = reinterpret_cast<const double2 *>(M + (size_t) (k0 + s) * ldm + k0 + cb);
     double2 v[16];
 #pragma unroll
-    for (int q = 0; q < 16; ++q) {
-      const int chunk = q * 128 + tid;               // 0 .. 2047, 32 chunks of 16 B per row
-      v[q] = *reinterpret_cast<const double2 *>(M + (size_t) (k0 + (chunk >> 5)) * ldm + k0 + (chunk & 31) * 2);
-    }
+    for (int q = 0; q < 16; ++q) v[q] = src[q];
 #pragma unroll
-    for (int q = 0; q < 16; ++q) {
-      const int chunk = q * 128 + tid;
-      *reinterpret_cast<double2 *>(&sU[chunk >> 5][(chunk & 31) * 2]) = v[q];
-    }
+    for (int q = 0; q < 16; ++q) *reinterpret_cast<double2 *>(&sU[s][cb + 2 * q]) = v[q];
   }
   if (tid < NB) {
     sD[tid] = dinv[k0 + tid];
     sY[tid] = rhs != nullptr ? rhs[k0 + tid] : 0.0;
   }
-  NCM_PROBE(50);
   const int j    = k0 + NB + blockIdx.x * blockDim.x + tid;
   const bool jv  = j < n;
   const int jj   = jv ? j : n - 1;
@@ -256,7 +220,6 @@ __global__ void __launch_bounds__(128) chol_panel_kernel(double *__restrict__ M,
 #pragma unroll
   for (int rr = 0; rr < 8; ++rr) t[rr] = M[(size_t) (k0 + rr) * ldm + jj];
   __syncthreads();
-  NCM_PROBE(51);
   double x[NB];
   double dot = 0.0;
 #pragma unroll
@@ -289,10 +252,8 @@ __global__ void __launch_bounds__(128) chol_panel_kernel(double *__restrict__ M,
 #pragma unroll
       for (int rr = 0; rr < 8; ++rr) t[rr] = tn[rr];
     }
-    NCM_PROBE(52 + blk);
   }
   if (jv && rhs != nullptr) rhs[j] -= dot;
-  NCM_PROBE(60);
 }
 
 // Back substitution step for block row kb (k0 = kb * NB), given x of block kb + 1 already in y:
@@ -309,18 +270,15 @@ __global__ void __launch_bounds__(256) chol_backsolve_kernel(const double *__res
   __shared__ double sU[NB][NB + 1];
   if (tid < NB) sx[tid] = (tid < nb1) ? y[k1 + tid] : 0.0;
   if (blockIdx.x == 0) {
-    // 16 independent loads per thread; a warp reads 32 consecutive doubles of one row per instruction
+    const int r = tid >> 2, cb = (tid & 3) * 16;
     double v[16];
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
-      const int e = q * 256 + tid, r = e >> 6, cidx = e & 63;
+      const int cidx = cb + q;
       v[q] = (r < nb && cidx < nb && cidx >= r) ? M[(size_t) (k0 + r) * ldm + k0 + cidx] : 0.0;
     }
 #pragma unroll
-    for (int q = 0; q < 16; ++q) {
-      const int e = q * 256 + tid;
-      sU[e >> 6][e & 63] = v[q];
-    }
+    for (int q = 0; q < 16; ++q) sU[r][cb + q] = v[q];
   }
   __syncthreads();
   if (blockIdx.x > 0) {
@@ -335,25 +293,16 @@ __global__ void __launch_bounds__(256) chol_backsolve_kernel(const double *__res
     }
     return;
   }
-  // CTA 0: update own rows with x of the next block (all loads of the warp's 8 rows issued up front) ...
-  {
-    double u0[8], u1[8], yy[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int r     = warp + 8 * q;
-      const double *u = M + (size_t) (k0 + min(r, nb - 1)) * ldm + k1;
-      u0[q]           = (r < nb && lane < nb1) ? u[lane] : 0.0;
-      u1[q]           = (r < nb && lane + 32 < nb1) ? u[lane + 32] : 0.0;
-      yy[q]           = (r < nb && lane == 0) ? y[k0 + r] : 0.0;
-    }
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      double sacc = fma(u1[q], sx[lane + 32], u0[q] * sx[lane]);
-#pragma unroll
+  // CTA 0: update own rows with x of the next block ...
+  for (int r = warp; r < nb; r += 8) {
+    double sacc = 0.0;
+    if (nb1 > 0) {
+      const double *u = M + (size_t) (k0 + r) * ldm + k1;
+      sacc            = (lane < nb1 ? u[lane] : 0.0) * sx[lane];
+      sacc            = fma(lane + 32 < nb1 ? u[lane + 32] : 0.0, sx[lane + 32], sacc);
       for (int off = 16; off > 0; off >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, off);
-      const int r = warp + 8 * q;
-      if (lane == 0 && r < nb) sy[r] = yy[q] - sacc;
     }
+    if (lane == 0) sy[r] = y[k0 + r] - sacc;
   }
   __syncthreads();
   // ... then one warp solves the 64 x 64 upper system: lane holds rows lane and lane + 32
