@@ -4,7 +4,7 @@
 //                   - trailing update of the blocked Cholesky (alpha = -1, beta = 1, P = panel rows of U)
 //   gemv kernels    b = A^T f, r = f - A x, g = A^T r           (cblas_dgemv, ncm_nnls.c:710-726, 791-792)
 //
-// ata_kernel: 128 x 128 CTA tile, 8 warps as 2 (M) x 4 (N), warp tile 64 x 32 = 8 x 4 DMMA tiles,
+// ata_kernel: 128 x 128 (or 64 x 64) CTA tile, warp tiles of 8 x 4 (4 x 4) DMMA tiles,
 // K consumed 16 rows per stage through a 4-stage cp.async ring.  P^T is never materialised: both
 // DMMA operands are read from the same row-major K x 128 slabs (fragment element (i, r) = P[r][i]),
 // stored with a row pitch of 132 doubles so that the 4 rows x 4 columns a half-warp touches fall
@@ -13,61 +13,76 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4;
-constexpr int PITCH = 132;                       // doubles; 132 * 8 B = 1056 = 8 * 128 + 32
-constexpr int SLAB  = BK * PITCH;                // doubles per operand per stage
-constexpr int ATA_THREADS = 256;
-constexpr size_t ATA_SMEM = (size_t) STAGES * 2 * SLAB * sizeof(double);   // 135168 B
+constexpr int BK = 16;
+
+// Tile configurations.  Big: 128 x 128 CTA tile, 8 warps as 2 x 4, warp tile 64 x 32 (8 x 4 DMMA tiles) -- the
+// throughput shape (SYRK of the normal equations, large trailing updates).  Small: 64 x 64 CTA tile, 4 warps as
+// 2 x 2, warp tile 32 x 32 -- four times more CTAs of a quarter of the latency each, for the K = 64 trailing
+// updates of mid-size Cholesky factorisations where a 128-tile grid would be a single under-filled wave.
+struct AtaBig {
+  static constexpr int TB = 128, WN = 4, MI = 8, NI = 4, THREADS = 256, MINB = 1, STAGES = 4;
+};
+struct AtaSmall {
+  static constexpr int TB = 64, WN = 2, MI = 4, NI = 4, THREADS = 128, MINB = 4, STAGES = 3;
+};
+template <typename Cfg>
+struct AtaDerived {
+  static constexpr int PITCH = Cfg::TB + 4;            // (TB + 4) * 8 B = k * 128 + 32: conflict-free fragment loads
+  static constexpr int SLAB  = BK * PITCH;             // doubles per operand per stage
+  static constexpr size_t SMEM = (size_t) Cfg::STAGES * 2 * SLAB * sizeof(double);
+  static constexpr int CHUNKS = BK * (Cfg::TB / 2) / Cfg::THREADS;   // 16-byte chunks per thread per operand per stage
+};
 
 __device__ __forceinline__ void tile_from_linear(int t, int nt, int &ti, int &tj) {
   // upper-triangular tiles enumerated row by row: row ti has (nt - ti) tiles
-  int i = 0, rem = t;
-  // closed form with a correction loop (nt is at most a few hundred)
   double disc = (2.0 * nt + 1.0) * (2.0 * nt + 1.0) - 8.0 * t;
-  i = (int) ((2.0 * nt + 1.0 - sqrt(disc)) * 0.5);
+  int i       = (int) ((2.0 * nt + 1.0 - sqrt(disc)) * 0.5);
   if (i < 0) i = 0;
   while (i > 0 && (i * (2 * nt - i + 1)) / 2 > t) --i;
   while (((i + 1) * (2 * nt - i)) / 2 <= t) ++i;
-  rem = t - (i * (2 * nt - i + 1)) / 2;
-  ti  = i;
-  tj  = i + rem;
+  ti = i;
+  tj = i + (t - (i * (2 * nt - i + 1)) / 2);
 }
 
-template <bool SUBC>   // SUBC: C -= P^T P (alpha = -1, beta = 1): C is loaded into the accumulators up front, epilogue = stores only
-__global__ void __launch_bounds__(ATA_THREADS, 1)
+// SUBC: C -= P^T P (alpha = -1, beta = 1): C is loaded into the accumulators up front (the loads overlap with the
+// cp.async prologue), the A fragments are negated, and the epilogue is stores only.
+template <typename Cfg, bool SUBC>
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB)
 ata_kernel(const double *__restrict__ P, int ldp, int K, int n, double *__restrict__ C, int ldc, double alpha, double beta, int nt) {
+  using D = AtaDerived<Cfg>;
+  constexpr int TB = Cfg::TB, PITCH = D::PITCH, SLAB = D::SLAB, MI = Cfg::MI, NI = Cfg::NI, STAGES = Cfg::STAGES;
   extern __shared__ __align__(16) double smem[];
   int ti, tj;
   tile_from_linear(blockIdx.x, nt, ti, tj);
-  const int i0 = ti * BM, j0 = tj * BN;
+  const int i0 = ti * TB, j0 = tj * TB;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp >> 2, wn = warp & 3;           // 2 x 4 warps
+  const int wm = warp / Cfg::WN, wn = warp % Cfg::WN;
   const int lr = lane & 3, lc = lane >> 2;           // fragment coordinates
+  const int rm = wm * (MI * 8), cn = wn * (NI * 8);  // warp tile origin inside the CTA tile
 
   auto load_stage = [&](int kb, int st) {
     double *sA = smem + (size_t) st * 2 * SLAB;
     double *sB = sA + SLAB;
     const int r0 = kb * BK;
-    // each operand slab: BK rows x 128 doubles = 16 x 64 chunks of 16 B; 256 threads -> 4 chunks each per operand
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int chunk = tid + it * ATA_THREADS;      // 0 .. 1023
-      const int r     = chunk >> 6;                  // 0 .. 15
-      const int cc    = (chunk & 63) * 2;            // column (doubles) within the slab
+    for (int it = 0; it < D::CHUNKS; ++it) {
+      const int chunk = tid + it * Cfg::THREADS;
+      const int r     = chunk / (TB / 2);
+      const int cc    = (chunk % (TB / 2)) * 2;       // column (doubles) within the slab
       const int gr    = r0 + r;
       const bool rv   = gr < K;
       {
-        const int gc   = i0 + cc;
-        int bytes      = rv ? (n - gc) * 8 : 0;
-        bytes          = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
+        const int gc = i0 + cc;
+        int bytes    = rv ? (n - gc) * 8 : 0;
+        bytes        = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
         const double *src = (bytes > 0) ? (P + (size_t) gr * ldp + gc) : P;
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(sA + r * PITCH + cc)), "l"(src), "r"(bytes) : "memory");
       }
       {
-        const int gc   = j0 + cc;
-        int bytes      = rv ? (n - gc) * 8 : 0;
-        bytes          = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
+        const int gc = j0 + cc;
+        int bytes    = rv ? (n - gc) * 8 : 0;
+        bytes        = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
         const double *src = (bytes > 0) ? (P + (size_t) gr * ldp + gc) : P;
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(sB + r * PITCH + cc)), "l"(src), "r"(bytes) : "memory");
       }
@@ -81,16 +96,15 @@ ata_kernel(const double *__restrict__ P, int ldp, int K, int n, double *__restri
     cp_async_commit();
   }
 
-  double acc[8][4][2];
+  double acc[MI][NI][2];
 #pragma unroll
-  for (int a = 0; a < 8; ++a) {
-    const int gi = i0 + wm * 64 + a * 8 + lc;
+  for (int a = 0; a < MI; ++a) {
+    const int gi = i0 + rm + a * 8 + lc;
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
+    for (int b = 0; b < NI; ++b) {
       acc[a][b][0] = acc[a][b][1] = 0.0;
       if (SUBC) {
-        // the 64 loads of this thread's C fragment overlap with the cp.async prologue
-        const int gj = j0 + wn * 32 + b * 8 + 2 * lr;
+        const int gj = j0 + cn + b * 8 + 2 * lr;
         if (gi < n && gj + 1 < n) {
           const double2 v = *reinterpret_cast<const double2 *>(C + (size_t) gi * ldc + gj);
           acc[a][b][0]    = v.x;
@@ -114,29 +128,29 @@ ata_kernel(const double *__restrict__ P, int ldp, int K, int n, double *__restri
     const double *sB = sA + SLAB;
 #pragma unroll
     for (int ks = 0; ks < BK / 4; ++ks) {
-      double af[8], bf[4];
-      const double *pa = sA + (ks * 4 + lr) * PITCH + wm * 64 + lc;
-      const double *pb = sB + (ks * 4 + lr) * PITCH + wn * 32 + lc;
+      double af[MI], bf[NI];
+      const double *pa = sA + (ks * 4 + lr) * PITCH + rm + lc;
+      const double *pb = sB + (ks * 4 + lr) * PITCH + cn + lc;
 #pragma unroll
-      for (int a = 0; a < 8; ++a) af[a] = SUBC ? -pa[a * 8] : pa[a * 8];
+      for (int a = 0; a < MI; ++a) af[a] = SUBC ? -pa[a * 8] : pa[a * 8];
 #pragma unroll
-      for (int b = 0; b < 4; ++b) bf[b] = pb[b * 8];
+      for (int b = 0; b < NI; ++b) bf[b] = pb[b * 8];
 #pragma unroll
-      for (int a = 0; a < 8; ++a)
+      for (int a = 0; a < MI; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+        for (int b = 0; b < NI; ++b) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
     }
   }
   cp_async_wait<0>();
 
   // epilogue: lane holds C[row = lc][cols 2 lr, 2 lr + 1] of each 8 x 8 tile
 #pragma unroll
-  for (int a = 0; a < 8; ++a) {
-    const int gi = i0 + wm * 64 + a * 8 + lc;
+  for (int a = 0; a < MI; ++a) {
+    const int gi = i0 + rm + a * 8 + lc;
     if (gi >= n) continue;
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int gj = j0 + wn * 32 + b * 8 + 2 * lr;
+    for (int b = 0; b < NI; ++b) {
+      const int gj = j0 + cn + b * 8 + 2 * lr;
       double *pc   = C + (size_t) gi * ldc + gj;
       if (SUBC) {
         if (gj + 1 < n)
@@ -161,6 +175,20 @@ ata_kernel(const double *__restrict__ P, int ldp, int K, int n, double *__restri
       }
     }
   }
+}
+
+template <typename Cfg, bool SUBC>
+cudaError_t ata_launch(cudaStream_t st, const double *dP, int ldp, int K, int n, double *dC, int ldc, double alpha, double beta) {
+  using D = AtaDerived<Cfg>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(ata_kernel<Cfg, SUBC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) D::SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int nt = (n + Cfg::TB - 1) / Cfg::TB;
+  ata_kernel<Cfg, SUBC><<<nt * (nt + 1) / 2, Cfg::THREADS, D::SMEM, st>>>(dP, ldp, K, n, dC, ldc, alpha, beta, nt);
+  return cudaGetLastError();
 }
 
 // out[j] (+)= sum_r A[r][j] v[r]   (v == nullptr means v = 1): two-pass, deterministic.
@@ -226,18 +254,16 @@ int dsyrk_ata_general(ncm_sd_gpu_ctx *c, int K, int n, const double *dP, int ldp
   if (n <= 0 || K <= 0) return NCM_SD_GPU_OK;
   if ((ldp & 1) || (ldc & 1) || (((uintptr_t) dP) & 15) || (((uintptr_t) dC) & 15))
     return c->fail(NCM_SD_GPU_EINVAL, "ata: operands must be 16-byte aligned with even leading dimensions");
-  static bool attr_set = false;
-  if (!attr_set) {
-    NCM_CUDA_OK(c, cudaFuncSetAttribute(ata_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ATA_SMEM));
-    NCM_CUDA_OK(c, cudaFuncSetAttribute(ata_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ATA_SMEM));
-    attr_set = true;
-  }
-  const int nt     = (n + BM - 1) / BM;
-  const int ntiles = nt * (nt + 1) / 2;
-  if (alpha == -1.0 && beta == 1.0)
-    ata_kernel<true><<<ntiles, ATA_THREADS, ATA_SMEM, c->stream>>>(dP, ldp, K, n, dC, ldc, alpha, beta, nt);
+  // small tiles when K is short and the whole 64-tile grid is co-resident (latency-bound regime)
+  const int nt64     = (n + 63) / 64;
+  const bool small   = (K <= 128) && (nt64 * (nt64 + 1) / 2 <= 4 * c->n_sm);   // all 64-tiles resident at 4 CTAs per SM
+  const bool subc    = (alpha == -1.0 && beta == 1.0);
+  cudaError_t e;
+  if (small)
+    e = subc ? ata_launch<AtaSmall, true>(c->stream, dP, ldp, K, n, dC, ldc, alpha, beta) : ata_launch<AtaSmall, false>(c->stream, dP, ldp, K, n, dC, ldc, alpha, beta);
   else
-    ata_kernel<false><<<ntiles, ATA_THREADS, ATA_SMEM, c->stream>>>(dP, ldp, K, n, dC, ldc, alpha, beta, nt);
+    e = subc ? ata_launch<AtaBig, true>(c->stream, dP, ldp, K, n, dC, ldc, alpha, beta) : ata_launch<AtaBig, false>(c->stream, dP, ldp, K, n, dC, ldc, alpha, beta);
+  NCM_CUDA_OK(c, e);
   c->n_launches++;
   NCM_CUDA_OK(c, cudaGetLastError());
   return NCM_SD_GPU_OK;
