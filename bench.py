@@ -206,6 +206,8 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:   # the ranks share the host cores: no OpenMP oversubscription in the host-side prepare_kernel
+        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // world))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; numcosmo_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -213,6 +215,8 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = S.lib()
     lib.ncm_b200_set_device(local_rank)
+    if world > 1:
+        lib.ncm_b200_set_num_threads(max(1, (os.cpu_count() or 1) // world))
 
     W, d = args.walkers, args.dim
     N = W // 2
@@ -325,9 +329,12 @@ def run_b200(args):
         c.enable_timers(True)
         c.reset_timers()
     nroof = 3
-    nchol = 0
+    nchol, chol_flops = 0, 0.0
     for _ in range(nroof):
-        nchol += half_step(0)["n_chol"] + half_step(1)["n_chol"]
+        for b in range(2):
+            st = half_step(b)
+            nchol += st["n_chol"]
+            chol_flops += st["chol_flops"]
     tm = {k: 0.0 for k in capi.T_NAMES}
     for c in gctx:
         t, _ = c.get_timers()
@@ -335,13 +342,22 @@ def run_b200(args):
             tm[k] += t[k] / nroof
         c.enable_timers(False)
     rows_local = N // world
-    syrk_flops = float(rows_local) * N * N                 # n_obs . n_kernels^2 (SURVEY.md section 8d), one SYRK launch per half-step
-    syrk_ms = tm["syrk"] / 2.0
-    achieved = syrk_flops / (syrk_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "ata_kernel (DMMA SYRK M = IM^T IM, n = k = %d)" % N, "achieved": achieved, "peak": peaks["fp64_dgemm_tflops"],
-                "unit": "TFLOP/s", "frac": achieved / peaks["fp64_dgemm_tflops"], "traffic": None,
-                "peak_source": "FP64 is not in MEASURED_PEAKS.json; cuBLAS DGEMM 8192^3 measured on this pool (profiles/r01_fp64_peaks.jsonl)",
-                "step_share_ms": {k: round(v, 4) for k, v in tm.items()}, "chol_solves_per_step": nchol / nroof}
+    # dominant component of the step (ncu launch list: chol_diag + chol_panel + ata<Small> + chol_backsolve > 90 % of the
+    # device time): the passive-set Cholesky solves of the NNLS.  Algorithmic flops = sum |P|^3 / 3.
+    chol_ach = chol_flops / nroof / (tm["chol"] * 1e-3) / 1e12
+    syrk_flops = float(rows_local) * N * N                 # n_obs . n_kernels^2, one SYRK launch per half-step
+    syrk_ach = 2.0 * syrk_flops / (tm["syrk"] * 1e-3) / 1e12
+    P64 = peaks["fp64_dgemm_tflops"]
+    roofline = {"bound": "tensor", "kernel": "blocked Cholesky solve of the NNLS passive-set systems (chol_diag_kernel + chol_panel_kernel + "
+                                             "ata_kernel<AtaSmall,SUBC> trailing updates + chol_backsolve_kernel)",
+                "achieved": chol_ach, "peak": P64, "unit": "TFLOP/s", "frac": chol_ach / P64, "traffic": None,
+                "flops_per_launch_group": chol_flops / max(nchol, 1), "solves_per_step": nchol / nroof, "ms_per_step": tm["chol"],
+                "note": "latency-bound: 32 sequential 64-column phases per |P| = 2048 solve; the DMMA trailing updates are 18 % of its time",
+                "peak_source": "FP64 is not in MEASURED_PEAKS.json (bf16 + HBM only); cuBLAS DGEMM 8192^3 measured on this pool, "
+                               "profiles/r01_fp64_peaks.jsonl",
+                "syrk": {"kernel": "ata_kernel<AtaBig> (M = IM^T IM, n = k = %d)" % N, "achieved": syrk_ach, "frac": syrk_ach / P64,
+                         "ms_per_launch": tm["syrk"] / 2.0},
+                "step_share_ms": {k: round(v, 4) for k, v in tm.items()}}
 
     # ---------------- CPU baseline (rank 0, bounded sample) ----------------
     cpu = None
@@ -375,10 +391,197 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------------
+def sweep_problem(d, N, Q, sd, seed=5):
+    """configs[4] inputs: centres and queries i.i.d. from a d-dim MVND, Dirichlet-like weights
+    with 10 % exact zeros, href = 1.  For VKDE the per-centre factors are synthetic: the global factor times a random
+    well-conditioned upper-triangular perturbation (running the kNN prepare_kernel on 65536 centres is not what is timed here)."""
+    rs = np.random.default_rng(seed)
+    sig = rs.uniform(2e-2, 5e-2, size=d)
+    R = rs.normal(size=(d, d)) / np.sqrt(d)
+    cor = 0.7 * np.eye(d) + 0.3 * (R @ R.T)
+    cov = cor * np.outer(sig, sig)
+    Ug = np.ascontiguousarray(np.linalg.cholesky(cov).T)          # upper factor, cov = Ug^T Ug
+    mu = rs.uniform(1.0, 2.0, size=d)
+    C = np.ascontiguousarray(mu + rs.normal(size=(N, d)) @ Ug)
+    X = np.ascontiguousarray(mu + rs.normal(size=(Q, d)) @ Ug)
+    w = rs.uniform(size=N)
+    w[rs.uniform(size=N) < 0.1] = 0.0
+    w /= w.sum()
+    lndet_g = 2.0 * np.log(np.diag(Ug)).sum()
+    if sd == "kde":
+        return mu, Ug, C, X, w, None, lndet_g
+    U_all = np.empty((N, d, d))
+    blk = 8192
+    for i0 in range(0, N, blk):
+        n = min(blk, N - i0)
+        T = np.triu(rs.normal(size=(n, d, d)) * (0.15 / np.sqrt(d)), 1)
+        T[:, np.arange(d), np.arange(d)] = rs.uniform(0.3, 0.6, size=(n, d))
+        U_all[i0:i0 + n] = np.triu(T @ Ug)
+    return mu, Ug, C, X, w, U_all, lndet_g
+
+
+def run_sweep(args):
+    """--workload eval_sweep: batched eval_m2lnp, Q proposals x N centres (BASELINE.json configs[4])."""
+    import torch
+    import torch.distributed as dist
+
+    from numcosmo_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; numcosmo_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    d, N, Q = args.dim, args.sweep_n, args.sweep_q
+    ktn, okind, nu = KT[args.kernel]
+    peaks = load_peaks()
+    mu, Ug, Cn, X, w, U_all, lndet_g = sweep_problem(d, N, Q, args.sd)
+    ctx = capi.Context(local_rank)
+    ctx.set_kernel(okind, nu, d)
+    lg = lambda z: float(__import__("math").lgamma(z))
+    def lnnorm_of(lndet):   # _kernel_gauss.c:201-207 / _kernel_st.c:240-252
+        if okind == 0:
+            return 0.5 * (d * np.log(2.0 * np.pi) + lndet)
+        return lg(nu / 2.0) - lg((nu + d) / 2.0) + 0.5 * d * (np.log(np.pi) + np.log(nu)) + 0.5 * lndet
+    if args.sd == "kde":
+        Zc = np.ascontiguousarray(np.linalg.solve(Ug.T, Cn.T).T)     # invUsample = sample . U^-1
+        ctx.upload_kde(Zc, N, Ug, lnnorm_of(lndet_g))
+    else:
+        lnn = lnnorm_of(2.0 * np.log(np.abs(U_all[:, np.arange(d), np.arange(d)])).sum(axis=1))
+        ctx.upload_vkde(Cn, N, U_all, lnn)
+        del U_all
+    ctx.set_weights(w, 1.0)
+    q0, q1 = (Q * rank) // world, (Q * (rank + 1)) // world
+    Xl = np.ascontiguousarray(X[q0:q1])
+    hX = torch.from_numpy(Xl).pin_memory()
+    dX = hX.cuda()
+    dOut = torch.empty(q1 - q0, dtype=torch.float64, device="cuda")
+    stream = torch.cuda.ExternalStream(ctx.stream)
+    # L2 policy: the centre records (N x REC x 8 B) are re-streamed once per query tile; between timed steps a 256 MB buffer is
+    # overwritten so that no step starts with the records of the previous one in the 126 MB L2.
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")
+
+    def step():
+        ctx.eval_m2lnp_dev(q1 - q0, dX.data_ptr(), d, dOut.data_ptr())
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    ctx.synchronize()
+    ctx.reset_timers()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with ClockSampler(local_rank) as clk:
+        for it in range(args.steps):
+            with torch.cuda.stream(stream):
+                flush.fill_(float(it))
+            ev[it][0].record(stream)
+            step()
+            ev[it][1].record(stream)
+        ctx.synchronize()
+    torch.cuda.synchronize()
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t_dev = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    ms = float(t_dev.item()) / args.steps
+    pairs = float(Q) * N
+    value = pairs / (ms * 1e-3)
+    launches = ctx.get_timers()[1]
+
+    # e2e: host buffers in, host results out, through the C ABI call a user makes (ncm_sd_gpu_eval_m2lnp)
+    out = np.empty(q1 - q0)
+    ctx.eval_m2lnp(Xl, out)
+    ctx.reset_timers()
+    ne = max(2, min(args.steps, 5))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(ne):
+        ctx.eval_m2lnp(Xl, out)
+    e2e_dt = torch.tensor([(time.perf_counter() - t0) / ne], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
+    e2e_dt = float(e2e_dt.item())
+    h2d, d2h = ctx.get_traffic()
+
+    # roofline of the eval kernel (it is > 99 % of the step): flops per pair from SURVEY.md section 8d
+    P64 = peaks["fp64_dgemm_tflops"]
+    if args.sd == "kde":
+        fl_pair = 2.0 * d + 3.0
+        kname = "kde_kernel (DMMA.8x8x4 GEMM + online LSE)"
+    else:
+        fl_pair = d * d + 2.0 * d + 1.0
+        kname = "vkde_kernel (per-centre forward substitution + online LSE)"
+    ach = (pairs / world) * fl_pair / (ms * 1e-3) / 1e12
+    # epilogue-inclusive model (DESIGN.md section 4): one FP64 exp (Gauss) or log1p + exp (ST) per pair on the same FP64 pipe;
+    # measured issue-loop throughputs (profiles/r01_fp64_peaks.jsonl): exp 0.80 T/s, log1p 0.40 T/s  => flop-equivalents
+    epi = 33.9 / 0.80 + (33.9 / 0.40 if okind == 1 else 0.0)
+    ach_epi = (pairs / world) * (fl_pair + epi) / (ms * 1e-3) / 1e12
+    rec_bytes = None
+    if args.sd == "vkde":
+        rec_bytes = (d * (d + 1) / 2 + d + 2) * 8.0
+    roofline = {"bound": "tensor", "kernel": kname, "achieved": ach, "peak": P64, "unit": "TFLOP/s", "frac": ach / P64, "traffic": None,
+                "flops_per_pair": fl_pair, "with_epilogue": {"flop_equiv_per_pair": fl_pair + epi, "achieved": ach_epi, "frac": ach_epi / P64},
+                "streamed_GBs": (None if rec_bytes is None else ((q1 - q0) / 128.0) * N * rec_bytes / (ms * 1e-3) / 1e9),
+                "peak_source": "FP64 is not in MEASURED_PEAKS.json (bf16 + HBM only); cuBLAS DGEMM 8192^3 measured on this pool, "
+                               "profiles/r01_fp64_peaks.jsonl"}
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cpu = cpu_sweep(args, d, N, Q)
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"batched eval_m2lnp sweep: {Q} proposals x {N} centres, d={d}, {args.sd.upper()} {args.kernel} kernel; "
+                                       "query rows sharded over ranks, centres replicated",
+                           "l2_policy": "256 MB flush buffer overwritten before every timed step"},
+                "e2e": {"value": pairs / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": h2d / ne, "d2h_bytes_per_step": d2h / ne, "ms_per_step": e2e_dt * 1e3,
+                        "api": "ncm_sd_gpu_eval_m2lnp (host X in, host m2lnp out)"},
+                "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_sweep(args, d, N, Q, budget_s=15.0):
+    """Oracle port of eval_m2lnp on the host cores for a bounded query sub-sample (all centres), extrapolated linearly in Q."""
+    from oracle import ncm_oracle as O
+
+    ncores = os.cpu_count() or 1
+    _, okind, nu = KT[args.kernel]
+    mu, Ug, Cn, X, w, U_all, lndet_g = sweep_problem(d, min(N, 16384), 4096, args.sd)
+    Nc = Cn.shape[0]
+    sd = O.StatsDist(O.SD_KDE if args.sd == "kde" else O.SD_VKDE, okind, d, nu)
+    sd.set_use_threads(True)
+    sd.set_local_frac(0.01)
+    sd.add_obs_matrix(Cn)
+    assert sd.prepare() == 0
+    qs = 256
+    t0 = time.perf_counter()
+    sd.eval_m2lnp_batch(X[:qs], ncores)
+    dt = time.perf_counter() - t0
+    qn = int(max(qs, min(4096, qs * budget_s / max(dt, 1e-3))))
+    t0 = time.perf_counter()
+    sd.eval_m2lnp_batch(X[:qn], ncores)
+    dt = time.perf_counter() - t0
+    return {"value": qn * float(Nc) / dt, "unit": UNIT, "cores": ncores, "kind": "port",
+            "sample": f"{qn} queries x {Nc} centres (oracle port, OpenMP over queries as ncm_fit_esmcmc.c:2158; factors from the oracle's own "
+                      f"prepare_kernel with local_frac 0.01); pairs/s is size-independent, so it extrapolates linearly to {Q} x {N}"}
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "eval_sweep":
+        run_sweep(args)
     else:
         run_b200(args)
 

@@ -64,6 +64,16 @@ int ncm_sd_gpu_upload_kde (ncm_sd_gpu_ctx *ctx, int n_obs, int n_kernels, const 
  *   lnnorms [n_kernels] (no d ln h). */
 int ncm_sd_gpu_upload_vkde (ncm_sd_gpu_ctx *ctx, int n_obs, int n_kernels, const double *sample, int ld,
                             const double *U_all, const double *lnnorms);
+/* VKDE prepare_kernel ON THE DEVICE: the OpenMP loop of _ncm_stats_dist_vkde_build_cov_array_kdtree
+ * (ncm_stats_dist_vkde.c:428-493).  sample [n_obs x d] raw, invUsample [n_obs x d] whitened (both host),
+ * k = max (local_frac * n_obs, 2) neighbours.  Returns the upper factors U_all_out [n_kernels x d x d] and
+ * fail_out [n_kernels] (1 = covariance not positive definite: the caller applies the reference's
+ * nearPD / diagonal fallback, kde.c:344-367, and passes the repaired factors to vkde_finish).  The points
+ * and factors stay on the device; vkde_finish uploads the per-kernel lnnorms (which the host computes from
+ * the factors, _kernel_gauss.c:201-207 / _kernel_st.c:240-252) and packs the records.  n_obs <= 16384. */
+int ncm_sd_gpu_vkde_prepare (ncm_sd_gpu_ctx *ctx, int n_obs, int n_kernels, const double *sample, int ld, const double *invUsample, int ldz,
+                             int k, double *U_all_out, int *fail_out);
+int ncm_sd_gpu_vkde_finish (ncm_sd_gpu_ctx *ctx, const double *lnnorms, int n_fixed, const int *fixed_idx, const double *fixed_U);
 /* weights + bandwidth: self->weights / self->href of NcmStatsDistPrivate
  * (ncm_stats_dist_private.h:39-76), set by _ncm_stats_dist_prepare (ncm_stats_dist.c:753-767). */
 int ncm_sd_gpu_set_weights (ncm_sd_gpu_ctx *ctx, int n_kernels, const double *weights, double href);
@@ -98,6 +108,8 @@ typedef struct ncm_sd_gpu_nnls_stats
   int n_retry;   /* factorisations that needed the regularised retry */
   int n_outer;   /* accepted outer iterations */
   int n_passive; /* final passive-set size */
+  double chol_flops; /* sum over the factorisations of |P|^3 / 3 (algorithmic flops of the Cholesky solves) */
+  double syrk_flops; /* nrows * ncols^2 (normal equations) */
 } ncm_sd_gpu_nnls_stats;
 
 int ncm_sd_gpu_nnls_solve (ncm_sd_gpu_ctx *ctx, double reltol, double *x_out, double *rnorm_out, ncm_sd_gpu_nnls_stats *stats);
@@ -136,6 +148,7 @@ enum
   NCM_SD_GPU_T_NNLS_MISC, /* gathers, residuals, gradients */
   NCM_SD_GPU_T_H2D,
   NCM_SD_GPU_T_D2H,
+  NCM_SD_GPU_T_PREP,      /* VKDE prepare_kernel: kNN + local covariance + Cholesky */
   NCM_SD_GPU_T_LEN
 };
 /* device time (CUDA events on the ctx stream) accumulated per stage, milliseconds, and the

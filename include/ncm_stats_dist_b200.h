@@ -43,6 +43,11 @@ typedef void (*NcmB200ErrorHandler) (const char *msg, void *user_data);
 void ncm_b200_set_error_handler (NcmB200ErrorHandler handler, void *user_data);
 /* device used by objects created afterwards (default: $NCM_SD_GPU_DEVICE or 0) */
 void ncm_b200_set_device (gint device);
+/* OpenMP threads of the host-side prepare_kernel (use cores / ranks when several ranks share a host) */
+void ncm_b200_set_num_threads (gint n);
+/* parity switch: TRUE runs the VKDE prepare_kernel loop (kNN + local covariance + Cholesky) on the host instead of
+ * the device (default: device; also set by $NCM_B200_HOST_PREPARE_KERNEL).  Both produce bit-identical factors. */
+void ncm_b200_set_host_prepare_kernel (gboolean on);
 
 /* ---- NcmVector / NcmMatrix (ncm_vector.h, ncm_matrix.h) ---- */
 typedef struct _NcmVector NcmVector;

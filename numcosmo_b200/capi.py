@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libncm_sd_gpu.so")
 
 KERNEL_GAUSS, KERNEL_ST = 0, 1
 KDE, VKDE = 0, 1
-T_NAMES = ("eval", "IM", "syrk", "chol", "nnls_misc", "h2d", "d2h")
+T_NAMES = ("eval", "IM", "syrk", "chol", "nnls_misc", "h2d", "d2h", "prep")
 
 OK, EINVAL, ENODEV, ECUDA, ENOTPD, ENCCL, ENOMEM = range(7)
 
@@ -28,6 +28,7 @@ SYMBOLS = (
     "ncm_sd_gpu_compute_IM", "ncm_sd_gpu_nnls_solve", "ncm_sd_gpu_nnls_solve_host", "ncm_sd_gpu_sample_apply", "ncm_sd_gpu_sample_philox",
     "ncm_sd_gpu_comm_unique_id", "ncm_sd_gpu_comm_init", "ncm_sd_gpu_set_row_shard", "ncm_sd_gpu_get_timers", "ncm_sd_gpu_reset_timers",
     "ncm_sd_gpu_enable_timers", "ncm_sd_gpu_get_traffic", "ncm_sd_gpu_dsyrk_ata_dev", "ncm_sd_gpu_dpotrf_upper_dev",
+    "ncm_sd_gpu_vkde_prepare", "ncm_sd_gpu_vkde_finish",
 )
 
 
@@ -38,7 +39,8 @@ class GpuError(RuntimeError):
 
 
 class NNLSStats(C.Structure):
-    _fields_ = [("n_chol", C.c_int), ("n_retry", C.c_int), ("n_outer", C.c_int), ("n_passive", C.c_int)]
+    _fields_ = [("n_chol", C.c_int), ("n_retry", C.c_int), ("n_outer", C.c_int), ("n_passive", C.c_int), ("chol_flops", C.c_double),
+                ("syrk_flops", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -70,6 +72,8 @@ def load():
             "ncm_sd_gpu_set_kernel": (i, [vp, i, d, i]),
             "ncm_sd_gpu_upload_kde": (i, [vp, i, i, _dp, i, _dp, i, d]),
             "ncm_sd_gpu_upload_vkde": (i, [vp, i, i, _dp, i, _dp, _dp]),
+            "ncm_sd_gpu_vkde_prepare": (i, [vp, i, i, _dp, i, _dp, i, i, _dp, _ip]),
+            "ncm_sd_gpu_vkde_finish": (i, [vp, _dp, i, _ip, _dp]),
             "ncm_sd_gpu_set_weights": (i, [vp, i, _dp, d]),
             "ncm_sd_gpu_set_href": (i, [vp, d]),
             "ncm_sd_gpu_get_weights": (i, [vp, i, _dp]),
@@ -160,6 +164,23 @@ class Context:
         assert U_all.shape == (n_kernels, self.d, self.d) and lnnorms.shape == (n_kernels,)
         self._ck(load().ncm_sd_gpu_upload_vkde(self._h, sample.shape[0], n_kernels, _p(sample), sample.shape[1], _p(U_all), _p(lnnorms)))
         self.n_obs, self.n_kernels = sample.shape[0], n_kernels
+
+    def vkde_prepare(self, sample, invUsample, n_kernels: int, k: int):
+        """kNN + local covariance + Cholesky on the device; returns (U_all [n x d x d], fail [n])."""
+        sample, invUsample = _f64(sample), _f64(invUsample)
+        U = np.empty((n_kernels, self.d, self.d))
+        fail = np.empty(n_kernels, dtype=np.int32)
+        self._ck(load().ncm_sd_gpu_vkde_prepare(self._h, sample.shape[0], n_kernels, _p(sample), sample.shape[1], _p(invUsample), invUsample.shape[1],
+                                                 k, _p(U), fail.ctypes.data_as(_ip)))
+        self.n_obs, self.n_kernels = sample.shape[0], n_kernels
+        return U, fail
+
+    def vkde_finish(self, lnnorms, fixed_idx=None, fixed_U=None):
+        lnnorms = _f64(lnnorms)
+        nf = 0 if fixed_idx is None else len(fixed_idx)
+        fi = np.ascontiguousarray(fixed_idx, dtype=np.int32) if nf else None
+        fu = _f64(fixed_U) if nf else None
+        self._ck(load().ncm_sd_gpu_vkde_finish(self._h, _p(lnnorms), nf, fi.ctypes.data_as(_ip) if nf else None, _p(fu) if nf else None))
 
     def set_weights(self, weights, href: float):
         weights = _f64(weights)

@@ -233,6 +233,70 @@ int ncm_sd_gpu_upload_vkde(ncm_sd_gpu_ctx *c, int n_obs, int n_kernels, const do
   return NCM_SD_GPU_OK;
 }
 
+int ncm_sd_gpu_vkde_prepare(ncm_sd_gpu_ctx *c, int n_obs, int n_kernels, const double *sample, int ld, const double *invUsample, int ldz, int k,
+                            double *U_all_out, int *fail_out) {
+  if (c == nullptr) return NCM_SD_GPU_EINVAL;
+  if (c->d <= 0) return c->fail(NCM_SD_GPU_EINVAL, "set_kernel first");
+  if (n_kernels <= 0 || n_obs < n_kernels || sample == nullptr || invUsample == nullptr || U_all_out == nullptr || fail_out == nullptr ||
+      ld < c->d || ldz < c->d || k < 2 || k > n_obs)
+    return c->fail(NCM_SD_GPU_EINVAL, "vkde_prepare: bad arguments");
+  cudaSetDevice(c->device);
+  const int d = c->d;
+  if (!c->sample.reserve((size_t) n_obs * d * sizeof(double)) || !c->zc.reserve((size_t) n_obs * d * sizeof(double)) ||
+      !c->Ufull.reserve((size_t) n_kernels * d * d * sizeof(double)) || !c->lnu.reserve((size_t) (n_kernels + 8) * sizeof(double)) ||
+      !c->weights.reserve((size_t) (n_kernels + 8) * sizeof(double)) || !c->nn_idx.reserve(((size_t) n_kernels * k + n_kernels + 16) * sizeof(int)))
+    return c->fail(NCM_SD_GPU_ENOMEM, "vkde_prepare: out of device memory");
+  {
+    StageTimer t(c, NCM_SD_GPU_T_H2D);
+    NCM_CUDA_OK(c, ncm_memcpy2d_async(c, c->sample.p, d * sizeof(double), sample, ld * sizeof(double), d * sizeof(double), n_obs, cudaMemcpyHostToDevice, c->stream));
+    NCM_CUDA_OK(c, ncm_memcpy2d_async(c, c->zc.p, d * sizeof(double), invUsample, ldz * sizeof(double), d * sizeof(double), n_obs, cudaMemcpyHostToDevice, c->stream));
+  }
+  int *dNbr  = c->nn_idx.as<int>();
+  int *dFail = dNbr + (size_t) n_kernels * k;
+  int rc;
+  {
+    StageTimer t(c, NCM_SD_GPU_T_PREP);
+    rc = vkde_prepare_dev(c, n_obs, n_kernels, k, c->zc.as<double>(), c->sample.as<double>(), dNbr, c->Ufull.as<double>(), dFail);
+    if (rc != NCM_SD_GPU_OK) return rc;
+  }
+  {
+    StageTimer t(c, NCM_SD_GPU_T_D2H);
+    NCM_CUDA_OK(c, ncm_memcpy_async(c, U_all_out, c->Ufull.p, (size_t) n_kernels * d * d * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    NCM_CUDA_OK(c, ncm_memcpy_async(c, fail_out, dFail, (size_t) n_kernels * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    NCM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  }
+  c->type      = NCM_SD_GPU_VKDE;
+  c->n_obs     = n_obs;
+  c->n_kernels = n_kernels;
+  c->row0      = 0;
+  c->nrows     = n_obs;
+  c->have_weights = false;
+  c->prep_pending = true;
+  return NCM_SD_GPU_OK;
+}
+
+int ncm_sd_gpu_vkde_finish(ncm_sd_gpu_ctx *c, const double *lnnorms, int n_fixed, const int *fixed_idx, const double *fixed_U) {
+  if (c == nullptr) return NCM_SD_GPU_EINVAL;
+  if (!c->prep_pending || c->type != NCM_SD_GPU_VKDE) return c->fail(NCM_SD_GPU_EINVAL, "vkde_finish: call vkde_prepare first");
+  if (lnnorms == nullptr || n_fixed < 0 || (n_fixed > 0 && (fixed_idx == nullptr || fixed_U == nullptr))) return c->fail(NCM_SD_GPU_EINVAL, "vkde_finish: bad arguments");
+  cudaSetDevice(c->device);
+  const int d = c->d;
+  {
+    StageTimer t(c, NCM_SD_GPU_T_H2D);
+    NCM_CUDA_OK(c, ncm_memcpy_async(c, c->lnu.p, lnnorms, (size_t) c->n_kernels * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    for (int f = 0; f < n_fixed; ++f) {
+      if (fixed_idx[f] < 0 || fixed_idx[f] >= c->n_kernels) return c->fail(NCM_SD_GPU_EINVAL, "vkde_finish: fixed index out of range");
+      NCM_CUDA_OK(c, ncm_memcpy_async(c, c->Ufull.as<double>() + (size_t) fixed_idx[f] * d * d, fixed_U + (size_t) f * d * d, (size_t) d * d * sizeof(double),
+                                      cudaMemcpyHostToDevice, c->stream));
+    }
+  }
+  int rc = vkde_pack(c, c->Ufull.as<double>());
+  if (rc != NCM_SD_GPU_OK) return rc;
+  NCM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  c->prep_pending = false;
+  return NCM_SD_GPU_OK;
+}
+
 int ncm_sd_gpu_set_weights(ncm_sd_gpu_ctx *c, int n_kernels, const double *weights, double href) {
   int rc = check_ready(c, false);
   if (rc != NCM_SD_GPU_OK) return rc;

@@ -44,6 +44,7 @@ struct ncm_sd_gpu_ctx {
   double lnnorm = 0.0;       // KDE common lnnorm
   int row0 = 0, nrows = 0;   // IM row shard on this rank
   bool have_weights = false;
+  bool prep_pending = false;   // vkde_prepare done, vkde_finish (lnnorms + record packing) still to come
 
   // VKDE buffers
   DevBuf sample;     // [n_obs x d] raw points (row-major, ld = d)
@@ -129,6 +130,7 @@ struct StageTimer {
 // ---- kernels' host launchers (defined in the .cu files) --------------------------------------------
 int vkde_pad_dim(int d);
 int vkde_pack(ncm_sd_gpu_ctx *c, const double *dU_all /* n x d x d */);
+int vkde_prepare_dev(ncm_sd_gpu_ctx *c, int n_obs, int n_kernels, int k, const double *dZ, const double *dX, int *dNbr, double *dU_all, int *dFail);
 int vkde_eval_launch(ncm_sd_gpu_ctx *c, int q, const double *dX, int ldx, double *dOut, bool as_density);
 int vkde_im_launch(ncm_sd_gpu_ctx *c, const double *dRowScale);
 

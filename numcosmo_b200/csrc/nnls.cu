@@ -195,7 +195,10 @@ int solve_unconstrained(NnlsWork &w, const std::vector<int> &P) {
       int rc = dpotrf_upper_solve(c, np, w.dMU, w.ldm, w.drhs, w.ddinv, w.dinfo, &info);
       if (rc != NCM_SD_GPU_OK) return rc;
     }
-    if (w.st) w.st->n_chol++;
+    if (w.st) {
+      w.st->n_chol++;
+      w.st->chol_flops += (double) np * np * np / 3.0;
+    }
     if (info == 0) {
       NCM_CUDA_OK(c, ncm_memcpy_async(c,w.h_buf, w.drhs, sizeof(double) * np, cudaMemcpyDeviceToHost, c->stream));
       NCM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
@@ -335,6 +338,7 @@ int nnls_solve_dev(ncm_sd_gpu_ctx *c, int nrows, int ncols, const double *dA, in
     StageTimer t(c, NCM_SD_GPU_T_SYRK);
     rc = dsyrk_ata_general(c, nrows, n, dA, lda, w.dM, ldm, 1.0, 0.0);
     if (rc != NCM_SD_GPU_OK) return rc;
+    if (stats) stats->syrk_flops = (double) nrows * n * n;
     rc = allreduce_sum(c, w.dM, (size_t) n * ldm);
     if (rc != NCM_SD_GPU_OK) return rc;
   }

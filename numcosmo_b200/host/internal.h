@@ -67,6 +67,7 @@ struct _NcmStatsDist {
   ncm_sd_gpu_ctx *gpu;
   ncm_sd_gpu_nnls_stats nnls_stats;
   double host_prepare_kernel_ms;
+  bool resident;   // prepare_kernel ran on the device: points, factors and records are already in HBM (no upload)
 };
 
 void ncm_b200_error(const char *fmt, ...);
@@ -80,3 +81,4 @@ double ncm_b200_cholesky_lndet(const double *U, int n, int ld);        // ncm_ma
 void ncm_b200_cholesky_decomp_fallback(double *cov_decomp, const double *cov, int d, int maxiter);   // kde.c:344-367
 
 int ncm_b200_default_device();
+bool ncm_b200_host_prepare_kernel();   // debugging / parity switch: run the VKDE prepare_kernel loop on the host

@@ -5,6 +5,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <cfloat>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include "internal.h"
 
 static NcmB200ErrorHandler g_handler   = nullptr;
@@ -18,6 +21,22 @@ extern "C" void ncm_b200_set_error_handler(NcmB200ErrorHandler handler, void *us
 }
 
 extern "C" void ncm_b200_set_device(gint device) { g_device = device; }
+
+// OpenMP threads used by the host-side prepare_kernel (several ranks share one host)
+extern "C" void ncm_b200_set_num_threads(gint n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void) n;
+#endif
+}
+
+static int g_host_prepare = -1;
+extern "C" void ncm_b200_set_host_prepare_kernel(gboolean on) { g_host_prepare = on ? 1 : 0; }
+bool ncm_b200_host_prepare_kernel() {
+  if (g_host_prepare < 0) g_host_prepare = getenv("NCM_B200_HOST_PREPARE_KERNEL") != nullptr ? 1 : 0;
+  return g_host_prepare == 1;
+}
 
 int ncm_b200_default_device() {
   if (g_device >= 0) return g_device;

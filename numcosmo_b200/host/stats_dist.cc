@@ -73,6 +73,7 @@ NcmStatsDist *sd_new(int type, NcmStatsDistKernel *sdk, NcmStatsDistCV cv_type) 
   sd->gpu           = nullptr;
   memset(&sd->nnls_stats, 0, sizeof(sd->nnls_stats));
   sd->host_prepare_kernel_ms = 0.0;
+  sd->resident               = false;
   sd->sample_view.pdata      = nullptr;
   sd->sample_view.len        = 0;
   return sd;
@@ -200,6 +201,64 @@ bool vkde_build_cov_array(NcmStatsDist *sd) {
     }
     sd->lnnorms.assign(nk, 0.0);
   }
+  // one centre on the host: exact kNN, online covariance in neighbour order, Cholesky with the nearPD / diagonal fallback
+  auto host_centre = [&](int i, StatsVec &sv, std::vector<std::pair<double, int>> &items, std::vector<double> &cov) {
+    const double *target = &sd->invUsample[(size_t) i * d];
+    for (int m = 0; m < n_obs; m++) {
+      const double *c1 = &sd->invUsample[(size_t) m * d];
+      double dist      = 0;
+      for (int r = 0; r < d; r++) {
+        const double df = c1[r] - target[r];
+        dist += df * df;
+      }
+      items[m] = {dist, m};
+    }
+    const size_t kk = std::min(k, (size_t) n_obs);
+    std::partial_sort(items.begin(), items.begin() + kk, items.end());
+    sv.reset();
+    for (size_t j = 0; j < kk; j++) sv.append(((NcmVector *) sd->sample[items[j].second])->data);
+    sv.get_cov(cov.data());
+    ncm_b200_cholesky_decomp_fallback(&sd->cov_slab[(size_t) i * d * d], cov.data(), d, (int) sd->nearPD_maxiter);
+  };
+
+  // Device path: kNN + covariance + Cholesky in libncm_sd_gpu, bit-identical to host_centre;
+  // only the matrices whose plain Cholesky fails come back to the host for the reference's fallback chain.
+  const bool host_only = ncm_b200_host_prepare_kernel();
+  if (!host_only && n_obs <= 16384 && ensure_gpu(sd)) {
+    std::vector<int> fail(nk, 0);
+    int rc;
+    {
+      std::lock_guard<std::mutex> lk(g_gpu_mutex);
+      rc = ncm_sd_gpu_set_kernel(sd->gpu, sd->kernel->kind, sd->kernel->nu, d);
+      if (rc == NCM_SD_GPU_OK)
+        rc = ncm_sd_gpu_vkde_prepare(sd->gpu, n_obs, nk, sd->sample_matrix.data(), d, sd->invUsample.data(), d, (int) std::min(k, (size_t) n_obs),
+                                     sd->cov_slab.data(), fail.data());
+    }
+    if (!gpu_ok(sd, rc, "_ncm_stats_dist_vkde_build_cov_array_kdtree")) return false;
+    std::vector<int> fixed_idx;
+    for (int i = 0; i < nk; i++)
+      if (fail[i]) fixed_idx.push_back(i);
+    std::vector<double> fixed_U((size_t) fixed_idx.size() * d * d);
+    if (!fixed_idx.empty()) {
+      StatsVec sv(d);
+      std::vector<std::pair<double, int>> items(n_obs);
+      std::vector<double> cov((size_t) d * d);
+      for (size_t f = 0; f < fixed_idx.size(); f++) {
+        host_centre(fixed_idx[f], sv, items, cov);
+        memcpy(&fixed_U[f * d * d], &sd->cov_slab[(size_t) fixed_idx[f] * d * d], sizeof(double) * d * d);
+      }
+    }
+#pragma omp parallel for if (sd->use_threads)
+    for (int i = 0; i < nk; i++) sd->lnnorms[i] = ncm_stats_dist_kernel_get_lnnorm(sd->kernel, sd->cov_array[i]);
+    {
+      std::lock_guard<std::mutex> lk(g_gpu_mutex);
+      rc = ncm_sd_gpu_vkde_finish(sd->gpu, sd->lnnorms.data(), (int) fixed_idx.size(), fixed_idx.data(), fixed_U.data());
+    }
+    if (!gpu_ok(sd, rc, "_ncm_stats_dist_vkde_build_cov_array_kdtree")) return false;
+    sd->resident = true;
+    return true;
+  }
+
 #pragma omp parallel if (sd->use_threads)
   {
     StatsVec sv(d);
@@ -207,31 +266,17 @@ bool vkde_build_cov_array(NcmStatsDist *sd) {
     std::vector<double> cov((size_t) d * d);
 #pragma omp for schedule(dynamic, 1)
     for (int i = 0; i < nk; i++) {
-      const double *target = &sd->invUsample[(size_t) i * d];
-      for (int m = 0; m < n_obs; m++) {
-        const double *c1 = &sd->invUsample[(size_t) m * d];
-        double dist      = 0;
-        for (int r = 0; r < d; r++) {
-          const double df = c1[r] - target[r];
-          dist += df * df;
-        }
-        items[m] = {dist, m};
-      }
-      const size_t kk = std::min(k, (size_t) n_obs);
-      std::partial_sort(items.begin(), items.begin() + kk, items.end());
-      sv.reset();
-      for (size_t j = 0; j < kk; j++) sv.append(((NcmVector *) sd->sample[items[j].second])->data);
-      sv.get_cov(cov.data());
-      double *cd = &sd->cov_slab[(size_t) i * d * d];
-      ncm_b200_cholesky_decomp_fallback(cd, cov.data(), d, (int) sd->nearPD_maxiter);
+      host_centre(i, sv, items, cov);
       sd->lnnorms[i] = ncm_stats_dist_kernel_get_lnnorm(sd->kernel, sd->cov_array[i]);
     }
   }
+  sd->resident = false;
   return true;
 }
 
 bool upload(NcmStatsDist *sd) {
   if (!ensure_gpu(sd)) return false;
+  if (sd->type == NCM_SD_GPU_VKDE && sd->resident) return true;   // ncm_sd_gpu_vkde_prepare / _finish left everything in HBM
   std::lock_guard<std::mutex> lk(g_gpu_mutex);
   if (!gpu_ok(sd, ncm_sd_gpu_set_kernel(sd->gpu, sd->kernel->kind, sd->kernel->nu, (int) sd->d), "ncm_stats_dist_prepare_kernel")) return false;
   int rc;
@@ -252,6 +297,7 @@ bool prepare_kernel(NcmStatsDist *sd) {
                    sd->local_frac, sd->n_obs);
     return false;
   }
+  sd->resident = false;
   if (!kde_prepare_kernel(sd)) return false;
   if (sd->type == NCM_SD_GPU_VKDE && !vkde_build_cov_array(sd)) return false;
   sd->host_prepare_kernel_ms += now_ms() - t0;

@@ -89,6 +89,8 @@ def lib():
         sig = {
             "ncm_b200_set_error_handler": (None, [_ERR_CB, _vp]),
             "ncm_b200_set_device": (None, [i]),
+            "ncm_b200_set_num_threads": (None, [i]),
+            "ncm_b200_set_host_prepare_kernel": (None, [i]),
             "ncm_vector_new_data_static": (VP, [_dp, u, u]),
             "ncm_vector_free": (None, [VP]),
             "ncm_matrix_free": (None, [MP]),

@@ -264,6 +264,9 @@ solve_normal_cholesky (orc_nnls *self, const orc_iset *Pset, const double *f)
   if (self->st != NULL)
     self->st->n_chol++;
 
+  if (getenv ("ORC_NNLS_TRACE") != NULL)   /* debugging aid: passive-set size of every factorisation */
+    fprintf (stderr, "orc_nnls: chol |P| = %d info = %d\n", self->uncols, info);
+
   if (info > 0)
     solve_normal_LU (self, Pset, f);
 }
