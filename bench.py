@@ -261,6 +261,12 @@ def run_b200(args):
     for b in range(2):
         mlc = ml[N:] if b == 0 else ml[:N]
         c = ctxs[b]
+        # sd_b's centres are the OTHER half of the ensemble (walker_apes.c:751-811).  Block 1 moved after sd0 was last prepared, so
+        # re-run prepare_kernel on the current positions: centres, factors and m2lnL in the context are then those of a real half-step.
+        sds[b].reset()
+        for xrow in (theta[N:] if b == 0 else theta[:N]):
+            sds[b].add_obs(xrow)
+        sds[b].prepare()
         c.n_kernels = c.n_obs = N
         c.d = d
         href = sds[b].get_href()
