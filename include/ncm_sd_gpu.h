@@ -162,6 +162,9 @@ int ncm_sd_gpu_enable_timers (ncm_sd_gpu_ctx *ctx, int enable);
 /* plain FP64 building blocks exported for tests and microbenchmarks (device pointers) */
 int ncm_sd_gpu_dsyrk_ata_dev (ncm_sd_gpu_ctx *ctx, int nrows, int ncols, const double *dA, int lda, double *dM, int ldm);
 int ncm_sd_gpu_dpotrf_upper_dev (ncm_sd_gpu_ctx *ctx, int n, double *dM, int ldm, int *info_host);
+/* dposv 'U' as ncm_matrix_cholesky_solve calls it (ncm_matrix.c:1199-1210): factor the upper triangle of dM in place and
+ * overwrite dRhs [n] with the solution of M x = rhs */
+int ncm_sd_gpu_dposv_upper_dev (ncm_sd_gpu_ctx *ctx, int n, double *dM, int ldm, double *dRhs, int *info_host);
 
 #ifdef __cplusplus
 }

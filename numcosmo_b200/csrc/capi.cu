@@ -148,7 +148,7 @@ int ncm_sd_gpu_ctx_free(ncm_sd_gpu_ctx *c) {
   if (c->nccl_comm != nullptr && nccl_api().ok) nccl_api().CommDestroy((ncclComm_t) c->nccl_comm);
   DevBuf *bufs[] = {&c->sample, &c->vrec, &c->lnu, &c->cterm, &c->weights, &c->Ufull, &c->zc, &c->zmean, &c->bfrag, &c->kde_U, &c->qX,
                     &c->qOut, &c->qA, &c->part, &c->IM, &c->rowscale, &c->M, &c->MU, &c->nn_b, &c->nn_x, &c->nn_r, &c->nn_g, &c->nn_tmp,
-                    &c->nn_idx, &c->nn_f};
+                    &c->nn_idx, &c->nn_f, &c->chol_flags, &c->chol_part};
   for (DevBuf *b : bufs) b->release();
   c->pinX.release();
   c->pinOut.release();
@@ -539,7 +539,24 @@ int ncm_sd_gpu_dpotrf_upper_dev(ncm_sd_gpu_ctx *c, int n, double *dM, int ldm, i
   if (c == nullptr) return NCM_SD_GPU_EINVAL;
   cudaSetDevice(c->device);
   if (!c->nn_b.reserve((size_t) (n + 64) * sizeof(double)) || !c->nn_idx.reserve(64)) return c->fail(NCM_SD_GPU_ENOMEM, "dpotrf: out of device memory");
-  return dpotrf_upper_solve(c, n, dM, ldm, nullptr, c->nn_b.as<double>(), c->nn_idx.as<int>(), info_host);
+  return dpotrf_upper_solve_any(c, n, dM, ldm, nullptr, c->nn_b.as<double>(), c->nn_idx.as<int>(), info_host);
+}
+
+// debugging aid (tools/chol_trace.py): per-CTA event trace of the next single-launch Cholesky calls; dTrace = device buffer of
+// n_sm * cap * 2 int64 (zero it before each call), or null to switch tracing off.  Not part of the public header.
+int ncm_sd_gpu_chol_trace(ncm_sd_gpu_ctx *c, long long *dTrace, int cap) {
+  if (c == nullptr) return NCM_SD_GPU_EINVAL;
+  c->chol_trace     = dTrace;
+  c->chol_trace_cap = cap;
+  return NCM_SD_GPU_OK;
+}
+
+int ncm_sd_gpu_dposv_upper_dev(ncm_sd_gpu_ctx *c, int n, double *dM, int ldm, double *dRhs, int *info_host) {
+  if (c == nullptr) return NCM_SD_GPU_EINVAL;
+  if (dRhs == nullptr) return c->fail(NCM_SD_GPU_EINVAL, "dposv: rhs required");
+  cudaSetDevice(c->device);
+  if (!c->nn_b.reserve((size_t) (n + 64) * sizeof(double)) || !c->nn_idx.reserve(64)) return c->fail(NCM_SD_GPU_ENOMEM, "dposv: out of device memory");
+  return dpotrf_upper_solve_any(c, n, dM, ldm, dRhs, c->nn_b.as<double>(), c->nn_idx.as<int>(), info_host);
 }
 
 }   // extern "C"

@@ -17,6 +17,8 @@
 // rsqrt 67, shuffle 27, LDS 29, __syncthreads 29): the serial pivot chain rsqrt -> mul -> fma costs about
 // 83 cycles per column whatever the layout, so the design goal is to keep everything else (global loads,
 // barriers, shared-memory round trips) off that chain.
+#include <cstdlib>
+#include <string>
 #include "ctx.h"
 
 int dsyrk_ata_general(ncm_sd_gpu_ctx *c, int K, int n, const double *dP, int ldp, double *dC, int ldc, double alpha, double beta);
@@ -412,4 +414,15 @@ int dpotrf_upper_solve(ncm_sd_gpu_ctx *c, int n, double *dM, int ldm, double *dR
     NCM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
   }
   return NCM_SD_GPU_OK;
+}
+
+// Dispatch: the single-launch data-flow kernel (chol_fused.cu) up to its maximum order, the launch-per-step
+// schedule above beyond it (there the DMMA trailing updates carry the time).  $NCM_SD_GPU_CHOL=legacy forces the latter.
+int dpotrf_upper_solve_any(ncm_sd_gpu_ctx *c, int n, double *dM, int ldm, double *dRhs, double *dDinv, int *dInfo, int *info_host) {
+  static const bool legacy = [] {
+    const char *e = getenv("NCM_SD_GPU_CHOL");
+    return e != nullptr && std::string(e) == "legacy";
+  }();
+  if (!legacy && n <= chol_fused_max_n()) return dpotrf_upper_solve_fused(c, n, dM, ldm, dRhs, info_host);
+  return dpotrf_upper_solve(c, n, dM, ldm, dRhs, dDinv, dInfo, info_host);
 }

@@ -1,0 +1,776 @@
+// Single-launch Cholesky solve  M x = b  for the NNLS passive-set systems (n <= 4096): one persistent
+// cooperative kernel, one CTA per SM, tile-level data flow instead of one launch per step.
+//
+// Replaces ncm_matrix_cholesky_solve (dposv 'U', ncm_matrix.c:1199-1210) as called from
+// _ncm_nnls_solve_normal_cholesky (ncm_nnls.c:655-666), like chol.cu, whose three-launches-per-block-row
+// schedule spends most of its time in launch gaps and under-filled grids at |P| ~ 2000 (profiles/r01b).
+//
+// The upper triangle (row-major, M = U^T U) is cut in 64 x 64 tiles (I, J), I <= J; the right-hand side is one
+// more block column (J = nb, width 1), so the forward substitution y = U^-T b needs no code of its own.
+// Tile t = (I, J) in row-major order of the upper triangle belongs to CTA  t mod gridDim.x  for the whole
+// factorisation, hence all updates of a tile are applied by the same CTA in phase order and the only
+// cross-CTA dependencies are "U_kk is final" (flagD[k]) and "panel block U[k, J] is final" (flagP[k][J]):
+//   diag  (k, k)   factor the 64 x 64 block in shared memory (the register-blocked scheme of chol.cu)
+//   panel (k, J)   U[k, J] = U_kk^-T M[k, J]          one thread per column, forward substitution in registers
+//   update(k,I,J)  M[I, J] -= U[k, I]^T U[k, J]       DMMA.8x8x4, operands staged by cp.async, C in registers
+// Every CTA walks its own tiles in the global order (phase k: panels of row k, then updates with row k), each
+// step waits only on flags of strictly earlier steps, and all CTAs are co-resident (cooperative launch), so the
+// schedule cannot deadlock.  The updated (k+1, k+1) tile is handed to the diagonal factorisation through shared
+// memory, which keeps the L2 round trip off the critical path  diag k -> panel (k, k+1) -> update (k+1, k+1).
+// The back substitution U x = y runs in the same launch: tile (I, J) contributes U[I, J] x_J as soon as x_J is
+// published, the owner of (I, I) adds the contributions in ascending J (deterministic) and solves its block.
+// Flags carry the epoch of the call, so they never need clearing.
+#include "ctx.h"
+
+namespace {
+
+constexpr int FB = 64;        // tile size
+constexpr int FPITCH = FB + 4;   // operand pitch: (lane%4) * 68 + lane/4 hits 16 distinct 8-byte bank pairs per half-warp
+constexpr int FT = 256;       // threads per CTA
+constexpr long long SPIN_LIMIT = 1LL << 27;
+
+struct FusedArgs {
+  double *M;
+  int ldm, n;
+  double *rhs;     // may be null: factorisation only
+  double *part;    // [nb][nb][64] contributions U[I, J] x_J of the back substitution
+  double *dinv;    // [n] 1 / U_rr
+  int *flagD;      // [nb]
+  int *flagP;      // [nb x (nb + 1)]
+  int *flagX;      // [nb]
+  int *flagQ;      // [nb x nb]
+  int *info;       // first non-positive pivot (1-based), 0 otherwise
+  int *abort_flag; // set when a wait ran into SPIN_LIMIT (a bug, never data): every CTA then drains
+  int epoch, nb, nbc;
+  long long *trace;   // optional: per-CTA event records {t_ns, code} (tools/chol_trace.py); null in production
+  int trace_cap;
+};
+
+__device__ __forceinline__ int ld_acquire(const int *p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v) { asm volatile("st.release.gpu.global.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+// all threads call; returns after the flag carries this call's epoch (or the launch is aborting)
+__device__ __forceinline__ void wait_flag(const FusedArgs &a, const int *f) {
+  if (threadIdx.x == 0) {
+    long long spins = 0;
+    while (ld_acquire(f) != a.epoch) {
+      if (++spins > SPIN_LIMIT) {
+        atomicExch(a.abort_flag, 1);
+        break;
+      }
+      if ((spins & 1023) == 0 && ld_acquire(a.abort_flag) != 0) break;
+    }
+  }
+  __syncthreads();
+}
+// all threads call after their global writes
+__device__ __forceinline__ void post_flag(const FusedArgs &a, int *f) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    st_release(f, a.epoch);
+  }
+}
+
+// event record: code = type << 24 | a << 12 | b ; type 1 diag, 2 panel, 3 update, 4 backsolve, 5 backprod; +8 = end, +16 = after the waits
+__device__ __forceinline__ void trace_ev(const FusedArgs &a, int type, int x, int y) {
+  if (a.trace != nullptr && threadIdx.x == 0) {
+    long long *base = a.trace + (size_t) blockIdx.x * a.trace_cap * 2;
+    const long long n = base[0];
+    if (n + 1 < a.trace_cap) {
+      long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      base[2 * (n + 1)]     = t;
+      base[2 * (n + 1) + 1] = ((long long) type << 24) | ((long long) x << 12) | y;
+      base[0]               = n + 1;
+    }
+  }
+}
+
+__device__ __forceinline__ int row_start(int I, int nbc) { return I * nbc - (I * (I - 1)) / 2; }
+
+
+// ---- 8-row strip sweep ------------------------------------------------------------------------------------
+// Left-looking step shared by the diagonal factorisation and the panel solve: for the strip of rows
+// b0 .. b0+7 of X (64 columns, pitch FPITCH)
+//     X[b0 + r][c] -= sum_{s < b0} Asrc[s][b0 + r] * X[s][c]
+// on DMMA.8x8x4: warp w owns columns 8w .. 8w+7 (tiles w_first <= w < w_end), two independent accumulator
+// chains.  Asrc holds the upper factor (U_kk); for the diagonal block Asrc == X.
+__device__ __forceinline__ void strip_sweep(const double *Asrc, double *X, int b0, int w_first, int w_end) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int lr = lane & 3, lc = lane >> 2;
+  if (w >= w_first && w < w_end && b0 > 0) {
+    double *px = X + (b0 + lc) * FPITCH + 8 * w + 2 * lr;
+    double c0 = px[0], c1 = px[1], d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0;
+    const double *pa = Asrc + lr * FPITCH + b0 + lc;
+    const double *pb = X + lr * FPITCH + 8 * w + lc;
+    int s0 = 0;
+    for (; s0 + 16 <= b0; s0 += 16) {   // four independent accumulator chains
+      const double a0 = -pa[s0 * FPITCH], b_0 = pb[s0 * FPITCH];
+      const double a1 = -pa[(s0 + 4) * FPITCH], b_1 = pb[(s0 + 4) * FPITCH];
+      const double a2 = -pa[(s0 + 8) * FPITCH], b_2 = pb[(s0 + 8) * FPITCH];
+      const double a3 = -pa[(s0 + 12) * FPITCH], b_3 = pb[(s0 + 12) * FPITCH];
+      dmma884(c0, c1, a0, b_0);
+      dmma884(d0, d1, a1, b_1);
+      dmma884(e0, e1, a2, b_2);
+      dmma884(f0, f1, a3, b_3);
+    }
+    if (s0 < b0) {
+      const double a0 = -pa[s0 * FPITCH], b_0 = pb[s0 * FPITCH];
+      const double a1 = -pa[(s0 + 4) * FPITCH], b_1 = pb[(s0 + 4) * FPITCH];
+      dmma884(c0, c1, a0, b_0);
+      dmma884(d0, d1, a1, b_1);
+    }
+    c0 += e0; c1 += e1;
+    d0 += f0; d1 += f1;
+    px[0] = c0 + d0;
+    px[1] = c1 + d1;
+  }
+}
+
+// Division-free elimination of 4 pivots (J0 = 0 or 4) of the 8 x 8 pivot block held in registers, together with the
+// thread's own column.  With A = s T (T the true Schur complement, s_0 = 1):
+//     A'_rq = A_rq pi_j - A_jr A_jq ,  pi_j = A_jj ,  s_{j+1} = s_j pi_j ,  U_jq = A_jq rsqrt(s_{j+1}) ,  1/U_jj = s_j rsqrt(s_{j+1})
+// so the pivot chain is mul -> fma (16 cycles) instead of rsqrt -> mul -> fma (~200 cycles measured in situ), and the
+// four rsqrt of the group are independent.  The group starts from true values scaled by an exact power of 4 taken from
+// its first pivot, which keeps s_4 ~ t_1^4 t_2^2 t_3 far inside the double range.
+template <int J0>
+__device__ __forceinline__ void pivot_group4(double (&dgl)[8][8], double (&col)[8], double (&inv)[8], double (&x)[8], int &bad, int kbase) {
+  const int hi   = __double2hiint(dgl[J0][J0]);
+  const int be   = (hi >> 20) & 0x7ff;
+  const int half = (be - 1023) >> 1;                                   // floor(exponent / 2)
+  const bool scal_ok = (hi > 0) && (be > 64) && (be < 1983);
+  const double sc  = scal_ok ? __hiloint2double((1023 - 2 * half) << 20, 0) : 1.0;   // 4^-half
+  const double usc = scal_ok ? __hiloint2double((1023 + half) << 20, 0) : 1.0;       // 2^half = sqrt(1 / sc)
+  const double isc = scal_ok ? __hiloint2double((1023 - half) << 20, 0) : 1.0;       // 2^-half
+#pragma unroll
+  for (int r = J0; r < 8; ++r) {
+#pragma unroll
+    for (int q = r; q < 8; ++q) dgl[r][q] *= sc;
+    col[r] *= sc;
+  }
+  double ss[5];
+  ss[0] = 1.0;
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) {
+    const int j     = J0 + jj;
+    const double pj = dgl[j][j];
+    if (!(pj > 0.0)) bad = (bad == 0) ? kbase + j + 1 : bad;
+    ss[jj + 1] = ss[jj] * pj;
+#pragma unroll
+    for (int r = j + 1; r < 8; ++r) {
+#pragma unroll
+      for (int q = r; q < 8; ++q) dgl[r][q] = fma(-dgl[j][r], dgl[j][q], dgl[r][q] * pj);
+      col[r] = fma(-dgl[j][r], col[j], col[r] * pj);
+    }
+  }
+  double rsq[4];
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) rsq[jj] = rsqrt(ss[jj + 1]);
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) {
+    const int j    = J0 + jj;
+    const double f = rsq[jj] * usc;
+    inv[j]         = ss[jj] * rsq[jj] * isc;
+    x[j]           = col[j] * f;
+#pragma unroll
+    for (int q = j; q < 8; ++q) dgl[j][q] *= f;
+  }
+  if (J0 == 0) {
+    // back to true values for the second group: T = A / (s_4 sc)
+    const double back = 1.0 / (ss[4] * sc);
+#pragma unroll
+    for (int r = 4; r < 8; ++r) {
+#pragma unroll
+      for (int q = r; q < 8; ++q) dgl[r][q] *= back;
+      col[r] *= back;
+    }
+  }
+}
+
+// ---- diagonal block ---------------------------------------------------------------------------------
+// S (pitch FPITCH) holds the block (upper part valid, identity padding beyond nbk); on return S holds U_kk and
+// sDinv the reciprocal pivots.  Per 8-row strip: DMMA sweep with the rows already factored, then every thread
+// that owns one of the remaining columns factors the 8 x 8 pivot block redundantly in its registers (nothing
+// but arithmetic on the pivot chain rsqrt -> mul -> fma) and solves its column against it.
+__device__ void diag_factor(const FusedArgs &a, double *S, double *sDinv, int *sBad, int k0) {
+  const int tid = threadIdx.x;
+#pragma unroll 1
+  for (int kb = 0; kb < FB / 8; ++kb) {
+    const int b0 = 8 * kb;
+    if (kb > 0) {
+      strip_sweep(S, S, b0, kb, FB / 8);
+      __syncthreads();
+    }
+    trace_ev(a, 6, kb, 0);
+    const int ncols   = FB - b0;
+    const bool solver = tid >= 8 && tid < ncols;
+    const bool writer = tid >= 224 && tid < 232;
+    if (solver || writer) {
+      const int ci = solver ? b0 + tid : b0;
+      double dgl[8][8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int q = r; q < 8; ++q) dgl[r][q] = S[(b0 + r) * FPITCH + b0 + q];
+      double col[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) col[r] = S[(b0 + r) * FPITCH + ci];
+      double inv[8], x[8];
+      int bad = 0;
+      pivot_group4<0>(dgl, col, inv, x, bad, k0 + b0);
+      pivot_group4<4>(dgl, col, inv, x, bad, k0 + b0);
+      const int wq = tid - 224;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        double v = x[r];
+        if (writer) {
+#pragma unroll
+          for (int q = r; q < 8; ++q) v = (q == wq) ? dgl[r][q] : v;
+        }
+        const int cc = writer ? b0 + wq : ci;
+        if (solver || (writer && wq >= r)) S[(b0 + r) * FPITCH + cc] = v;
+      }
+      if (writer && wq == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sDinv[b0 + j] = inv[j];
+        if (bad != 0 && *sBad == 0) *sBad = bad;
+      }
+    }
+    __syncthreads();
+    trace_ev(a, 6, kb, 1);
+  }
+}
+
+// from_smem: the block was left in S by do_update; otherwise it is read from global memory
+__device__ void do_diag(const FusedArgs &a, int k, bool from_smem, double *S, double *sDinv, int *sBad) {
+  const int tid = threadIdx.x;
+  const int k0  = k * FB;
+  const int nbk = min(FB, a.n - k0);
+  trace_ev(a, 1, k, k);
+  if (tid == 0) *sBad = 0;
+  if (!from_smem) {
+    const int r = tid >> 2, cb = (tid & 3) * 16;
+    double v[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int cidx = cb + q;
+      v[q] = (r < nbk && cidx < nbk && cidx >= r) ? __ldcg(a.M + (size_t) (k0 + r) * a.ldm + k0 + cidx) : ((r == cidx && r >= nbk) ? 1.0 : 0.0);
+    }
+#pragma unroll
+    for (int q = 0; q < 16; ++q) S[r * FPITCH + cb + q] = v[q];
+  }
+  __syncthreads();
+  diag_factor(a, S, sDinv, sBad, k0);
+  {
+    // the lower triangle of the block is scratch for every reader: rows are written whole, 16 bytes per store
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int chunk = q * FT + tid;
+      const int r = chunk >> 5, cc = (chunk & 31) * 2;
+      if (r < nbk && cc + 1 >= r) {
+        double *dst = a.M + (size_t) (k0 + r) * a.ldm + k0 + cc;
+        if (cc + 1 < nbk)
+          *reinterpret_cast<double2 *>(dst) = *reinterpret_cast<const double2 *>(S + r * FPITCH + cc);
+        else if (cc < nbk)
+          dst[0] = S[r * FPITCH + cc];
+      }
+    }
+  }
+  if (tid < nbk) a.dinv[k0 + tid] = sDinv[tid];
+  if (tid == 0 && *sBad != 0) atomicCAS(a.info, 0, *sBad);
+  post_flag(a, a.flagD + k);
+  __syncthreads();
+  trace_ev(a, 1 + 8, k, k);
+}
+
+// ---- panel block (k, J): U[k, J] = U_kk^-T M[k, J] ------------------------------------------------------
+// sU: U_kk (pitch FPITCH, identity beyond nbk), sX: the tile, solved in place strip by strip:
+// DMMA sweep with the rows already solved, then one thread per column finishes the 8 x 8 triangular part.
+__device__ void do_panel(const FusedArgs &a, int k, int J, double *sU, double *sX, double *sD) {
+  const int tid = threadIdx.x;
+  const int k0  = k * FB;
+  const int nbk = min(FB, a.n - k0);
+  const bool isR = (a.rhs != nullptr) && (J == a.nbc - 1);
+  const int width = isR ? 1 : min(FB, a.n - J * FB);
+  const int J0 = J * FB;
+  trace_ev(a, 2, k, J);
+  // the tile itself was last written by this CTA: fetch it while waiting for U_kk
+  double2 tv[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int chunk = q * FT + tid;
+    const int r = chunk >> 5, cc = (chunk & 31) * 2;
+    double2 v = make_double2(0.0, 0.0);
+    if (r < nbk) {
+      if (isR) {
+        if (cc == 0) v.x = __ldcg(a.rhs + k0 + r);
+      } else if (cc + 1 < width) {
+        v = __ldcg(reinterpret_cast<const double2 *>(a.M + (size_t) (k0 + r) * a.ldm + J0 + cc));
+      } else if (cc < width) {
+        v.x = __ldcg(a.M + (size_t) (k0 + r) * a.ldm + J0 + cc);
+      }
+    }
+    tv[q] = v;
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int chunk = q * FT + tid;
+    *reinterpret_cast<double2 *>(sX + (chunk >> 5) * FPITCH + (chunk & 31) * 2) = tv[q];
+  }
+  wait_flag(a, a.flagD + k);
+  trace_ev(a, 2 + 16, k, J);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int chunk = q * FT + tid;
+    const int r = chunk >> 5, cc = (chunk & 31) * 2;
+    double2 v = make_double2(0.0, 0.0);
+    if (r < nbk) {
+      if (cc + 1 < nbk)
+        v = __ldcg(reinterpret_cast<const double2 *>(a.M + (size_t) (k0 + r) * a.ldm + k0 + cc));
+      else if (cc < nbk)
+        v.x = __ldcg(a.M + (size_t) (k0 + r) * a.ldm + k0 + cc);
+    } else {
+      if (cc == r) v.x = 1.0;
+      if (cc + 1 == r) v.y = 1.0;
+    }
+    tv[q] = v;
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int chunk = q * FT + tid;
+    *reinterpret_cast<double2 *>(sU + (chunk >> 5) * FPITCH + (chunk & 31) * 2) = tv[q];
+  }
+  if (tid < FB) sD[tid] = tid < nbk ? __ldcg(a.dinv + k0 + tid) : 1.0;
+  __syncthreads();
+  const int w_end = (width + 7) >> 3;
+#pragma unroll 1
+  for (int blk = 0; blk < FB / 8; ++blk) {
+    const int b0 = 8 * blk;
+    if (blk > 0) {
+      strip_sweep(sU, sX, b0, 0, w_end);
+      __syncthreads();
+    }
+    trace_ev(a, 7, blk, 0);
+    if (tid < width) {
+      double u[8][8], t[8], inv[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+#pragma unroll
+        for (int q = r + 1; q < 8; ++q) u[r][q] = sU[(b0 + r) * FPITCH + b0 + q];
+        t[r]   = sX[(b0 + r) * FPITCH + tid];
+        inv[r] = sD[b0 + r];
+      }
+      double x[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        double tt = t[r];
+#pragma unroll
+        for (int s = 0; s < r; ++s) tt = fma(-u[s][r], x[s], tt);
+        x[r] = tt * inv[r];
+        sX[(b0 + r) * FPITCH + tid] = x[r];
+      }
+    }
+    __syncthreads();
+    trace_ev(a, 7, blk, 1);
+  }
+  // write the solved tile back
+  if (isR) {
+    if (tid < nbk) a.rhs[k0 + tid] = sX[tid * FPITCH];
+  } else {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int chunk = q * FT + tid;
+      const int r = chunk >> 5, cc = (chunk & 31) * 2;
+      if (r < nbk) {
+        double *dst = a.M + (size_t) (k0 + r) * a.ldm + J0 + cc;
+        if (cc + 1 < width)
+          *reinterpret_cast<double2 *>(dst) = *reinterpret_cast<const double2 *>(sX + r * FPITCH + cc);
+        else if (cc < width)
+          dst[0] = sX[r * FPITCH + cc];
+      }
+    }
+  }
+  post_flag(a, a.flagP + k * (a.nb + 1) + J);
+  __syncthreads();
+  trace_ev(a, 2 + 8, k, J);
+}
+
+// ---- trailing update (k, I, J): M[I, J] -= U[k, I]^T U[k, J] ------------------------------------------------
+// 8 warps as 2 x 4, warp tile 32 x 16 (4 x 2 DMMA tiles).  to_S: the result is left in S (pitch FPITCH, identity
+// padded) for do_diag instead of being written to global memory.
+__device__ void do_update(const FusedArgs &a, int k, int I, int J, double *sA, double *sB, double *S, bool to_S) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 2, wn = warp & 3;
+  const int lr = lane & 3, lc = lane >> 2;
+  const int rm = wm * 32, cn = wn * 16;
+  const int k0 = k * FB, I0 = I * FB, J0 = J * FB;
+  const bool isR = (a.rhs != nullptr) && (J == a.nbc - 1);
+  const int hI = min(FB, a.n - I0);                    // valid rows of the tile
+  const int wJ = isR ? 1 : min(FB, a.n - J0);          // valid columns
+
+  trace_ev(a, 3, I, J);
+  wait_flag(a, a.flagP + k * (a.nb + 1) + I);
+  if (J != I) wait_flag(a, a.flagP + k * (a.nb + 1) + J);
+  trace_ev(a, 3 + 16, I, J);
+
+  // operands: rows k0 .. k0+63 (always a full block row), columns of block I (A) and block J (B)
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int chunk = q * FT + tid;
+    const int r = chunk >> 5, cc = (chunk & 31) * 2;
+    {
+      const int gc = I0 + cc;
+      int bytes    = (a.n - gc) * 8;
+      bytes        = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
+      const double *src = bytes > 0 ? a.M + (size_t) (k0 + r) * a.ldm + gc : a.M;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(sA + r * FPITCH + cc)), "l"(src), "r"(bytes) : "memory");
+    }
+    if (J != I && !isR) {
+      const int gc = J0 + cc;
+      int bytes    = (a.n - gc) * 8;
+      bytes        = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
+      const double *src = bytes > 0 ? a.M + (size_t) (k0 + r) * a.ldm + gc : a.M;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(sB + r * FPITCH + cc)), "l"(src), "r"(bytes) : "memory");
+    }
+  }
+  cp_async_commit();
+  if (isR) {
+    // B = y_k as column 0 (the other columns feed accumulators that are never stored)
+    for (int e = tid; e < FB * 8; e += FT) sB[(e >> 3) * FPITCH + (e & 7)] = 0.0;
+    __syncthreads();
+    if (tid < FB) sB[tid * FPITCH] = __ldcg(a.rhs + k0 + tid);
+  }
+
+  const bool fast = !isR && hI == FB && wJ == FB && (J0 + FB <= a.n);
+  double acc[4][2][2];
+  if (fast) {
+#pragma unroll
+    for (int am = 0; am < 4; ++am)
+#pragma unroll
+      for (int bn = 0; bn < 2; ++bn) {
+        const double2 v = __ldcg(reinterpret_cast<const double2 *>(a.M + (size_t) (I0 + rm + am * 8 + lc) * a.ldm + J0 + cn + bn * 8 + 2 * lr));
+        acc[am][bn][0]  = v.x;
+        acc[am][bn][1]  = v.y;
+      }
+  } else {
+#pragma unroll
+    for (int am = 0; am < 4; ++am)
+#pragma unroll
+      for (int bn = 0; bn < 2; ++bn)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int ti = rm + am * 8 + lc, tj = cn + bn * 8 + 2 * lr + e;
+          double v = 0.0;
+          if (ti < hI && tj < wJ) v = isR ? __ldcg(a.rhs + I0 + ti) : __ldcg(a.M + (size_t) (I0 + ti) * a.ldm + J0 + tj);
+          acc[am][bn][e] = v;
+        }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  const double *pB = (J == I) ? sA : sB;
+#pragma unroll
+  for (int ks = 0; ks < FB / 4; ++ks) {
+    double af[4], bf[2];
+    const double *pa = sA + (ks * 4 + lr) * FPITCH + rm + lc;
+    const double *pb = pB + (ks * 4 + lr) * FPITCH + cn + lc;
+#pragma unroll
+    for (int am = 0; am < 4; ++am) af[am] = -pa[am * 8];
+#pragma unroll
+    for (int bn = 0; bn < 2; ++bn) bf[bn] = pb[bn * 8];
+#pragma unroll
+    for (int am = 0; am < 4; ++am)
+#pragma unroll
+      for (int bn = 0; bn < 2; ++bn) dmma884(acc[am][bn][0], acc[am][bn][1], af[am], bf[bn]);
+  }
+  if (to_S) {
+#pragma unroll
+    for (int am = 0; am < 4; ++am)
+#pragma unroll
+      for (int bn = 0; bn < 2; ++bn)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int ti = rm + am * 8 + lc, tj = cn + bn * 8 + 2 * lr + e;
+          S[ti * FPITCH + tj] = (ti < hI && tj < wJ) ? acc[am][bn][e] : (ti == tj ? 1.0 : 0.0);
+        }
+  } else if (fast) {
+#pragma unroll
+    for (int am = 0; am < 4; ++am)
+#pragma unroll
+      for (int bn = 0; bn < 2; ++bn)
+        *reinterpret_cast<double2 *>(a.M + (size_t) (I0 + rm + am * 8 + lc) * a.ldm + J0 + cn + bn * 8 + 2 * lr) =
+            make_double2(acc[am][bn][0], acc[am][bn][1]);
+  } else {
+#pragma unroll
+    for (int am = 0; am < 4; ++am)
+#pragma unroll
+      for (int bn = 0; bn < 2; ++bn)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int ti = rm + am * 8 + lc, tj = cn + bn * 8 + 2 * lr + e;
+          if (ti < hI && tj < wJ) {
+            if (isR)
+              a.rhs[I0 + ti] = acc[am][bn][e];
+            else
+              a.M[(size_t) (I0 + ti) * a.ldm + J0 + tj] = acc[am][bn][e];
+          }
+        }
+  }
+  __syncthreads();
+  trace_ev(a, 3 + 8, I, J);
+}
+
+
+// ---- back substitution --------------------------------------------------------------------------------
+// warp 0 polls count <= 64 consecutive flags in parallel (one L2 round trip instead of one per flag)
+__device__ __forceinline__ void wait_flags_many(const FusedArgs &a, const int *f0, int count) {
+  if (threadIdx.x < 32 && count > 0) {
+    const int lane = threadIdx.x;
+    long long spins = 0;
+    while (true) {
+      bool ok = true;
+      if (lane < count) ok = ld_acquire(f0 + lane) == a.epoch;
+      if (lane + 32 < count) ok = ok && (ld_acquire(f0 + lane + 32) == a.epoch);
+      if (__all_sync(0xffffffffu, ok)) break;
+      if (++spins > SPIN_LIMIT / 64) {
+        if (lane == 0) atomicExch(a.abort_flag, 1);
+        break;
+      }
+      if ((spins & 255) == 0 && ld_acquire(a.abort_flag) != 0) break;
+    }
+  }
+  __syncthreads();
+}
+
+// contribution of tile (I, J), J >= I + 2:  part[I][J][r] = sum_c U[I0 + r][J0 + c] x_J[c]
+__device__ void do_backprod(const FusedArgs &a, int I, int J, double *sx) {
+  const int tid = threadIdx.x;
+  const int I0 = I * FB, J0 = J * FB;
+  const int wJ = min(FB, a.n - J0);
+  trace_ev(a, 5, I, J);
+  const int r = tid >> 2, q = tid & 3;   // 4 threads per row, 16 columns each
+  const double *u = a.M + (size_t) (I0 + r) * a.ldm + J0 + q * 16;
+  const bool full = J0 + FB <= a.n;
+  double2 v[8];
+  if (full) {   // the tile was finalised by this CTA: fetch it before waiting for x_J
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = __ldcg(reinterpret_cast<const double2 *>(u) + e);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int cidx = q * 16 + 2 * e;
+      v[e].x = cidx < wJ ? __ldcg(u + 2 * e) : 0.0;
+      v[e].y = cidx + 1 < wJ ? __ldcg(u + 2 * e + 1) : 0.0;
+    }
+  }
+  wait_flag(a, a.flagX + J);
+  trace_ev(a, 5 + 16, I, J);
+  if (tid < FB) sx[tid] = tid < wJ ? __ldcg(a.rhs + J0 + tid) : 0.0;
+  __syncthreads();
+  double s = 0.0;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s = fma(v[e].y, sx[q * 16 + 2 * e + 1], fma(v[e].x, sx[q * 16 + 2 * e], s));
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  if (q == 0) a.part[((size_t) I * a.nb + J) * FB + r] = s;
+  post_flag(a, a.flagQ + I * a.nb + J);
+  __syncthreads();
+  trace_ev(a, 5 + 8, I, J);
+}
+
+// x_J = U_JJ^-1 (y_J - sum_{J' >= J+2} part[J][J'] - U[J, J+1] x_{J+1}); the product with the neighbouring
+// block, the one that closes the dependency chain, is done here from a prefetched copy of the tile.
+__device__ void do_backsolve(const FusedArgs &a, int J, double *sU /* [64][65] */, double *sT /* [64][FPITCH] */, double *sy /* [5][64] */) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int J0  = J * FB;
+  const int nbk = min(FB, a.n - J0);
+  const bool has_next = J + 1 < a.nb;
+  const int J1 = J0 + FB;
+  const int w1 = has_next ? min(FB, a.n - J1) : 0;
+  trace_ev(a, 4, J, J);
+  {
+    double v[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int e = q * FT + tid, r = e >> 6, cidx = e & 63;
+      v[q] = (r < nbk && cidx < nbk && cidx >= r) ? __ldcg(a.M + (size_t) (J0 + r) * a.ldm + J0 + cidx) : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int e = q * FT + tid;
+      sU[(e >> 6) * (FB + 1) + (e & 63)] = v[q];
+    }
+  }
+  if (has_next) {   // tile (J, J+1): rows of block J are always full when a next block exists
+    wait_flag(a, a.flagP + J * (a.nb + 1) + J + 1);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int chunk = q * FT + tid;
+      const int r = chunk >> 5, cc = (chunk & 31) * 2;
+      const int gc = J1 + cc;
+      int bytes    = (a.n - gc) * 8;
+      bytes        = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
+      const double *src = bytes > 0 ? a.M + (size_t) (J0 + r) * a.ldm + gc : a.M;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(sT + r * FPITCH + cc)), "l"(src), "r"(bytes) : "memory");
+    }
+    cp_async_commit();
+  }
+  wait_flag(a, a.flagP + J * (a.nb + 1) + (a.nbc - 1));   // y_J is final
+  wait_flags_many(a, a.flagQ + J * a.nb + J + 2, a.nb - J - 2);
+  {
+    // y_J - sum of the contributions, 4 groups of blocks summed independently, then combined in a fixed order
+    const int r = tid & 63, g = tid >> 6;
+    double v[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int Jp = J + 2 + g + 4 * q;
+      v[q]         = Jp < a.nb ? __ldcg(a.part + ((size_t) J * a.nb + Jp) * FB + r) : 0.0;
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) s += v[q];
+    sy[(1 + g) * FB + r] = s;
+  }
+  if (has_next) wait_flag(a, a.flagX + J + 1);
+  trace_ev(a, 4 + 16, J, J);
+  if (tid < FB) sy[tid] = (has_next && tid < w1) ? __ldcg(a.rhs + J1 + tid) : 0.0;   // x_{J+1}
+  cp_async_wait<0>();
+  __syncthreads();
+  {
+    const int r = tid >> 2, q = tid & 3;
+    double s = 0.0;
+    if (has_next) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) s = fma(sT[r * FPITCH + q * 16 + e], sy[q * 16 + e], s);
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    __syncthreads();   // everyone has read x_{J+1} from sy[0..63]
+    if (q == 0) {
+      const double y = r < nbk ? __ldcg(a.rhs + J0 + r) : 0.0;
+      sy[r] = (((y - sy[FB + r]) - sy[2 * FB + r]) - sy[3 * FB + r]) - sy[4 * FB + r] - s;
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    double y0 = lane < nbk ? sy[lane] : 0.0, y1 = lane + 32 < nbk ? sy[lane + 32] : 0.0;
+    const double d0 = lane < nbk ? __ldcg(a.dinv + J0 + lane) : 1.0, d1 = lane + 32 < nbk ? __ldcg(a.dinv + J0 + lane + 32) : 1.0;
+#pragma unroll 8
+    for (int r = FB - 1; r >= 32; --r) {
+      const double xr = __shfl_sync(0xffffffffu, y1 * d1, r - 32);
+      if (lane + 32 == r) y1 = xr;
+      if (lane + 32 < r) y1 = fma(-sU[(lane + 32) * (FB + 1) + r], xr, y1);
+      y0 = fma(-sU[lane * (FB + 1) + r], xr, y0);
+    }
+#pragma unroll 8
+    for (int r = 31; r >= 0; --r) {
+      const double xr = __shfl_sync(0xffffffffu, y0 * d0, r);
+      if (lane == r) y0 = xr;
+      if (lane < r) y0 = fma(-sU[lane * (FB + 1) + r], xr, y0);
+    }
+    if (lane < nbk) a.rhs[J0 + lane] = y0;
+    if (lane + 32 < nbk) a.rhs[J0 + lane + 32] = y1;
+  }
+  post_flag(a, a.flagX + J);
+  __syncthreads();
+  trace_ev(a, 4 + 8, J, J);
+}
+
+__global__ void __launch_bounds__(FT, 1) chol_fused_kernel(const FusedArgs a) {
+  extern __shared__ __align__(16) double fsm[];
+  double *sA    = fsm;                      // [64][68]   operand A / U_kk of the panel solve / U_JJ of the back solve
+  double *sB    = sA + FB * FPITCH;         // [64][68]   operand B
+  double *S     = sB + FB * FPITCH;         // [64][68]   diagonal block
+  double *sDinv = S + FB * FPITCH;          // [64]
+  double *sVec  = sDinv + FB;               // [5][64]
+  int *sBad     = reinterpret_cast<int *>(sVec + 5 * FB);
+  const int G = gridDim.x, bid = blockIdx.x;
+  const int nb = a.nb, nbc = a.nbc;
+  const int T = row_start(nb, nbc);
+
+  if (bid == 0) do_diag(a, 0, false, S, sDinv, sBad);
+  for (int k = 0; k < nb; ++k) {
+    // panels of block row k
+    {
+      const int t0 = row_start(k, nbc);
+      for (int J = k + 1; J < nbc; ++J)
+        if ((t0 + (J - k)) % G == bid) do_panel(a, k, J, sA, sB, sDinv);
+    }
+    // updates with block row k, in tile order: block row k + 1 (next diagonal block and next panels) comes first
+    if (k + 1 < nb) {
+      const int t1 = row_start(k + 1, nbc);
+      int t        = t1 + ((bid - t1) % G + G) % G;
+      int I        = k + 1;
+      for (; t < T; t += G) {
+        while (t >= row_start(I + 1, nbc)) ++I;
+        const int J      = I + (t - row_start(I, nbc));
+        const bool isdiag = (I == k + 1 && J == k + 1);
+        do_update(a, k, I, J, sA, sB, S, isdiag);
+        if (isdiag) do_diag(a, k + 1, true, S, sDinv, sBad);
+      }
+    }
+  }
+  if (a.rhs == nullptr) return;
+  for (int J = nb - 1; J >= 0; --J) {
+    if (row_start(J, nbc) % G == bid) do_backsolve(a, J, sA, sB, sVec);
+    for (int I = J - 2; I >= 0; --I)
+      if ((row_start(I, nbc) + (J - I)) % G == bid) do_backprod(a, I, J, sVec);
+  }
+}
+
+}   // namespace
+
+static constexpr size_t FUSED_SMEM = (size_t) (3 * FB * FPITCH + 6 * FB) * sizeof(double) + 16;
+
+// Largest order served by the single-launch path (flags and the contribution buffer are sized for it).
+int chol_fused_max_n() { return 4096; }
+
+// In-place factorisation of the upper triangle of dM (n x n, ld = ldm even, 16-byte aligned rows) and, when
+// dRhs != nullptr, solution of M x = rhs in place.  info_host: 0 or the 1-based index of the first non-positive pivot.
+int dpotrf_upper_solve_fused(ncm_sd_gpu_ctx *c, int n, double *dM, int ldm, double *dRhs, int *info_host) {
+  if (n <= 0 || n > chol_fused_max_n()) return c->fail(NCM_SD_GPU_EINVAL, "chol_fused: order out of range");
+  const int nb  = (n + FB - 1) / FB;
+  const int nbc = nb + (dRhs != nullptr ? 1 : 0);
+  const int nbm = chol_fused_max_n() / FB;
+  const size_t n_flags = (size_t) nbm + (size_t) nbm * (nbm + 1) + nbm + (size_t) nbm * nbm + 8;
+  if (c->chol_flags.cap == 0) {
+    if (!c->chol_flags.reserve(n_flags * sizeof(int))) return c->fail(NCM_SD_GPU_ENOMEM, "chol_fused: out of device memory");
+    NCM_CUDA_OK(c, cudaMemsetAsync(c->chol_flags.p, 0, c->chol_flags.cap, c->stream));
+    NCM_CUDA_OK(c, cudaFuncSetAttribute(chol_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FUSED_SMEM));
+    int per_sm = 0;
+    NCM_CUDA_OK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_fused_kernel, FT, FUSED_SMEM));
+    if (per_sm < 1) return c->fail(NCM_SD_GPU_ECUDA, "chol_fused: kernel does not fit on an SM");
+    c->chol_epoch = 0;
+  }
+  if (!c->chol_part.reserve(((size_t) nb * nb * FB + (size_t) n + 64) * sizeof(double)))
+    return c->fail(NCM_SD_GPU_ENOMEM, "chol_fused: out of device memory");
+  FusedArgs a;
+  a.M = dM; a.ldm = ldm; a.n = n; a.rhs = dRhs;
+  a.part  = c->chol_part.as<double>();
+  a.dinv  = a.part + (size_t) nb * nb * FB;
+  int *f  = c->chol_flags.as<int>();
+  a.info = f; a.abort_flag = f + 1;
+  a.flagD = f + 8;
+  a.flagP = a.flagD + nbm;
+  a.flagX = a.flagP + (size_t) nbm * (nbm + 1);
+  a.flagQ = a.flagX + nbm;
+  a.epoch = ++c->chol_epoch;
+  a.nb = nb; a.nbc = nbc;
+  a.trace = c->chol_trace; a.trace_cap = c->chol_trace_cap;
+  NCM_CUDA_OK(c, cudaMemsetAsync(f, 0, 2 * sizeof(int), c->stream));
+  void *params[] = {&a};
+  NCM_CUDA_OK(c, cudaLaunchCooperativeKernel((const void *) chol_fused_kernel, dim3(c->n_sm), dim3(FT), params, FUSED_SMEM, c->stream));
+  c->n_launches++;
+  if (info_host != nullptr) {
+    int h[2] = {0, 0};
+    NCM_CUDA_OK(c, ncm_memcpy_async(c, h, f, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    NCM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    if (h[1] != 0) return c->fail(NCM_SD_GPU_ECUDA, "chol_fused: a tile dependency was never satisfied (internal error)");
+    *info_host = h[0];
+  }
+  return NCM_SD_GPU_OK;
+}

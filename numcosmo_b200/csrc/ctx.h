@@ -70,6 +70,10 @@ struct ncm_sd_gpu_ctx {
   DevBuf IM;         // [nrows_local x n_kernels]
   DevBuf rowscale;   // [n_obs]
   DevBuf M, MU, nn_b, nn_x, nn_r, nn_g, nn_tmp, nn_idx, nn_f;
+  DevBuf chol_flags, chol_part;   // single-launch Cholesky (chol_fused.cu): dependency flags, back-substitution contributions
+  int chol_epoch = 0;
+  long long *chol_trace = nullptr;   // device buffer [n_sm][cap][2] set by ncm_sd_gpu_chol_trace (debugging aid)
+  int chol_trace_cap = 0;
   PinBuf pin_nn;
 
   // NCCL
@@ -141,6 +145,9 @@ int kde_im_launch(ncm_sd_gpu_ctx *c, const double *dRowScale);
 
 int update_cterm(ncm_sd_gpu_ctx *c);
 
+int chol_fused_max_n();
+int dpotrf_upper_solve_fused(ncm_sd_gpu_ctx *c, int n, double *dM, int ldm, double *dRhs, int *info_host);
+int dpotrf_upper_solve_any(ncm_sd_gpu_ctx *c, int n, double *dM, int ldm, double *dRhs, double *dDinv, int *dInfo, int *info_host);
 int dsyrk_ata(ncm_sd_gpu_ctx *c, int nrows, int ncols, const double *dA, int lda, double *dM, int ldm);
 int dpotrf_upper(ncm_sd_gpu_ctx *c, int n, double *dM, int ldm, double *dRhs /* optional, solved in place */, int *info_host);
 int nnls_solve_dev(ncm_sd_gpu_ctx *c, int nrows, int ncols, const double *dA, int lda, const double *dF, double reltol, double *x_host,

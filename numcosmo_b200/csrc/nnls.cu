@@ -192,7 +192,7 @@ int solve_unconstrained(NnlsWork &w, const std::vector<int> &P) {
     int info = 0;
     {
       StageTimer t(c, NCM_SD_GPU_T_CHOL);
-      int rc = dpotrf_upper_solve(c, np, w.dMU, w.ldm, w.drhs, w.ddinv, w.dinfo, &info);
+      int rc = dpotrf_upper_solve_any(c, np, w.dMU, w.ldm, w.drhs, w.ddinv, w.dinfo, &info);
       if (rc != NCM_SD_GPU_OK) return rc;
     }
     if (w.st) {

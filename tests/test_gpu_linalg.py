@@ -48,3 +48,33 @@ def test_dpotrf_upper(gpu_ctx, n):
     torch.cuda.synchronize()
     info = gpu_ctx.dpotrf_upper_dev(n, dM.data_ptr(), ld)
     assert info == k + 1
+
+
+@pytest.mark.parametrize("n", [1, 5, 63, 64, 65, 128, 200, 1000, 1899, 2048, 3001])
+def test_dposv_upper(gpu_ctx, n):
+    """dposv 'U' (ncm_matrix_cholesky_solve, ncm_matrix.c:1199-1210): factor + forward + back substitution."""
+    import torch
+
+    rs = np.random.default_rng(1000 + n)
+    B = rs.standard_normal((n + 10, n))
+    S = B.T @ B + 0.1 * np.eye(n)
+    b = rs.standard_normal(n)
+    ld = (n + 7) // 8 * 8
+    dM = torch.full((n, ld), float("nan"), dtype=torch.float64, device="cuda")   # the lower triangle must never be read
+    dM[:, :n] = torch.from_numpy(np.triu(S) + np.tril(np.full((n, n), np.nan), -1)).cuda()
+    dB = torch.from_numpy(b).cuda()
+    torch.cuda.synchronize()
+    info = gpu_ctx.dposv_upper_dev(n, dM.data_ptr(), ld, dB.data_ptr())
+    assert info == 0
+    x = dB.cpu().numpy()
+    xref = np.linalg.solve(S, b)
+    assert np.max(np.abs(x - xref)) < 1e-9 * np.abs(xref).max()
+    U = np.triu(dM.cpu().numpy()[:, :n])
+    Uref = np.linalg.cholesky(S).T
+    assert np.max(np.abs(U - Uref)) < 1e-10 * np.abs(Uref).max()
+    # repeat on the same buffers (flag epochs) and check determinism
+    dM[:, :n] = torch.from_numpy(np.triu(S)).cuda()
+    dB.copy_(torch.from_numpy(b).cuda())
+    torch.cuda.synchronize()
+    assert gpu_ctx.dposv_upper_dev(n, dM.data_ptr(), ld, dB.data_ptr()) == 0
+    assert np.array_equal(dB.cpu().numpy(), x)

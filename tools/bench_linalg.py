@@ -32,5 +32,14 @@ for n in sizes:
         assert info == 0
         best = min(best, e0.elapsed_time(e1))
     syrk.update({"potrf_ms": best, "potrf_tflops": n**3 / 3 / best / 1e9})
+    rhs = torch.randn(n, dtype=torch.float64, device="cuda")
+    best = 1e9
+    for _ in range(4):
+        W = M2.clone(); r = rhs.clone(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st); info = ctx.dposv_upper_dev(n, W.data_ptr(), ld, r.data_ptr()); e1.record(st); ctx.synchronize()
+        assert info == 0
+        best = min(best, e0.elapsed_time(e1))
+    syrk.update({"posv_ms": best, "posv_tflops": n**3 / 3 / best / 1e9})
     print(json.dumps(syrk), flush=True)
     del A, M, M2, W
