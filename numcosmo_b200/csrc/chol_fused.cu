@@ -7,19 +7,23 @@
 //
 // The upper triangle (row-major, M = U^T U) is cut in 64 x 64 tiles (I, J), I <= J; the right-hand side is one
 // more block column (J = nb, width 1), so the forward substitution y = U^-T b needs no code of its own.
-// Tile t = (I, J) in row-major order of the upper triangle belongs to CTA  t mod gridDim.x  for the whole
-// factorisation, hence all updates of a tile are applied by the same CTA in phase order and the only
-// cross-CTA dependencies are "U_kk is final" (flagD[k]) and "panel block U[k, J] is final" (flagP[k][J]):
-//   diag  (k, k)   factor the 64 x 64 block in shared memory (the register-blocked scheme of chol.cu)
-//   panel (k, J)   U[k, J] = U_kk^-T M[k, J]          one thread per column, forward substitution in registers
-//   update(k,I,J)  M[I, J] -= U[k, I]^T U[k, J]       DMMA.8x8x4, operands staged by cp.async, C in registers
-// Every CTA walks its own tiles in the global order (phase k: panels of row k, then updates with row k), each
-// step waits only on flags of strictly earlier steps, and all CTAs are co-resident (cooperative launch), so the
-// schedule cannot deadlock.  The updated (k+1, k+1) tile is handed to the diagonal factorisation through shared
-// memory, which keeps the L2 round trip off the critical path  diag k -> panel (k, k+1) -> update (k+1, k+1).
-// The back substitution U x = y runs in the same launch: tile (I, J) contributes U[I, J] x_J as soon as x_J is
-// published, the owner of (I, I) adds the contributions in ascending J (deterministic) and solves its block.
-// Flags carry the epoch of the call, so they never need clearing.
+//
+//   spine (CTA 0)    runs the serial chain of the factorisation without leaving the SM:
+//                    factor (k, k) -> solve the panel block (k, k+1) -> update (k+1, k+1) -> factor ...
+//                    and afterwards the chain of the back substitution  x_J = U_JJ^-1 (y_J - ... - U[J, J+1] x_{J+1}).
+//   workers (1..G-1) tile t = (I, J) in row-major order of the upper triangle belongs to worker t mod (G - 1) for the
+//                    whole factorisation, so all updates of a tile are applied by one CTA in phase order:
+//                      panel (k, J), J >= k+2   U[k, J] = U_kk^-T M[k, J]     (after flagD[k])
+//                      update(k, I, J)          M[I, J] -= U[k, I]^T U[k, J]  (after flagP[k][I], flagP[k][J]); DMMA.8x8x4
+//                    a worker hands tile (I, I) to the spine after phase I-2 (flagTd[I]) and tile (I, I+1) after
+//                    phase I-1 (flagTs[I]); in the back substitution it contributes U[I, J] x_J, J >= I+2 (flagQ[I][J]).
+// Every CTA walks its work in one global order (phase k: panels of row k, then updates with row k) and every wait is on a
+// strictly earlier item; all CTAs are co-resident (cooperative launch), so the schedule cannot deadlock.  Flags carry the
+// epoch of the call and never need clearing.  Panel solves and the diagonal factorisation work on 8-row strips: a DMMA
+// sweep with the rows already done, then an 8 x 8 triangular step in registers (no inverses are formed anywhere).
+//
+// Measured (tools/chol_trace.py, n = 2048): 21 us per 64-column phase = factor 8.3 + store/flag 1.5 + panel 5.7 + update 2.5
+// + waits; the 8 x 8 pivot chain (rsqrt -> mul -> fma, ~110 cycles per pivot, one warp) is the floor of the factor step.
 #include "ctx.h"
 
 namespace {
@@ -39,6 +43,8 @@ struct FusedArgs {
   int *flagP;      // [nb x (nb + 1)]
   int *flagX;      // [nb]
   int *flagQ;      // [nb x nb]
+  int *flagTd;     // [nb]  tile (I, I) carries all updates of the phases < I - 1
+  int *flagTs;     // [nb]  tile (I, I + 1) carries all updates of the phases < I
   int *info;       // first non-positive pivot (1-based), 0 otherwise
   int *abort_flag; // set when a wait ran into SPIN_LIMIT (a bug, never data): every CTA then drains
   int epoch, nb, nbc;
@@ -132,174 +138,14 @@ __device__ __forceinline__ void strip_sweep(const double *Asrc, double *X, int b
   }
 }
 
-// Division-free elimination of 4 pivots (J0 = 0 or 4) of the 8 x 8 pivot block held in registers, together with the
-// thread's own column.  With A = s T (T the true Schur complement, s_0 = 1):
-//     A'_rq = A_rq pi_j - A_jr A_jq ,  pi_j = A_jj ,  s_{j+1} = s_j pi_j ,  U_jq = A_jq rsqrt(s_{j+1}) ,  1/U_jj = s_j rsqrt(s_{j+1})
-// so the pivot chain is mul -> fma (16 cycles) instead of rsqrt -> mul -> fma (~200 cycles measured in situ), and the
-// four rsqrt of the group are independent.  The group starts from true values scaled by an exact power of 4 taken from
-// its first pivot, which keeps s_4 ~ t_1^4 t_2^2 t_3 far inside the double range.
-template <int J0>
-__device__ __forceinline__ void pivot_group4(double (&dgl)[8][8], double (&col)[8], double (&inv)[8], double (&x)[8], int &bad, int kbase) {
-  const int hi   = __double2hiint(dgl[J0][J0]);
-  const int be   = (hi >> 20) & 0x7ff;
-  const int half = (be - 1023) >> 1;                                   // floor(exponent / 2)
-  const bool scal_ok = (hi > 0) && (be > 64) && (be < 1983);
-  const double sc  = scal_ok ? __hiloint2double((1023 - 2 * half) << 20, 0) : 1.0;   // 4^-half
-  const double usc = scal_ok ? __hiloint2double((1023 + half) << 20, 0) : 1.0;       // 2^half = sqrt(1 / sc)
-  const double isc = scal_ok ? __hiloint2double((1023 - half) << 20, 0) : 1.0;       // 2^-half
-#pragma unroll
-  for (int r = J0; r < 8; ++r) {
-#pragma unroll
-    for (int q = r; q < 8; ++q) dgl[r][q] *= sc;
-    col[r] *= sc;
-  }
-  double ss[5];
-  ss[0] = 1.0;
-#pragma unroll
-  for (int jj = 0; jj < 4; ++jj) {
-    const int j     = J0 + jj;
-    const double pj = dgl[j][j];
-    if (!(pj > 0.0)) bad = (bad == 0) ? kbase + j + 1 : bad;
-    ss[jj + 1] = ss[jj] * pj;
-#pragma unroll
-    for (int r = j + 1; r < 8; ++r) {
-#pragma unroll
-      for (int q = r; q < 8; ++q) dgl[r][q] = fma(-dgl[j][r], dgl[j][q], dgl[r][q] * pj);
-      col[r] = fma(-dgl[j][r], col[j], col[r] * pj);
-    }
-  }
-  double rsq[4];
-#pragma unroll
-  for (int jj = 0; jj < 4; ++jj) rsq[jj] = rsqrt(ss[jj + 1]);
-#pragma unroll
-  for (int jj = 0; jj < 4; ++jj) {
-    const int j    = J0 + jj;
-    const double f = rsq[jj] * usc;
-    inv[j]         = ss[jj] * rsq[jj] * isc;
-    x[j]           = col[j] * f;
-#pragma unroll
-    for (int q = j; q < 8; ++q) dgl[j][q] *= f;
-  }
-  if (J0 == 0) {
-    // back to true values for the second group: T = A / (s_4 sc)
-    const double back = 1.0 / (ss[4] * sc);
-#pragma unroll
-    for (int r = 4; r < 8; ++r) {
-#pragma unroll
-      for (int q = r; q < 8; ++q) dgl[r][q] *= back;
-      col[r] *= back;
-    }
-  }
-}
-
-// ---- diagonal block ---------------------------------------------------------------------------------
-// S (pitch FPITCH) holds the block (upper part valid, identity padding beyond nbk); on return S holds U_kk and
-// sDinv the reciprocal pivots.  Per 8-row strip: DMMA sweep with the rows already factored, then every thread
-// that owns one of the remaining columns factors the 8 x 8 pivot block redundantly in its registers (nothing
-// but arithmetic on the pivot chain rsqrt -> mul -> fma) and solves its column against it.
-__device__ void diag_factor(const FusedArgs &a, double *S, double *sDinv, int *sBad, int k0) {
+// ---- tiles between global and shared memory -------------------------------------------------------------------
+// rows k0 .. k0+nbk-1 of block column J (width columns; the rhs block is one column of a.rhs) -> sX, zero padded
+__device__ __forceinline__ void tile_fetch(const FusedArgs &a, int k, int J, double *sX) {
   const int tid = threadIdx.x;
-#pragma unroll 1
-  for (int kb = 0; kb < FB / 8; ++kb) {
-    const int b0 = 8 * kb;
-    if (kb > 0) {
-      strip_sweep(S, S, b0, kb, FB / 8);
-      __syncthreads();
-    }
-    trace_ev(a, 6, kb, 0);
-    const int ncols   = FB - b0;
-    const bool solver = tid >= 8 && tid < ncols;
-    const bool writer = tid >= 224 && tid < 232;
-    if (solver || writer) {
-      const int ci = solver ? b0 + tid : b0;
-      double dgl[8][8];
-#pragma unroll
-      for (int r = 0; r < 8; ++r)
-#pragma unroll
-        for (int q = r; q < 8; ++q) dgl[r][q] = S[(b0 + r) * FPITCH + b0 + q];
-      double col[8];
-#pragma unroll
-      for (int r = 0; r < 8; ++r) col[r] = S[(b0 + r) * FPITCH + ci];
-      double inv[8], x[8];
-      int bad = 0;
-      pivot_group4<0>(dgl, col, inv, x, bad, k0 + b0);
-      pivot_group4<4>(dgl, col, inv, x, bad, k0 + b0);
-      const int wq = tid - 224;
-#pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        double v = x[r];
-        if (writer) {
-#pragma unroll
-          for (int q = r; q < 8; ++q) v = (q == wq) ? dgl[r][q] : v;
-        }
-        const int cc = writer ? b0 + wq : ci;
-        if (solver || (writer && wq >= r)) S[(b0 + r) * FPITCH + cc] = v;
-      }
-      if (writer && wq == 0) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) sDinv[b0 + j] = inv[j];
-        if (bad != 0 && *sBad == 0) *sBad = bad;
-      }
-    }
-    __syncthreads();
-    trace_ev(a, 6, kb, 1);
-  }
-}
-
-// from_smem: the block was left in S by do_update; otherwise it is read from global memory
-__device__ void do_diag(const FusedArgs &a, int k, bool from_smem, double *S, double *sDinv, int *sBad) {
-  const int tid = threadIdx.x;
-  const int k0  = k * FB;
-  const int nbk = min(FB, a.n - k0);
-  trace_ev(a, 1, k, k);
-  if (tid == 0) *sBad = 0;
-  if (!from_smem) {
-    const int r = tid >> 2, cb = (tid & 3) * 16;
-    double v[16];
-#pragma unroll
-    for (int q = 0; q < 16; ++q) {
-      const int cidx = cb + q;
-      v[q] = (r < nbk && cidx < nbk && cidx >= r) ? __ldcg(a.M + (size_t) (k0 + r) * a.ldm + k0 + cidx) : ((r == cidx && r >= nbk) ? 1.0 : 0.0);
-    }
-#pragma unroll
-    for (int q = 0; q < 16; ++q) S[r * FPITCH + cb + q] = v[q];
-  }
-  __syncthreads();
-  diag_factor(a, S, sDinv, sBad, k0);
-  {
-    // the lower triangle of the block is scratch for every reader: rows are written whole, 16 bytes per store
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int chunk = q * FT + tid;
-      const int r = chunk >> 5, cc = (chunk & 31) * 2;
-      if (r < nbk && cc + 1 >= r) {
-        double *dst = a.M + (size_t) (k0 + r) * a.ldm + k0 + cc;
-        if (cc + 1 < nbk)
-          *reinterpret_cast<double2 *>(dst) = *reinterpret_cast<const double2 *>(S + r * FPITCH + cc);
-        else if (cc < nbk)
-          dst[0] = S[r * FPITCH + cc];
-      }
-    }
-  }
-  if (tid < nbk) a.dinv[k0 + tid] = sDinv[tid];
-  if (tid == 0 && *sBad != 0) atomicCAS(a.info, 0, *sBad);
-  post_flag(a, a.flagD + k);
-  __syncthreads();
-  trace_ev(a, 1 + 8, k, k);
-}
-
-// ---- panel block (k, J): U[k, J] = U_kk^-T M[k, J] ------------------------------------------------------
-// sU: U_kk (pitch FPITCH, identity beyond nbk), sX: the tile, solved in place strip by strip:
-// DMMA sweep with the rows already solved, then one thread per column finishes the 8 x 8 triangular part.
-__device__ void do_panel(const FusedArgs &a, int k, int J, double *sU, double *sX, double *sD) {
-  const int tid = threadIdx.x;
-  const int k0  = k * FB;
+  const int k0 = k * FB, J0 = J * FB;
   const int nbk = min(FB, a.n - k0);
   const bool isR = (a.rhs != nullptr) && (J == a.nbc - 1);
-  const int width = isR ? 1 : min(FB, a.n - J * FB);
-  const int J0 = J * FB;
-  trace_ev(a, 2, k, J);
-  // the tile itself was last written by this CTA: fetch it while waiting for U_kk
+  const int width = isR ? 1 : min(FB, a.n - J0);
   double2 tv[8];
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
@@ -322,31 +168,166 @@ __device__ void do_panel(const FusedArgs &a, int k, int J, double *sU, double *s
     const int chunk = q * FT + tid;
     *reinterpret_cast<double2 *>(sX + (chunk >> 5) * FPITCH + (chunk & 31) * 2) = tv[q];
   }
-  wait_flag(a, a.flagD + k);
-  trace_ev(a, 2 + 16, k, J);
+}
+// same through cp.async (not for the rhs block); the caller commits and waits
+__device__ __forceinline__ void tile_fetch_async(const FusedArgs &a, int k, int J, double *sX) {
+  const int tid = threadIdx.x;
+  const int k0 = k * FB, J0 = J * FB;
+  const int nbk = min(FB, a.n - k0);
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const int chunk = q * FT + tid;
     const int r = chunk >> 5, cc = (chunk & 31) * 2;
-    double2 v = make_double2(0.0, 0.0);
-    if (r < nbk) {
-      if (cc + 1 < nbk)
-        v = __ldcg(reinterpret_cast<const double2 *>(a.M + (size_t) (k0 + r) * a.ldm + k0 + cc));
-      else if (cc < nbk)
-        v.x = __ldcg(a.M + (size_t) (k0 + r) * a.ldm + k0 + cc);
-    } else {
-      if (cc == r) v.x = 1.0;
-      if (cc + 1 == r) v.y = 1.0;
-    }
-    tv[q] = v;
+    const int gc = J0 + cc;
+    int bytes    = r < nbk ? (a.n - gc) * 8 : 0;
+    bytes        = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
+    const double *src = bytes > 0 ? a.M + (size_t) (k0 + r) * a.ldm + gc : a.M;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(sX + r * FPITCH + cc)), "l"(src), "r"(bytes) : "memory");
+  }
+}
+__device__ __forceinline__ void tile_store(const FusedArgs &a, int k, int J, const double *sX) {
+  const int tid = threadIdx.x;
+  const int k0 = k * FB, J0 = J * FB;
+  const int nbk = min(FB, a.n - k0);
+  const bool isR = (a.rhs != nullptr) && (J == a.nbc - 1);
+  const int width = isR ? 1 : min(FB, a.n - J0);
+  if (isR) {
+    if (tid < nbk) a.rhs[k0 + tid] = sX[tid * FPITCH];
+    return;
   }
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const int chunk = q * FT + tid;
-    *reinterpret_cast<double2 *>(sU + (chunk >> 5) * FPITCH + (chunk & 31) * 2) = tv[q];
+    const int r = chunk >> 5, cc = (chunk & 31) * 2;
+    if (r < nbk) {
+      double *dst = a.M + (size_t) (k0 + r) * a.ldm + J0 + cc;
+      if (cc + 1 < width)
+        *reinterpret_cast<double2 *>(dst) = *reinterpret_cast<const double2 *>(sX + r * FPITCH + cc);
+      else if (cc < width)
+        dst[0] = sX[r * FPITCH + cc];
+    }
   }
-  if (tid < FB) sD[tid] = tid < nbk ? __ldcg(a.dinv + k0 + tid) : 1.0;
-  __syncthreads();
+}
+// write the factored diagonal block (upper part; the lower triangle of M is scratch for every reader) and 1 / U_rr
+__device__ __forceinline__ void diag_store(const FusedArgs &a, int k, const double *S, const double *sDinv) {
+  const int tid = threadIdx.x;
+  const int k0  = k * FB;
+  const int nbk = min(FB, a.n - k0);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int chunk = q * FT + tid;
+    const int r = chunk >> 5, cc = (chunk & 31) * 2;
+    if (r < nbk && cc + 1 >= r) {
+      double *dst = a.M + (size_t) (k0 + r) * a.ldm + k0 + cc;
+      if (cc + 1 < nbk)
+        *reinterpret_cast<double2 *>(dst) = *reinterpret_cast<const double2 *>(S + r * FPITCH + cc);
+      else if (cc < nbk)
+        dst[0] = S[r * FPITCH + cc];
+    }
+  }
+  if (tid < nbk) a.dinv[k0 + tid] = sDinv[tid];
+}
+
+// ---- diagonal block ---------------------------------------------------------------------------------
+// S (pitch FPITCH) holds the block (upper part valid, identity padding beyond nbk); on return S holds U_kk and
+// sDinv the reciprocal pivots.  Per 8-row strip: DMMA sweep with the rows already factored; warp 0 factors the
+// 8 x 8 pivot block in registers (every lane the same arithmetic: nothing but rsqrt -> mul -> fma on the pivot
+// chain); then one thread per remaining column solves its 8 entries against it.
+// While warp 0 is busy with a pivot block, an otherwise idle lane polls the two flags the spine will need next (want_*:
+// still to be fetched); the tiles are then fetched with cp.async from inside the factorisation, so a worker that is on
+// time never puts an L2 round trip on the chain.
+__device__ void diag_factor(const FusedArgs &a, double *S, double *sDinv, int *sBad, int k0, int k, bool &want_panel, bool &want_next, double *sX,
+                            double *sC, int *sPoll) {
+  const int tid = threadIdx.x;
+  int pf0 = 0, pf1 = 0;
+#pragma unroll 1
+  for (int kb = 0; kb < FB / 8; ++kb) {
+    const int b0 = 8 * kb;
+    if (kb > 0) {
+      strip_sweep(S, S, b0, kb, FB / 8);
+      __syncthreads();
+    }
+    trace_ev(a, 6, kb, 0);
+    if (tid < 32) {
+      double dgl[8][8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int q = r; q < 8; ++q) dgl[r][q] = S[(b0 + r) * FPITCH + b0 + q];
+      double inv[8];
+      int bad = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const double piv = dgl[j][j];
+        if (!(piv > 0.0)) bad = (bad == 0) ? k0 + b0 + j + 1 : bad;   // the factor is garbage (NaN) from here on; info reports it
+        inv[j]    = rsqrt(piv);
+        dgl[j][j] = piv * inv[j];
+#pragma unroll
+        for (int q = j + 1; q < 8; ++q) dgl[j][q] *= inv[j];
+#pragma unroll
+        for (int r = j + 1; r < 8; ++r)
+#pragma unroll
+          for (int q = r; q < 8; ++q) dgl[r][q] = fma(-dgl[j][r], dgl[j][q], dgl[r][q]);
+      }
+      if (tid == 0) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+#pragma unroll
+          for (int q = r; q < 8; ++q) S[(b0 + r) * FPITCH + b0 + q] = dgl[r][q];
+          sDinv[b0 + r] = inv[r];
+        }
+        if (bad != 0 && *sBad == 0) *sBad = bad;
+      }
+    }
+    if (tid == 224) {
+      // the values loaded one strip ago are consumed now and the next loads are issued: the L2 round trip of a poll
+      // spans a whole strip instead of stretching this stage
+      sPoll[0] = (want_panel && kb > 0) ? (pf0 == a.epoch) : 0;
+      sPoll[1] = (want_next && kb > 0) ? (pf1 == a.epoch) : 0;
+      pf0 = ld_acquire(a.flagTs + k);
+      pf1 = ld_acquire(a.flagTd + k + 1);
+    }
+    __syncthreads();
+    if (sPoll[0] != 0 || sPoll[1] != 0) {
+      if (sPoll[0] != 0) {
+        tile_fetch_async(a, k, k + 1, sX);
+        want_panel = false;
+      }
+      if (sPoll[1] != 0) {
+        tile_fetch_async(a, k + 1, k + 1, sC);
+        want_next = false;
+      }
+      cp_async_commit();
+    }
+    const int ci = b0 + 8 + tid;
+    if (ci < FB) {
+      double u[8][8], t[8], inv[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+#pragma unroll
+        for (int q = r + 1; q < 8; ++q) u[r][q] = S[(b0 + r) * FPITCH + b0 + q];
+        t[r]   = S[(b0 + r) * FPITCH + ci];
+        inv[r] = sDinv[b0 + r];
+      }
+      double x[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        double tt = t[r];
+#pragma unroll
+        for (int s = 0; s < r; ++s) tt = fma(-u[s][r], x[s], tt);
+        x[r] = tt * inv[r];
+        S[(b0 + r) * FPITCH + ci] = x[r];
+      }
+    }
+    __syncthreads();
+    trace_ev(a, 6, kb, 1);
+  }
+}
+
+// ---- panel solve in shared memory: sX <- sU^-T sX ----------------------------------------------------------
+// sU: U_kk (pitch FPITCH, identity beyond the valid rows), sD: 1 / U_rr, sX: the tile, solved in place strip by strip.
+__device__ void panel_solve(const FusedArgs &a, const double *sU, double *sX, const double *sD, int width) {
+  const int tid   = threadIdx.x;
   const int w_end = (width + 7) >> 3;
 #pragma unroll 1
   for (int blk = 0; blk < FB / 8; ++blk) {
@@ -378,23 +359,47 @@ __device__ void do_panel(const FusedArgs &a, int k, int J, double *sU, double *s
     __syncthreads();
     trace_ev(a, 7, blk, 1);
   }
-  // write the solved tile back
-  if (isR) {
-    if (tid < nbk) a.rhs[k0 + tid] = sX[tid * FPITCH];
-  } else {
+}
+
+// worker: panel block (k, J), J >= k + 2
+__device__ void do_panel(const FusedArgs &a, int k, int J, double *sU, double *sX, double *sD) {
+  const int tid = threadIdx.x;
+  const int k0  = k * FB;
+  const int nbk = min(FB, a.n - k0);
+  const bool isR = (a.rhs != nullptr) && (J == a.nbc - 1);
+  const int width = isR ? 1 : min(FB, a.n - J * FB);
+  trace_ev(a, 2, k, J);
+  tile_fetch(a, k, J, sX);   // last written by this CTA: fetched while waiting for U_kk
+  wait_flag(a, a.flagD + k);
+  trace_ev(a, 2 + 16, k, J);
+  {
+    double2 tv[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const int chunk = q * FT + tid;
       const int r = chunk >> 5, cc = (chunk & 31) * 2;
+      double2 v = make_double2(0.0, 0.0);
       if (r < nbk) {
-        double *dst = a.M + (size_t) (k0 + r) * a.ldm + J0 + cc;
-        if (cc + 1 < width)
-          *reinterpret_cast<double2 *>(dst) = *reinterpret_cast<const double2 *>(sX + r * FPITCH + cc);
-        else if (cc < width)
-          dst[0] = sX[r * FPITCH + cc];
+        if (cc + 1 < nbk)
+          v = __ldcg(reinterpret_cast<const double2 *>(a.M + (size_t) (k0 + r) * a.ldm + k0 + cc));
+        else if (cc < nbk)
+          v.x = __ldcg(a.M + (size_t) (k0 + r) * a.ldm + k0 + cc);
+      } else {
+        if (cc == r) v.x = 1.0;
+        if (cc + 1 == r) v.y = 1.0;
       }
+      tv[q] = v;
     }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int chunk = q * FT + tid;
+      *reinterpret_cast<double2 *>(sU + (chunk >> 5) * FPITCH + (chunk & 31) * 2) = tv[q];
+    }
+    if (tid < FB) sD[tid] = tid < nbk ? __ldcg(a.dinv + k0 + tid) : 1.0;
   }
+  __syncthreads();
+  panel_solve(a, sU, sX, sD, width);
+  tile_store(a, k, J, sX);
   post_flag(a, a.flagP + k * (a.nb + 1) + J);
   __syncthreads();
   trace_ev(a, 2 + 8, k, J);
@@ -545,7 +550,6 @@ __device__ __forceinline__ void wait_flags_many(const FusedArgs &a, const int *f
   }
   __syncthreads();
 }
-
 // contribution of tile (I, J), J >= I + 2:  part[I][J][r] = sum_c U[I0 + r][J0 + c] x_J[c]
 __device__ void do_backprod(const FusedArgs &a, int I, int J, double *sx) {
   const int tid = threadIdx.x;
@@ -582,149 +586,276 @@ __device__ void do_backprod(const FusedArgs &a, int I, int J, double *sx) {
   trace_ev(a, 5 + 8, I, J);
 }
 
-// x_J = U_JJ^-1 (y_J - sum_{J' >= J+2} part[J][J'] - U[J, J+1] x_{J+1}); the product with the neighbouring
-// block, the one that closes the dependency chain, is done here from a prefetched copy of the tile.
-__device__ void do_backsolve(const FusedArgs &a, int J, double *sU /* [64][65] */, double *sT /* [64][FPITCH] */, double *sy /* [5][64] */) {
+// ---- spine: the serial chain of the factorisation on one SM ----------------------------------------------------
+// S: current diagonal block, sX: panel block (k, k+1), sC: prefetched tile (k+1, k+1)
+__device__ void spine_factor(const FusedArgs &a, double *S, double *sX, double *sC, double *sDinv, int *sBad /* [3]: bad pivot, 2 poll results */) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int J0  = J * FB;
-  const int nbk = min(FB, a.n - J0);
-  const bool has_next = J + 1 < a.nb;
-  const int J1 = J0 + FB;
-  const int w1 = has_next ? min(FB, a.n - J1) : 0;
-  trace_ev(a, 4, J, J);
-  {
+  const int wm = warp >> 2, wn = warp & 3;
+  const int lr = lane & 3, lc = lane >> 2;
+  const int rm = wm * 32, cn = wn * 16;
+  const int nb = a.nb, nbc = a.nbc;
+  if (tid == 0) *sBad = 0;
+  {   // tile (0, 0), identity padded
+    const int nbk = min(FB, a.n);
+    const int r = tid >> 2, cb = (tid & 3) * 16;
     double v[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int cidx = cb + q;
+      v[q] = (r < nbk && cidx < nbk && cidx >= r) ? __ldcg(a.M + (size_t) r * a.ldm + cidx) : ((r == cidx && r >= nbk) ? 1.0 : 0.0);
+    }
+#pragma unroll
+    for (int q = 0; q < 16; ++q) S[r * FPITCH + cb + q] = v[q];
+  }
+  __syncthreads();
+  for (int k = 0; k < nb; ++k) {
+    const bool has_panel = k + 1 < nbc;
+    const bool has_next  = k + 1 < nb;
+    const bool panel_isR = has_panel && (a.rhs != nullptr) && (k + 1 == nbc - 1);
+    // tiles the workers owe us: (k, k+1) with all updates of the phases < k, (k+1, k+1) with those of the phases < k;
+    // both are fetched from inside the factorisation as soon as their flags are seen
+    bool want_panel = has_panel && !panel_isR, want_next = has_next;
+    if (want_panel && k == 0) {
+      tile_fetch_async(a, k, k + 1, sX);
+      want_panel = false;
+    }
+    if (want_next && k + 1 < 2) {
+      tile_fetch_async(a, k + 1, k + 1, sC);
+      want_next = false;
+    }
+    cp_async_commit();
+    trace_ev(a, 1, k, k);
+    diag_factor(a, S, sDinv, sBad, k * FB, k, want_panel, want_next, sX, sC, sBad + 1);
+    diag_store(a, k, S, sDinv);
+    if (tid == 0 && *sBad != 0) atomicCAS(a.info, 0, *sBad);
+    post_flag(a, a.flagD + k);
+    trace_ev(a, 1 + 8, k, k);
+    if (has_panel) {
+      trace_ev(a, 2, k, k + 1);
+      if (panel_isR) {
+        if (k > 0) wait_flag(a, a.flagTs + k);
+        tile_fetch(a, k, k + 1, sX);
+      } else if (want_panel) {
+        wait_flag(a, a.flagTs + k);
+        tile_fetch_async(a, k, k + 1, sX);
+        cp_async_commit();
+        cp_async_wait<0>();
+      } else {
+        cp_async_wait<0>();   // in flight or landed (together with the next diagonal tile if that was requested too)
+      }
+      __syncthreads();
+      trace_ev(a, 2 + 16, k, k + 1);
+      const int width = panel_isR ? 1 : min(FB, a.n - (k + 1) * FB);
+      panel_solve(a, S, sX, sDinv, width);
+      tile_store(a, k, k + 1, sX);
+      post_flag(a, a.flagP + k * (nb + 1) + k + 1);
+      trace_ev(a, 2 + 8, k, k + 1);
+    }
+    if (has_next) {
+      // S <- tile (k+1, k+1) - U[k, k+1]^T U[k, k+1], identity padded
+      trace_ev(a, 3, k + 1, k + 1);
+      if (want_next) {
+        if (k + 1 >= 2) wait_flag(a, a.flagTd + k + 1);
+        tile_fetch_async(a, k + 1, k + 1, sC);
+        cp_async_commit();
+      }
+      cp_async_wait<0>();
+      __syncthreads();
+      const int I0 = (k + 1) * FB;
+      const int hI = min(FB, a.n - I0);
+      double acc[4][2][2];
+#pragma unroll
+      for (int am = 0; am < 4; ++am)
+#pragma unroll
+        for (int bn = 0; bn < 2; ++bn) {
+          const double2 v = *reinterpret_cast<const double2 *>(sC + (rm + am * 8 + lc) * FPITCH + cn + bn * 8 + 2 * lr);
+          acc[am][bn][0]  = v.x;
+          acc[am][bn][1]  = v.y;
+        }
+#pragma unroll
+      for (int ks = 0; ks < FB / 4; ++ks) {
+        double af[4], bf[2];
+        const double *pa = sX + (ks * 4 + lr) * FPITCH + rm + lc;
+        const double *pb = sX + (ks * 4 + lr) * FPITCH + cn + lc;
+#pragma unroll
+        for (int am = 0; am < 4; ++am) af[am] = -pa[am * 8];
+#pragma unroll
+        for (int bn = 0; bn < 2; ++bn) bf[bn] = pb[bn * 8];
+#pragma unroll
+        for (int am = 0; am < 4; ++am)
+#pragma unroll
+          for (int bn = 0; bn < 2; ++bn) dmma884(acc[am][bn][0], acc[am][bn][1], af[am], bf[bn]);
+      }
+#pragma unroll
+      for (int am = 0; am < 4; ++am)
+#pragma unroll
+        for (int bn = 0; bn < 2; ++bn)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int ti = rm + am * 8 + lc, tj = cn + bn * 8 + 2 * lr + e;
+            S[ti * FPITCH + tj] = (ti < hI && tj < hI) ? acc[am][bn][e] : (ti == tj ? 1.0 : 0.0);
+          }
+      __syncthreads();
+      trace_ev(a, 3 + 8, k + 1, k + 1);
+    }
+  }
+}
+
+// ---- spine: the serial chain of the back substitution ----------------------------------------------------------
+// x_J = U_JJ^-1 (y_J - sum_{J' >= J+2} part[J][J'] - U[J, J+1] x_{J+1}); x_{J+1} never leaves shared memory and the two
+// tiles of the next step are fetched while this one waits for the workers' contributions.
+__device__ void spine_backsolve(const FusedArgs &a, double *bufU0, double *bufU1, double *bufT0, double *bufT1, double *sy /* [6][64] */) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nb = a.nb;
+  double *sxp = sy + 5 * FB;   // x_{J+1}
+  auto fetchU = [&](int J, double (&v)[16]) {
+    const int J0 = J * FB, nbk = min(FB, a.n - J0);
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
       const int e = q * FT + tid, r = e >> 6, cidx = e & 63;
       v[q] = (r < nbk && cidx < nbk && cidx >= r) ? __ldcg(a.M + (size_t) (J0 + r) * a.ldm + J0 + cidx) : 0.0;
     }
+  };
+  auto storeU = [&](double *sU, const double (&v)[16]) {
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
       const int e = q * FT + tid;
       sU[(e >> 6) * (FB + 1) + (e & 63)] = v[q];
     }
+  };
+  {
+    double v[16];
+    fetchU(nb - 1, v);
+    storeU(bufU0, v);
   }
-  if (has_next) {   // tile (J, J+1): rows of block J are always full when a next block exists
-    wait_flag(a, a.flagP + J * (a.nb + 1) + J + 1);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int chunk = q * FT + tid;
-      const int r = chunk >> 5, cc = (chunk & 31) * 2;
-      const int gc = J1 + cc;
-      int bytes    = (a.n - gc) * 8;
-      bytes        = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
-      const double *src = bytes > 0 ? a.M + (size_t) (J0 + r) * a.ldm + gc : a.M;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(sT + r * FPITCH + cc)), "l"(src), "r"(bytes) : "memory");
+  if (tid < FB) sxp[tid] = 0.0;
+  __syncthreads();
+  for (int J = nb - 1; J >= 0; --J) {
+    const int cur = (nb - 1 - J) & 1;
+    double *sU = cur ? bufU1 : bufU0, *sUn = cur ? bufU0 : bufU1;
+    double *sT = cur ? bufT1 : bufT0, *sTn = cur ? bufT0 : bufT1;
+    const int J0  = J * FB;
+    const int nbk = min(FB, a.n - J0);
+    const bool has_next = J + 1 < nb;     // block J+1 exists: x_{J+1} in sxp, tile (J, J+1) in sT
+    trace_ev(a, 4, J, J);
+    double vn[16];
+    if (J > 0) {
+      fetchU(J - 1, vn);
+      tile_fetch_async(a, J - 1, J, sTn);
     }
     cp_async_commit();
-  }
-  wait_flag(a, a.flagP + J * (a.nb + 1) + (a.nbc - 1));   // y_J is final
-  wait_flags_many(a, a.flagQ + J * a.nb + J + 2, a.nb - J - 2);
-  {
-    // y_J - sum of the contributions, 4 groups of blocks summed independently, then combined in a fixed order
-    const int r = tid & 63, g = tid >> 6;
-    double v[16];
+    wait_flag(a, a.flagP + J * (nb + 1) + (a.nbc - 1));   // y_J is final
+    wait_flags_many(a, a.flagQ + J * nb + J + 2, nb - J - 2);
+    trace_ev(a, 4 + 16, J, J);
+    {
+      const int r = tid & 63, g = tid >> 6;
+      double v[16];
 #pragma unroll
-    for (int q = 0; q < 16; ++q) {
-      const int Jp = J + 2 + g + 4 * q;
-      v[q]         = Jp < a.nb ? __ldcg(a.part + ((size_t) J * a.nb + Jp) * FB + r) : 0.0;
+      for (int q = 0; q < 16; ++q) {
+        const int Jp = J + 2 + g + 4 * q;
+        v[q]         = Jp < nb ? __ldcg(a.part + ((size_t) J * nb + Jp) * FB + r) : 0.0;
+      }
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) s += v[q];
+      sy[(1 + g) * FB + r] = s;
     }
-    double s = 0.0;
+    cp_async_wait<1>();   // tile (J, J+1), issued one step ago
+    __syncthreads();
+    {
+      const int r = tid >> 2, q = tid & 3;
+      double s = 0.0;
+      if (has_next) {
 #pragma unroll
-    for (int q = 0; q < 16; ++q) s += v[q];
-    sy[(1 + g) * FB + r] = s;
+        for (int e = 0; e < 16; ++e) s = fma(sT[r * FPITCH + q * 16 + e], sxp[q * 16 + e], s);
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (q == 0) {
+        const double y = r < nbk ? __ldcg(a.rhs + J0 + r) : 0.0;
+        sy[r] = (((y - sy[FB + r]) - sy[2 * FB + r]) - sy[3 * FB + r]) - sy[4 * FB + r] - s;
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {
+      double y0 = lane < nbk ? sy[lane] : 0.0, y1 = lane + 32 < nbk ? sy[lane + 32] : 0.0;
+      const double d0 = lane < nbk ? __ldcg(a.dinv + J0 + lane) : 1.0, d1 = lane + 32 < nbk ? __ldcg(a.dinv + J0 + lane + 32) : 1.0;
+#pragma unroll 8
+      for (int r = FB - 1; r >= 32; --r) {
+        const double xr = __shfl_sync(0xffffffffu, y1 * d1, r - 32);
+        if (lane + 32 == r) y1 = xr;
+        if (lane + 32 < r) y1 = fma(-sU[(lane + 32) * (FB + 1) + r], xr, y1);
+        y0 = fma(-sU[lane * (FB + 1) + r], xr, y0);
+      }
+#pragma unroll 8
+      for (int r = 31; r >= 0; --r) {
+        const double xr = __shfl_sync(0xffffffffu, y0 * d0, r);
+        if (lane == r) y0 = xr;
+        if (lane < r) y0 = fma(-sU[lane * (FB + 1) + r], xr, y0);
+      }
+      if (lane < nbk) a.rhs[J0 + lane] = y0;
+      if (lane + 32 < nbk) a.rhs[J0 + lane + 32] = y1;
+      sxp[lane]      = lane < nbk ? y0 : 0.0;
+      sxp[lane + 32] = lane + 32 < nbk ? y1 : 0.0;
+    }
+    if (J > 0) storeU(sUn, vn);
+    post_flag(a, a.flagX + J);
+    __syncthreads();
+    trace_ev(a, 4 + 8, J, J);
   }
-  if (has_next) wait_flag(a, a.flagX + J + 1);
-  trace_ev(a, 4 + 16, J, J);
-  if (tid < FB) sy[tid] = (has_next && tid < w1) ? __ldcg(a.rhs + J1 + tid) : 0.0;   // x_{J+1}
   cp_async_wait<0>();
-  __syncthreads();
-  {
-    const int r = tid >> 2, q = tid & 3;
-    double s = 0.0;
-    if (has_next) {
-#pragma unroll
-      for (int e = 0; e < 16; ++e) s = fma(sT[r * FPITCH + q * 16 + e], sy[q * 16 + e], s);
-    }
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    __syncthreads();   // everyone has read x_{J+1} from sy[0..63]
-    if (q == 0) {
-      const double y = r < nbk ? __ldcg(a.rhs + J0 + r) : 0.0;
-      sy[r] = (((y - sy[FB + r]) - sy[2 * FB + r]) - sy[3 * FB + r]) - sy[4 * FB + r] - s;
-    }
-  }
-  __syncthreads();
-  if (warp == 0) {
-    double y0 = lane < nbk ? sy[lane] : 0.0, y1 = lane + 32 < nbk ? sy[lane + 32] : 0.0;
-    const double d0 = lane < nbk ? __ldcg(a.dinv + J0 + lane) : 1.0, d1 = lane + 32 < nbk ? __ldcg(a.dinv + J0 + lane + 32) : 1.0;
-#pragma unroll 8
-    for (int r = FB - 1; r >= 32; --r) {
-      const double xr = __shfl_sync(0xffffffffu, y1 * d1, r - 32);
-      if (lane + 32 == r) y1 = xr;
-      if (lane + 32 < r) y1 = fma(-sU[(lane + 32) * (FB + 1) + r], xr, y1);
-      y0 = fma(-sU[lane * (FB + 1) + r], xr, y0);
-    }
-#pragma unroll 8
-    for (int r = 31; r >= 0; --r) {
-      const double xr = __shfl_sync(0xffffffffu, y0 * d0, r);
-      if (lane == r) y0 = xr;
-      if (lane < r) y0 = fma(-sU[lane * (FB + 1) + r], xr, y0);
-    }
-    if (lane < nbk) a.rhs[J0 + lane] = y0;
-    if (lane + 32 < nbk) a.rhs[J0 + lane + 32] = y1;
-  }
-  post_flag(a, a.flagX + J);
-  __syncthreads();
-  trace_ev(a, 4 + 8, J, J);
 }
+
 
 __global__ void __launch_bounds__(FT, 1) chol_fused_kernel(const FusedArgs a) {
   extern __shared__ __align__(16) double fsm[];
-  double *sA    = fsm;                      // [64][68]   operand A / U_kk of the panel solve / U_JJ of the back solve
-  double *sB    = sA + FB * FPITCH;         // [64][68]   operand B
-  double *S     = sB + FB * FPITCH;         // [64][68]   diagonal block
-  double *sDinv = S + FB * FPITCH;          // [64]
-  double *sVec  = sDinv + FB;               // [5][64]
-  int *sBad     = reinterpret_cast<int *>(sVec + 5 * FB);
-  const int G = gridDim.x, bid = blockIdx.x;
+  double *b0    = fsm;                      // four [64][68] tile buffers
+  double *b1    = b0 + FB * FPITCH;
+  double *b2    = b1 + FB * FPITCH;
+  double *b3    = b2 + FB * FPITCH;
+  double *sDinv = b3 + FB * FPITCH;         // [64]
+  double *sVec  = sDinv + FB;               // [6][64]
+  int *sBad     = reinterpret_cast<int *>(sVec + 6 * FB);
+  const int bid = blockIdx.x;
+  const int Gw  = gridDim.x - 1;            // workers
   const int nb = a.nb, nbc = a.nbc;
-  const int T = row_start(nb, nbc);
+  const int T  = row_start(nb, nbc);
 
-  if (bid == 0) do_diag(a, 0, false, S, sDinv, sBad);
+  if (bid == 0) {
+    spine_factor(a, b0, b1, b2, sDinv, sBad);
+    if (a.rhs != nullptr) spine_backsolve(a, b0, b1, b2, b3, sVec);
+    return;
+  }
+  const int me = bid - 1;
   for (int k = 0; k < nb; ++k) {
-    // panels of block row k
-    {
+    {   // panels of block row k; (k, k+1) is the spine's
       const int t0 = row_start(k, nbc);
-      for (int J = k + 1; J < nbc; ++J)
-        if ((t0 + (J - k)) % G == bid) do_panel(a, k, J, sA, sB, sDinv);
+      for (int J = k + 2; J < nbc; ++J)
+        if ((t0 + (J - k)) % Gw == me) do_panel(a, k, J, b0, b1, sDinv);
     }
-    // updates with block row k, in tile order: block row k + 1 (next diagonal block and next panels) comes first
-    if (k + 1 < nb) {
+    if (k + 1 < nb) {   // updates with block row k, in tile order; (k+1, k+1) is the spine's
       const int t1 = row_start(k + 1, nbc);
-      int t        = t1 + ((bid - t1) % G + G) % G;
+      int t        = t1 + ((me - t1) % Gw + Gw) % Gw;
       int I        = k + 1;
-      for (; t < T; t += G) {
+      for (; t < T; t += Gw) {
         while (t >= row_start(I + 1, nbc)) ++I;
-        const int J      = I + (t - row_start(I, nbc));
-        const bool isdiag = (I == k + 1 && J == k + 1);
-        do_update(a, k, I, J, sA, sB, S, isdiag);
-        if (isdiag) do_diag(a, k + 1, true, S, sDinv, sBad);
+        const int J = I + (t - row_start(I, nbc));
+        if (I == k + 1 && J == k + 1) continue;
+        do_update(a, k, I, J, b0, b1, b2, false);
+        if (J == I && I == k + 2) post_flag(a, a.flagTd + I);        // the spine applies phase I-1 itself
+        if (J == I + 1 && I == k + 1) post_flag(a, a.flagTs + I);    // ready for the spine's panel solve
       }
     }
   }
   if (a.rhs == nullptr) return;
-  for (int J = nb - 1; J >= 0; --J) {
-    if (row_start(J, nbc) % G == bid) do_backsolve(a, J, sA, sB, sVec);
+  for (int J = nb - 1; J >= 2; --J)
     for (int I = J - 2; I >= 0; --I)
-      if ((row_start(I, nbc) + (J - I)) % G == bid) do_backprod(a, I, J, sVec);
-  }
+      if ((row_start(I, nbc) + (J - I)) % Gw == me) do_backprod(a, I, J, sVec);
 }
 
 }   // namespace
 
-static constexpr size_t FUSED_SMEM = (size_t) (3 * FB * FPITCH + 6 * FB) * sizeof(double) + 16;
+static constexpr size_t FUSED_SMEM = (size_t) (4 * FB * FPITCH + 7 * FB) * sizeof(double) + 16;
 
 // Largest order served by the single-launch path (flags and the contribution buffer are sized for it).
 int chol_fused_max_n() { return 4096; }
@@ -736,7 +867,7 @@ int dpotrf_upper_solve_fused(ncm_sd_gpu_ctx *c, int n, double *dM, int ldm, doub
   const int nb  = (n + FB - 1) / FB;
   const int nbc = nb + (dRhs != nullptr ? 1 : 0);
   const int nbm = chol_fused_max_n() / FB;
-  const size_t n_flags = (size_t) nbm + (size_t) nbm * (nbm + 1) + nbm + (size_t) nbm * nbm + 8;
+  const size_t n_flags = (size_t) nbm + (size_t) nbm * (nbm + 1) + nbm + (size_t) nbm * nbm + 2 * nbm + 8;
   if (c->chol_flags.cap == 0) {
     if (!c->chol_flags.reserve(n_flags * sizeof(int))) return c->fail(NCM_SD_GPU_ENOMEM, "chol_fused: out of device memory");
     NCM_CUDA_OK(c, cudaMemsetAsync(c->chol_flags.p, 0, c->chol_flags.cap, c->stream));
@@ -758,6 +889,8 @@ int dpotrf_upper_solve_fused(ncm_sd_gpu_ctx *c, int n, double *dM, int ldm, doub
   a.flagP = a.flagD + nbm;
   a.flagX = a.flagP + (size_t) nbm * (nbm + 1);
   a.flagQ = a.flagX + nbm;
+  a.flagTd = a.flagQ + (size_t) nbm * nbm;
+  a.flagTs = a.flagTd + nbm;
   a.epoch = ++c->chol_epoch;
   a.nb = nb; a.nbc = nbc;
   a.trace = c->chol_trace; a.trace_cap = c->chol_trace_cap;
