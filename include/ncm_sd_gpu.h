@@ -159,6 +159,11 @@ int ncm_sd_gpu_reset_timers (ncm_sd_gpu_ctx *ctx);
 int ncm_sd_gpu_get_traffic (ncm_sd_gpu_ctx *ctx, long long *h2d_bytes, long long *d2h_bytes);
 int ncm_sd_gpu_enable_timers (ncm_sd_gpu_ctx *ctx, int enable);
 
+/* which VKDE evaluation kernel serves the uploaded factors: 1 = DMMA path with explicit inverses (d >= 13 and
+ * max_i cond_1 (U_i) <= 1e5, reported in cond_max), 0 = forward substitution (vkde.cu).  Both replace
+ * ncm_stats_dist_vkde.c:631-723 / :517-606. */
+int ncm_sd_gpu_vkde_path (ncm_sd_gpu_ctx *ctx, int *uses_mma, double *cond_max);
+
 /* plain FP64 building blocks exported for tests and microbenchmarks (device pointers) */
 int ncm_sd_gpu_dsyrk_ata_dev (ncm_sd_gpu_ctx *ctx, int nrows, int ncols, const double *dA, int lda, double *dM, int ldm);
 int ncm_sd_gpu_dpotrf_upper_dev (ncm_sd_gpu_ctx *ctx, int n, double *dM, int ldm, int *info_host);

@@ -28,7 +28,7 @@ SYMBOLS = (
     "ncm_sd_gpu_compute_IM", "ncm_sd_gpu_nnls_solve", "ncm_sd_gpu_nnls_solve_host", "ncm_sd_gpu_sample_apply", "ncm_sd_gpu_sample_philox",
     "ncm_sd_gpu_comm_unique_id", "ncm_sd_gpu_comm_init", "ncm_sd_gpu_set_row_shard", "ncm_sd_gpu_get_timers", "ncm_sd_gpu_reset_timers",
     "ncm_sd_gpu_enable_timers", "ncm_sd_gpu_get_traffic", "ncm_sd_gpu_dsyrk_ata_dev", "ncm_sd_gpu_dpotrf_upper_dev",
-    "ncm_sd_gpu_vkde_prepare", "ncm_sd_gpu_vkde_finish", "ncm_sd_gpu_dposv_upper_dev",
+    "ncm_sd_gpu_vkde_prepare", "ncm_sd_gpu_vkde_finish", "ncm_sd_gpu_dposv_upper_dev", "ncm_sd_gpu_vkde_path",
 )
 
 
@@ -95,6 +95,7 @@ def load():
             "ncm_sd_gpu_dsyrk_ata_dev": (i, [vp, i, i, vp, i, vp, i]),
             "ncm_sd_gpu_dpotrf_upper_dev": (i, [vp, i, vp, i, _ip]),
             "ncm_sd_gpu_dposv_upper_dev": (i, [vp, i, vp, i, vp, _ip]),
+            "ncm_sd_gpu_vkde_path": (i, [vp, _ip, _dp]),
         }
         for name, (res, args) in sig.items():
             f = getattr(L, name)
@@ -288,6 +289,12 @@ class Context:
 
     def dsyrk_ata_dev(self, nrows, ncols, dA_ptr, lda, dM_ptr, ldm):
         self._ck(load().ncm_sd_gpu_dsyrk_ata_dev(self._h, nrows, ncols, dA_ptr, lda, dM_ptr, ldm))
+
+    def vkde_path(self):
+        """(uses_mma, max cond_1 of the factors) of the last VKDE upload."""
+        m, cnd = C.c_int(), C.c_double()
+        self._ck(load().ncm_sd_gpu_vkde_path(self._h, C.byref(m), C.byref(cnd)))
+        return bool(m.value), cnd.value
 
     def dposv_upper_dev(self, n, dM_ptr, ldm, dRhs_ptr) -> int:
         info = C.c_int()

@@ -69,6 +69,37 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, const double a, 
                : "d"(a), "d"(b));
 }
 
+// ---- exp for non-positive arguments ------------------------------------------------------------------------
+// The log-sum-exp terms exp(-|t - m|) and the Gaussian kernel exp(-chi2/2) are the most expensive FP64 operation of
+// the path (libdevice exp: ~21 DFMA issue slots measured, tools/microbench/fp64_peaks.cu).  Here: k = rint(x log2 e) by
+// the magic-number add, r = (x - k ln 2) / 4 in two FMAs (Cody-Waite), degree-9 Taylor polynomial on |r| <= 0.087
+// (truncation 7e-18), two squarings, exponent patched in with integer adds: 15 FP64 operations, relative error <= 9e-16
+// (tools/check_fast_exp.py).  Results below 2^-1020 are flushed to zero (they can never reach a sum that contains the
+// arg-max term 1, and the kernel-matrix entries are compared relative to their maximum).
+__device__ __forceinline__ double exp_nonpos_fast(const double x) {
+  const double MAGIC = 6755399441055744.0;   // 1.5 * 2^52
+  const double t  = fma(x, 1.4426950408889634074, MAGIC);
+  const int k     = __double2loint(t);
+  const double kf = t - MAGIC;
+  double r = fma(kf, -6.93147180369123816490e-01, x);
+  r        = fma(kf, -1.90821492927058770002e-10, r);
+  r *= 0.25;
+  double p = 2.75573192239858906526e-06;           // 1/9!
+  p = fma(p, r, 2.48015873015873015873e-05);        // 1/8!
+  p = fma(p, r, 1.98412698412698412698e-04);        // 1/7!
+  p = fma(p, r, 1.38888888888888888889e-03);        // 1/6!
+  p = fma(p, r, 8.33333333333333333333e-03);        // 1/5!
+  p = fma(p, r, 4.16666666666666666667e-02);        // 1/4!
+  p = fma(p, r, 1.66666666666666666667e-01);        // 1/3!
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  p *= p;
+  p *= p;
+  const double v = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+  return (x > -707.0) ? v : 0.0;   // also covers x = -inf (ln of a zero weight); k >= -1020 whenever x > -707
+}
+
 // ---- log-sum-exp state -----------------------------------------------------------------------------
 // (m, s): log-sum = m + log(s), s counts the arg-max term as 1 (the reference returns
 // gamma = m and lambda = s - 1, ncm_stats_dist_kernel_gauss.c:246-289).
@@ -83,7 +114,7 @@ __device__ __forceinline__ void lse_init(Lse &a) {
 
 __device__ __forceinline__ void lse_push(Lse &a, const double t) {
   const double d = t - a.m;
-  const double e = exp(-fabs(d));
+  const double e = exp_nonpos_fast(-fabs(d));
   if (d > 0.0) {
     a.s = fma(a.s, e, 1.0);
     a.m = t;
@@ -94,7 +125,7 @@ __device__ __forceinline__ void lse_push(Lse &a, const double t) {
 
 __device__ __forceinline__ void lse_merge(Lse &a, const double m2, const double s2) {
   const double d = m2 - a.m;
-  const double e = exp(-fabs(d));
+  const double e = exp_nonpos_fast(-fabs(d));
   if (d > 0.0) {
     a.s = fma(a.s, e, s2);
     a.m = m2;
@@ -125,5 +156,5 @@ __device__ __forceinline__ double kern_lnK(const KernParams &kp, const double ch
 }
 // Kbar(chi2) as the reference evaluates it (eval_unnorm): exp(-chi2/2) or pow(1 + chi2/nu, kappa)
 __device__ __forceinline__ double kern_K(const KernParams &kp, const double chi2) {
-  return kp.kind == 0 ? exp(-0.5 * chi2) : pow(1.0 + chi2 * kp.inv_nu, kp.kappa);
+  return kp.kind == 0 ? exp_nonpos_fast(-0.5 * chi2) : pow(1.0 + chi2 * kp.inv_nu, kp.kappa);
 }

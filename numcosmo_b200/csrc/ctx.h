@@ -50,6 +50,10 @@ struct ncm_sd_gpu_ctx {
   DevBuf sample;     // [n_obs x d] raw points (row-major, ld = d)
   DevBuf vrec;       // [n_kernels x vrec_len] packed records: theta[dp], Lp[dp(dp+1)/2] (diag = 1/U_kk)
   int vrec_len = 0;
+  DevBuf vrec_mma;   // tensor-core records (vkde_mma.cu): theta[dp], W = L^-1 in DMMA fragment order
+  int vrec_mma_len = 0;
+  bool vkde_mma = false;      // the tensor-core path serves eval / IM (d >= 13 and max cond below VKDE_MMA_MAX_COND)
+  double vkde_cond = 0.0;     // max_i |L_i|_1 |L_i^-1|_1 of the last pack
   DevBuf lnu;        // [n_kernels] per-kernel lnnorm (VKDE) -- without d ln h
   DevBuf cterm;      // [n_kernels] ln w_i - lnu_i
   DevBuf weights;    // [n_kernels]
@@ -135,6 +139,10 @@ struct StageTimer {
 int vkde_pad_dim(int d);
 int vkde_pack(ncm_sd_gpu_ctx *c, const double *dU_all /* n x d x d */);
 int vkde_prepare_dev(ncm_sd_gpu_ctx *c, int n_obs, int n_kernels, int k, const double *dZ, const double *dX, int *dNbr, double *dU_all, int *dFail);
+int vkde_mma_pad_dim(int d);
+int vkde_mma_pack(ncm_sd_gpu_ctx *c, const double *dU_all, double *cond_max_host);
+int vkde_mma_eval_launch(ncm_sd_gpu_ctx *c, int q, const double *dX, int ldx, double *dOut, bool as_density);
+int vkde_mma_im_launch(ncm_sd_gpu_ctx *c, const double *dInvNorm, const double *dRowScale);
 int vkde_eval_launch(ncm_sd_gpu_ctx *c, int q, const double *dX, int ldx, double *dOut, bool as_density);
 int vkde_im_launch(ncm_sd_gpu_ctx *c, const double *dRowScale);
 

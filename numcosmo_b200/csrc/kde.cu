@@ -242,14 +242,14 @@ __global__ void __launch_bounds__(KDE_THREADS) kde_kernel(const KdeArgs a) {
 #pragma unroll
         for (int ni = 0; ni < NI; ++ni) bm = fmax(bm, fmax(acc[mi][ni][0], acc[mi][ni][1]));
         if (bm > st[mi].m) {
-          st[mi].s *= exp(st[mi].m - bm);
+          st[mi].s *= exp_nonpos_fast(st[mi].m - bm);
           st[mi].m = bm;
         }
         double s0 = 0.0, s1 = 0.0;
 #pragma unroll
         for (int ni = 0; ni < NI; ++ni) {
-          s0 += exp(acc[mi][ni][0] - st[mi].m);
-          s1 += exp(acc[mi][ni][1] - st[mi].m);
+          s0 += exp_nonpos_fast(acc[mi][ni][0] - st[mi].m);
+          s1 += exp_nonpos_fast(acc[mi][ni][1] - st[mi].m);
         }
         st[mi].s += s0 + s1;
       }
@@ -263,8 +263,8 @@ __global__ void __launch_bounds__(KDE_THREADS) kde_kernel(const KdeArgs a) {
             const int col = c0 + ni * 8 + 2 * lr;
             double k0, k1;
             if (MODE == 1) {
-              k0 = exp(acc[mi][ni][0]);
-              k1 = exp(acc[mi][ni][1]);
+              k0 = exp_nonpos_fast(acc[mi][ni][0]);
+              k1 = exp_nonpos_fast(acc[mi][ni][1]);
             } else {
               k0 = pow(1.0 + acc[mi][ni][0], a.kp.kappa);
               k1 = pow(1.0 + acc[mi][ni][1], a.kp.kappa);

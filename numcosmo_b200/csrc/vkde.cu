@@ -10,7 +10,11 @@
 // the forward substitution in registers, then the kernel function and an online
 // log-sum-exp.  The centre range is split across gridDim.y so that small query batches
 // still fill 148 SMs; partial (max, sum) pairs are merged by lse_finalize_kernel.
+#include <cstdlib>
+#include <cstring>
 #include "ctx.h"
+
+static constexpr double VKDE_MMA_MAX_COND = 1.0e5;   // see vkde_mma.cu: chi2 then stays within ~1e5 eps of the substitution
 
 namespace {
 
@@ -209,6 +213,16 @@ int vkde_pack(ncm_sd_gpu_ctx *c, const double *dU_all) {
                                                       c->vrec_len);
   c->n_launches++;
   NCM_CUDA_OK(c, cudaGetLastError());
+  // tensor-core path (vkde_mma.cu) for d >= 13 when every factor is conditioned well enough for its explicit inverse;
+  // $NCM_SD_GPU_VKDE = subst | mma overrides the choice (parity experiments)
+  c->vkde_mma = false;
+  static const char *force = getenv("NCM_SD_GPU_VKDE");
+  const bool no_mma = force != nullptr && strcmp(force, "subst") == 0;
+  if (vkde_mma_pad_dim(c->d) != 0 && !no_mma) {
+    int rc = vkde_mma_pack(c, dU_all, &c->vkde_cond);
+    if (rc != NCM_SD_GPU_OK) return rc;
+    c->vkde_mma = (c->vkde_cond <= VKDE_MMA_MAX_COND) || (force != nullptr && strcmp(force, "mma") == 0);
+  }
   return NCM_SD_GPU_OK;
 }
 
@@ -251,6 +265,7 @@ static int pick_splits(const ncm_sd_gpu_ctx *c, int q_tiles, int n, int ch, int 
 }
 
 int vkde_eval_launch(ncm_sd_gpu_ctx *c, int q, const double *dX, int ldx, double *dOut, bool as_density) {
+  if (c->vkde_mma) return vkde_mma_eval_launch(c, q, dX, ldx, dOut, as_density);
   const int dp      = c->dp;
   const int ch      = vkde_ch(c, dp);
   const int q_tiles = (q + 127) / 128;
@@ -286,6 +301,7 @@ int vkde_im_launch(ncm_sd_gpu_ctx *c, const double *dRowScale) {
   vkde_invnorm_kernel<<<(c->n_kernels + 255) / 256, 256, 0, c->stream>>>(c->lnu.as<double>(), c->n_kernels, c->d * log(c->href),
                                                                         c->nn_tmp.as<double>());
   c->n_launches++;
+  if (c->vkde_mma) return vkde_mma_im_launch(c, c->nn_tmp.as<double>(), dRowScale);
   const int q_tiles = (q + 127) / 128;
   int splits        = pick_splits(c, q_tiles, c->n_kernels, ch, 4);
   int per_split     = ((c->n_kernels + splits - 1) / splits + ch - 1) / ch * ch;

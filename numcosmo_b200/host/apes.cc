@@ -192,10 +192,12 @@ void setup_block(NcmFitESMCMCWalkerAPES *a, int block, const double *lb, const d
   memcpy(ncm_matrix_data(Q), &a->thetastar[(size_t) ki * d], sizeof(double) * nb * d);
   memcpy(ncm_matrix_data(Q) + (size_t) nb * d, &theta[(size_t) ki * d], sizeof(double) * nb * d);
   ncm_stats_dist_eval_m2lnp_array(sd, Q, out);
-  for (guint k = ki; k < kf; k++) {
+  // per-walker and independent (erf-heavy when the random-walk mixture is on): threads change nothing in the values
+#pragma omp parallel for schedule(static) if (a->use_threads)
+  for (long k = (long) ki; k < (long) kf; k++) {
     const double *th = &theta[(size_t) k * d], *ts = &a->thetastar[(size_t) k * d];
-    a->m2lnp_star[k] = transition_prob(a, rw, th, ts, ncm_vector_get(out, k - ki));
-    a->m2lnp_cur[k]  = transition_prob(a, rw, ts, th, ncm_vector_get(out, nb + k - ki));
+    a->m2lnp_star[k] = transition_prob(a, rw, th, ts, ncm_vector_get(out, (guint) (k - ki)));
+    a->m2lnp_cur[k]  = transition_prob(a, rw, ts, th, ncm_vector_get(out, (guint) (nb + k - ki)));
   }
   ncm_matrix_free(Q);
   ncm_vector_free(out);

@@ -142,3 +142,30 @@ def test_empty_and_errors(gpu_ctx):
     with pytest.raises(capi.GpuError):
         ctx.set_kernel(capi.KERNEL_GAUSS, 1.0, 64)  # dimension out of range
     ctx.close()
+
+
+@pytest.mark.parametrize("d,n,k_s", [(21, 640, "gauss"), (24, 700, "st"), (27, 555, "st"), (30, 700, "gauss"), (32, 650, "gauss")])
+def test_vkde_tensor_core_path(oracle, gpu_ctx, d, n, k_s):
+    """d >= 21 is served by the DMMA kernel (vkde_mma.cu, explicit inverses gated on the condition number):
+    eval and IM against the oracle at the north-star tolerance, ragged sizes, exact-zero weights."""
+    from numcosmo_b200 import capi
+
+    kernel = oracle.KERNEL_GAUSS if k_s == "gauss" else oracle.KERNEL_ST
+    mu, cov, X, m2lnL = mvnd_problem(oracle, d, n, seed=500 + d)
+    sd = make_sd(oracle, oracle.SD_VKDE, kernel, 3.0, X, local_frac=0.15)
+    rs = np.random.default_rng(d)
+    w = rs.uniform(size=n)
+    w[rs.uniform(size=n) < 0.1] = 0.0
+    w /= w.sum()
+    href = upload_from_oracle(gpu_ctx, capi, oracle, sd, oracle.SD_VKDE, kernel, 3.0, X, weights=w)
+    uses_mma, cond = gpu_ctx.vkde_path()
+    assert uses_mma and cond < 1e5, (uses_mma, cond)
+    sd.set_weights(w)
+    Q = np.vstack([X[:77] + 0.01, mu + 3.0 * (X[77:200] - mu), X[:5]])
+    assert rel_err(gpu_ctx.eval_m2lnp(Q), sd.eval_m2lnp_batch(Q, 4)) < TOL
+    IM = gpu_ctx.compute_IM(None, fetch=True, nrows=n)
+    IM_ref = sd.compute_IM()
+    scale = np.abs(IM_ref).max()
+    assert np.max(np.abs(IM - IM_ref)) < 1e-12 * scale
+    big = np.abs(IM_ref) > 1e-200 * scale
+    assert np.max(np.abs(IM[big] - IM_ref[big]) / np.abs(IM_ref[big])) < 1e-9
