@@ -354,15 +354,25 @@ def run_b200(args):
     syrk_flops = float(rows_local) * N * N                 # n_obs . n_kernels^2, one SYRK launch per half-step
     syrk_ach = 2.0 * syrk_flops / (tm["syrk"] * 1e-3) / 1e12
     P64 = peaks["fp64_dgemm_tflops"]
-    roofline = {"bound": "tensor", "kernel": "blocked Cholesky solve of the NNLS passive-set systems (chol_diag_kernel + chol_panel_kernel + "
-                                             "ata_kernel<AtaSmall,SUBC> trailing updates + chol_backsolve_kernel)",
-                "achieved": chol_ach, "peak": P64, "unit": "TFLOP/s", "frac": chol_ach / P64, "traffic": None,
-                "flops_per_launch_group": chol_flops / max(nchol, 1), "solves_per_step": nchol / nroof, "ms_per_step": tm["chol"],
-                "note": "latency-bound: 32 sequential 64-column phases per |P| = 2048 solve; the DMMA trailing updates are 18 % of its time",
+    roofline = {"bound": "tensor",
+                "kernel": "chol_fused_kernel: single-launch Cholesky solve (dposv) of the NNLS passive-set systems, one persistent cooperative "
+                          "launch per solve (spine CTA + 147 tile workers, DMMA.8x8x4 updates)",
+                "achieved": chol_ach, "peak": P64, "unit": "TFLOP/s", "frac": chol_ach / P64,
+                # one `ncu --set full` capture of this kernel at n = 2048 (profiles/r01c_ncu_full_chol_fused.txt): dram read + write per launch;
+                # the algorithmic traffic is the upper triangle once (16.8 MB), the factor is written back to L2 only
+                "traffic": 17456640 + 2304,
+                "flops_per_launch": chol_flops / max(nchol, 1), "launches_per_step": nchol / nroof, "ms_per_step": tm["chol"],
+                "ms_per_launch": tm["chol"] / max(nchol / nroof, 1),
+                "note": "latency-bound by construction: n sequential pivots (rsqrt -> mul -> fma, ~110 cycles each) and 3 dependent tile steps per "
+                        "64-column phase, 21 us per phase measured (tools/chol_trace.py); sm__throughput 10 % in the ncu capture.  The throughput kernels "
+                        "of the step are listed under `others` with their own fractions.",
                 "peak_source": "FP64 is not in MEASURED_PEAKS.json (bf16 + HBM only); cuBLAS DGEMM 8192^3 measured on this pool, "
                                "profiles/r01_fp64_peaks.jsonl",
-                "syrk": {"kernel": "ata_kernel<AtaBig> (M = IM^T IM, n = k = %d)" % N, "achieved": syrk_ach, "frac": syrk_ach / P64,
-                         "ms_per_launch": tm["syrk"] / 2.0},
+                "others": {"syrk": {"kernel": "ata_kernel<AtaBig> (M = IM^T IM, n = k = %d, DMMA.8x8x4)" % N, "achieved": syrk_ach, "frac": syrk_ach / P64,
+                                    "ms_per_launch": tm["syrk"] / 2.0},
+                           "vkde_eval+IM": {"kernel": "vkde_kernel<10,0/1>", "pairs_per_s": pairs_step / world / ((tm["eval"] + tm["IM"]) * 1e-3),
+                                            "achieved": pairs_step / world * (d * d + 2.0 * d + 1.0) / ((tm["eval"] + tm["IM"]) * 1e-3) / 1e12,
+                                            "frac": pairs_step / world * (d * d + 2.0 * d + 1.0) / ((tm["eval"] + tm["IM"]) * 1e-3) / 1e12 / P64}},
                 "step_share_ms": {k: round(v, 4) for k, v in tm.items()}}
 
     # ---------------- CPU baseline (rank 0, bounded sample) ----------------
@@ -525,16 +535,24 @@ def run_sweep(args):
         kname = "kde_kernel (DMMA.8x8x4 GEMM + online LSE)"
     else:
         fl_pair = d * d + 2.0 * d + 1.0
-        kname = "vkde_kernel (per-centre forward substitution + online LSE)"
+        kname = ("vkde_mma_kernel (per-centre W = L^-1 products on DMMA.8x8x4 + online LSE)" if d >= 21 else
+                 "vkde_kernel (per-centre forward substitution in registers + online LSE)")
     ach = (pairs / world) * fl_pair / (ms * 1e-3) / 1e12
-    # epilogue-inclusive model: one FP64 exp (Gauss) or log1p + exp (ST) per pair on the same FP64 pipe;
-    # measured issue-loop throughputs (profiles/r01_fp64_peaks.jsonl): exp 0.80 T/s, log1p 0.40 T/s  => flop-equivalents
-    epi = 33.9 / 0.80 + (33.9 / 0.40 if okind == 1 else 0.0)
+    # epilogue-inclusive model: per pair the kernel function + online log-sum-exp run on the same FP64 datapath as the
+    # contraction: exp_nonpos_fast = 15 FP64 operations + 3 for the LSE update = 36 flop-equivalents (Gauss); Student-t adds one libdevice
+    # log1p, measured at 0.40 T/s against 33.9 TFLOP/s of DFMA issue (profiles/r01_fp64_peaks.jsonl) = 85 flop-equivalents
+    epi = 36.0 + (33.9 / 0.40 if okind == 1 else 0.0)
     ach_epi = (pairs / world) * (fl_pair + epi) / (ms * 1e-3) / 1e12
     rec_bytes = None
     if args.sd == "vkde":
         rec_bytes = (d * (d + 1) / 2 + d + 2) * 8.0
-    roofline = {"bound": "tensor", "kernel": kname, "achieved": ach, "peak": P64, "unit": "TFLOP/s", "frac": ach / P64, "traffic": None,
+    # dram read + write per launch from the `ncu --set full` captures under profiles/ (only for the captured configurations)
+    captured = {("vkde", "gauss", 30, 32768, 32768): 387631360 + 7327744, ("kde", "gauss", 10, 65536, 65536): 12609024,
+                ("vkde", "gauss", 10, 65536, 65536): 40420608 + 68096}
+    traffic = captured.get((args.sd, args.kernel, d, Q, N)) if world == 1 else None
+    roofline = {"bound": "tensor", "kernel": kname, "achieved": ach, "peak": P64, "unit": "TFLOP/s", "frac": ach / P64, "traffic": traffic,
+                "pipe_note": "ncu (profiles/r01c_ncu_full_*.txt): sm__pipe_shared_cycles_active (the FP64 datapath DMMA and DFMA share) 90 % (vkde_mma d=30), "
+                             "88 % (kde d=10) of the active cycles; LSU wavefronts 84 % for the substitution kernel (vkde d=10)",
                 "flops_per_pair": fl_pair, "with_epilogue": {"flop_equiv_per_pair": fl_pair + epi, "achieved": ach_epi, "frac": ach_epi / P64},
                 "streamed_GBs": (None if rec_bytes is None else ((q1 - q0) / 128.0) * N * rec_bytes / (ms * 1e-3) / 1e9),
                 "peak_source": "FP64 is not in MEASURED_PEAKS.json (bf16 + HBM only); cuBLAS DGEMM 8192^3 measured on this pool, "
