@@ -50,6 +50,10 @@ def parse():
     ap.add_argument("--sd", default="vkde", choices=["kde", "vkde"])
     ap.add_argument("--kernel", default="gauss", choices=["gauss", "st3", "cauchy"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--apes-multi", default="replicas", choices=["replicas", "sharded"],
+                    help="APES workload at N > 1: one independent ensemble per GPU (default, weak scaling) or one ensemble with IM / query rows "
+                         "sharded over the ranks (strong scaling; at 4096 walkers the replicated passive-set Cholesky is 81 %% of the step, so "
+                         "sharding only adds the all-reduce: 11.85 -> 13.06 ms at 2 GPUs, profiles/r01c_bench_2gpu_sharded.log)")
     return ap.parse_args()
 
 
@@ -221,7 +225,10 @@ def run_b200(args):
     W, d = args.walkers, args.dim
     N = W // 2
     pairs_step = 6.0 * N * N
-    mu, cov, U_tgt, X, m2lnL = make_problem_b200(S, W, d)
+    sharded = world > 1 and args.apes_multi == "sharded"
+    nshard, shard_rank = (world, rank) if sharded else (1, 0)     # ranks one ensemble is split over
+    replicas = 1 if sharded or world == 1 else world              # independent ensembles (one per GPU)
+    mu, cov, U_tgt, X, m2lnL = make_problem_b200(S, W, d, seed=1 + (rank if replicas > 1 else 0))
     ktn, okind, nu = KT[args.kernel]
     lb, ub = np.full(d, -50.0), np.full(d, 50.0)
     peaks = load_peaks()
@@ -270,7 +277,7 @@ def run_b200(args):
         c.n_kernels = c.n_obs = N
         c.d = d
         href = sds[b].get_href()
-        if world > 1:
+        if sharded:
             uid = [capi.comm_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(uid, src=0)
             c.comm_init(world, rank, uid[0])
@@ -281,7 +288,7 @@ def run_b200(args):
         rowscale.append(1.0 / f)
         blk = theta[:N] if b == 0 else theta[N:]
         q_all = np.vstack([blk + 1e-3, blk])            # theta*_k and theta_k of the block: 2N query points
-        q0, q1 = (2 * N * rank) // world, (2 * N * (rank + 1)) // world
+        q0, q1 = (2 * N * shard_rank) // nshard, (2 * N * (shard_rank + 1)) // nshard
         dQ.append(torch.from_numpy(np.ascontiguousarray(q_all[q0:q1])).cuda())
         dOut.append(torch.empty(q1 - q0, dtype=torch.float64, device="cuda"))
         gctx.append(c)
@@ -327,7 +334,11 @@ def run_b200(args):
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
     dev_ms = float(t_dev.item())
     ms_per_step = dev_ms / args.steps
-    value = pairs_step / (ms_per_step * 1e-3)
+    value = replicas * pairs_step / (ms_per_step * 1e-3)
+    if world > 1:   # e2e: every rank ran the host-API iteration on its own GPU; the job's rate is set by the slowest rank
+        t_e2e = torch.tensor([e2e_dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        e2e_dt = float(t_e2e.item())
     launches = sum(c.get_timers()[1] for c in gctx)
 
     # ---------------- roofline of the dominant kernel (separate pass, per-stage CUDA-event timers on) ----------------
@@ -347,7 +358,7 @@ def run_b200(args):
         for k in tm:
             tm[k] += t[k] / nroof
         c.enable_timers(False)
-    rows_local = N // world
+    rows_local = N // nshard
     # dominant component of the step (ncu launch list: chol_diag + chol_panel + ata<Small> + chol_backsolve > 90 % of the
     # device time): the passive-set Cholesky solves of the NNLS.  Algorithmic flops = sum |P|^3 / 3.
     chol_ach = chol_flops / nroof / (tm["chol"] * 1e-3) / 1e12
@@ -370,9 +381,9 @@ def run_b200(args):
                                "profiles/r01_fp64_peaks.jsonl",
                 "others": {"syrk": {"kernel": "ata_kernel<AtaBig> (M = IM^T IM, n = k = %d, DMMA.8x8x4)" % N, "achieved": syrk_ach, "frac": syrk_ach / P64,
                                     "ms_per_launch": tm["syrk"] / 2.0},
-                           "vkde_eval+IM": {"kernel": "vkde_kernel<10,0/1>", "pairs_per_s": pairs_step / world / ((tm["eval"] + tm["IM"]) * 1e-3),
-                                            "achieved": pairs_step / world * (d * d + 2.0 * d + 1.0) / ((tm["eval"] + tm["IM"]) * 1e-3) / 1e12,
-                                            "frac": pairs_step / world * (d * d + 2.0 * d + 1.0) / ((tm["eval"] + tm["IM"]) * 1e-3) / 1e12 / P64}},
+                           "vkde_eval+IM": {"kernel": "vkde_kernel<10,0/1>", "pairs_per_s": pairs_step / nshard / ((tm["eval"] + tm["IM"]) * 1e-3),
+                                            "achieved": pairs_step / nshard * (d * d + 2.0 * d + 1.0) / ((tm["eval"] + tm["IM"]) * 1e-3) / 1e12,
+                                            "frac": pairs_step / nshard * (d * d + 2.0 * d + 1.0) / ((tm["eval"] + tm["IM"]) * 1e-3) / 1e12 / P64}},
                 "step_share_ms": {k: round(v, 4) for k, v in tm.items()}}
 
     # ---------------- CPU baseline (rank 0, bounded sample) ----------------
@@ -387,17 +398,20 @@ def run_b200(args):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"APES iteration, VKDE {args.kernel} kernel, {d}-D MVND, {W} walkers (6 N^2 pairs/step, N={N}); "
-                                   "IM rows and query rows sharded over ranks, centres replicated",
+            "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"APES iteration, VKDE {args.kernel} kernel, {d}-D MVND, {W} walkers (6 N^2 pairs/step, N={N}); " +
+                                   ("one ensemble, IM rows and query rows sharded over ranks, centres replicated" if sharded else
+                                    f"{replicas} independent ensemble(s), one per GPU, no data-path collective"),
+                       "multi_gpu": args.apes_multi if world > 1 else "single",
                        "l2_policy": "each half-step streams a fresh 33.5 MB IM + 2 x 33.5 MB normal matrices; the two half-steps alternate contexts, "
                                     "so no timed kernel re-reads data left by its previous launch (working set per step > 126 MB L2)"},
-            "walker_steps_per_s": W / (ms_per_step * 1e-3),
-            "e2e": {"value": pairs_step / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
-                    "ms_per_step": e2e_dt * 1e3, "walker_steps_per_s": W / e2e_dt, "accept_rate": accept_rate,
+            "walker_steps_per_s": replicas * W / (ms_per_step * 1e-3),
+            "e2e": {"value": replicas * pairs_step / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": replicas * h2d_step, "d2h_bytes_per_step": replicas * d2h_step,
+                    "ms_per_step": e2e_dt * 1e3, "walker_steps_per_s": replicas * W / e2e_dt, "accept_rate": accept_rate,
                     "stage_ms_per_step": {k: round(v, 3) for k, v in stage.items()}, "gpu_launches_per_step": e2e_launches / args.steps,
-                    "api": "ncm_b200_esmcmc_run -> ncm_stats_dist_prepare_interp / ncm_stats_dist_eval_m2lnp_array -> C ABI (single GPU per ensemble)"},
-            "gpu_launches": int(launches),
+                    "api": "ncm_b200_esmcmc_run -> ncm_stats_dist_prepare_interp / ncm_stats_dist_eval_m2lnp_array -> C ABI (one GPU per ensemble; "
+                           "with --apes-multi sharded every rank repeats the same host-API iteration, so e2e does not scale there)"},
+            "gpu_launches": int(launches) * replicas,
             "clocks": clk.summary(),
             "roofline": roofline,
             "cpu_baseline": cpu,
@@ -600,12 +614,124 @@ def cpu_sweep(args, d, N, Q, budget_s=15.0):
                       f"prepare_kernel with local_frac 0.01); pairs/s is size-independent, so it extrapolates linearly to {Q} x {N}"}
 
 
+# ---------------------------------------------------------------------------------------------------
+def run_prepare_interp(args):
+    """--workload prepare_interp (BASELINE.json configs[2]): interpolation matrix + NNLS weights for N centres in d dimensions,
+    IM row blocks sharded over ranks, normal equations all-reduced by NCCL inside the C ABI, passive-set Cholesky replicated."""
+    import torch
+    import torch.distributed as dist
+
+    from numcosmo_b200 import capi, shard
+    from numcosmo_b200 import stats_dist as S
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; numcosmo_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = S.lib()
+    lib.ncm_b200_set_device(local_rank)
+    d, N = args.dim, args.sweep_n
+    ktn, okind, nu = KT[args.kernel]
+    peaks = load_peaks()
+    rs = np.random.default_rng(2)
+    sig = rs.uniform(2e-2, 5e-2, size=d)
+    R = rs.normal(size=(d, d)) / np.sqrt(d)
+    cov = (0.7 * np.eye(d) + 0.3 * (R @ R.T)) * np.outer(sig, sig)
+    Ug = np.linalg.cholesky(cov).T
+    z = rs.normal(size=(N, d))
+    X = np.ascontiguousarray(rs.uniform(1.0, 2.0, size=d) + z @ Ug)
+    m2lnp = np.einsum("ij,ij->i", z, z)                     # exact MVND -2 ln L at the centres
+    kern = S.StatsDistKernelGauss(d) if okind == 0 else S.StatsDistKernelST(d, nu)
+    sd = (S.StatsDistVKDE if args.sd == "vkde" else S.StatsDistKDE)(kern, S.StatsDistCV.NONE)
+    sd.set_use_threads(True)
+    for x in X:
+        sd.add_obs(x)
+    t0 = time.perf_counter()
+    sd.prepare()                                             # prepare_kernel (kNN + local covariances + factors) + upload
+    torch.cuda.synchronize()
+    t_prepare_kernel = time.perf_counter() - t0
+    c = capi.Context.borrowed(lib.ncm_stats_dist_b200_peek_ctx(sd._h))
+    c.n_kernels = c.n_obs = N
+    c.d = d
+    if world > 1:
+        uid = [capi.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        c.comm_init(world, rank, uid[0])
+    r0, r1 = shard.row_range(N, rank, world)
+    c.set_row_shard(r0, r1 - r0)
+    rowscale = 1.0 / np.exp(-0.5 * (m2lnp - m2lnp.min()))
+    c.set_href(sd.get_href())
+    stream = torch.cuda.ExternalStream(c.stream)
+
+    def step():
+        c.compute_IM(rowscale)
+        return c.nnls_solve()
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        x, rnorm, st = step()
+    c.synchronize()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    steps = max(1, min(args.steps, 5))
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    with ClockSampler(local_rank) as clk:
+        for it in range(steps):
+            ev[it][0].record(stream)
+            x, rnorm, st = step()
+            ev[it][1].record(stream)
+        c.synchronize()
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+    if world > 1:
+        dist.barrier()
+        ms = shard.max_over_ranks(ms)
+    # per-stage device time (one more step with the stage timers on)
+    c.enable_timers(True)
+    c.reset_timers()
+    step()
+    tm, launches = c.get_timers()
+    c.enable_timers(False)
+    pairs = float(N) * N
+    P64 = peaks["fp64_dgemm_tflops"]
+    syrk_ach = float(r1 - r0) * N * N / (tm["syrk"] * 1e-3) / 1e12
+    chol_ach = st["chol_flops"] / (tm["chol"] * 1e-3) / 1e12
+    dom = "syrk" if tm["syrk"] >= tm["chol"] else "chol"
+    roofline = {"bound": "tensor",
+                "kernel": ("ata_kernel<AtaBig> (normal equations M = IM^T IM, DMMA.8x8x4)" if dom == "syrk" else
+                           "blocked Cholesky solve (chol_diag/panel kernels + ata_kernel trailing updates on DMMA.8x8x4)"),
+                "achieved": syrk_ach if dom == "syrk" else chol_ach, "peak": P64, "unit": "TFLOP/s",
+                "frac": (syrk_ach if dom == "syrk" else chol_ach) / P64, "traffic": None,
+                "syrk_tflops": syrk_ach, "chol_tflops": chol_ach, "n_chol": st["n_chol"], "n_passive": st["n_passive"],
+                "stage_ms": {k: round(v, 3) for k, v in tm.items()},
+                "peak_source": "cuBLAS DGEMM 8192^3 measured on this pool, profiles/r01_fp64_peaks.jsonl"}
+    if rank == 0:
+        line = {"metric": METRIC, "value": pairs / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup, "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"prepare_interp: interpolation matrix + NNLS weights, N={N} centres, d={d}, {args.sd.upper()} {args.kernel} kernel; "
+                                       "IM row blocks sharded over ranks, normal equations all-reduced (NCCL), passive-set Cholesky replicated",
+                           "l2_policy": "IM, M and the gathered passive-set copy are 3 x N^2 x 8 B, far beyond the 126 MB L2 at N = 16384"},
+                "prepare_kernel_s": t_prepare_kernel, "rnorm": rnorm, "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roofline,
+                "e2e": None, "cpu_baseline": None}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "eval_sweep":
         run_sweep(args)
+    elif args.workload == "prepare_interp":
+        if args.sweep_n == 65536 and args.dim == 10:   # the defaults of the other workloads: use configs[2] sizes
+            args.sweep_n, args.dim = 16384, 20
+        run_prepare_interp(args)
     else:
         run_b200(args)
 
