@@ -22,7 +22,9 @@ template <int DP>
 struct VkdeCfg {
   static constexpr int REC = (DP + DP * (DP + 1) / 2 + 1) & ~1;   // doubles per record (even => 16 B multiple)
   static constexpr int CH  = DP <= 8 ? 64 : DP <= 12 ? 32 : DP <= 16 ? 16 : DP <= 24 ? 8 : 4;   // centres per stage
-  static constexpr int TQ  = 128;                                  // queries (= threads) per CTA
+  static constexpr int TQ  = 128;                                  // threads per CTA
+  static constexpr int QPT = DP <= 12 ? 2 : 1;                     // queries per thread: each factor element read from shared memory feeds QPT
+                                                                   // FMAs (the kernel is LSU-bound otherwise: 84 % LSU wavefronts at d = 10, ncu r01c)
 };
 
 // ---- record packing -------------------------------------------------------------------------------
@@ -77,8 +79,14 @@ __global__ void __launch_bounds__(VkdeCfg<DP>::TQ) vkde_kernel(const VkdeArgs a)
   uint64_t *bars    = reinterpret_cast<uint64_t *>(scv + 2 * CH);       // [2]
 
   const int tid = threadIdx.x;
-  const int qi  = blockIdx.x * Cfg::TQ + tid;
-  const bool qv = qi < a.q;
+  constexpr int QPT = Cfg::QPT;
+  int qi[QPT];
+  bool qv[QPT];
+#pragma unroll
+  for (int u = 0; u < QPT; ++u) {
+    qi[u] = (blockIdx.x * QPT + u) * Cfg::TQ + tid;
+    qv[u] = qi[u] < a.q;
+  }
 
   const int c_begin = blockIdx.y * a.per_split;
   const int c_end   = min(a.n, c_begin + a.per_split);
@@ -104,13 +112,19 @@ __global__ void __launch_bounds__(VkdeCfg<DP>::TQ) vkde_kernel(const VkdeArgs a)
 
   if (tid == 0 && nch > 0) issue(0);
 
-  double x[DP];
+  double x[QPT][DP];
 #pragma unroll
-  for (int k = 0; k < DP; ++k) x[k] = (qv && k < a.d) ? a.X[(size_t) qi * a.ldx + k] : 0.0;
+  for (int u = 0; u < QPT; ++u)
+#pragma unroll
+    for (int k = 0; k < DP; ++k) x[u][k] = (qv[u] && k < a.d) ? a.X[(size_t) qi[u] * a.ldx + k] : 0.0;
 
-  Lse acc;
-  lse_init(acc);
-  const double rs = (MODE == 1 && qv && a.rowscale != nullptr) ? a.rowscale[qi] : 1.0;
+  Lse acc[QPT];
+  double rs[QPT];
+#pragma unroll
+  for (int u = 0; u < QPT; ++u) {
+    lse_init(acc[u]);
+    rs[u] = (MODE == 1 && qv[u] && a.rowscale != nullptr) ? a.rowscale[qi[u]] : 1.0;
+  }
 
   for (int ch = 0; ch < nch; ++ch) {
     if (tid == 0 && ch + 1 < nch) issue(ch + 1);
@@ -123,29 +137,50 @@ __global__ void __launch_bounds__(VkdeCfg<DP>::TQ) vkde_kernel(const VkdeArgs a)
     for (int c = 0; c < cnt; ++c) {
       const double *r = base + c * REC;
       const double *L = r + DP;
-      double y[DP];
-      double chi2 = 0.0;
+      double y[QPT][DP];
+      double chi2[QPT];
+#pragma unroll
+      for (int u = 0; u < QPT; ++u) chi2[u] = 0.0;
 #pragma unroll
       for (int k = 0; k < DP; ++k) {
-        double t = x[k] - r[k];
+        const double th = r[k];
+        double t[QPT];
 #pragma unroll
-        for (int j = 0; j < k; ++j) t = fma(-L[k * (k + 1) / 2 + j], y[j], t);
-        y[k] = t * L[k * (k + 1) / 2 + k];
-        chi2 = fma(y[k], y[k], chi2);
+        for (int u = 0; u < QPT; ++u) t[u] = x[u][k] - th;
+#pragma unroll
+        for (int j = 0; j < k; ++j) {
+          const double l = L[k * (k + 1) / 2 + j];
+#pragma unroll
+          for (int u = 0; u < QPT; ++u) t[u] = fma(-l, y[u][j], t[u]);
+        }
+        const double dinv = L[k * (k + 1) / 2 + k];
+#pragma unroll
+        for (int u = 0; u < QPT; ++u) {
+          y[u][k] = t[u] * dinv;
+          chi2[u] = fma(y[u][k], y[u][k], chi2[u]);
+        }
       }
-      chi2 *= a.inv_h2;
-      if (MODE == 0) {
-        lse_push(acc, kern_lnK(a.kp, chi2) + cv[c]);
-      } else {
-        if (qv) a.IM[(size_t) qi * a.ldim + (c0 + c)] = kern_K(a.kp, chi2) * cv[c] * rs;
+      const double cvc = cv[c];
+#pragma unroll
+      for (int u = 0; u < QPT; ++u) {
+        const double c2 = chi2[u] * a.inv_h2;
+        if (MODE == 0) {
+          lse_push(acc[u], kern_lnK(a.kp, c2) + cvc);
+        } else {
+          if (qv[u]) a.IM[(size_t) qi[u] * a.ldim + (c0 + c)] = kern_K(a.kp, c2) * cvc * rs[u];
+        }
       }
     }
     __syncthreads();   // everyone is done with stage (ch & 1) before it is refilled
   }
 
-  if (MODE == 0 && qv) {
-    a.part_m[(size_t) blockIdx.y * a.q + qi] = acc.m;
-    a.part_s[(size_t) blockIdx.y * a.q + qi] = acc.s;
+  if (MODE == 0) {
+#pragma unroll
+    for (int u = 0; u < QPT; ++u)
+      if (qv[u]) {
+        a.part_m[(size_t) blockIdx.y * a.q + qi[u]] = acc[u].m;
+        a.part_s[(size_t) blockIdx.y * a.q + qi[u]] = acc[u].s;
+      }
   }
 }
 
@@ -158,7 +193,7 @@ int launch_t(ncm_sd_gpu_ctx *c, const VkdeArgs &a, int n_splits) {
     NCM_CUDA_OK(c, cudaFuncSetAttribute(vkde_kernel<DP, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     attr_set = true;
   }
-  dim3 grid((a.q + Cfg::TQ - 1) / Cfg::TQ, n_splits);
+  dim3 grid((a.q + Cfg::TQ * Cfg::QPT - 1) / (Cfg::TQ * Cfg::QPT), n_splits);
   vkde_kernel<DP, MODE><<<grid, Cfg::TQ, smem, c->stream>>>(a);
   c->n_launches++;
   NCM_CUDA_OK(c, cudaGetLastError());
@@ -167,6 +202,8 @@ int launch_t(ncm_sd_gpu_ctx *c, const VkdeArgs &a, int n_splits) {
 
 template <int DP>
 int ch_of() { return VkdeCfg<DP>::CH; }
+template <int DP>
+int qtile_of() { return VkdeCfg<DP>::TQ * VkdeCfg<DP>::QPT; }
 
 #define VKDE_DISPATCH(DPV, CALL)                 \
   switch (DPV) {                                 \
@@ -203,6 +240,11 @@ static int vkde_ch(ncm_sd_gpu_ctx *c, int dp) {
   int ch = 0;
   VKDE_DISPATCH(dp, ch = ch_of<DP>());
   return ch;
+}
+static int vkde_qtile(ncm_sd_gpu_ctx *c, int dp) {
+  int qt = 0;
+  VKDE_DISPATCH(dp, qt = qtile_of<DP>());
+  return qt;
 }
 
 int vkde_pack(ncm_sd_gpu_ctx *c, const double *dU_all) {
@@ -268,7 +310,8 @@ int vkde_eval_launch(ncm_sd_gpu_ctx *c, int q, const double *dX, int ldx, double
   if (c->vkde_mma) return vkde_mma_eval_launch(c, q, dX, ldx, dOut, as_density);
   const int dp      = c->dp;
   const int ch      = vkde_ch(c, dp);
-  const int q_tiles = (q + 127) / 128;
+  const int qtile   = vkde_qtile(c, dp);
+  const int q_tiles = (q + qtile - 1) / qtile;
   int splits        = pick_splits(c, q_tiles, c->n_kernels, ch, 4);
   int per_split     = ((c->n_kernels + splits - 1) / splits + ch - 1) / ch * ch;
   splits            = (c->n_kernels + per_split - 1) / per_split;
@@ -302,7 +345,8 @@ int vkde_im_launch(ncm_sd_gpu_ctx *c, const double *dRowScale) {
                                                                         c->nn_tmp.as<double>());
   c->n_launches++;
   if (c->vkde_mma) return vkde_mma_im_launch(c, c->nn_tmp.as<double>(), dRowScale);
-  const int q_tiles = (q + 127) / 128;
+  const int qtile   = vkde_qtile(c, dp);
+  const int q_tiles = (q + qtile - 1) / qtile;
   int splits        = pick_splits(c, q_tiles, c->n_kernels, ch, 4);
   int per_split     = ((c->n_kernels + splits - 1) / splits + ch - 1) / ch * ch;
   splits            = (c->n_kernels + per_split - 1) / per_split;
