@@ -42,7 +42,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="apes_vkde_gauss_mvnd10_w4096",
-                    choices=["apes_vkde_gauss_mvnd10_w4096", "eval_sweep", "prepare_interp"])
+                    choices=["apes_vkde_gauss_mvnd10_w4096", "eval_sweep", "prepare_interp", "apes_e2e"])
+    ap.add_argument("--target", default="funnel", choices=["funnel", "rosenbrock"], help="--workload apes_e2e: configs[3] (funnel) / configs[0] (rosenbrock)")
+    ap.add_argument("--over-smooth", type=float, default=None)
     ap.add_argument("--walkers", type=int, default=4096)
     ap.add_argument("--dim", type=int, default=10)
     ap.add_argument("--sweep-q", type=int, default=65536)
@@ -722,12 +724,88 @@ def run_prepare_interp(args):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------------
+def run_apes_e2e(args):
+    """--workload apes_e2e: whole APES iterations through the host API on ONE GPU for the other BASELINE.json chains:
+    configs[3] (VKDE Student-t on the 30-D Neal funnel, 32768 walkers: --target funnel --walkers 32768 --dim 30 --kernel cauchy) and
+    configs[0] (example_apes.py: 2-D Rosenbrock, 400 walkers, ST kernel: --target rosenbrock --walkers 400 --dim 2 --kernel st3)."""
+    import torch
+
+    from numcosmo_b200 import capi
+    from numcosmo_b200 import stats_dist as S
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; numcosmo_b200 has no CPU fallback")
+    lib = S.lib()
+    lib.ncm_b200_set_device(0)
+    W, d = args.walkers, args.dim
+    N = W // 2
+    ktn, okind, nu = KT[args.kernel]
+    rs = np.random.default_rng(4)
+    if args.target == "funnel":
+        # ncm_data_funnel.c:113-132; init nu ~ N(0, 3^2), x_i ~ N(0, e^nu); numcosmo_py/experiments/funnel.py:52 over_smooth 0.2
+        nuv = rs.normal(0.0, 3.0, size=W)
+        X = np.empty((W, d))
+        X[:, 0] = nuv
+        X[:, 1:] = rs.normal(size=(W, d - 1)) * np.exp(0.5 * nuv)[:, None]
+        lb = np.concatenate([[-1000.0], np.full(d - 1, -1.0e6)])
+        ub = np.concatenate([[1000.0], np.full(d - 1, 1.0e6)])
+        m2lnL = (d - 1) * nuv + (nuv / 3.0) ** 2 + np.sum(X[:, 1:] ** 2, axis=1) * np.exp(-nuv)
+        os_ = 0.2 if args.over_smooth is None else args.over_smooth
+        target = S.TARGET_FUNNEL
+    else:
+        # ncm_model_rosenbrock.c:139-142 bounds; numcosmo_py/experiments/rosenbrock.py:46-49 init
+        X = np.array([1.0, 1.0])[None, :] + 1.0e2 * rs.normal(size=(W, 2)) * 0.01
+        lb, ub = np.array([-200.0, -400.0]), np.array([200.0, 800.0])
+        m2lnL = 0.1 * (100.0 * (X[:, 1] - X[:, 0] ** 2) ** 2 + (1.0 - X[:, 0]) ** 2)
+        os_ = 1.1 if args.over_smooth is None else args.over_smooth
+        target = S.TARGET_ROSENBROCK
+    X = np.ascontiguousarray(X)
+    apes = S.FitESMCMCWalkerAPES(W, d, S.FitESMCMCWalkerAPESMethod.VKDE, getattr(S.FitESMCMCWalkerAPESKType, ktn), os_, True)
+    apes.set_use_threads(True)
+    theta, ml = X.copy(), np.ascontiguousarray(m2lnL)
+    rng = S.RNG(4)
+    warm = max(1, min(args.warmup, 2))
+    apes.run(target, lb, ub, theta, ml, warm, rng, record_accept=False)
+    sds = apes.peek_sds()
+    ctxs = [capi.Context.borrowed(lib.ncm_stats_dist_b200_peek_ctx(sd._h)) for sd in sds]
+    for c in ctxs:
+        c.reset_timers()
+    torch.cuda.synchronize()
+    steps = max(1, args.steps)
+    with ClockSampler(0) as clk:
+        t0 = time.perf_counter()
+        acc, _ = apes.run(target, lb, ub, theta, ml, steps, rng, record_accept=True)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / steps
+    traffic = [c.get_traffic() for c in ctxs]
+    launches = sum(c.get_timers()[1] for c in ctxs)
+    apes.enable_timers(True)
+    _, stage = apes.run(target, lb, ub, theta, ml, 1, rng, record_accept=False)
+    apes.enable_timers(False)
+    nn = [sd.nnls_stats() for sd in sds]
+    uses = [c.vkde_path() for c in ctxs]
+    pairs_step = 6.0 * N * N
+    line = {"metric": METRIC, "value": pairs_step / dt, "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"APES iteration end to end (host API, host buffers), VKDE {args.kernel} kernel, {d}-D {args.target}, {W} walkers, "
+                                   f"over_smooth {os_} (6 N^2 pairs/step, N={N})"},
+            "walker_steps_per_s": W / dt, "accept_rate": float(np.mean(acc)),
+            "e2e": {"value": pairs_step / dt, "unit": UNIT, "h2d_bytes_per_step": sum(t[0] for t in traffic) / steps,
+                    "d2h_bytes_per_step": sum(t[1] for t in traffic) / steps, "stage_ms_per_step": {k: round(v, 3) for k, v in stage.items()}},
+            "vkde_tensor_core_path": [bool(u[0]) for u in uses], "vkde_max_cond": [u[1] for u in uses], "nnls": nn,
+            "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": None, "cpu_baseline": None}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "eval_sweep":
         run_sweep(args)
+    elif args.workload == "apes_e2e":
+        run_apes_e2e(args)
     elif args.workload == "prepare_interp":
         if args.sweep_n == 65536 and args.dim == 10:   # the defaults of the other workloads: use configs[2] sizes
             args.sweep_n, args.dim = 16384, 20
