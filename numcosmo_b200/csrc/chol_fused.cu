@@ -57,6 +57,12 @@ __device__ __forceinline__ int ld_acquire(const int *p) {
   asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// relaxed poll: unlike ld.acquire it does not hold back the warp's later memory operations while it is in flight
+__device__ __forceinline__ int ld_relaxed(const int *p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ void st_release(int *p, int v) { asm volatile("st.release.gpu.global.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 // all threads call; returns after the flag carries this call's epoch (or the launch is aborting)
@@ -284,11 +290,12 @@ __device__ void diag_factor(const FusedArgs &a, double *S, double *sDinv, int *s
       // spans a whole strip instead of stretching this stage
       sPoll[0] = (want_panel && kb > 0) ? (pf0 == a.epoch) : 0;
       sPoll[1] = (want_next && kb > 0) ? (pf1 == a.epoch) : 0;
-      pf0 = ld_acquire(a.flagTs + k);
-      pf1 = ld_acquire(a.flagTd + k + 1);
+      pf0 = ld_relaxed(a.flagTs + k);
+      pf1 = ld_relaxed(a.flagTd + k + 1);
     }
     __syncthreads();
     if (sPoll[0] != 0 || sPoll[1] != 0) {
+      __threadfence();   // relaxed poll + fence = acquire: the tile data is ordered after the flag that announced it
       if (sPoll[0] != 0) {
         tile_fetch_async(a, k, k + 1, sX);
         want_panel = false;
