@@ -135,6 +135,30 @@ struct StageTimer {
   }
 };
 
+// Number of centre splits for the eval / IM grids: q_tiles x splits CTAs on `slots` resident CTA slots.  The smallest
+// split count that fills the device and leaves a last wave at least 92 % full (a 512-tile grid on 296 slots is 1.73 waves:
+// 13 % of the launch is tail, ncu r01c); more splits only cost 16 bytes of partials per query and split.
+inline int ncm_pick_splits(int slots, int q_tiles, int max_splits) {
+  if (max_splits < 1) max_splits = 1;
+  int first = (slots + q_tiles - 1) / q_tiles;
+  if (first < 1) first = 1;
+  if (first > max_splits) return max_splits;
+  int best = first;
+  double best_eff = 0.0;
+  const int hi = first + 16 < max_splits ? first + 16 : max_splits;
+  for (int s = first; s <= hi; ++s) {
+    const long ctas  = (long) q_tiles * s;
+    const long waves = (ctas + slots - 1) / slots;
+    const double eff = (double) ctas / (double) (waves * slots);
+    if (eff > best_eff + 1e-9) {
+      best_eff = eff;
+      best     = s;
+    }
+    if (eff >= 0.92) return s;
+  }
+  return best;
+}
+
 // ---- kernels' host launchers (defined in the .cu files) --------------------------------------------
 int vkde_pad_dim(int d);
 int vkde_pack(ncm_sd_gpu_ctx *c, const double *dU_all /* n x d x d */);

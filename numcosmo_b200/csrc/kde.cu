@@ -333,14 +333,7 @@ void fill_kp(const ncm_sd_gpu_ctx *c, KernParams &kp) {
   kp.inv_nu = 1.0 / c->nu;
 }
 
-int pick_splits(const ncm_sd_gpu_ctx *c, int q_tiles, int n_pad) {
-  const int target = c->n_sm * 2;
-  int splits       = (target + q_tiles - 1) / q_tiles;
-  const int max_sp = n_pad / CHK;
-  if (splits > max_sp) splits = max_sp;
-  if (splits < 1) splits = 1;
-  return splits;
-}
+int pick_splits(const ncm_sd_gpu_ctx *c, int q_tiles, int n_pad) { return ncm_pick_splits(c->n_sm * 2, q_tiles, n_pad / CHK); }
 
 }   // namespace
 

@@ -23,7 +23,7 @@ struct VkdeCfg {
   static constexpr int REC = (DP + DP * (DP + 1) / 2 + 1) & ~1;   // doubles per record (even => 16 B multiple)
   static constexpr int CH  = DP <= 8 ? 64 : DP <= 12 ? 32 : DP <= 16 ? 16 : DP <= 24 ? 8 : 4;   // centres per stage
   static constexpr int TQ  = 128;                                  // threads per CTA
-  static constexpr int QPT = DP <= 12 ? 2 : 1;                     // queries per thread: each factor element read from shared memory feeds QPT
+  static constexpr int QPT = DP <= 20 ? 2 : 1;                     // queries per thread: each factor element read from shared memory feeds QPT
                                                                    // FMAs (the kernel is LSU-bound otherwise: 84 % LSU wavefronts at d = 10, ncu r01c)
 };
 
@@ -298,12 +298,7 @@ static void fill_kp(const ncm_sd_gpu_ctx *c, KernParams &kp) {
 
 // choose the number of centre splits so that the grid is about two waves of resident CTAs
 static int pick_splits(const ncm_sd_gpu_ctx *c, int q_tiles, int n, int ch, int ctas_per_sm) {
-  const int target = c->n_sm * ctas_per_sm;
-  int splits       = (target + q_tiles - 1) / q_tiles;
-  const int max_sp = (n + ch - 1) / ch;
-  if (splits > max_sp) splits = max_sp;
-  if (splits < 1) splits = 1;
-  return splits;
+  return ncm_pick_splits(c->n_sm * ctas_per_sm, q_tiles, (n + ch - 1) / ch);
 }
 
 int vkde_eval_launch(ncm_sd_gpu_ctx *c, int q, const double *dX, int ldx, double *dOut, bool as_density) {

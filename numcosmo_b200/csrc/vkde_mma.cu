@@ -272,11 +272,7 @@ void fill_kp(const ncm_sd_gpu_ctx *c, KernParams &kp) {
 
 void splits_for(const ncm_sd_gpu_ctx *c, int q, int n, int ch, int &splits, int &per_split) {
   const int q_tiles = (q + 127) / 128;
-  const int target  = c->n_sm * 2;
-  splits            = (target + q_tiles - 1) / q_tiles;
-  const int max_sp  = (n + ch - 1) / ch;
-  if (splits > max_sp) splits = max_sp;
-  if (splits < 1) splits = 1;
+  splits            = ncm_pick_splits(c->n_sm * 2, q_tiles, (n + ch - 1) / ch);
   per_split = ((n + splits - 1) / splits + ch - 1) / ch * ch;
   splits    = (n + per_split - 1) / per_split;
 }
