@@ -555,9 +555,9 @@ def run_sweep(args):
                  "vkde_kernel (per-centre forward substitution in registers + online LSE)")
     ach = (pairs / world) * fl_pair / (ms * 1e-3) / 1e12
     # epilogue-inclusive model: per pair the kernel function + online log-sum-exp run on the same FP64 datapath as the
-    # contraction: exp_nonpos_fast = 15 FP64 operations + 3 for the LSE update = 36 flop-equivalents (Gauss); Student-t adds one libdevice
-    # log1p, measured at 0.40 T/s against 33.9 TFLOP/s of DFMA issue (profiles/r01_fp64_peaks.jsonl) = 85 flop-equivalents
-    epi = 36.0 + (33.9 / 0.40 if okind == 1 else 0.0)
+    # contraction: exp_nonpos_fast = 15 FP64 operations + 3 for the LSE update = 36 flop-equivalents (Gauss); Student-t adds
+    # log1p_nonneg_fast (14 operations) + the kappa multiply = 30 more
+    epi = 36.0 + (30.0 if okind == 1 else 0.0)
     ach_epi = (pairs / world) * (fl_pair + epi) / (ms * 1e-3) / 1e12
     rec_bytes = None
     if args.sd == "vkde":

@@ -231,8 +231,8 @@ __global__ void __launch_bounds__(KDE_THREADS) kde_kernel(const KdeArgs a) {
           const double2 cw = *reinterpret_cast<const double2 *>(ct + ni * 8 + 2 * lr);
 #pragma unroll
           for (int mi = 0; mi < MI; ++mi) {
-            acc[mi][ni][0] = fma(a.kp.kappa, log1p(acc[mi][ni][0]), cw.x);
-            acc[mi][ni][1] = fma(a.kp.kappa, log1p(acc[mi][ni][1]), cw.y);
+            acc[mi][ni][0] = fma(a.kp.kappa, log1p_nonneg_fast(fmax(acc[mi][ni][0], 0.0)), cw.x);
+            acc[mi][ni][1] = fma(a.kp.kappa, log1p_nonneg_fast(fmax(acc[mi][ni][1], 0.0)), cw.y);
           }
         }
       }
@@ -266,8 +266,8 @@ __global__ void __launch_bounds__(KDE_THREADS) kde_kernel(const KdeArgs a) {
               k0 = exp_nonpos_fast(acc[mi][ni][0]);
               k1 = exp_nonpos_fast(acc[mi][ni][1]);
             } else {
-              k0 = pow(1.0 + acc[mi][ni][0], a.kp.kappa);
-              k1 = pow(1.0 + acc[mi][ni][1], a.kp.kappa);
+              k0 = exp_nonpos_fast(a.kp.kappa * log1p_nonneg_fast(fmax(acc[mi][ni][0], 0.0)));
+              k1 = exp_nonpos_fast(a.kp.kappa * log1p_nonneg_fast(fmax(acc[mi][ni][1], 0.0)));
             }
             double *dst = a.IM + (size_t) row * a.ldim + col;
             if (col + 1 < a.n)
