@@ -13,6 +13,8 @@
 #ifndef NCM_SD_GPU_H
 #define NCM_SD_GPU_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -158,6 +160,10 @@ int ncm_sd_gpu_reset_timers (ncm_sd_gpu_ctx *ctx);
 /* bytes this context copied host->device / device->host since the last reset_timers */
 int ncm_sd_gpu_get_traffic (ncm_sd_gpu_ctx *ctx, long long *h2d_bytes, long long *d2h_bytes);
 int ncm_sd_gpu_enable_timers (ncm_sd_gpu_ctx *ctx, int enable);
+
+/* page-locked host memory for the large arrays that cross PCIe every prepare (the factor slab U_all_out): cudaHostAlloc / cudaFreeHost */
+int ncm_sd_gpu_host_alloc (void **ptr, size_t bytes);
+int ncm_sd_gpu_host_free (void *ptr);
 
 /* which VKDE evaluation kernel serves the uploaded factors: 1 = DMMA path with explicit inverses (d >= 13 and
  * max_i cond_1 (U_i) <= 1e5, reported in cond_max), 0 = forward substitution (vkde.cu).  Both replace

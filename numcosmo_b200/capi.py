@@ -28,7 +28,7 @@ SYMBOLS = (
     "ncm_sd_gpu_compute_IM", "ncm_sd_gpu_nnls_solve", "ncm_sd_gpu_nnls_solve_host", "ncm_sd_gpu_sample_apply", "ncm_sd_gpu_sample_philox",
     "ncm_sd_gpu_comm_unique_id", "ncm_sd_gpu_comm_init", "ncm_sd_gpu_set_row_shard", "ncm_sd_gpu_get_timers", "ncm_sd_gpu_reset_timers",
     "ncm_sd_gpu_enable_timers", "ncm_sd_gpu_get_traffic", "ncm_sd_gpu_dsyrk_ata_dev", "ncm_sd_gpu_dpotrf_upper_dev",
-    "ncm_sd_gpu_vkde_prepare", "ncm_sd_gpu_vkde_finish", "ncm_sd_gpu_dposv_upper_dev", "ncm_sd_gpu_vkde_path",
+    "ncm_sd_gpu_vkde_prepare", "ncm_sd_gpu_vkde_finish", "ncm_sd_gpu_dposv_upper_dev", "ncm_sd_gpu_vkde_path", "ncm_sd_gpu_host_alloc", "ncm_sd_gpu_host_free",
 )
 
 

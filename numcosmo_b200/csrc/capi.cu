@@ -148,7 +148,7 @@ int ncm_sd_gpu_ctx_free(ncm_sd_gpu_ctx *c) {
   if (c->nccl_comm != nullptr && nccl_api().ok) nccl_api().CommDestroy((ncclComm_t) c->nccl_comm);
   DevBuf *bufs[] = {&c->sample, &c->vrec, &c->lnu, &c->cterm, &c->weights, &c->Ufull, &c->zc, &c->zmean, &c->bfrag, &c->kde_U, &c->qX,
                     &c->qOut, &c->qA, &c->part, &c->IM, &c->rowscale, &c->M, &c->MU, &c->nn_b, &c->nn_x, &c->nn_r, &c->nn_g, &c->nn_tmp,
-                    &c->nn_idx, &c->nn_f, &c->chol_flags, &c->chol_part, &c->vrec_mma};
+                    &c->nn_idx, &c->nn_f, &c->chol_flags, &c->chol_part, &c->vrec_mma, &c->dist};
   for (DevBuf *b : bufs) b->release();
   c->pinX.release();
   c->pinOut.release();
@@ -540,6 +540,24 @@ int ncm_sd_gpu_dpotrf_upper_dev(ncm_sd_gpu_ctx *c, int n, double *dM, int ldm, i
   cudaSetDevice(c->device);
   if (!c->nn_b.reserve((size_t) (n + 64) * sizeof(double)) || !c->nn_idx.reserve(64)) return c->fail(NCM_SD_GPU_ENOMEM, "dpotrf: out of device memory");
   return dpotrf_upper_solve_any(c, n, dM, ldm, nullptr, c->nn_b.as<double>(), c->nn_idx.as<int>(), info_host);
+}
+
+int ncm_sd_gpu_host_alloc(void **ptr, size_t bytes) {
+  if (ptr == nullptr) return NCM_SD_GPU_EINVAL;
+  *ptr = nullptr;
+  if (cudaHostAlloc(ptr, bytes, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    *ptr = nullptr;
+    return NCM_SD_GPU_ENOMEM;
+  }
+  return NCM_SD_GPU_OK;
+}
+int ncm_sd_gpu_host_free(void *ptr) {
+  if (ptr != nullptr && cudaFreeHost(ptr) != cudaSuccess) {
+    cudaGetLastError();
+    return NCM_SD_GPU_ECUDA;
+  }
+  return NCM_SD_GPU_OK;
 }
 
 int ncm_sd_gpu_vkde_path(ncm_sd_gpu_ctx *c, int *uses_mma, double *cond_max) {

@@ -74,6 +74,7 @@ struct ncm_sd_gpu_ctx {
   DevBuf IM;         // [nrows_local x n_kernels]
   DevBuf rowscale;   // [n_obs]
   DevBuf M, MU, nn_b, nn_x, nn_r, nn_g, nn_tmp, nn_idx, nn_f;
+  DevBuf dist;   // VKDE prepare_kernel: squared distances centre x point [n_kernels x n_obs]
   DevBuf chol_flags, chol_part;   // single-launch Cholesky (chol_fused.cu): dependency flags, back-substitution contributions
   int chol_epoch = 0;
   long long *chol_trace = nullptr;   // device buffer [n_sm][cap][2] set by ncm_sd_gpu_chol_trace (debugging aid)

@@ -1,10 +1,48 @@
 // Internal definitions of libncm_stats_dist_b200 (host-side mirror of the reference interface).
 #pragma once
 #include <cstddef>
+#include <cstdlib>
 #include <string>
 #include <vector>
 #include "../../include/ncm_sd_gpu.h"
 #include "../../include/ncm_stats_dist_b200.h"
+
+// page-locked host array (cudaHostAlloc through the C ABI, plain malloc when no device is usable): the VKDE factor
+// slab comes back from the device every prepare_kernel (118 MB at N = 16384, d = 30) and pageable memory halves that copy
+struct NcmB200PinnedVec {
+  double *p = nullptr;
+  size_t n = 0;
+  bool pinned = false;
+  NcmB200PinnedVec() = default;
+  NcmB200PinnedVec(const NcmB200PinnedVec &) = delete;
+  NcmB200PinnedVec &operator=(const NcmB200PinnedVec &) = delete;
+  ~NcmB200PinnedVec() { release(); }
+  void release() {
+    if (p != nullptr) {
+      if (pinned) ncm_sd_gpu_host_free(p); else free(p);
+    }
+    p = nullptr;
+    n = 0;
+  }
+  void assign(size_t count, double v) {
+    if (count != n) {
+      release();
+      void *q = nullptr;
+      if (count > 0 && ncm_sd_gpu_host_alloc(&q, count * sizeof(double)) == NCM_SD_GPU_OK && q != nullptr) {
+        p = static_cast<double *>(q);
+        pinned = true;
+      } else if (count > 0) {
+        p = static_cast<double *>(malloc(count * sizeof(double)));
+        pinned = false;
+      }
+      n = count;
+    }
+    for (size_t i = 0; i < n; i++) p[i] = v;
+  }
+  double *data() { return p; }
+  double &operator[](size_t i) { return p[i]; }
+  size_t size() const { return n; }
+};
 
 struct _NcmVector {
   double *data;
@@ -60,7 +98,7 @@ struct _NcmStatsDist {
   double kernel_lnnorm;
   std::vector<double> sample_matrix, invUsample;   // [n_obs x d]
   // VKDE (NcmStatsDistVKDEPrivate): cov_array as live NcmMatrix objects over one slab
-  std::vector<double> cov_slab;                    // [n_kernels x d x d]
+  NcmB200PinnedVec cov_slab;                       // [n_kernels x d x d], page-locked
   std::vector<NcmMatrix *> cov_array;
   std::vector<double> lnnorms;
   // GPU
