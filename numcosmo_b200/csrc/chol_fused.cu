@@ -90,15 +90,22 @@ __device__ __forceinline__ void post_flag(const FusedArgs &a, int *f) {
 
 // event record: code = type << 24 | a << 12 | b ; type 1 diag, 2 panel, 3 update, 4 backsolve, 5 backprod; +8 = end, +16 = after the waits
 __device__ __forceinline__ void trace_ev(const FusedArgs &a, int type, int x, int y) {
+  __shared__ int s_trace_n;   // event count of this CTA (shared memory: reading a counter back from global memory would put an
+                              // L2 round trip on thread 0 at every event and distort the very chain being measured)
   if (a.trace != nullptr && threadIdx.x == 0) {
     long long *base = a.trace + (size_t) blockIdx.x * a.trace_cap * 2;
-    const long long n = base[0];
+    if (type == 0) {          // reset (first call of the kernel)
+      s_trace_n = 0;
+      return;
+    }
+    const int n = s_trace_n;
     if (n + 1 < a.trace_cap) {
       long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       base[2 * (n + 1)]     = t;
       base[2 * (n + 1) + 1] = ((long long) type << 24) | ((long long) x << 12) | y;
       base[0]               = n + 1;
+      s_trace_n             = n + 1;
     }
   }
 }
@@ -825,6 +832,7 @@ __global__ void __launch_bounds__(FT, 1) chol_fused_kernel(const FusedArgs a) {
   int *sBad     = reinterpret_cast<int *>(sVec + 6 * FB);
   const int bid = blockIdx.x;
   const int Gw  = gridDim.x - 1;            // workers
+  trace_ev(a, 0, 0, 0);
   const int nb = a.nb, nbc = a.nbc;
   const int T  = row_start(nb, nbc);
 
