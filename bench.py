@@ -390,7 +390,7 @@ def run_b200(args):
 
     # ---------------- CPU baseline (rank 0, bounded sample) ----------------
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:   # reported at N = 1 only (the other ranks would sit idle behind it)
         ncores = os.cpu_count() or 1
         cdt, ctm = cpu_apes(args, W, d, 3, ncores)
         cpu = {"value": pairs_step / cdt, "unit": UNIT, "cores": ncores, "kind": "port",
@@ -574,7 +574,7 @@ def run_sweep(args):
                 "peak_source": "FP64 is not in MEASURED_PEAKS.json (bf16 + HBM only); cuBLAS DGEMM 8192^3 measured on this pool, "
                                "profiles/r01_fp64_peaks.jsonl"}
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_sweep(args, d, N, Q)
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
@@ -800,6 +800,11 @@ def run_apes_e2e(args):
 
 def main():
     args = parse()
+    # torchrun exports OMP_NUM_THREADS=1; the host-side OpenMP loops (oracle port for the reference arm, prepare_kernel pieces and the
+    # per-walker transition terms for the B200 arm) read it when their library is first loaded, so it is set here, before any of them is
+    ncores = os.cpu_count() or 1
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    os.environ["OMP_NUM_THREADS"] = str(ncores if args.impl == "reference" else max(1, ncores // world))
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "eval_sweep":
