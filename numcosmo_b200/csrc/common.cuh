@@ -6,6 +6,7 @@
 #include <cmath>
 
 #define NCM_WARP 32
+#define NCM_MAX_DEVICES 64
 #define NCM_NEG_BIG (-1.0e300)   // running-max seed: finite, so (t - m) never evaluates inf - inf
 
 // ---- shared-memory / mbarrier / bulk-copy (TMA 1-D) primitives ------------------------------

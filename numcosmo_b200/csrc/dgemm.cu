@@ -180,11 +180,14 @@ ata_kernel(const double *__restrict__ P, int ldp, int K, int n, double *__restri
 template <typename Cfg, bool SUBC>
 cudaError_t ata_launch(cudaStream_t st, const double *dP, int ldp, int K, int n, double *dC, int ldc, double alpha, double beta) {
   using D = AtaDerived<Cfg>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[NCM_MAX_DEVICES] = {};   // function attributes are per device
+  int dev__ = 0;
+  cudaGetDevice(&dev__);
+  dev__ = dev__ < 0 || dev__ >= NCM_MAX_DEVICES ? 0 : dev__;
+  if (!attr_set[dev__]) {
     cudaError_t e = cudaFuncSetAttribute(ata_kernel<Cfg, SUBC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) D::SMEM);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set[dev__] = true;
   }
   const int nt = (n + Cfg::TB - 1) / Cfg::TB;
   ata_kernel<Cfg, SUBC><<<nt * (nt + 1) / 2, Cfg::THREADS, D::SMEM, st>>>(dP, ldp, K, n, dC, ldc, alpha, beta, nt);

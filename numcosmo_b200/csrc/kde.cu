@@ -298,10 +298,10 @@ __global__ void __launch_bounds__(KDE_THREADS) kde_kernel(const KdeArgs a) {
 template <int KS, int MODE>
 int kde_launch_t(ncm_sd_gpu_ctx *c, const KdeArgs &a, int splits) {
   const size_t smem = (size_t) (2 * CHK * KS * 4 + 2 * CHK) * sizeof(double) + 2 * sizeof(uint64_t);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[NCM_MAX_DEVICES] = {};   // function attributes are per device
+  if (!attr_set[c->device % NCM_MAX_DEVICES]) {
     NCM_CUDA_OK(c, cudaFuncSetAttribute(kde_kernel<KS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    attr_set = true;
+    attr_set[c->device % NCM_MAX_DEVICES] = true;
   }
   dim3 grid((a.q + QT - 1) / QT, splits);
   kde_kernel<KS, MODE><<<grid, KDE_THREADS, smem, c->stream>>>(a);

@@ -188,10 +188,10 @@ template <int DP, int MODE>
 int launch_t(ncm_sd_gpu_ctx *c, const VkdeArgs &a, int n_splits) {
   using Cfg = VkdeCfg<DP>;
   const size_t smem = (size_t) (2 * Cfg::CH * Cfg::REC + 2 * Cfg::CH) * sizeof(double) + 2 * sizeof(uint64_t);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[NCM_MAX_DEVICES] = {};   // function attributes are per device
+  if (!attr_set[c->device % NCM_MAX_DEVICES]) {
     NCM_CUDA_OK(c, cudaFuncSetAttribute(vkde_kernel<DP, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    attr_set = true;
+    attr_set[c->device % NCM_MAX_DEVICES] = true;
   }
   dim3 grid((a.q + Cfg::TQ * Cfg::QPT - 1) / (Cfg::TQ * Cfg::QPT), n_splits);
   vkde_kernel<DP, MODE><<<grid, Cfg::TQ, smem, c->stream>>>(a);

@@ -240,10 +240,10 @@ template <int DP, int MODE>
 int mma_launch_t(ncm_sd_gpu_ctx *c, const MmaArgs &a, int n_splits) {
   using Cfg = MmaCfg<DP>;
   const size_t smem = (size_t) (2 * Cfg::CH * Cfg::REC + 2 * Cfg::CH) * sizeof(double) + 2 * sizeof(uint64_t);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[NCM_MAX_DEVICES] = {};   // function attributes are per device
+  if (!attr_set[c->device % NCM_MAX_DEVICES]) {
     NCM_CUDA_OK(c, cudaFuncSetAttribute(vkde_mma_kernel<DP, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    attr_set = true;
+    attr_set[c->device % NCM_MAX_DEVICES] = true;
   }
   dim3 grid((a.q + Cfg::TQ - 1) / Cfg::TQ, n_splits);
   vkde_mma_kernel<DP, MODE><<<grid, Cfg::WARPS * 32, smem, c->stream>>>(a);
@@ -302,10 +302,10 @@ int vkde_mma_pack(ncm_sd_gpu_ctx *c, const double *dU_all, double *cond_max_host
   NCM_CUDA_OK(c, cudaMemsetAsync(dcond, 0, sizeof(unsigned long long), c->stream));
   const int wpb     = 4;
   const size_t smem = (size_t) wpb * 2 * 32 * 33 * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[NCM_MAX_DEVICES] = {};   // function attributes are per device
+  if (!attr_set[c->device % NCM_MAX_DEVICES]) {
     NCM_CUDA_OK(c, cudaFuncSetAttribute(vkde_mma_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    attr_set = true;
+    attr_set[c->device % NCM_MAX_DEVICES] = true;
   }
   vkde_mma_pack_kernel<<<(c->n_kernels + wpb - 1) / wpb, wpb * 32, smem, c->stream>>>(c->sample.as<double>(), dU_all, c->vrec_mma.as<double>(), c->n_kernels,
                                                                                    c->d, dp, c->vrec_mma_len, dcond);

@@ -316,7 +316,9 @@ int vkde_prepare_dev(ncm_sd_gpu_ctx *c, int n_obs, int n_kernels, int k, const d
   const size_t smem_knn = (size_t) n_obs * sizeof(double) + (size_t) kpow2 * (sizeof(double) + sizeof(int)) + (2048 + 16) * sizeof(int) +
                           (size_t) d * sizeof(double) + 16;
   if (smem_knn > 220 * 1024) return c->fail(NCM_SD_GPU_EINVAL, "vkde_prepare: n_obs too large for the shared-memory neighbour selection");
-  static size_t knn_attr = 0, cov_attr = 0;
+  static size_t knn_attr_tab[NCM_MAX_DEVICES] = {};   // function attributes are per device
+  size_t &knn_attr = knn_attr_tab[c->device % NCM_MAX_DEVICES];
+  const size_t cov_attr = 0;   // the covariance kernel's attribute is set at every launch (four instantiations)
   if (smem_knn > knn_attr) {
     NCM_CUDA_OK(c, cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_knn));
     knn_attr = smem_knn;
