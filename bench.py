@@ -96,13 +96,16 @@ class ClockSampler:
             self._stop.wait(0.2)
 
     def __enter__(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
+        # rank 0 only: nvidia-smi costs ~0.1 s of a host core per call, and the ranks share the host cores with the NNLS decisions
+        if int(os.environ.get("RANK", "0")) == 0:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
         return self
 
     def __exit__(self, *a):
         self._stop.set()
-        self._t.join(timeout=6)
+        if self._t is not None:
+            self._t.join(timeout=6)
 
     def summary(self):
         sm, mx, reasons = [], [], set()
