@@ -566,12 +566,12 @@ def run_sweep(args):
     if args.sd == "vkde":
         rec_bytes = (d * (d + 1) / 2 + d + 2) * 8.0
     # dram read + write per launch from the `ncu --set full` captures under profiles/ (only for the captured configurations)
-    captured = {("vkde", "gauss", 30, 32768, 32768): 387631360 + 7327744, ("kde", "gauss", 10, 65536, 65536): 12609024,
-                ("vkde", "gauss", 10, 65536, 65536): 40420608 + 68096}
+    captured = {("vkde", "gauss", 30, 65536, 65536): 1449735000 + 11664640, ("vkde", "gauss", 30, 32768, 32768): 387631360 + 7327744,
+                ("kde", "gauss", 10, 65536, 65536): 12617216, ("vkde", "gauss", 20, 65536, 65536): 139484928 + 9936384}
     traffic = captured.get((args.sd, args.kernel, d, Q, N)) if world == 1 else None
     roofline = {"bound": "tensor", "kernel": kname, "achieved": ach, "peak": P64, "unit": "TFLOP/s", "frac": ach / P64, "traffic": traffic,
-                "pipe_note": "ncu (profiles/r01c_ncu_full_*.txt): sm__pipe_shared_cycles_active (the FP64 datapath DMMA and DFMA share) 90 % (vkde_mma d=30), "
-                             "88 % (kde d=10) of the active cycles; LSU wavefronts 84 % for the substitution kernel (vkde d=10)",
+                "pipe_note": "ncu (profiles/r01d_ncu_full_*.txt, 65536^2): sm__pipe_shared_cycles_active (the FP64 datapath DMMA and DFMA share) 89 % of the "
+                             "elapsed cycles for vkde_mma d=30 and 87 % for kde d=10; 74 % (LSU wavefronts 62 %) for the substitution kernel at d=20",
                 "flops_per_pair": fl_pair, "with_epilogue": {"flop_equiv_per_pair": fl_pair + epi, "achieved": ach_epi, "frac": ach_epi / P64},
                 "streamed_GBs": (None if rec_bytes is None else ((q1 - q0) / 128.0) * N * rec_bytes / (ms * 1e-3) / 1e9),
                 "peak_source": "FP64 is not in MEASURED_PEAKS.json (bf16 + HBM only); cuBLAS DGEMM 8192^3 measured on this pool, "
