@@ -50,9 +50,10 @@ def test_dpotrf_upper(gpu_ctx, n):
     assert info == k + 1
 
 
-@pytest.mark.parametrize("n", [1, 5, 63, 64, 65, 128, 200, 1000, 1899, 2048, 3001])
+@pytest.mark.parametrize("n", [1, 5, 63, 64, 65, 128, 200, 1000, 1899, 2048, 3001, 4096, 4200])
 def test_dposv_upper(gpu_ctx, n):
-    """dposv 'U' (ncm_matrix_cholesky_solve, ncm_matrix.c:1199-1210): factor + forward + back substitution."""
+    """dposv 'U' (ncm_matrix_cholesky_solve, ncm_matrix.c:1199-1210): factor + forward + back substitution.
+    n <= 4096 runs the single-launch kernel (chol_fused.cu), n = 4200 the launch-per-step path (chol.cu)."""
     import torch
 
     rs = np.random.default_rng(1000 + n)
