@@ -178,7 +178,7 @@ ata_kernel(const double *__restrict__ P, int ldp, int K, int n, double *__restri
 }
 
 template <typename Cfg, bool SUBC>
-cudaError_t ata_launch(cudaStream_t st, const double *dP, int ldp, int K, int n, double *dC, int ldc, double alpha, double beta) {
+cudaError_t ata_launch(cudaStream_t st, const double *dP, int ldp, int K, int n, double *dC, int ldc, double alpha, double beta, bool first_row_only = false) {
   using D = AtaDerived<Cfg>;
   static bool attr_set[NCM_MAX_DEVICES] = {};   // function attributes are per device
   int dev__ = 0;
@@ -190,7 +190,8 @@ cudaError_t ata_launch(cudaStream_t st, const double *dP, int ldp, int K, int n,
     attr_set[dev__] = true;
   }
   const int nt = (n + Cfg::TB - 1) / Cfg::TB;
-  ata_kernel<Cfg, SUBC><<<nt * (nt + 1) / 2, Cfg::THREADS, D::SMEM, st>>>(dP, ldp, K, n, dC, ldc, alpha, beta, nt);
+  // tiles are enumerated row by row over the upper triangle: the first nt of them are tile row 0
+  ata_kernel<Cfg, SUBC><<<first_row_only ? nt : nt * (nt + 1) / 2, Cfg::THREADS, D::SMEM, st>>>(dP, ldp, K, n, dC, ldc, alpha, beta, nt);
   return cudaGetLastError();
 }
 
@@ -267,6 +268,18 @@ int dsyrk_ata_general(ncm_sd_gpu_ctx *c, int K, int n, const double *dP, int ldp
   else
     e = subc ? ata_launch<AtaBig, true>(c->stream, dP, ldp, K, n, dC, ldc, alpha, beta) : ata_launch<AtaBig, false>(c->stream, dP, ldp, K, n, dC, ldc, alpha, beta);
   NCM_CUDA_OK(c, e);
+  c->n_launches++;
+  NCM_CUDA_OK(c, cudaGetLastError());
+  return NCM_SD_GPU_OK;
+}
+
+// C[0:64, 0:n] -= P[:, 0:64]^T P  (the first 64-row block of the trailing update only): lets the blocked Cholesky factor two
+// 64-wide panels before it touches the rest of the matrix, so that the big update runs with K = 128
+int dsyrk_ata_first_rows64(ncm_sd_gpu_ctx *c, int K, int n, const double *dP, int ldp, double *dC, int ldc) {
+  if (n <= 0 || K <= 0) return NCM_SD_GPU_OK;
+  if ((ldp & 1) || (ldc & 1) || (((uintptr_t) dP) & 15) || (((uintptr_t) dC) & 15))
+    return c->fail(NCM_SD_GPU_EINVAL, "ata: operands must be 16-byte aligned with even leading dimensions");
+  NCM_CUDA_OK(c, (ata_launch<AtaSmall, true>(c->stream, dP, ldp, K, n, dC, ldc, -1.0, 1.0, true)));
   c->n_launches++;
   NCM_CUDA_OK(c, cudaGetLastError());
   return NCM_SD_GPU_OK;
