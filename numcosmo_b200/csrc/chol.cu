@@ -389,30 +389,40 @@ __global__ void __launch_bounds__(256) chol_backsolve_kernel(const double *__res
 int dpotrf_upper_solve(ncm_sd_gpu_ctx *c, int n, double *dM, int ldm, double *dRhs, double *dDinv, int *dInfo, int *info_host) {
   NCM_CUDA_OK(c, cudaMemsetAsync(dInfo, 0, sizeof(int), c->stream));
   const int nblk = (n + NB - 1) / NB;
-  // Panels are factored two at a time: after panel A only the next 64 rows are brought up to date (a thin K = 64 update),
-  // panel B is factored, and the rest of the matrix receives both panels in one K = 128 update -- half as many passes over
-  // the trailing matrix and twice the depth for the DMMA pipeline of ata_kernel (which matters at n >> 4096, where this
-  // path runs: 17 -> 2x TFLOP/s at n = 16384 were the K = 64 updates).
-  for (int kb = 0; kb < nblk; kb += 2) {
+  // Panels are factored GP at a time: before panel p of a group is factored, only its own 64 rows are brought up to date
+  // with the p panels of the group already done (a thin update, K = 64 p); after the last one the rest of the matrix receives
+  // the whole group in one update of depth K = 64 GP -- GP times fewer passes over the trailing matrix and a deeper DMMA
+  // pipeline in ata_kernel (which matters at n >> 4096, where this path runs: the K = 64 updates ran at 17 TFLOP/s at n = 16384).
+  static const int gp_env = getenv("NCM_SD_GPU_CHOL_GROUP") != nullptr ? atoi(getenv("NCM_SD_GPU_CHOL_GROUP")) : 0;
+  const int GP = gp_env > 0 ? gp_env : (n >= 12288 ? 8 : (n >= 6144 ? 4 : 2));   // measured at n = 16384: 68.0 / 62.2 / 60.1 ms for 2 / 4 / 8
+  bool done = false;
+  for (int kb = 0; kb < nblk && !done; kb += GP) {
     const int k0 = kb * NB;
-    chol_diag_kernel<<<1, 256, 0, c->stream>>>(dM, ldm, n, k0, dRhs, dDinv, dInfo);
-    c->n_launches++;
-    const int m = n - k0 - NB;
-    if (m <= 0) break;
-    chol_panel_kernel<<<(m + 127) / 128, 128, 0, c->stream>>>(dM, ldm, n, k0, dRhs, dDinv);
-    c->n_launches++;
-    const int k1 = k0 + NB;
-    // rows k1 .. k1+63 of the trailing matrix
-    int rc = dsyrk_ata_first_rows64(c, NB, m, dM + (size_t) k0 * ldm + k1, ldm, dM + (size_t) k1 * ldm + k1, ldm);
-    if (rc != NCM_SD_GPU_OK) return rc;
-    chol_diag_kernel<<<1, 256, 0, c->stream>>>(dM, ldm, n, k1, dRhs, dDinv, dInfo);
-    c->n_launches++;
-    const int m2 = n - k1 - NB;
-    if (m2 <= 0) break;
-    chol_panel_kernel<<<(m2 + 127) / 128, 128, 0, c->stream>>>(dM, ldm, n, k1, dRhs, dDinv);
-    c->n_launches++;
-    const int k2 = k1 + NB;
-    rc = dsyrk_ata_general(c, 2 * NB, m2, dM + (size_t) k0 * ldm + k2, ldm, dM + (size_t) k2 * ldm + k2, ldm, -1.0, 1.0);
+    for (int p = 0; p < GP; ++p) {
+      const int kp = k0 + p * NB;
+      if (kp >= n) {
+        done = true;
+        break;
+      }
+      if (p > 0) {
+        int rc = dsyrk_ata_first_rows64(c, p * NB, n - kp, dM + (size_t) k0 * ldm + kp, ldm, dM + (size_t) kp * ldm + kp, ldm);
+        if (rc != NCM_SD_GPU_OK) return rc;
+      }
+      chol_diag_kernel<<<1, 256, 0, c->stream>>>(dM, ldm, n, kp, dRhs, dDinv, dInfo);
+      c->n_launches++;
+      const int m = n - kp - NB;
+      if (m <= 0) {
+        done = true;
+        break;
+      }
+      chol_panel_kernel<<<(m + 127) / 128, 128, 0, c->stream>>>(dM, ldm, n, kp, dRhs, dDinv);
+      c->n_launches++;
+    }
+    if (done) break;
+    const int kg = k0 + GP * NB;
+    const int mg = n - kg;
+    if (mg <= 0) break;
+    int rc = dsyrk_ata_general(c, GP * NB, mg, dM + (size_t) k0 * ldm + kg, ldm, dM + (size_t) kg * ldm + kg, ldm, -1.0, 1.0);
     if (rc != NCM_SD_GPU_OK) return rc;
   }
   if (dRhs != nullptr) {
