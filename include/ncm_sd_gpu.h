@@ -72,7 +72,8 @@ int ncm_sd_gpu_upload_vkde (ncm_sd_gpu_ctx *ctx, int n_obs, int n_kernels, const
  * fail_out [n_kernels] (1 = covariance not positive definite: the caller applies the reference's
  * nearPD / diagonal fallback, kde.c:344-367, and passes the repaired factors to vkde_finish).  The points
  * and factors stay on the device; vkde_finish uploads the per-kernel lnnorms (which the host computes from
- * the factors, _kernel_gauss.c:201-207 / _kernel_st.c:240-252) and packs the records.  n_obs <= 16384. */
+ * the factors, _kernel_gauss.c:201-207 / _kernel_st.c:240-252) and packs the records.  Beyond n_obs ~ 25000 one row of
+ * distances no longer fits in shared memory and the n_kernels x n_obs distance matrix must fit in device memory. */
 int ncm_sd_gpu_vkde_prepare (ncm_sd_gpu_ctx *ctx, int n_obs, int n_kernels, const double *sample, int ld, const double *invUsample, int ldz,
                              int k, double *U_all_out, int *fail_out);
 int ncm_sd_gpu_vkde_finish (ncm_sd_gpu_ctx *ctx, const double *lnnorms, int n_fixed, const int *fixed_idx, const double *fixed_U);

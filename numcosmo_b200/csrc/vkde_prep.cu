@@ -70,11 +70,13 @@ __global__ void __launch_bounds__(256) dist_kernel(const double *__restrict__ Z,
 // distance on the order-preserving bit patterns (6 digit passes over n_obs keys instead of a full bitonic sort of n_obs:
 // 46 ms -> a few ms at n_obs = 16384), ordered compaction of the k winners (ties at the threshold are taken in index
 // order, as the (distance, index) ordering of the reference's neighbour list demands), bitonic sort of those k only.
-__global__ void __launch_bounds__(512) knn_kernel(const double *__restrict__ Z, const double *__restrict__ D, size_t ldd, int n_obs, int d, int kpow2, int k,
-                                                  int *__restrict__ nbr) {
+__global__ void __launch_bounds__(512) knn_kernel(const double *__restrict__ Z, const double *__restrict__ D, size_t ldd, int n_obs, int n_smem, int d,
+                                                  int kpow2, int k, int *__restrict__ nbr) {
   extern __shared__ __align__(16) unsigned char knn_smem[];
-  double *sd   = reinterpret_cast<double *>(knn_smem);           // [n_obs] distances
-  double *kd   = sd + n_obs;                                     // [kpow2] selected distances
+  // distances: a shared-memory copy when it fits (n_smem = n_obs), else the row of the precomputed matrix in global memory
+  // (n_smem = 0; the six selection passes and the compaction then stream it from L2)
+  double *ssd  = reinterpret_cast<double *>(knn_smem);           // [n_smem]
+  double *kd   = ssd + n_smem;                                   // [kpow2] selected distances
   int *ki      = reinterpret_cast<int *>(kd + kpow2);            // [kpow2] selected indices
   int *hist    = ki + kpow2;                                     // [2048]
   int *sscan   = hist + 2048;                                    // [16] warp totals
@@ -82,9 +84,13 @@ __global__ void __launch_bounds__(512) knn_kernel(const double *__restrict__ Z, 
   __shared__ unsigned long long s_prefix;
   __shared__ int s_rank;
   const int c = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
-  if (D != nullptr) {   // distances precomputed by dist_kernel
+  const double *sd;
+  if (n_smem == 0) {
+    sd = D + (size_t) c * ldd;   // host guarantees D != nullptr here
+  } else if (D != nullptr) {     // distances precomputed by dist_kernel
     const double *row = D + (size_t) c * ldd;
-    for (int m = tid; m < n_obs; m += nt) sd[m] = row[m];
+    for (int m = tid; m < n_obs; m += nt) ssd[m] = row[m];
+    sd = ssd;
   } else {
     for (int r = tid; r < d; r += nt) st[r] = Z[(size_t) c * d + r];
     __syncthreads();
@@ -96,8 +102,9 @@ __global__ void __launch_bounds__(512) knn_kernel(const double *__restrict__ Z, 
         const double df = __dsub_rn(p[r], st[r]);
         dist = __dadd_rn(dist, __dmul_rn(df, df));
       }
-      sd[m] = dist;
+      ssd[m] = dist;
     }
+    sd = ssd;
   }
   if (tid == 0) {
     s_prefix = 0ull;
@@ -313,9 +320,11 @@ int vkde_prepare_dev(ncm_sd_gpu_ctx *c, int n_obs, int n_kernels, int k, const d
   const int d = c->d;
   int kpow2 = 1;
   while (kpow2 < k) kpow2 <<= 1;
-  const size_t smem_knn = (size_t) n_obs * sizeof(double) + (size_t) kpow2 * (sizeof(double) + sizeof(int)) + (2048 + 16) * sizeof(int) +
-                          (size_t) d * sizeof(double) + 16;
-  if (smem_knn > 220 * 1024) return c->fail(NCM_SD_GPU_EINVAL, "vkde_prepare: n_obs too large for the shared-memory neighbour selection");
+  const size_t smem_fixed = (size_t) kpow2 * (sizeof(double) + sizeof(int)) + (2048 + 16) * sizeof(int) + (size_t) d * sizeof(double) + 16;
+  if (smem_fixed > 200 * 1024) return c->fail(NCM_SD_GPU_EINVAL, "vkde_prepare: too many neighbours for the shared-memory sort");
+  int n_smem = n_obs;   // distances of one centre in shared memory when they fit
+  if (smem_fixed + (size_t) n_obs * sizeof(double) > 220 * 1024) n_smem = 0;
+  const size_t smem_knn = smem_fixed + (size_t) n_smem * sizeof(double);
   static size_t knn_attr_tab[NCM_MAX_DEVICES] = {};   // function attributes are per device
   size_t &knn_attr = knn_attr_tab[c->device % NCM_MAX_DEVICES];
   const size_t cov_attr = 0;   // the covariance kernel's attribute is set at every launch (four instantiations)
@@ -337,7 +346,9 @@ int vkde_prepare_dev(ncm_sd_gpu_ctx *c, int n_obs, int n_kernels, int k, const d
       dD = c->dist.as<double>();
     }   // else: not enough memory for the matrix, every CTA computes its own distances
   }
-  knn_kernel<<<n_kernels, threads, smem_knn, c->stream>>>(dZ, dD, ldd, n_obs, d, kpow2, k, dNbr);
+  if (n_smem == 0 && dD == nullptr)
+    return c->fail(NCM_SD_GPU_ENOMEM, "vkde_prepare: the distance matrix does not fit in device memory and one row does not fit in shared memory");
+  knn_kernel<<<n_kernels, threads, smem_knn, c->stream>>>(dZ, dD, ldd, n_obs, n_smem, d, kpow2, k, dNbr);
   const int wpb = 8;
   const size_t smem_cov = (size_t) wpb * (2 * d + d * d) * sizeof(double);
   const int npair = d * (d - 1) / 2;

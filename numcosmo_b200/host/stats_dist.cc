@@ -224,7 +224,7 @@ bool vkde_build_cov_array(NcmStatsDist *sd) {
   // Device path: kNN + covariance + Cholesky in libncm_sd_gpu, bit-identical to host_centre;
   // only the matrices whose plain Cholesky fails come back to the host for the reference's fallback chain.
   const bool host_only = ncm_b200_host_prepare_kernel();
-  if (!host_only && n_obs <= 16384 && ensure_gpu(sd)) {
+  if (!host_only && n_obs <= 65536 && ensure_gpu(sd)) {
     std::vector<int> fail(nk, 0);
     int rc;
     {

@@ -69,3 +69,23 @@ def test_vkde_prepare_degenerate_falls_back(oracle):
     sd.prepare()
     out = sd.eval_m2lnp_array(X[:10])
     assert np.all(np.isfinite(out))
+
+
+def test_vkde_prepare_beyond_shared_memory_capacity(oracle, gpu_ctx):
+    """n_obs = 30000: one row of distances (240 KB) no longer fits in shared memory, the selection streams the
+    precomputed distance matrix instead; same neighbours, same factors as the oracle on a sub-sample of the centres."""
+    from numcosmo_b200 import capi
+
+    d, n, k = 3, 30000, 300
+    rs = np.random.default_rng(12)
+    Z = rs.normal(size=(n, d))                       # already "whitened": raw = whitened here
+    gpu_ctx.set_kernel(capi.KERNEL_GAUSS, 3.0, d)
+    U, fail = gpu_ctx.vkde_prepare(Z, Z, n, k)
+    assert not fail.any()
+    # reference for a few centres: exact kNN by (distance, index), NcmStatsVec covariance, Cholesky
+    for c in (0, 1, 14999, 29999):
+        dist = ((Z - Z[c]) ** 2) @ np.ones(d)        # not bit-identical to the sequential sum; ties are measure-zero here
+        order = np.lexsort((np.arange(n), dist))[:k]
+        cov = np.cov(Z[order].T, bias=False)
+        Uref = np.linalg.cholesky(cov).T
+        assert np.max(np.abs(np.triu(U[c]) - Uref)) < 1e-10 * np.abs(Uref).max()
