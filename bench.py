@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="apes_vkde_gauss_mvnd10_w4096",
                     choices=["apes_vkde_gauss_mvnd10_w4096", "eval_sweep", "prepare_interp", "apes_e2e"])
-    ap.add_argument("--target", default="funnel", choices=["funnel", "rosenbrock"], help="--workload apes_e2e: configs[3] (funnel) / configs[0] (rosenbrock)")
+    ap.add_argument("--target", default="funnel", choices=["funnel", "rosenbrock", "mvnd"], help="--workload apes_e2e: configs[3] (funnel) / configs[0] (rosenbrock)")
     ap.add_argument("--over-smooth", type=float, default=None)
     ap.add_argument("--walkers", type=int, default=4096)
     ap.add_argument("--dim", type=int, default=10)
@@ -756,6 +756,12 @@ def run_apes_e2e(args):
         m2lnL = (d - 1) * nuv + (nuv / 3.0) ** 2 + np.sum(X[:, 1:] ** 2, axis=1) * np.exp(-nuv)
         os_ = 0.2 if args.over_smooth is None else args.over_smooth
         target = S.TARGET_FUNNEL
+    elif args.target == "mvnd":
+        # the configs[1] recipe at any size (e.g. --walkers 65536: the largest ensemble the north star names)
+        mu_t, cov_t, U_t, X, m2lnL = make_problem_b200(S, W, d)
+        lb, ub = np.full(d, -50.0), np.full(d, 50.0)
+        os_ = 1.0 if args.over_smooth is None else args.over_smooth
+        target = S.TARGET_MVND
     else:
         # ncm_model_rosenbrock.c:139-142 bounds; numcosmo_py/experiments/rosenbrock.py:46-49 init
         X = np.array([1.0, 1.0])[None, :] + 1.0e2 * rs.normal(size=(W, 2)) * 0.01
@@ -769,7 +775,8 @@ def run_apes_e2e(args):
     theta, ml = X.copy(), np.ascontiguousarray(m2lnL)
     rng = S.RNG(4)
     warm = max(1, min(args.warmup, 2))
-    apes.run(target, lb, ub, theta, ml, warm, rng, record_accept=False)
+    targs = (mu_t, U_t) if args.target == "mvnd" else None
+    apes.run(target, lb, ub, theta, ml, warm, rng, target_args=targs, record_accept=False)
     sds = apes.peek_sds()
     ctxs = [capi.Context.borrowed(lib.ncm_stats_dist_b200_peek_ctx(sd._h)) for sd in sds]
     for c in ctxs:
@@ -778,13 +785,13 @@ def run_apes_e2e(args):
     steps = max(1, args.steps)
     with ClockSampler(0) as clk:
         t0 = time.perf_counter()
-        acc, _ = apes.run(target, lb, ub, theta, ml, steps, rng, record_accept=True)
+        acc, _ = apes.run(target, lb, ub, theta, ml, steps, rng, target_args=targs, record_accept=True)
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / steps
     traffic = [c.get_traffic() for c in ctxs]
     launches = sum(c.get_timers()[1] for c in ctxs)
     apes.enable_timers(True)
-    _, stage = apes.run(target, lb, ub, theta, ml, 1, rng, record_accept=False)
+    _, stage = apes.run(target, lb, ub, theta, ml, 1, rng, target_args=targs, record_accept=False)
     apes.enable_timers(False)
     nn = [sd.nnls_stats() for sd in sds]
     uses = [c.vkde_path() for c in ctxs]
