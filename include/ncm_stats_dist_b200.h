@@ -234,6 +234,9 @@ void ncm_stats_dist_vkde_set_use_rot_href (NcmStatsDistVKDE *sdvkde, const gbool
 gboolean ncm_stats_dist_vkde_get_use_rot_href (NcmStatsDistVKDE *sdvkde);
 
 /* instrumentation of the GPU path behind an object (not in the reference) */
+/* optimiser trace of the last prepare / prepare_interp under a cross-validation mode: the number of objective evaluations and,
+ * for the first cap of them, (ln over_smooth, objective value or NNLS rnorm) in evaluation order */
+gint ncm_stats_dist_b200_get_cv_trace (NcmStatsDist *sd, gdouble *lnos, gdouble *val, gint cap);
 void ncm_stats_dist_b200_get_nnls_stats (NcmStatsDist *sd, gint *n_chol, gint *n_retry, gint *n_outer, gint *n_passive);
 void ncm_stats_dist_b200_get_timers (NcmStatsDist *sd, gdouble *ms7, long long *n_launches, gdouble *host_prepare_kernel_ms);
 void ncm_stats_dist_b200_enable_timers (NcmStatsDist *sd, gboolean on);

@@ -2,6 +2,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdlib>
+#include <functional>
 #include <string>
 #include <vector>
 #include "../../include/ncm_sd_gpu.h"
@@ -106,6 +107,10 @@ struct _NcmStatsDist {
   ncm_sd_gpu_nnls_stats nnls_stats;
   double host_prepare_kernel_ms;
   bool resident;   // prepare_kernel ran on the device: points, factors and records are already in HBM (no upload)
+  // cross-validation (ncm_stats_dist.c:175-178): self->rng seeded 0, used by the CV_SPLIT random tries
+  NcmRNG *cv_rng;
+  std::vector<double> cv_trace;   // (ln over_smooth, objective) per objective evaluation of the last prepare / prepare_interp
+  std::vector<double> IM_host;    // host copy of the interpolation matrix for the CV_LOO objectives
 };
 
 void ncm_b200_error(const char *fmt, ...);
@@ -117,6 +122,12 @@ int ncm_b200_cholesky_upper(double *a, int n, int ld);                 // A = U^
 int ncm_b200_nearPD_upper(double *a, int n, int maxiter);              // Higham nearPD + Cholesky, ncm_matrix.c:1248-1343
 double ncm_b200_cholesky_lndet(const double *U, int n, int ld);        // ncm_matrix.c:1157-1185
 void ncm_b200_cholesky_decomp_fallback(double *cov_decomp, const double *cov, int d, int maxiter);   // kde.c:344-367
+
+// one-parameter optimisers of the cross-validation modes (host/optim.cc)
+int ncm_b200_simplex1_minimize(const std::function<double(double)> &f, double x0, double step, double size_tol, int max_iter, double *x_best,
+                               double *f_best);
+int ncm_b200_lm1_dif(const std::function<void(double, double *)> &func, double *p_io, const double *x, int n, int itmax, const double opts[5],
+                     double info[10]);
 
 int ncm_b200_default_device();
 bool ncm_b200_host_prepare_kernel();   // debugging / parity switch: run the VKDE prepare_kernel loop on the host

@@ -3,8 +3,11 @@
 //
 //   prepare_kernel   host, O(N d^2) (+ kNN for VKDE): ncm_stats_dist_kde.c:378-490, ncm_stats_dist_vkde.c:362-515
 //                    -> ncm_sd_gpu_upload_kde / ncm_sd_gpu_upload_vkde
-//   prepare          ncm_stats_dist.c:703-789 (CV_NONE)           -> ncm_sd_gpu_set_weights
+//   prepare          ncm_stats_dist.c:703-789                     -> ncm_sd_gpu_set_weights
 //   prepare_interp   ncm_stats_dist.c:878-1094                    -> ncm_sd_gpu_compute_IM + ncm_sd_gpu_nnls_solve
+//   cross-validation ncm_stats_dist.c:484-701, 806-876, 1018-1072: every objective evaluation is a GPU pass
+//                    (batched eval of the held-out points / IM / IM + NNLS + eval), the one-parameter
+//                    optimisers run on the host (host/optim.cc)
 //   eval[_m2lnp]     ncm_stats_dist.c:1527-1554                   -> ncm_sd_gpu_eval[_m2lnp] (q = 1, or a whole batch
 //                                                                    through the new ncm_stats_dist_eval_m2lnp_array)
 //   kernel_choose / sample   ncm_stats_dist.c:1565-1627           host, serial RNG stream in reference order
@@ -76,6 +79,7 @@ NcmStatsDist *sd_new(int type, NcmStatsDistKernel *sdk, NcmStatsDistCV cv_type) 
   sd->resident               = false;
   sd->sample_view.pdata      = nullptr;
   sd->sample_view.len        = 0;
+  sd->cv_rng                 = ncm_rng_seeded_new(nullptr, 0);
   return sd;
 }
 
@@ -304,16 +308,154 @@ bool prepare_kernel(NcmStatsDist *sd) {
   return upload(sd);
 }
 
+bool push_weights(NcmStatsDist *sd) {
+  std::lock_guard<std::mutex> lk(g_gpu_mutex);
+  return gpu_ok(sd, ncm_sd_gpu_set_weights(sd->gpu, (int) sd->n_kernels, sd->weights->data, sd->href), "ncm_stats_dist_prepare");
+}
+
+// ---- cross-validation objectives ------------------------------------------------------
+// Each one sets over_smooth / href as a side effect, exactly as the reference's callbacks do: after the simplex
+// stops, the object keeps the bandwidth of the LAST point evaluated (ncm_stats_dist.c:660-701 never copies the
+// best corner back).
+
+void cv_trace_add(NcmStatsDist *sd, double lnos, double val) {
+  sd->cv_trace.push_back(lnos);
+  sd->cv_trace.push_back(val);
+}
+
+// _ncm_stats_dist_m2lnp, ncm_stats_dist.c:484-511: -2 ln L of the held-out observations [n_kernels, n_obs), one batched eval
+double cv_obj_m2lnp(NcmStatsDist *sd, double lnos) {
+  sd->over_smooth = exp(lnos);
+  sd->href        = sd_href(sd);
+  const int d = (int) sd->d, q = (int) (sd->n_obs - sd->n_kernels);
+  std::vector<double> out((size_t) std::max(q, 1));
+  if (!push_weights(sd)) return NAN;
+  if (q > 0) {
+    std::lock_guard<std::mutex> lk(g_gpu_mutex);
+    if (!gpu_ok(sd, ncm_sd_gpu_eval_m2lnp(sd->gpu, q, &sd->sample_matrix[(size_t) sd->n_kernels * d], d, out.data()), "_ncm_stats_dist_m2lnp")) return NAN;
+  }
+  double m2lnp = 0.0;
+  for (int i = 0; i < q; i++) m2lnp += out[i];
+  if (sd->print_fit) fprintf(stderr, "# over-smooth: % 22.15g, m2lnp = % 22.15g\n", sd->over_smooth, m2lnp);
+  cv_trace_add(sd, lnos, m2lnp);
+  return m2lnp;
+}
+
+bool cv_IM_to_host(NcmStatsDist *sd, const char *where) {
+  sd->IM_host.resize((size_t) sd->n_obs * sd->n_kernels);
+  std::lock_guard<std::mutex> lk(g_gpu_mutex);
+  if (!gpu_ok(sd, ncm_sd_gpu_set_href(sd->gpu, sd->href), where)) return false;
+  return gpu_ok(sd, ncm_sd_gpu_compute_IM(sd->gpu, nullptr, sd->IM_host.data()), where);
+}
+
+// _ncm_stats_dist_amise_kde_gauss, ncm_stats_dist.c:513-558
+double cv_obj_amise_kde_gauss(NcmStatsDist *sd, double lnos) {
+  const guint nk = sd->n_kernels;
+  double amise   = 0.0;
+  sd->over_smooth = exp(lnos);
+  sd->href        = sqrt(2.0) * sd_href(sd);
+  if (!cv_IM_to_host(sd, "_ncm_stats_dist_amise_kde_gauss")) return NAN;
+  const double *IM = sd->IM_host.data();
+  for (guint i = 0; i < nk; i++)
+    for (guint j = 0; j < nk; j++) amise += IM[(size_t) i * nk + j] / ((double) nk * (double) nk);
+  sd->over_smooth = exp(lnos);
+  sd->href        = sd_href(sd);
+  if (!cv_IM_to_host(sd, "_ncm_stats_dist_amise_kde_gauss")) return NAN;
+  IM               = sd->IM_host.data();
+  const double nn1 = (double) (nk * (nk - 1));   // guint product, as in the reference
+  for (guint i = 0; i < nk; i++) {
+    for (guint j = 0; j < i; j++) amise -= 2.0 * IM[(size_t) i * nk + j] / nn1;
+    for (guint j = i + 1; j < nk; j++) amise -= 2.0 * IM[(size_t) i * nk + j] / nn1;
+  }
+  if (sd->print_fit) fprintf(stderr, "# over-smooth: % 22.15g, amise = % 22.15g\n", sd->over_smooth, amise);
+  cv_trace_add(sd, lnos, amise);
+  return amise;
+}
+
+// _ncm_stats_dist_amise, ncm_stats_dist.c:562-658: leave-one-out term from the IM rows + Monte-Carlo integral of p^2 with
+// the antithetic kernel pairs of ncm_stats_dist_sample2 (:1629-1651); the two densities of a pair are one q = 2 batch
+double cv_obj_amise(NcmStatsDist *sd, double lnos) {
+  const guint nk = sd->n_kernels;
+  const int d    = (int) sd->d;
+  double amise   = 0.0;
+  sd->over_smooth = exp(lnos);
+  sd->href        = sd_href(sd);
+  if (!cv_IM_to_host(sd, "_ncm_stats_dist_amise")) return NAN;
+  const double *IM = sd->IM_host.data();
+  const double nn1 = (double) (nk * (nk - 1));
+  std::vector<double> dens(nk);
+  std::vector<size_t> sort(nk);
+  for (guint i = 0; i < nk; i++) {
+    double row_sum = 0.0;
+    for (guint j = 0; j < i; j++) row_sum += IM[(size_t) i * nk + j];
+    for (guint j = i + 1; j < nk; j++) row_sum += IM[(size_t) i * nk + j];
+    amise -= 2.0 * row_sum / nn1;
+    dens[i] = (row_sum + IM[(size_t) i * nk + i]) / nk;
+    sort[i] = i;
+  }
+  // gsl_sort_index is a heapsort; equal keys (not expected for densities) are ordered by index here
+  std::stable_sort(sort.begin(), sort.end(), [&](size_t a, size_t b) { return dens[a] < dens[b]; });
+  if (!push_weights(sd)) return NAN;
+
+  NcmRNG *rng = ncm_rng_seeded_new(nullptr, 0);
+  StatsVec stats(2);
+  NcmMatrix *X = ncm_matrix_new(2, sd->d);
+  NcmVector x1{X->data, sd->d, 1, 1, false}, x2{X->data + d, sd->d, 1, 1, false};
+  double p12[2], mean = 0.0;
+  bool ok = true;
+  auto draw_pair = [&]() {
+    const guint i   = ncm_stats_dist_kernel_choose(sd, rng);
+    const guint o_i = (guint) sort[i];
+    ncm_stats_dist_kernel_sample(sd->kernel, ncm_stats_dist_peek_cov_decomp(sd, o_i), sd->href, (NcmVector *) sd->sample[o_i], &x1, rng);
+    const guint j   = (guint) sd->sample.size() - 1 - i;
+    const guint o_j = (guint) sort[j];
+    ncm_stats_dist_kernel_sample(sd->kernel, ncm_stats_dist_peek_cov_decomp(sd, o_j), sd->href, (NcmVector *) sd->sample[o_j], &x2, rng);
+    std::lock_guard<std::mutex> lk(g_gpu_mutex);
+    ok = ok && gpu_ok(sd, ncm_sd_gpu_eval(sd->gpu, 2, X->data, d, p12), "_ncm_stats_dist_amise");
+    stats.append(p12);
+  };
+  for (guint it = 0; it < 100 && ok; it++) draw_pair();
+  const guint max_iter = 100000000;
+  for (guint it = 0; it < max_iter && ok; it++) {
+    draw_pair();
+    mean             = 0.5 * (stats.mean[0] + stats.mean[1]);
+    const double var = 0.25 * (stats.var[0] * stats.bias_wt + stats.var[1] * stats.bias_wt + 2.0 * (stats.cov[0 * 2 + 1] * stats.bias_wt));
+    const double msd = sqrt(var / (it + 101.0)) / mean;
+    if (msd < 1.0e-2) break;
+  }
+  amise += mean;
+  ncm_matrix_free(X);
+  ncm_rng_free(rng);
+  if (!ok) return NAN;
+  if (sd->print_fit) fprintf(stderr, "# over-smooth: % 22.15g, amise = % 22.15g\n", sd->over_smooth, amise);
+  cv_trace_add(sd, lnos, amise);
+  return amise;
+}
+
+// _ncm_stats_dist_minimize_obj, ncm_stats_dist.c:660-701
+void cv_minimize_obj(NcmStatsDist *sd, double (*objective)(NcmStatsDist *, double)) {
+  std::function<double(double)> f = [&](double lnos) { return objective(sd, lnos); };
+  double x_best = 0.0, f_best = 0.0;
+  const int iter = ncm_b200_simplex1_minimize(f, log(sd->over_smooth), 0.1, 1.0e-3, 1000, &x_best, &f_best);
+  if (sd->print_fit) printf("# iter: %d, over-smooth: % 22.15g, m2lnp = % 22.15g\n", iter, sd->over_smooth, f_best);
+}
+
 // ncm_stats_dist.c:703-789
 bool do_prepare(NcmStatsDist *sd) {
+  sd->cv_trace.clear();
   switch (sd->cv_type) {
+    case NCM_STATS_DIST_CV_LOO:
     case NCM_STATS_DIST_CV_NONE:
       sd->n_obs     = (guint) sd->sample.size();
       sd->n_kernels = (guint) sd->sample.size();
       break;
+    case NCM_STATS_DIST_CV_SPLIT:
+    case NCM_STATS_DIST_CV_SPLIT_NOFIT:
+      sd->n_obs     = (guint) sd->sample.size();
+      sd->n_kernels = (guint) ceil(sd->sample.size() * sd->split_frac);
+      break;
     default:
-      ncm_b200_error("_ncm_stats_dist_prepare: cross-validation modes other than NCM_STATS_DIST_CV_NONE are outside the APES "
-                     "path and not served by the B200 build.");
+      ncm_b200_error("_ncm_stats_dist_prepare: code should not be reached (unknown cross-validation type %d).", (int) sd->cv_type);
       return false;
   }
   if (sd->n_obs <= sd->d) {
@@ -331,12 +473,23 @@ bool do_prepare(NcmStatsDist *sd) {
   ncm_vector_set_all(sd->weights, 1.0 / (1.0 * sd->n_kernels));
   sd->wcum_ready = FALSE;
   sd->prepared   = true;
-  return true;
-}
-
-bool push_weights(NcmStatsDist *sd) {
-  std::lock_guard<std::mutex> lk(g_gpu_mutex);
-  return gpu_ok(sd, ncm_sd_gpu_set_weights(sd->gpu, (int) sd->n_kernels, sd->weights->data, sd->href), "ncm_stats_dist_prepare");
+  switch (sd->cv_type) {
+    case NCM_STATS_DIST_CV_NONE:
+    case NCM_STATS_DIST_CV_SPLIT:
+      break;
+    case NCM_STATS_DIST_CV_SPLIT_NOFIT:
+      cv_minimize_obj(sd, &cv_obj_m2lnp);
+      break;
+    case NCM_STATS_DIST_CV_LOO:
+      if (sd->type == NCM_SD_GPU_KDE && sd->kernel->kind == NCM_SD_GPU_KERNEL_GAUSS)
+        cv_minimize_obj(sd, &cv_obj_amise_kde_gauss);
+      else
+        cv_minimize_obj(sd, &cv_obj_amise);
+      break;
+    default:
+      break;
+  }
+  return !ncm_b200_error_pending();
 }
 
 }   // namespace
@@ -361,6 +514,7 @@ void ncm_stats_dist_free(NcmStatsDist *sd) {
   ncm_vector_clear(&sd->weights);
   ncm_vector_clear(&sd->wcum);
   if (sd->gpu != nullptr) ncm_sd_gpu_ctx_free(sd->gpu);
+  ncm_rng_clear(&sd->cv_rng);
   delete sd;
 }
 void ncm_stats_dist_clear(NcmStatsDist **sd) {
@@ -545,14 +699,61 @@ void ncm_stats_dist_prepare_interp(NcmStatsDist *sd, NcmVector *m2lnp) {
     inv_f[i]         = 1.0 / f_i;                                                 // row scaling of :791-804
   }
   if (sd->n_kernels > 20000) fprintf(stderr, "_ncm_stats_dist_prepare_interp: very large system n = %u!\n", sd->n_kernels);
-  {
+  // _ncm_stats_dist_compute_IM_full + NCM_NNLS_SOLVE at the current href; the raw solution lands in sd->weights
+  auto IM_nnls = [&](double *rnorm_out) -> bool {
     std::lock_guard<std::mutex> lk(g_gpu_mutex);
     // compute_IM needs the bandwidth (weights are irrelevant for IM)
-    if (!gpu_ok(sd, ncm_sd_gpu_set_href(sd->gpu, sd->href), "prepare_interp")) return;
-    if (!gpu_ok(sd, ncm_sd_gpu_compute_IM(sd->gpu, inv_f.data(), nullptr), "_ncm_stats_dist_compute_IM_full")) return;
-    double rnorm = 0.0;
-    if (!gpu_ok(sd, ncm_sd_gpu_nnls_solve(sd->gpu, DBL_EPSILON, sd->weights->data, &rnorm, &sd->nnls_stats), "ncm_nnls_solve")) return;
-    sd->rnorm = rnorm;
+    if (!gpu_ok(sd, ncm_sd_gpu_set_href(sd->gpu, sd->href), "prepare_interp")) return false;
+    if (!gpu_ok(sd, ncm_sd_gpu_compute_IM(sd->gpu, inv_f.data(), nullptr), "_ncm_stats_dist_compute_IM_full")) return false;
+    return gpu_ok(sd, ncm_sd_gpu_nnls_solve(sd->gpu, DBL_EPSILON, sd->weights->data, rnorm_out, &sd->nnls_stats), "ncm_nnls_solve");
+  };
+  if (sd->cv_type == NCM_STATS_DIST_CV_SPLIT) {
+    // ncm_stats_dist.c:1018-1072: ten Gaussian tries around ln over_smooth, then a one-parameter levmar fit of the
+    // interpolation residuals expm1 (-(m2lnp_interp - m2lnp_target) / 2) over ALL observations
+    const double opts[5] = {1e-3 /* LM_INIT_MU */, 1.0e-7, 1.0e-7, 1.0e-10, 1e-6 /* LM_DIFF_DELTA */};
+    double info[10], rnorm0 = 0.0;
+    double ln_os = log(sd->over_smooth);
+    if (!IM_nnls(&rnorm0)) return;
+    cv_trace_add(sd, ln_os, rnorm0);
+    for (int i = 0; i < 10; i++) {
+      const double ln_os_try = ncm_rng_gaussian_gen(sd->cv_rng, ln_os, 0.5);
+      double rnorm_try       = 0.0;
+      sd->over_smooth        = exp(ln_os_try);
+      sd->href               = sd_href(sd);
+      if (!IM_nnls(&rnorm_try)) return;
+      cv_trace_add(sd, ln_os_try, rnorm_try);
+      if (rnorm_try < rnorm0) {
+        ln_os  = ln_os_try;
+        rnorm0 = rnorm_try;
+      }
+    }
+    bool ok = true;
+    std::vector<double> m2lnpi(sd->n_obs);
+    // _ncm_stats_dist_prepare_interp_fit_nnls_f, ncm_stats_dist.c:815-851 (eval_m2lnp reads the raw NNLS solution)
+    std::function<void(double, double *)> fit_f = [&](double p, double *hx) {
+      double rnorm    = 0.0;
+      sd->over_smooth = exp(p);
+      sd->href        = sd_href(sd);
+      ok              = ok && IM_nnls(&rnorm) && push_weights(sd);
+      if (ok) {
+        std::lock_guard<std::mutex> lk(g_gpu_mutex);
+        ok = gpu_ok(sd, ncm_sd_gpu_eval_m2lnp(sd->gpu, (int) sd->n_obs, sd->sample_matrix.data(), (int) sd->d, m2lnpi.data()),
+                    "_ncm_stats_dist_prepare_interp_fit_nnls_f");
+      }
+      for (guint i = 0; i < sd->n_obs; i++) {
+        const double m2lnpt_i = ncm_vector_get(m2lnp, i) - sd->min_m2lnp;
+        hx[i]                 = ok ? expm1(-0.5 * (m2lnpi[i] - m2lnpt_i)) : NAN;
+      }
+      if (sd->print_fit) fprintf(stderr, "# over-smooth: % 22.15g, rnorm = % 22.15g\n", sd->over_smooth, rnorm);
+      cv_trace_add(sd, p, rnorm);
+    };
+    ncm_b200_lm1_dif(fit_f, &ln_os, nullptr, (int) sd->n_obs, 10000, opts, info);
+    if (!ok) return;
+    sd->over_smooth = exp(ln_os);
+    sd->href        = sd_href(sd);
+    if (!IM_nnls(&sd->rnorm)) return;
+  } else {
+    if (!IM_nnls(&sd->rnorm)) return;
   }
   {
     // ncm_stats_dist.c:1087-1093
@@ -566,7 +767,7 @@ void ncm_stats_dist_prepare_interp(NcmStatsDist *sd, NcmVector *m2lnp) {
     for (guint i = 0; i < sd->n_kernels; i++) sd->weights->data[i] *= s;
     for (guint i = 0; i < sd->n_kernels; i++) sd->weights->data[i] += c;
   }
-  sd->wcum_ready = FALSE;
+  // the reference does not invalidate wcum here: _ncm_stats_dist_prepare did, and only CV_LOO's sample2 rebuilds it in between
   push_weights(sd);
 }
 
@@ -694,6 +895,14 @@ void ncm_stats_dist_b200_get_nnls_stats(NcmStatsDist *sd, gint *n_chol, gint *n_
   if (n_retry) *n_retry = sd->nnls_stats.n_retry;
   if (n_outer) *n_outer = sd->nnls_stats.n_outer;
   if (n_passive) *n_passive = sd->nnls_stats.n_passive;
+}
+gint ncm_stats_dist_b200_get_cv_trace(NcmStatsDist *sd, gdouble *lnos, gdouble *val, gint cap) {
+  const gint n = (gint) (sd->cv_trace.size() / 2);
+  for (gint i = 0; i < n && i < cap; i++) {
+    lnos[i] = sd->cv_trace[2 * i];
+    val[i]  = sd->cv_trace[2 * i + 1];
+  }
+  return n;
 }
 void ncm_stats_dist_b200_get_timers(NcmStatsDist *sd, gdouble *ms7, long long *n_launches, gdouble *host_prepare_kernel_ms) {
   if (sd->gpu != nullptr) ncm_sd_gpu_get_timers(sd->gpu, ms7, n_launches);

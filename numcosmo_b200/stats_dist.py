@@ -163,6 +163,7 @@ def lib():
             "ncm_stats_dist_vkde_set_use_rot_href": (None, [_vp, i]),
             "ncm_stats_dist_vkde_get_use_rot_href": (i, [_vp]),
             "ncm_stats_dist_b200_get_nnls_stats": (None, [_vp, C.POINTER(i), C.POINTER(i), C.POINTER(i), C.POINTER(i)]),
+            "ncm_stats_dist_b200_get_cv_trace": (i, [_vp, _dp, _dp, i]),
             "ncm_stats_dist_b200_get_timers": (None, [_vp, _dp, C.POINTER(C.c_longlong), _dp]),
             "ncm_stats_dist_b200_enable_timers": (None, [_vp, i]),
             "ncm_stats_dist_b200_peek_ctx": (_vp, [_vp]),
@@ -467,6 +468,14 @@ class StatsDist:
         lib().ncm_stats_dist_b200_get_nnls_stats(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d))
         return {"n_chol": a.value, "n_retry": b.value, "n_outer": c.value, "n_passive": d.value}
 
+    def cv_trace(self):
+        """(ln over_smooth, objective or rnorm) of every objective evaluation of the last prepare / prepare_interp
+        under a cross-validation mode (ncm_stats_dist.c:484-701, 1018-1072)."""
+        n = lib().ncm_stats_dist_b200_get_cv_trace(self._h, None, None, 0)
+        a, b = np.zeros(max(n, 1)), np.zeros(max(n, 1))
+        lib().ncm_stats_dist_b200_get_cv_trace(self._h, a.ctypes.data_as(_dp), b.ctypes.data_as(_dp), n)
+        return a[:n], b[:n]
+
     def enable_timers(self, on=True):
         lib().ncm_stats_dist_b200_enable_timers(self._h, int(on))
         _check()
@@ -556,6 +565,14 @@ class FitESMCMCWalkerAPES:
         a, b = C.c_void_p(), C.c_void_p()
         lib().ncm_fit_esmcmc_walker_apes_peek_sds(self._h, C.byref(a), C.byref(b))
         return _BorrowedSD(a, self.nparams), _BorrowedSD(b, self.nparams)
+
+    def cv_trace(self):
+        """(ln over_smooth, objective or rnorm) of every objective evaluation of the last prepare / prepare_interp
+        under a cross-validation mode (ncm_stats_dist.c:484-701, 1018-1072)."""
+        n = lib().ncm_stats_dist_b200_get_cv_trace(self._h, None, None, 0)
+        a, b = np.zeros(max(n, 1)), np.zeros(max(n, 1))
+        lib().ncm_stats_dist_b200_get_cv_trace(self._h, a.ctypes.data_as(_dp), b.ctypes.data_as(_dp), n)
+        return a[:n], b[:n]
 
     def enable_timers(self, on=True):
         for sd in self.peek_sds():

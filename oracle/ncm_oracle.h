@@ -80,6 +80,24 @@ double orc_nnls_solve (const double *A, int nrows, int ncols, int lda, double *x
 void orc_sort_smallest_index (int *p, int k, const double *src, int stride, int n);
 void orc_sort_largest_index (int *p, int k, const double *src, int stride, int n);
 
+/* ---------------- optimisers behind the cross-validation modes (orc_optim.c) ---------------- */
+typedef double (*orc_fmin_fn) (const double *x, int n, void *params);
+typedef struct orc_nmsimplex2 orc_nmsimplex2;   /* gsl_multimin_fminimizer_nmsimplex2 restated (parity unpinned: GSL absent) */
+orc_nmsimplex2 *orc_nmsimplex2_new (int n);
+void orc_nmsimplex2_free (orc_nmsimplex2 *s);
+int orc_nmsimplex2_set (orc_nmsimplex2 *s, orc_fmin_fn f, void *params, const double *x, const double *step_size);
+int orc_nmsimplex2_iterate (orc_nmsimplex2 *s);
+const double *orc_nmsimplex2_x (const orc_nmsimplex2 *s);
+double orc_nmsimplex2_fval (const orc_nmsimplex2 *s);
+double orc_nmsimplex2_size (const orc_nmsimplex2 *s);
+/* the iterate / gsl_multimin_test_size loop of ncm_stats_dist.c:681-692; returns the iteration count */
+int orc_nmsimplex2_minimize (orc_nmsimplex2 *s, orc_fmin_fn f, void *params, const double *x0, const double *step, double size_tol, int max_iter);
+/* levmar's dlevmar_dif (numcosmo/external/levmar/lm_core.c:436-851) restated; pinned against oracle/_ref/liblevmar_ref.so */
+typedef void (*orc_lm_fn) (double *p, double *hx, int m, int n, void *adata);
+/* register the reference's own dlevmar_dif (from oracle/_ref/liblevmar_ref.so) for the CV_SPLIT fit; NULL = the restatement */
+void orc_set_levmar_dif (void *dlevmar_dif_fn);
+int orc_lm_dif (orc_lm_fn func, double *p, const double *x, int m, int n, int itmax, const double *opts, double *info, void *adata);
+
 /* ---------------- NcmStatsDist (orc_stats_dist.c) ---------------- */
 enum { ORC_SD_KDE = 0, ORC_SD_VKDE = 1 };
 enum { ORC_CV_NONE = 0, ORC_CV_SPLIT, ORC_CV_SPLIT_NOFIT, ORC_CV_LOO };
@@ -116,6 +134,10 @@ int orc_sd_get_dim (const orc_sd *sd);
 int orc_sd_get_sample_size (const orc_sd *sd);
 int orc_sd_get_n_obs (const orc_sd *sd);
 int orc_sd_get_n_kernels (const orc_sd *sd);
+double orc_sd_get_over_smooth (const orc_sd *sd);       /* the cross-validation modes leave their fitted value here */
+/* optimiser trace of the last prepare / prepare_interp with a CV mode: number of objective evaluations and, per
+ * evaluation, (ln over_smooth, objective or rnorm); at most cap entries are copied */
+int orc_sd_get_cv_trace (const orc_sd *sd, double *lnos, double *val, int cap);
 double orc_sd_get_href (orc_sd *sd);
 double orc_sd_get_rnorm (const orc_sd *sd);             /* returns rnorm^2 as ncm_stats_dist.c:1664-1669 */
 double orc_sd_get_lnnorm (orc_sd *sd, int i);

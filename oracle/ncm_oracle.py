@@ -13,10 +13,11 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_build", "libncm_oracle.so")
+_REF_LEVMAR_PATH = os.path.join(_HERE, "_ref", "liblevmar_ref.so")   # the reference's own levmar, built by `make ref`
 
 KERNEL_GAUSS, KERNEL_ST = 0, 1
 SD_KDE, SD_VKDE = 0, 1
-CV_NONE = 0
+CV_NONE, CV_SPLIT, CV_SPLIT_NOFIT, CV_LOO = 0, 1, 2, 3
 COV_SAMPLE, COV_FIXED = 0, 1
 TARGET_MVND, TARGET_ROSENBROCK, TARGET_FUNNEL = 0, 1, 2
 
@@ -25,9 +26,34 @@ _dp = C.POINTER(C.c_double)
 
 def build(force: bool = False) -> str:
     """Compile the oracle with its Makefile (gcc + SciPy's OpenBLAS)."""
-    if force or not os.path.exists(_LIB_PATH):
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h")) or f == "Makefile"]
+    stale = (not os.path.exists(_LIB_PATH)) or any(os.path.getmtime(f) > os.path.getmtime(_LIB_PATH) for f in srcs)
+    if force or stale:
         subprocess.check_call(["make", "-C", _HERE], stdout=subprocess.DEVNULL)
     return _LIB_PATH
+
+
+_FMIN_FN = C.CFUNCTYPE(C.c_double, C.POINTER(C.c_double), C.c_int, C.c_void_p)
+_LM_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.c_int, C.c_void_p)
+_ref_levmar = None
+
+
+def ref_levmar():
+    """The reference's own levmar (oracle/_ref/liblevmar_ref.so), or None when it was never built."""
+    global _ref_levmar
+    if _ref_levmar is None and os.path.exists(_REF_LEVMAR_PATH):
+        L = C.CDLL(_REF_LEVMAR_PATH)
+        L.dlevmar_dif.restype = C.c_int
+        L.dlevmar_dif.argtypes = [_LM_FN, _dp, _dp, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, C.c_void_p]
+        _ref_levmar = L
+    return _ref_levmar
+
+
+def use_ref_levmar(on: bool = True) -> bool:
+    """Route the oracle's CV_SPLIT fit through the reference's dlevmar_dif (True) or the restatement (False)."""
+    L = ref_levmar() if on else None
+    lib().orc_set_levmar_dif(C.cast(L.dlevmar_dif, C.c_void_p) if L is not None else None)
+    return L is not None
 
 
 class _RNG(C.Structure):
@@ -74,6 +100,18 @@ def lib():
             "orc_nnls_solve": (d, [_dp, i, i, i, _dp, _dp, d, vp]),
             "orc_sort_smallest_index": (None, [C.POINTER(C.c_int), i, _dp, i, i]),
             "orc_sort_largest_index": (None, [C.POINTER(C.c_int), i, _dp, i, i]),
+            "orc_nmsimplex2_new": (vp, [i]),
+            "orc_nmsimplex2_free": (None, [vp]),
+            "orc_nmsimplex2_set": (i, [vp, _FMIN_FN, vp, _dp, _dp]),
+            "orc_nmsimplex2_iterate": (i, [vp]),
+            "orc_nmsimplex2_x": (_dp, [vp]),
+            "orc_nmsimplex2_fval": (d, [vp]),
+            "orc_nmsimplex2_size": (d, [vp]),
+            "orc_nmsimplex2_minimize": (i, [vp, _FMIN_FN, vp, _dp, _dp, d, i]),
+            "orc_lm_dif": (i, [_LM_FN, _dp, _dp, i, i, i, _dp, _dp, vp]),
+            "orc_set_levmar_dif": (None, [vp]),
+            "orc_sd_get_over_smooth": (d, [vp]),
+            "orc_sd_get_cv_trace": (i, [vp, _dp, _dp, i]),
             "orc_sd_new": (vp, [i, i, d, i, i]),
             "orc_sd_free": (None, [vp]),
             "orc_sd_set_over_smooth": (None, [vp, d]),
@@ -245,6 +283,46 @@ def nnls_solve(A: np.ndarray, f: np.ndarray, reltol: float = np.finfo(float).eps
     return x, rnorm, stats
 
 
+def nmsimplex2_minimize(f, x0, step, size_tol=1e-3, max_iter=1000):
+    """GSL nmsimplex2 restatement driven as ncm_stats_dist.c:681-692 does; f maps a numpy vector to a float."""
+    x0 = np.ascontiguousarray(x0, dtype=np.float64)
+    step = np.ascontiguousarray(step, dtype=np.float64)
+    n = len(x0)
+    cb = _FMIN_FN(lambda xp, nn, _: float(f(np.array([xp[k] for k in range(nn)]))))
+    h = lib().orc_nmsimplex2_new(n)
+    try:
+        it = lib().orc_nmsimplex2_minimize(h, cb, None, _p(x0), _p(step), float(size_tol), int(max_iter))
+        xp = lib().orc_nmsimplex2_x(h)
+        return np.array([xp[k] for k in range(n)]), lib().orc_nmsimplex2_fval(h), lib().orc_nmsimplex2_size(h), it
+    finally:
+        lib().orc_nmsimplex2_free(h)
+
+
+def lm_dif(func, p0, n, x=None, itmax=1000, opts=None, reference=False):
+    """dlevmar_dif: the restatement (orc_lm_dif) or, with reference=True, the reference's own build.
+    func(p) -> residual model hx[n]; returns (p, info[10], iterations)."""
+    p = np.ascontiguousarray(p0, dtype=np.float64).copy()
+    m = len(p)
+
+    def _cb(pp, hx, mm, nn, _):
+        v = np.asarray(func(np.array([pp[k] for k in range(mm)])), dtype=np.float64)
+        for k in range(nn):
+            hx[k] = v[k]
+
+    cb = _LM_FN(_cb)
+    info = np.zeros(10)
+    xo = None if x is None else np.ascontiguousarray(x, dtype=np.float64)
+    o = None if opts is None else np.ascontiguousarray(opts, dtype=np.float64)
+    if reference:
+        L = ref_levmar()
+        if L is None:
+            raise RuntimeError("oracle/_ref/liblevmar_ref.so not built")
+        it = L.dlevmar_dif(cb, _p(p), None if xo is None else _p(xo), m, n, itmax, None if o is None else _p(o), _p(info), None, None, None)
+    else:
+        it = lib().orc_lm_dif(cb, _p(p), None if xo is None else _p(xo), m, n, itmax, None if o is None else _p(o), _p(info), None)
+    return p, info, it
+
+
 class StatsDist:
     """orc_sd wrapper mirroring the ncm_stats_dist_* call names."""
 
@@ -260,6 +338,15 @@ class StatsDist:
 
     def set_over_smooth(self, v): lib().orc_sd_set_over_smooth(self._h, float(v))
     def set_shrink(self, v): lib().orc_sd_set_shrink(self._h, float(v))
+    def set_split_frac(self, v): lib().orc_sd_set_split_frac(self._h, float(v))
+    def get_over_smooth(self): return lib().orc_sd_get_over_smooth(self._h)
+
+    def cv_trace(self):
+        """(ln over_smooth, objective) of every objective evaluation of the last CV prepare / prepare_interp."""
+        n = lib().orc_sd_get_cv_trace(self._h, None, None, 0)
+        a, b = np.zeros(max(n, 1)), np.zeros(max(n, 1))
+        lib().orc_sd_get_cv_trace(self._h, _p(a), _p(b), n)
+        return a[:n], b[:n]
     def set_use_threads(self, v): lib().orc_sd_set_use_threads(self._h, int(v))
     def set_cov_type(self, v): lib().orc_sd_set_cov_type(self._h, int(v))
     def set_local_frac(self, v): lib().orc_sd_set_local_frac(self._h, float(v))

@@ -11,8 +11,9 @@
  *   (distance, index); restated as a brute-force selection, which returns the same set
  *   in the same order).
  *
- * Cross-validation modes other than CV_NONE and the ROBUST covariance types are
- * outside the APES path (last paragraph) and return -2 here.
+ * Cross-validation modes: ncm_stats_dist.c:484-701 (objectives, simplex driver),
+ * :703-789 (prepare), :806-876 and :1018-1072 (CV_SPLIT: random tries + levmar fit of ln over_smooth).
+ * The ROBUST covariance types return -2 here.
  */
 #include <math.h>
 #include <stdio.h>
@@ -56,6 +57,12 @@ struct orc_sd
   int cov_array_len;
   orc_nnls_stats nnls_stats;
   double timers[3];
+  /* cross-validation: self->fmin (nmsimplex2, 1 parameter), self->rng (seeded 0), ncm_stats_dist.c:175-178 */
+  orc_nmsimplex2 *fmin;
+  orc_rng cv_rng;
+  const double *cv_m2lnp; /* the target of the CV_SPLIT fit (NcmStatsDistEval.m2lnp) */
+  double *cv_trace;       /* (ln over_smooth, objective) per objective evaluation */
+  int cv_trace_len, cv_trace_cap;
 };
 
 /* The reference environment pins an OpenMP build of OpenBLAS (environment.yml), where BLAS calls made
@@ -129,6 +136,8 @@ orc_sd_new (int type, int kernel_kind, double nu, int d, int cv_type)
   sd->nearPD_maxiter = 200;
   sd->cov            = (double *) calloc ((size_t) d * d, sizeof (double));
   sd->cov_decomp     = (double *) calloc ((size_t) d * d, sizeof (double));
+  sd->fmin           = orc_nmsimplex2_new (1);
+  orc_rng_set (&sd->cv_rng, 0);
 
   return sd;
 }
@@ -149,6 +158,8 @@ orc_sd_free (orc_sd *sd)
   free (sd->invUsample);
   free (sd->cov_array);
   free (sd->lnnorms);
+  free (sd->cv_trace);
+  orc_nmsimplex2_free (sd->fmin);
   free (sd);
 }
 
@@ -603,18 +614,245 @@ orc_sd_get_href (orc_sd *sd)
     return sd->over_smooth;
 }
 
-/* ncm_stats_dist.c:703-789 (CV_NONE only) */
+static void
+cv_trace_add (orc_sd *sd, double lnos, double val)
+{
+  if (sd->cv_trace_len == sd->cv_trace_cap)
+  {
+    sd->cv_trace_cap = sd->cv_trace_cap ? 2 * sd->cv_trace_cap : 64;
+    sd->cv_trace     = (double *) realloc (sd->cv_trace, sizeof (double) * 2 * sd->cv_trace_cap);
+  }
+
+  sd->cv_trace[2 * sd->cv_trace_len + 0] = lnos;
+  sd->cv_trace[2 * sd->cv_trace_len + 1] = val;
+  sd->cv_trace_len++;
+}
+
+/* _ncm_stats_dist_m2lnp, ncm_stats_dist.c:484-511: the CV_SPLIT_NOFIT objective, minus twice the log-likelihood
+ * of the held-out observations.  The reference accumulates inside an OpenMP loop without a reduction clause; the
+ * defined (use_threads = FALSE) behaviour is the index-ordered sum restated here. */
+static double
+cv_obj_m2lnp (const double *v, int n, void *params)
+{
+  orc_sd *sd        = (orc_sd *) params;
+  const double lnos = v[0];
+  double m2lnp      = 0.0;
+  int i;
+
+  sd->over_smooth = exp (lnos);
+  sd->href        = orc_sd_get_href (sd);
+
+  for (i = sd->n_kernels; i < sd->n_obs; i++)
+    m2lnp += orc_sd_eval_m2lnp (sd, sd->sample[i]);
+
+  cv_trace_add (sd, lnos, m2lnp);
+
+  return m2lnp;
+}
+
+static void
+cv_alloc_IM (orc_sd *sd)
+{
+  if ((sd->n_obs != sd->alloc_n_obs) || (sd->n_kernels != sd->alloc_n_kernels))
+  {
+    free (sd->IM);
+    free (sd->f);
+    sd->IM = (double *) malloc (sizeof (double) * (size_t) sd->n_obs * sd->n_kernels);
+    sd->f  = (double *) malloc (sizeof (double) * sd->n_obs);
+
+    sd->alloc_n_obs     = sd->n_obs;
+    sd->alloc_n_kernels = sd->n_kernels;
+  }
+}
+
+/* _ncm_stats_dist_amise_kde_gauss, ncm_stats_dist.c:513-558 (CV_LOO, KDE with the Gaussian kernel) */
+static double
+cv_obj_amise_kde_gauss (const double *v, int n, void *params)
+{
+  orc_sd *sd        = (orc_sd *) params;
+  const double lnos = v[0];
+  const int nk      = sd->n_kernels;
+  double amise      = 0.0;
+  int i, j;
+
+  sd->over_smooth = exp (lnos);
+  sd->href        = sqrt (2.0) * orc_sd_get_href (sd);
+
+  orc_sd_compute_IM (sd, sd->IM);
+
+  for (i = 0; i < nk; i++)
+    for (j = 0; j < nk; j++)
+      amise += sd->IM[(size_t) i * nk + j] / ((double) nk * (double) nk);
+
+  sd->over_smooth = exp (lnos);
+  sd->href        = orc_sd_get_href (sd);
+
+  orc_sd_compute_IM (sd, sd->IM);
+
+  for (i = 0; i < nk; i++)
+  {
+    for (j = 0; j < i; j++)
+      amise -= 2.0 * sd->IM[(size_t) i * nk + j] / (double) ((unsigned int) nk * (unsigned int) (nk - 1));
+
+    for (j = i + 1; j < nk; j++)
+      amise -= 2.0 * sd->IM[(size_t) i * nk + j] / (double) ((unsigned int) nk * (unsigned int) (nk - 1));
+  }
+
+  cv_trace_add (sd, lnos, amise);
+
+  return amise;
+}
+
+static int idx_cmp_ctx (const void *a, const void *b, void *ctx);
+
+/* ncm_stats_dist_sample2, ncm_stats_dist.c:1629-1651: antithetic pair of kernels, ranks i and len - 1 - i of the
+ * sorted leave-one-out densities */
+static void
+cv_sample2 (orc_sd *sd, const size_t *sort, double *x1, double *x2, orc_rng *rng)
+{
+  const int i   = orc_sd_kernel_choose (sd, rng);
+  const int o_i = (int) sort[i];
+
+  orc_kernel_sample (&sd->kernel, orc_sd_peek_cov_decomp (sd, o_i), sd->d, sd->href, sd->sample[o_i], x1, rng);
+
+  {
+    const int j   = sd->n_sample - 1 - i;
+    const int o_j = (int) sort[j];
+
+    orc_kernel_sample (&sd->kernel, orc_sd_peek_cov_decomp (sd, o_j), sd->d, sd->href, sd->sample[o_j], x2, rng);
+  }
+}
+
+/* _ncm_stats_dist_amise, ncm_stats_dist.c:562-658 (CV_LOO, every other class / kernel pair): leave-one-out term
+ * from the interpolation matrix plus a Monte-Carlo estimate of the integral of p^2 */
+static double
+cv_obj_amise (const double *v, int n, void *params)
+{
+  orc_sd *sd        = (orc_sd *) params;
+  const double lnos = v[0];
+  const int nk      = sd->n_kernels;
+  double amise      = 0.0;
+  double *dens      = (double *) malloc (sizeof (double) * nk);
+  size_t *sort      = (size_t *) malloc (sizeof (size_t) * nk);
+  int i, j;
+
+  sd->over_smooth = exp (lnos);
+  sd->href        = orc_sd_get_href (sd);
+
+  orc_sd_compute_IM (sd, sd->IM);
+
+  for (i = 0; i < nk; i++)
+  {
+    double row_sum = 0.0;
+
+    for (j = 0; j < i; j++)
+      row_sum += sd->IM[(size_t) i * nk + j];
+
+    for (j = i + 1; j < nk; j++)
+      row_sum += sd->IM[(size_t) i * nk + j];
+
+    amise -= 2.0 * row_sum / (double) ((unsigned int) nk * (unsigned int) (nk - 1));
+
+    dens[i] = (row_sum + sd->IM[(size_t) i * nk + i]) / nk;
+    sort[i] = i;
+  }
+
+  /* gsl_sort_index (heapsort, not stable): ties broken by index here */
+  qsort_r (sort, nk, sizeof (size_t), idx_cmp_ctx, (void *) dens);
+
+  {
+    orc_rng rng;
+    orc_stats_vec stats;
+    double *x1 = (double *) malloc (sizeof (double) * sd->d);
+    double *x2 = (double *) malloc (sizeof (double) * sd->d);
+    const unsigned int max_iter = 100000000;
+    double mean = 0.0, p12[2];
+    unsigned int it;
+
+    orc_rng_set (&rng, 0);
+    svec_init (&stats, 2);
+    svec_reset (&stats);
+
+    for (it = 0; it < 100; it++)
+    {
+      cv_sample2 (sd, sort, x1, x2, &rng);
+      p12[0] = orc_sd_eval (sd, x1);
+      p12[1] = orc_sd_eval (sd, x2);
+      svec_append (&stats, p12);
+    }
+
+    for (it = 0; it < max_iter; it++)
+    {
+      cv_sample2 (sd, sort, x1, x2, &rng);
+      p12[0] = orc_sd_eval (sd, x1);
+      p12[1] = orc_sd_eval (sd, x2);
+      svec_append (&stats, p12);
+
+      mean = 0.5 * (stats.mean[0] + stats.mean[1]);
+
+      {
+        const double var = 0.25 * (stats.var[0] * stats.bias_wt + stats.var[1] * stats.bias_wt + 2.0 * (stats.cov[0 * 2 + 1] * stats.bias_wt));
+        const double msd = sqrt (var / (it + 101.0)) / mean;
+
+        if (msd < 1.0e-2)
+          break;
+      }
+    }
+
+    amise += mean;
+
+    svec_free (&stats);
+    free (x1);
+    free (x2);
+  }
+
+  free (dens);
+  free (sort);
+
+  cv_trace_add (sd, lnos, amise);
+
+  return amise;
+}
+
+/* _ncm_stats_dist_minimize_obj, ncm_stats_dist.c:660-701.  The objective's side effects stay: over_smooth and
+ * href are those of the LAST point the simplex evaluated, not of the best corner. */
+static void
+cv_minimize_obj (orc_sd *sd, orc_fmin_fn objective)
+{
+  const double s    = 0.1;
+  const double lnos = log (sd->over_smooth);
+
+  orc_nmsimplex2_minimize (sd->fmin, objective, sd, &lnos, &s, 1.0e-3, 1000);
+}
+
+/* ncm_stats_dist.c:703-789 */
 int
 orc_sd_prepare (orc_sd *sd)
 {
   double t0 = now_s ();
   int ret, i;
 
-  if (sd->cv_type != ORC_CV_NONE)
-    return -2;
+  sd->cv_trace_len = 0;
 
-  sd->n_obs     = sd->n_sample;
-  sd->n_kernels = sd->n_sample;
+  switch (sd->cv_type)
+  {
+    case ORC_CV_LOO:
+      sd->n_obs     = sd->n_sample;
+      sd->n_kernels = sd->n_sample;
+      cv_alloc_IM (sd);
+      break;
+    case ORC_CV_NONE:
+      sd->n_obs     = sd->n_sample;
+      sd->n_kernels = sd->n_sample;
+      break;
+    case ORC_CV_SPLIT:
+    case ORC_CV_SPLIT_NOFIT:
+      sd->n_obs     = sd->n_sample;
+      sd->n_kernels = (int) ceil (sd->n_sample * sd->split_frac);
+      break;
+    default:
+      return -2;
+  }
 
   if (sd->n_obs <= sd->d)
     return -1; /* g_error ("_ncm_stats_dist_prepare: the sample is too small.") */
@@ -648,7 +886,26 @@ orc_sd_prepare (orc_sd *sd)
     sd->weights[i] = 1.0 / (1.0 * sd->n_kernels);
 
   sd->wcum_ready = 0;
-  sd->timers[0]  = now_s () - t0;
+
+  switch (sd->cv_type)
+  {
+    case ORC_CV_NONE:
+    case ORC_CV_SPLIT:
+      break;
+    case ORC_CV_SPLIT_NOFIT:
+      cv_minimize_obj (sd, &cv_obj_m2lnp);
+      break;
+    case ORC_CV_LOO:
+
+      if ((sd->type == ORC_SD_KDE) && (sd->kernel.kind == ORC_KERNEL_GAUSS))
+        cv_minimize_obj (sd, &cv_obj_amise_kde_gauss);
+      else
+        cv_minimize_obj (sd, &cv_obj_amise);
+
+      break;
+  }
+
+  sd->timers[0] = now_s () - t0;
 
   return 0;
 }
@@ -818,7 +1075,99 @@ idx_cmp_ctx (const void *a, const void *b, void *ctx)
   return (ia > ib) - (ia < ib);
 }
 
-/* ncm_stats_dist.c:878-1094 (CV_NONE branch) */
+/* _ncm_stats_dist_compute_IM_full, ncm_stats_dist.c:791-804 */
+static void
+sd_compute_IM_full (orc_sd *sd)
+{
+  const int nk = sd->n_kernels;
+  int i;
+
+  orc_sd_compute_IM (sd, sd->IM);
+
+  #pragma omp parallel for if (sd->use_threads)
+
+  for (i = 0; i < sd->n_obs; i++)
+  {
+    const double s = 1.0 / sd->f[i];
+    int j;
+
+    for (j = 0; j < nk; j++)
+      sd->IM[(size_t) i * nk + j] *= s;
+  }
+}
+
+/* NCM_NNLS_SOLVE (self->nnls, self->sub_IM, self->sub_x, self->f1); reltol default GSL_DBL_EPSILON, ncm_nnls.c:271-275 */
+static double
+sd_nnls (orc_sd *sd)
+{
+  double *f1 = (double *) malloc (sizeof (double) * sd->n_obs);
+  double rnorm;
+  int i;
+
+  for (i = 0; i < sd->n_obs; i++)
+    f1[i] = 1.0;
+
+  rnorm = orc_nnls_solve (sd->IM, sd->n_obs, sd->n_kernels, sd->n_kernels, sd->weights, f1, DBL_EPSILON, &sd->nnls_stats);
+  free (f1);
+
+  return rnorm;
+}
+
+double orc_sd_eval_m2lnp (orc_sd *sd, const double *x);
+
+/* _ncm_stats_dist_prepare_interp_fit_nnls_f, ncm_stats_dist.c:815-851: residuals of the CV_SPLIT fit at ln over_smooth = p[0].
+ * eval_m2lnp reads the raw NNLS solution left in self->weights (no normalisation, no shrink). */
+static void
+cv_fit_nnls_f (double *p, double *hx, int m, int n, void *adata)
+{
+  orc_sd *sd = (orc_sd *) adata;
+  double rnorm;
+  int i;
+
+  sd->over_smooth = exp (p[0]);
+  sd->href        = orc_sd_get_href (sd);
+
+  sd_compute_IM_full (sd);
+  rnorm = sd_nnls (sd);
+
+  #pragma omp parallel for if (sd->use_threads)
+
+  for (i = 0; i < sd->n_obs; i++)
+  {
+    const double m2lnpt_i = sd->cv_m2lnp[i] - sd->min_m2lnp;
+    const double m2lnpi_i = orc_sd_eval_m2lnp (sd, sd->sample[i]);
+
+    hx[i] = expm1 (-0.5 * (m2lnpi_i - m2lnpt_i));
+  }
+
+  cv_trace_add (sd, p[0], rnorm);
+}
+
+/* dlevmar_dif: the reference's own levmar when oracle/_ref/liblevmar_ref.so was registered (orc_set_levmar_dif),
+ * the restatement of orc_optim.c otherwise */
+typedef int (*dlevmar_dif_fn) (void (*func) (double *, double *, int, int, void *), double *p, double *x, int m, int n, int itmax, double *opts, double *info, double *work, double *covar, void *adata);
+static dlevmar_dif_fn ref_dlevmar_dif = NULL;
+
+void
+orc_set_levmar_dif (void *fn)
+{
+  ref_dlevmar_dif = (dlevmar_dif_fn) fn;
+}
+
+static int
+cv_lm_dif (orc_lm_fn func, double *p, const double *x, int m, int n, int itmax, const double *opts, double *info, void *adata)
+{
+  if (ref_dlevmar_dif != NULL)
+  {
+    double o[5] = {opts[0], opts[1], opts[2], opts[3], opts[4]};
+
+    return ref_dlevmar_dif (func, p, (double *) x, m, n, itmax, o, info, NULL, NULL, adata);
+  }
+
+  return orc_lm_dif (func, p, x, m, n, itmax, opts, info, adata);
+}
+
+/* ncm_stats_dist.c:878-1094 */
 int
 orc_sd_prepare_interp (orc_sd *sd, const double *m2lnp, int n)
 {
@@ -932,36 +1281,64 @@ orc_sd_prepare_interp (orc_sd *sd, const double *m2lnp, int n)
   for (i = 0; i < sd->n_obs; i++)
     sd->f[i] = exp (-0.5 * (m2lnp[i] - sd->min_m2lnp));
 
+  switch (sd->cv_type)
   {
-    double *f1 = (double *) malloc (sizeof (double) * sd->n_obs);
-    double t0  = now_s (), t1;
-    const int nk = sd->n_kernels;
-
-    for (i = 0; i < sd->n_obs; i++)
-      f1[i] = 1.0;
-
-    /* _ncm_stats_dist_compute_IM_full: ncm_stats_dist.c:791-804 */
-    orc_sd_compute_IM (sd, sd->IM);
-
-    #pragma omp parallel for if (sd->use_threads)
-
-    for (i = 0; i < sd->n_obs; i++)
+    case ORC_CV_SPLIT:
     {
-      const double s = 1.0 / sd->f[i];
-      int j;
+      /* ncm_stats_dist.c:1018-1072 */
+      const double opts[5] = {1e-3 /* LM_INIT_MU */, 1.0e-7, 1.0e-7, 1.0e-10, 1e-6 /* LM_DIFF_DELTA */};
+      double info[10];
+      double ln_os, rnorm0;
+      double t0 = now_s ();
 
-      for (j = 0; j < nk; j++)
-        sd->IM[(size_t) i * nk + j] *= s;
+      ln_os = log (sd->over_smooth);
+
+      sd_compute_IM_full (sd);
+      rnorm0 = sd_nnls (sd);
+      cv_trace_add (sd, ln_os, rnorm0);
+
+      for (i = 0; i < 10; i++)
+      {
+        const double ln_os_try = orc_ran_gaussian (&sd->cv_rng, 0.5) + ln_os;
+        double rnorm_try;
+
+        sd->over_smooth = exp (ln_os_try);
+        sd->href        = orc_sd_get_href (sd);
+
+        sd_compute_IM_full (sd);
+        rnorm_try = sd_nnls (sd);
+        cv_trace_add (sd, ln_os_try, rnorm_try);
+
+        if (rnorm_try < rnorm0)
+        {
+          ln_os  = ln_os_try;
+          rnorm0 = rnorm_try;
+        }
+      }
+
+      sd->cv_m2lnp = m2lnp;
+      cv_lm_dif (&cv_fit_nnls_f, &ln_os, NULL, 1, sd->n_obs, 10000, opts, info, sd);
+      sd->cv_m2lnp = NULL;
+
+      sd->over_smooth = exp (ln_os);
+      sd->href        = orc_sd_get_href (sd);
+
+      sd_compute_IM_full (sd);
+      sd->rnorm     = sd_nnls (sd);
+      sd->timers[2] = now_s () - t0;
+      break;
     }
+    default:
+    {
+      double t0 = now_s (), t1;
 
-    t1            = now_s ();
-    sd->timers[1] = t1 - t0;
-
-    /* reltol default GSL_DBL_EPSILON, ncm_nnls.c:271-275 */
-    sd->rnorm     = orc_nnls_solve (sd->IM, sd->n_obs, sd->n_kernels, sd->n_kernels, sd->weights, f1, DBL_EPSILON, &sd->nnls_stats);
-    sd->timers[2] = now_s () - t1;
-
-    free (f1);
+      sd_compute_IM_full (sd);
+      t1            = now_s ();
+      sd->timers[1] = t1 - t0;
+      sd->rnorm     = sd_nnls (sd);
+      sd->timers[2] = now_s () - t1;
+      break;
+    }
   }
 
   {
@@ -1304,6 +1681,22 @@ orc_sd_set_weights (orc_sd *sd, const double *w)
 }
 
 int orc_sd_get_dim (const orc_sd *sd) { return sd->d; }
+double orc_sd_get_over_smooth (const orc_sd *sd) { return sd->over_smooth; }
+
+int
+orc_sd_get_cv_trace (const orc_sd *sd, double *lnos, double *val, int cap)
+{
+  int i;
+
+  for (i = 0; i < sd->cv_trace_len && i < cap; i++)
+  {
+    lnos[i] = sd->cv_trace[2 * i + 0];
+    val[i]  = sd->cv_trace[2 * i + 1];
+  }
+
+  return sd->cv_trace_len;
+}
+
 int orc_sd_get_sample_size (const orc_sd *sd) { return sd->n_sample; }
 int orc_sd_get_n_obs (const orc_sd *sd) { return sd->n_obs; }
 int orc_sd_get_n_kernels (const orc_sd *sd) { return sd->n_kernels; }
