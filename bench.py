@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="apes_vkde_gauss_mvnd10_w4096",
-                    choices=["apes_vkde_gauss_mvnd10_w4096", "eval_sweep", "prepare_interp", "apes_e2e"])
+                    choices=["apes_vkde_gauss_mvnd10_w4096", "eval_sweep", "prepare_interp", "apes_e2e", "cv"])
     ap.add_argument("--target", default="funnel", choices=["funnel", "rosenbrock", "mvnd"], help="--workload apes_e2e: configs[3] (funnel) / configs[0] (rosenbrock)")
     ap.add_argument("--over-smooth", type=float, default=None)
     ap.add_argument("--walkers", type=int, default=4096)
@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--sweep-n", type=int, default=65536)
     ap.add_argument("--sd", default="vkde", choices=["kde", "vkde"])
     ap.add_argument("--kernel", default="gauss", choices=["gauss", "st3", "cauchy"])
+    ap.add_argument("--cv", default="split", choices=["split", "split_nofit", "loo"], help="--workload cv: the cross-validation mode")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--apes-multi", default="replicas", choices=["replicas", "sharded"],
                     help="APES workload at N > 1: one independent ensemble per GPU (default, weak scaling) or one ensemble with IM / query rows "
@@ -808,6 +809,87 @@ def run_apes_e2e(args):
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------------
+def run_cv(args):
+    """--workload cv: one prepare_interp under a cross-validation mode through the host API on ONE GPU, host
+    buffers, wall clock.  CV_SPLIT is what the reference's own callers use (tests/c/ncm/fit/test_ncm_fit_esmcmc.c:711, tools/mcat_analyze.c:422):
+    11 IM + NNLS passes, then a one-parameter levmar fit whose every residual evaluation is IM + NNLS + a batched eval of all observations."""
+    import torch
+
+    from numcosmo_b200 import stats_dist as S
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; numcosmo_b200 has no CPU fallback")
+    lib = S.lib()
+    lib.ncm_b200_set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    d, n_obs = args.dim, args.sweep_n
+    ktn, okind, nu = KT[args.kernel]
+    cv_name = args.cv.upper()
+
+    def problem(n, seed=2):
+        rs = np.random.default_rng(seed)
+        sig = rs.uniform(2e-2, 5e-2, size=d)
+        R = rs.normal(size=(d, d)) / np.sqrt(d)
+        cov = (0.7 * np.eye(d) + 0.3 * (R @ R.T)) * np.outer(sig, sig)
+        z = rs.normal(size=(n, d))
+        return np.ascontiguousarray(rs.uniform(1.0, 2.0, size=d) + z @ np.linalg.cholesky(cov).T), np.einsum("ij,ij->i", z, z)
+
+    X, m2lnp = problem(n_obs)
+    kern = S.StatsDistKernelGauss(d) if okind == 0 else S.StatsDistKernelST(d, nu)
+    sd = (S.StatsDistVKDE if args.sd == "vkde" else S.StatsDistKDE)(kern, getattr(S.StatsDistCV, cv_name))
+    sd.set_use_threads(True)
+    for x in X:
+        sd.add_obs(x)
+    steps, times, launches = max(1, min(args.steps, 3)), [], 0
+    with ClockSampler(0) as clk:
+        for it in range(1 + steps):                          # one warm-up call (allocations, first-launch costs)
+            sd.set_over_smooth(1.0)
+            sd.enable_timers(True) if it == steps else None
+            t0 = time.perf_counter()
+            sd.prepare_interp(m2lnp)
+            times.append(time.perf_counter() - t0)
+    tm, launches = sd.get_timers()
+    ms = 1e3 * float(np.mean(times[1:]))
+    lnos, val = sd.cv_trace()
+    nk = sd.get_n_kernels()
+    n_eval = len(lnos)
+    per_eval = {"split": float(n_obs) * nk, "split_nofit": float(n_obs - nk) * nk, "loo": float(nk) * nk}[args.cv]
+    if args.cv == "split":                                   # the levmar evaluations add a batched eval of all observations to IM + NNLS
+        pairs = 11 * per_eval + (n_eval - 11 + 1) * 2 * per_eval
+    elif args.cv == "loo" and not (args.sd == "kde" and okind == 0):
+        pairs = n_eval * per_eval
+    elif args.cv == "loo":
+        pairs = 2 * n_eval * per_eval
+    else:
+        pairs = n_eval * per_eval + float(n_obs) * nk
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import ncm_oracle as O
+
+        n_cpu = min(n_obs, 2048)
+        Xc, mc = problem(n_cpu)
+        o = O.StatsDist(O.SD_VKDE if args.sd == "vkde" else O.SD_KDE, okind, d, nu, getattr(O, "CV_" + cv_name))
+        o.set_use_threads(True)
+        o.add_obs_matrix(Xc)
+        O.lib().orc_set_blas_threads(os.cpu_count() or 1)
+        t0 = time.perf_counter()
+        assert o.prepare_interp(mc) == 0
+        t_cpu = time.perf_counter() - t0
+        cpu = {"value": 1.0 / t_cpu, "unit": "prepare_interp/s", "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": f"the same CV_{cv_name} prepare_interp on {n_cpu} observations (oracle port, all host cores), {len(o.cv_trace()[0])} objective "
+                         f"evaluations in {t_cpu:.2f} s -- NOT the same size as the GPU line unless n_obs <= 2048", "n_obs": n_cpu, "s": t_cpu}
+    line = {"metric": METRIC, "value": pairs / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": 1, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"prepare_interp with NCM_STATS_DIST_CV_{cv_name}: {args.sd.upper()} {args.kernel} kernel, {n_obs} observations, d={d}, "
+                                   f"{nk} kernels; end to end through the host API (host buffers, wall clock)",
+                       "l2_policy": "every objective evaluation rebuilds the IM (n_obs x n_kernels x 8 B) and the normal equations at a new bandwidth"},
+            "objective_evaluations": n_eval, "over_smooth": sd.get_over_smooth(), "rnorm": sd.get_rnorm(),
+            "stage_ms_last_call": {k: round(v, 3) for k, v in tm.items()}, "gpu_launches": int(launches), "clocks": clk.summary(),
+            "e2e": {"value": pairs / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": None, "d2h_bytes_per_step": None, "ms_per_step": ms},
+            "roofline": None, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse()
     # torchrun exports OMP_NUM_THREADS=1; the host-side OpenMP loops (oracle port for the reference arm, prepare_kernel pieces and the
@@ -821,6 +903,10 @@ def main():
         run_sweep(args)
     elif args.workload == "apes_e2e":
         run_apes_e2e(args)
+    elif args.workload == "cv":
+        if args.sweep_n == 65536:
+            args.sweep_n = 8192
+        run_cv(args)
     elif args.workload == "prepare_interp":
         if args.sweep_n == 65536 and args.dim == 10:   # the defaults of the other workloads: use configs[2] sizes
             args.sweep_n, args.dim = 16384, 20

@@ -129,5 +129,10 @@ int ncm_b200_simplex1_minimize(const std::function<double(double)> &f, double x0
 int ncm_b200_lm1_dif(const std::function<void(double, double *)> &func, double *p_io, const double *x, int n, int itmax, const double opts[5],
                      double info[10]);
 
+// robust covariance estimators (host/robust.cc) and the symmetric eigen-solver they share with nearPD (host/shim.cc)
+double ncm_b200_stats_Qn(std::vector<double> &data);
+bool ncm_b200_cov_robust(int kind, const double *const *rows, int n, int d, double *cov);
+void ncm_b200_jacobi_eig(std::vector<double> &A, int n, std::vector<double> &w, std::vector<double> &V);
+
 int ncm_b200_default_device();
 bool ncm_b200_host_prepare_kernel();   // debugging / parity switch: run the VKDE prepare_kernel loop on the host

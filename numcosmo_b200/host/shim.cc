@@ -199,7 +199,7 @@ double ncm_b200_cholesky_lndet(const double *U, int n, int ld) {
 }
 
 // cyclic Jacobi eigen-decomposition of a symmetric matrix (n <= 32): A = V diag(w) V^T, V columns
-static void jacobi_eig(std::vector<double> &A, int n, std::vector<double> &w, std::vector<double> &V) {
+void ncm_b200_jacobi_eig(std::vector<double> &A, int n, std::vector<double> &w, std::vector<double> &V) {
   V.assign((size_t) n * n, 0.0);
   for (int i = 0; i < n; i++) V[i * n + i] = 1.0;
   for (int sweep = 0; sweep < 64; sweep++) {
@@ -249,7 +249,7 @@ int ncm_b200_nearPD_upper(double *a, int n, int maxiter) {
     for (int i = 0; i < n * n; i++) cm[i] -= D_S[i];
     R = cm;
     X = cm;
-    jacobi_eig(X, n, w, V);
+    ncm_b200_jacobi_eig(X, n, w, V);
     double min_pos = INFINITY;
     for (int i = 0; i < n; i++)
       if (w[i] > 0.0 && w[i] < min_pos) min_pos = w[i];

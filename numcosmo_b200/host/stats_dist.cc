@@ -157,8 +157,18 @@ bool kde_prepare_kernel(NcmStatsDist *sd) {
       for (int i = 0; i < d; i++)
         for (int j = 0; j < d; j++) sd->cov->data[i * d + j] = ncm_matrix_get(sd->cov_fixed, i, j);
       break;   // cov_decomp was set by set_cov_fixed (kde.c:838-844)
+    case NCM_STATS_DIST_KDE_COV_TYPE_ROBUST_DIAG:
+    case NCM_STATS_DIST_KDE_COV_TYPE_ROBUST: {
+      // ncm_stats_dist_kde.c:423-441 over ncm_stats_vec.c:1821-2072 (host/robust.cc)
+      std::vector<const double *> rows(sd->n_kernels);
+      for (guint i = 0; i < sd->n_kernels; i++) rows[i] = ((NcmVector *) sd->sample[i])->data;
+      if (!ncm_b200_cov_robust(sd->cov_type == NCM_STATS_DIST_KDE_COV_TYPE_ROBUST ? 1 : 0, rows.data(), (int) sd->n_kernels, d, cov.data())) return false;
+      ncm_b200_cholesky_decomp_fallback(sd->cov_decomp->data, cov.data(), d, (int) sd->nearPD_maxiter);
+      memcpy(sd->cov->data, cov.data(), sizeof(double) * d * d);
+      break;
+    }
     default:
-      ncm_b200_error("_ncm_stats_dist_kde_prepare_kernel: robust covariance types are not implemented on the B200 path.");
+      ncm_b200_error("_ncm_stats_dist_kde_prepare_kernel: code should not be reached (unknown covariance type %d).", (int) sd->cov_type);
       return false;
   }
   sd->kernel_lnnorm = ncm_stats_dist_kernel_get_lnnorm(sd->kernel, sd->cov_decomp);
@@ -187,8 +197,9 @@ bool vkde_build_cov_array(NcmStatsDist *sd) {
   const int d = (int) sd->d, n_obs = (int) sd->n_obs, nk = (int) sd->n_kernels;
   const double kd = (sd->local_frac * n_obs > 2.0) ? sd->local_frac * n_obs : 2.0;   // GSL_MAX (local_frac * n_obs, 2)
   const size_t k  = (size_t) kd;
-  if (sd->cov_type != NCM_STATS_DIST_KDE_COV_TYPE_SAMPLE && sd->cov_type != NCM_STATS_DIST_KDE_COV_TYPE_FIXED) {
-    ncm_b200_error("_ncm_stats_dist_vkde_build_cov_array_kdtree: robust covariance types are not implemented on the B200 path.");
+  const bool robust = sd->cov_type == NCM_STATS_DIST_KDE_COV_TYPE_ROBUST_DIAG || sd->cov_type == NCM_STATS_DIST_KDE_COV_TYPE_ROBUST;
+  if (robust && std::min(k, (size_t) n_obs) < 4) {
+    ncm_b200_error("ncm_stats_vec_compute_cov_robust_diag: too few points to estimate the covariance [%d].", (int) std::min(k, (size_t) n_obs));
     return false;
   }
   if ((int) sd->cov_array.size() != nk) {
@@ -219,15 +230,23 @@ bool vkde_build_cov_array(NcmStatsDist *sd) {
     }
     const size_t kk = std::min(k, (size_t) n_obs);
     std::partial_sort(items.begin(), items.begin() + kk, items.end());
-    sv.reset();
-    for (size_t j = 0; j < kk; j++) sv.append(((NcmVector *) sd->sample[items[j].second])->data);
-    sv.get_cov(cov.data());
+    if (robust) {
+      // ncm_stats_dist_vkde.c:467-472: robust estimators over the neighbours in ascending-distance order
+      std::vector<const double *> rows(kk);
+      for (size_t j = 0; j < kk; j++) rows[j] = ((NcmVector *) sd->sample[items[j].second])->data;
+      ncm_b200_cov_robust(sd->cov_type == NCM_STATS_DIST_KDE_COV_TYPE_ROBUST ? 1 : 0, rows.data(), (int) kk, d, cov.data());
+    } else {
+      sv.reset();
+      for (size_t j = 0; j < kk; j++) sv.append(((NcmVector *) sd->sample[items[j].second])->data);
+      sv.get_cov(cov.data());
+    }
     ncm_b200_cholesky_decomp_fallback(&sd->cov_slab[(size_t) i * d * d], cov.data(), d, (int) sd->nearPD_maxiter);
   };
 
   // Device path: kNN + covariance + Cholesky in libncm_sd_gpu, bit-identical to host_centre;
   // only the matrices whose plain Cholesky fails come back to the host for the reference's fallback chain.
-  const bool host_only = ncm_b200_host_prepare_kernel();
+  // the robust estimators are sort-bound O(d^2 k log k) work per centre: they stay on the host, OpenMP over the centres
+  const bool host_only = ncm_b200_host_prepare_kernel() || robust;
   if (!host_only && n_obs <= 65536 && ensure_gpu(sd)) {
     std::vector<int> fail(nk, 0);
     int rc;

@@ -105,6 +105,11 @@ enum { ORC_COV_SAMPLE = 0, ORC_COV_FIXED, ORC_COV_ROBUST_DIAG, ORC_COV_ROBUST };
 
 typedef struct orc_sd orc_sd;
 
+/* robust covariance estimators of NcmStatsVec (ncm_stats_vec.c:1821-2072); rows[n] point to d-vectors; 0 or <0 (too few points) */
+double orc_stats_Qn_from_sorted_data (const double *sorted, int n);   /* gsl_stats_Qn_from_sorted_data restated: parity unpinned (GSL absent) */
+int orc_cov_robust_diag (const double *const *rows, int n, int d, double *cov);
+int orc_cov_robust_ogk (const double *const *rows, int n, int d, double *cov);
+
 orc_sd *orc_sd_new (int type, int kernel_kind, double nu, int d, int cv_type);
 void orc_sd_free (orc_sd *sd);
 void orc_sd_set_over_smooth (orc_sd *sd, double os);

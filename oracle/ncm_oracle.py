@@ -18,7 +18,7 @@ _REF_LEVMAR_PATH = os.path.join(_HERE, "_ref", "liblevmar_ref.so")   # the refer
 KERNEL_GAUSS, KERNEL_ST = 0, 1
 SD_KDE, SD_VKDE = 0, 1
 CV_NONE, CV_SPLIT, CV_SPLIT_NOFIT, CV_LOO = 0, 1, 2, 3
-COV_SAMPLE, COV_FIXED = 0, 1
+COV_SAMPLE, COV_FIXED, COV_ROBUST_DIAG, COV_ROBUST = 0, 1, 2, 3
 TARGET_MVND, TARGET_ROSENBROCK, TARGET_FUNNEL = 0, 1, 2
 
 _dp = C.POINTER(C.c_double)
@@ -112,6 +112,7 @@ def lib():
             "orc_set_levmar_dif": (None, [vp]),
             "orc_sd_get_over_smooth": (d, [vp]),
             "orc_sd_get_cv_trace": (i, [vp, _dp, _dp, i]),
+            "orc_stats_Qn_from_sorted_data": (d, [_dp, i]),
             "orc_sd_new": (vp, [i, i, d, i, i]),
             "orc_sd_free": (None, [vp]),
             "orc_sd_set_over_smooth": (None, [vp, d]),
@@ -281,6 +282,12 @@ def nnls_solve(A: np.ndarray, f: np.ndarray, reltol: float = np.finfo(float).eps
     rnorm = lib().orc_nnls_solve(_p(A), A.shape[0], A.shape[1], A.shape[1], _p(x), _p(f), reltol, C.byref(st))
     stats = {k: getattr(st, k) for k, _ in _NNLSStats._fields_}
     return x, rnorm, stats
+
+
+def stats_Qn(x) -> float:
+    """Rousseeuw-Croux Q_n scale of a sample (gsl_sort + gsl_stats_Qn_from_sorted_data)."""
+    v = np.sort(np.ascontiguousarray(x, dtype=np.float64))
+    return lib().orc_stats_Qn_from_sorted_data(_p(v), len(v))
 
 
 def nmsimplex2_minimize(f, x0, step, size_tol=1e-3, max_iter=1000):

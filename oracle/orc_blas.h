@@ -24,6 +24,8 @@ void   scipy_cblas_dgemv (int order, int trans, int m, int n, double alpha, cons
                           const double *x, int incx, double beta, double *y, int incy);
 void   scipy_cblas_dsyrk (int order, int uplo, int trans, int n, int k, double alpha, const double *a, int lda,
                           double beta, double *c, int ldc);
+void   scipy_cblas_dgemm (int order, int transa, int transb, int m, int n, int k, double alpha, const double *a, int lda,
+                          const double *b, int ldb, double beta, double *c, int ldc);
 void   scipy_cblas_dtrmv (int order, int uplo, int trans, int diag, int n, const double *a, int lda, double *x, int incx);
 void   scipy_cblas_dtrsv (int order, int uplo, int trans, int diag, int n, const double *a, int lda, double *x, int incx);
 void   scipy_cblas_dtrsm (int order, int side, int uplo, int trans, int diag, int m, int n, double alpha,

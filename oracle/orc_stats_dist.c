@@ -13,7 +13,7 @@
  *
  * Cross-validation modes: ncm_stats_dist.c:484-701 (objectives, simplex driver),
  * :703-789 (prepare), :806-876 and :1018-1072 (CV_SPLIT: random tries + levmar fit of ln over_smooth).
- * The ROBUST covariance types return -2 here.
+ * Robust covariance types (section 8f-4): ncm_stats_vec.c:1821-2072 (Q_n scale per coordinate; OGK).
  */
 #include <math.h>
 #include <stdio.h>
@@ -429,6 +429,218 @@ svec_get_cov_matrix (const orc_stats_vec *s, double *m)
     m[i] *= s->bias_wt;
 }
 
+/* ------------------------------------------------------------------------------------------------ */
+/* Robust covariance types: ncm_stats_vec.c:1821-2090                       */
+/* ------------------------------------------------------------------------------------------------ */
+
+static int
+dbl_cmp (const void *a, const void *b)
+{
+  const double x = *(const double *) a, y = *(const double *) b;
+
+  return (x > y) - (x < y);
+}
+
+/* gsl_stats_Qn_from_sorted_data (GSL >= 2.5, statistics/Qn.c; GSL is absent from /root/reference and from this image:
+ * PARITY UNPINNED for the finite-sample factors d_n below).  Rousseeuw & Croux's Q_n: the k-th smallest of the
+ * n (n - 1) / 2 differences x_i - x_j (i > j), k = h (h - 1) / 2, h = n / 2 + 1, times 2.21914 times d_n.  GSL finds the
+ * order statistic with the O(n log n) algorithm of Croux & Rousseeuw (1992); an order statistic does not depend on how
+ * it is found, so the restatement simply sorts all the differences. */
+double
+orc_stats_Qn_from_sorted_data (const double *sorted, int n)
+{
+  const double scale = 2.21914;
+  const long h = n / 2 + 1, k = h * (h - 1) / 2;
+  const size_t npairs = (size_t) n * (n - 1) / 2;
+  double *diff = (double *) malloc (sizeof (double) * (npairs > 0 ? npairs : 1));
+  double Qn0, dn = 1.0;
+  size_t t = 0;
+  int i, j;
+
+  for (i = 1; i < n; i++)
+    for (j = 0; j < i; j++)
+      diff[t++] = sorted[i] - sorted[j];
+
+  qsort (diff, npairs, sizeof (double), dbl_cmp);
+  Qn0 = (npairs > 0) ? diff[k - 1] : 0.0;
+  free (diff);
+
+  if (n <= 12)
+  {
+    static const double dn_small[13] = {1.0, 1.0, 0.399356, 0.99365, 0.51321, 0.84401, 0.61220, 0.85877, 0.66993, 0.87344, 0.72014, 0.88906, 0.75743};
+
+    dn = dn_small[n];
+  }
+  else
+  {
+    if (n % 2 == 1)
+      dn = 1.60188 + (-2.1284 - 5.172 / n) / n;
+    else
+      dn = 3.67561 + (1.9654 + (6.987 - 77.0 / n) / n) / n;
+
+    dn = 1.0 / (dn / (double) n + 1.0);
+  }
+
+  return scale * dn * Qn0;
+}
+
+static double
+column_Qn (const double *col, int stride, int n, double *data)
+{
+  int a;
+
+  for (a = 0; a < n; a++)
+    data[a] = col[(size_t) a * stride];
+
+  qsort (data, n, sizeof (double), dbl_cmp); /* gsl_sort */
+
+  return orc_stats_Qn_from_sorted_data (data, n);
+}
+
+/* ncm_stats_vec_compute_cov_robust_diag, ncm_stats_vec.c:1832-1882: rows[n] points to the saved observations */
+int
+orc_cov_robust_diag (const double *const *rows, int n, int d, double *cov)
+{
+  double *data = (double *) malloc (sizeof (double) * n);
+  int i, a;
+
+  if (n < 4)
+  {
+    free (data);
+
+    return -7; /* g_error ("... too few points to estimate the covariance") */
+  }
+
+  memset (cov, 0, sizeof (double) * d * d);
+
+  for (i = 0; i < d; i++)
+  {
+    double s;
+
+    for (a = 0; a < n; a++)
+      data[a] = rows[a][i];
+
+    qsort (data, n, sizeof (double), dbl_cmp);
+    s              = orc_stats_Qn_from_sorted_data (data, n);
+    cov[i * d + i] = s * s;
+  }
+
+  free (data);
+
+  return 0;
+}
+
+/* ncm_stats_vec_compute_cov_robust_ogk, ncm_stats_vec.c:1896-2072 (orthogonalised Gnanadesikan-Kettenring).  Only the
+ * upper triangle of the result is defined by the reference (dsyrk 'U' over a matrix dsyevr destroyed); the restatement
+ * mirrors it into the lower one. */
+int
+orc_cov_robust_ogk (const double *const *rows, int n, int d, double *cov)
+{
+  double *E       = (double *) malloc (sizeof (double) * d * d);
+  double *y       = (double *) malloc (sizeof (double) * (size_t) n * d);
+  double *z       = (double *) malloc (sizeof (double) * (size_t) n * d);
+  double *sigma_x = (double *) malloc (sizeof (double) * d);
+  double *sigma_z = (double *) malloc (sizeof (double) * d);
+  double *data    = (double *) malloc (sizeof (double) * (n > d ? n : d));
+  int a, i, j;
+
+  if (n < 4)
+  {
+    free (E); free (y); free (z); free (sigma_x); free (sigma_z); free (data);
+
+    return -7;
+  }
+
+  for (a = 0; a < n; a++)
+    memcpy (&y[(size_t) a * d], rows[a], sizeof (double) * d);
+
+  for (i = 0; i < d; i++)
+  {
+    const double sigma_i = column_Qn (&y[i], d, n, data);
+    const double s       = 1.0 / sigma_i;
+
+    sigma_x[i] = sigma_i;
+
+    for (a = 0; a < n; a++)
+      y[(size_t) a * d + i] *= s;
+  }
+
+  memset (cov, 0, sizeof (double) * d * d);
+
+  for (i = 0; i < d; i++)
+    cov[i * d + i] = 1.0;
+
+  for (i = 0; i < d; i++)
+  {
+    for (j = i + 1; j < d; j++)
+    {
+      double s_ipj, s_imj;
+
+      for (a = 0; a < n; a++)
+        data[a] = y[(size_t) a * d + i] + y[(size_t) a * d + j];
+
+      qsort (data, n, sizeof (double), dbl_cmp);
+      s_ipj = orc_stats_Qn_from_sorted_data (data, n);
+
+      for (a = 0; a < n; a++)
+        data[a] = y[(size_t) a * d + i] - y[(size_t) a * d + j];
+
+      qsort (data, n, sizeof (double), dbl_cmp);
+      s_imj = orc_stats_Qn_from_sorted_data (data, n);
+
+      cov[i * d + j] = 0.25 * (s_ipj * s_ipj - s_imj * s_imj);
+    }
+  }
+
+  {
+    /* ncm_lapack_dsyevr ('V', 'A', 'U' -> 'L', ...): eigenvector k lands in row k of the row-major E */
+    const double zero = 0.0;
+    const int izero   = 0;
+    int lwork = -1, liwork = -1, info = 0, liwq, neval = 0;
+    int *isuppz = (int *) malloc (sizeof (int) * 2 * d);
+    double wq, *work;
+    int *iwork;
+
+    scipy_dsyevr_ ("V", "A", "L", &d, cov, &d, &zero, &zero, &izero, &izero, &zero, &neval, data, E, &d, isuppz, &wq, &lwork, &liwq, &liwork, &info);
+    lwork  = (int) wq;
+    liwork = liwq;
+    work   = (double *) malloc (sizeof (double) * lwork);
+    iwork  = (int *) malloc (sizeof (int) * liwork);
+    scipy_dsyevr_ ("V", "A", "L", &d, cov, &d, &zero, &zero, &izero, &izero, &zero, &neval, data, E, &d, isuppz, work, &lwork, iwork, &liwork, &info);
+    free (work);
+    free (iwork);
+    free (isuppz);
+
+    if (info != 0)
+    {
+      free (E); free (y); free (z); free (sigma_x); free (sigma_z); free (data);
+
+      return -8;
+    }
+  }
+
+  /* z = E y^T  (d x n) */
+  scipy_cblas_dgemm (OrcRowMajor, OrcNoTrans, OrcTrans, d, n, d, 1.0, E, d, y, d, 0.0, z, n);
+
+  for (i = 0; i < d; i++)
+    sigma_z[i] = column_Qn (&z[(size_t) i * n], 1, n, data);
+
+  for (i = 0; i < d; i++)
+    for (j = 0; j < d; j++)
+      E[i * d + j] = sigma_z[i] * E[i * d + j] * sigma_x[j];
+
+  memset (cov, 0, sizeof (double) * d * d);
+  scipy_cblas_dsyrk (OrcRowMajor, OrcUpper, OrcTrans, d, d, 1.0, E, d, 0.0, cov, d);
+
+  for (i = 0; i < d; i++)
+    for (j = 0; j < i; j++)
+      cov[i * d + j] = cov[j * d + i];
+
+  free (E); free (y); free (z); free (sigma_x); free (sigma_z); free (data);
+
+  return 0;
+}
+
 /* kde.c:378-490 */
 static int
 kde_prepare_kernel (orc_sd *sd)
@@ -466,6 +678,25 @@ kde_prepare_kernel (orc_sd *sd)
       memcpy (sd->cov, sd->cov_fixed, sizeof (double) * d * d);
       _cholesky_decomp (sd->cov_decomp, sd->cov_fixed, d, sd->nearPD_maxiter);
       break;
+    case ORC_COV_ROBUST_DIAG:
+    case ORC_COV_ROBUST:
+    {
+      /* kde.c:423-441 */
+      const int rc = (sd->cov_type == ORC_COV_ROBUST_DIAG) ? orc_cov_robust_diag ((const double *const *) sd->sample, sd->n_kernels, d, cov)
+                                                           : orc_cov_robust_ogk ((const double *const *) sd->sample, sd->n_kernels, d, cov);
+
+      if (rc != 0)
+      {
+        svec_free (&sv);
+        free (cov);
+
+        return rc;
+      }
+
+      _cholesky_decomp (sd->cov_decomp, cov, d, sd->nearPD_maxiter);
+      memcpy (sd->cov, cov, sizeof (double) * d * d);
+      break;
+    }
     default:
       svec_free (&sv);
       free (cov);
@@ -529,8 +760,13 @@ vkde_build_cov_array (orc_sd *sd)
   const size_t k  = (size_t) kd;
   int i;
 
-  if ((sd->cov_type != ORC_COV_SAMPLE) && (sd->cov_type != ORC_COV_FIXED))
+  int robust_rc = 0;
+
+  if ((sd->cov_type < ORC_COV_SAMPLE) || (sd->cov_type > ORC_COV_ROBUST))
     return -2;
+
+  if ((sd->cov_type >= ORC_COV_ROBUST_DIAG) && (k < 4))
+    return -7; /* ncm_stats_vec.c:1842-1844: too few points to estimate the covariance */
 
   if (sd->cov_array_len != n_kernels)
   {
@@ -584,7 +820,26 @@ vkde_build_cov_array (orc_sd *sd)
       for (j = 0; j < k; j++)
         svec_append (&sv, sd->sample[items[j].idx]);
 
-      svec_get_cov_matrix (&sv, cov);
+      if (sd->cov_type >= ORC_COV_ROBUST_DIAG)
+      {
+        /* vkde.c:467-472: the neighbours in ascending-distance order are the saved rows of the NcmStatsVec */
+        const double **rows = (const double **) malloc (sizeof (double *) * k);
+        int rc;
+
+        for (j = 0; j < k; j++)
+          rows[j] = sd->sample[items[j].idx];
+
+        rc = (sd->cov_type == ORC_COV_ROBUST_DIAG) ? orc_cov_robust_diag (rows, (int) k, d, cov) : orc_cov_robust_ogk (rows, (int) k, d, cov);
+        free (rows);
+
+        if (rc != 0)
+          robust_rc = rc;
+      }
+      else
+      {
+        svec_get_cov_matrix (&sv, cov);
+      }
+
       _cholesky_decomp (&sd->cov_array[(size_t) i * d * d], cov, d, sd->nearPD_maxiter);
       sd->lnnorms[i] = orc_kernel_get_lnnorm (&sd->kernel, &sd->cov_array[(size_t) i * d * d], d);
     }
@@ -596,7 +851,7 @@ vkde_build_cov_array (orc_sd *sd)
 
   blas_leave_omp (blas_prev);
 
-  return 0;
+  return robust_rc;
 }
 
 /* ncm_stats_dist.c:476-482 ; vkde.c:316-335 */
