@@ -105,6 +105,8 @@ enum { ORC_COV_SAMPLE = 0, ORC_COV_FIXED, ORC_COV_ROBUST_DIAG, ORC_COV_ROBUST };
 
 typedef struct orc_sd orc_sd;
 
+/* the exact kNN ordering used by the VKDE prepare_kernel restatement (pinned against the reference's kd-tree, oracle/_ref/libkdtree_ref.so) */
+void orc_knn_brute (const double *points, int n, int d, int query, int k, long *idx_out, double *dist_out);
 /* robust covariance estimators of NcmStatsVec (ncm_stats_vec.c:1821-2072); rows[n] point to d-vectors; 0 or <0 (too few points) */
 double orc_stats_Qn_from_sorted_data (const double *sorted, int n);   /* gsl_stats_Qn_from_sorted_data restated: parity unpinned (GSL absent) */
 int orc_cov_robust_diag (const double *const *rows, int n, int d, double *cov);

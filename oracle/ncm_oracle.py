@@ -49,6 +49,40 @@ def ref_levmar():
     return _ref_levmar
 
 
+_REF_KDTREE_PATH = os.path.join(_HERE, "_ref", "libkdtree_ref.so")    # the reference's own kd-tree, built by `make ref`
+_ref_kdtree = None
+
+
+def ref_kdtree_knn(points, queries, k):
+    """k nearest neighbours of points[queries] by the REFERENCE'S kd-tree, in its list order; None when it was never built."""
+    global _ref_kdtree
+    if _ref_kdtree is None:
+        if not os.path.exists(_REF_KDTREE_PATH):
+            return None
+        L = C.CDLL(_REF_KDTREE_PATH)
+        L.orc_ref_kdtree_knn.restype = C.c_int
+        L.orc_ref_kdtree_knn.argtypes = [_dp, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(C.c_long), _dp]
+        _ref_kdtree = L
+    pts = np.ascontiguousarray(points, dtype=np.float64)
+    q = np.ascontiguousarray(queries, dtype=np.int32)
+    idx = np.zeros((len(q), k), dtype=np.int64)
+    dist = np.zeros((len(q), k))
+    rc = _ref_kdtree.orc_ref_kdtree_knn(_p(pts), pts.shape[0], pts.shape[1], q.ctypes.data_as(C.POINTER(C.c_int)), len(q), k,
+                                        idx.ctypes.data_as(C.POINTER(C.c_long)), _p(dist))
+    if rc != 0:
+        raise RuntimeError(f"reference kd-tree returned a list of the wrong length for query {-rc - 1}")
+    return idx, dist
+
+
+def knn_brute(points, query, k):
+    """The oracle's (squared distance, index)-ordered exact kNN (restatement used by the VKDE prepare_kernel)."""
+    pts = np.ascontiguousarray(points, dtype=np.float64)
+    idx = np.zeros(k, dtype=np.int64)
+    dist = np.zeros(k)
+    lib().orc_knn_brute(_p(pts), pts.shape[0], pts.shape[1], int(query), int(k), idx.ctypes.data_as(C.POINTER(C.c_long)), _p(dist))
+    return idx, dist
+
+
 def use_ref_levmar(on: bool = True) -> bool:
     """Route the oracle's CV_SPLIT fit through the reference's dlevmar_dif (True) or the restatement (False)."""
     L = ref_levmar() if on else None
@@ -113,6 +147,7 @@ def lib():
             "orc_sd_get_over_smooth": (d, [vp]),
             "orc_sd_get_cv_trace": (i, [vp, _dp, _dp, i]),
             "orc_stats_Qn_from_sorted_data": (d, [_dp, i]),
+            "orc_knn_brute": (None, [_dp, i, i, i, i, C.POINTER(C.c_long), _dp]),
             "orc_sd_new": (vp, [i, i, d, i, i]),
             "orc_sd_free": (None, [vp]),
             "orc_sd_set_over_smooth": (None, [vp, d]),

@@ -749,6 +749,42 @@ knn_cmp (const void *a, const void *b)
   return (ka->idx > kb->idx) - (ka->idx < kb->idx);
 }
 
+/* the neighbour search of vkde_build_cov_array on its own (test hook): the k nearest of points[n x d] to points[query],
+ * ordered by (squared distance, index), as kdtree.c:229-321 + rb_knn_list.c:31-40 return them */
+void
+orc_knn_brute (const double *points, int n, int d, int query, int k, long *idx_out, double *dist_out)
+{
+  knn_item *items      = (knn_item *) malloc (sizeof (knn_item) * n);
+  const double *target = &points[(size_t) query * d];
+  int m, r;
+
+  for (m = 0; m < n; m++)
+  {
+    const double *c1 = &points[(size_t) m * d];
+    double dist      = 0;
+
+    for (r = 0; r < d; r++)
+    {
+      const double df = c1[r] - target[r];
+
+      dist += df * df;
+    }
+
+    items[m].dist = dist;
+    items[m].idx  = m;
+  }
+
+  qsort (items, n, sizeof (knn_item), knn_cmp);
+
+  for (m = 0; m < k; m++)
+  {
+    idx_out[m]  = items[m].idx;
+    dist_out[m] = items[m].dist;
+  }
+
+  free (items);
+}
+
 /* vkde.c:362-496 */
 static int
 vkde_build_cov_array (orc_sd *sd)
