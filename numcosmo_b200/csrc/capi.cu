@@ -155,6 +155,9 @@ int ncm_sd_gpu_ctx_free(ncm_sd_gpu_ctx *c) {
   c->pin_nn.release();
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
+  if (c->ev_panel != nullptr) cudaEventDestroy(c->ev_panel);
+  if (c->ev_tail != nullptr) cudaEventDestroy(c->ev_tail);
+  if (c->stream_hi != nullptr) cudaStreamDestroy(c->stream_hi);
   cudaStreamDestroy(c->stream);
   delete c;
   return NCM_SD_GPU_OK;

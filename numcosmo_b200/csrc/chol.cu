@@ -23,6 +23,9 @@
 
 int dsyrk_ata_general(ncm_sd_gpu_ctx *c, int K, int n, const double *dP, int ldp, double *dC, int ldc, double alpha, double beta);
 int dsyrk_ata_first_rows64(ncm_sd_gpu_ctx *c, int K, int n, const double *dP, int ldp, double *dC, int ldc);
+int dsyrk_ata_general_on(ncm_sd_gpu_ctx *c, cudaStream_t st, int K, int n, const double *dP, int ldp, double *dC, int ldc, double alpha, double beta);
+int dsyrk_ata_first_rows64_on(ncm_sd_gpu_ctx *c, cudaStream_t st, int K, int n, const double *dP, int ldp, double *dC, int ldc);
+int dsyrk_ata_head_rows_on(ncm_sd_gpu_ctx *c, cudaStream_t st, int K, int n, int rows, const double *dP, int ldp, double *dC, int ldc);
 
 namespace {
 
@@ -395,6 +398,29 @@ int dpotrf_upper_solve(ncm_sd_gpu_ctx *c, int n, double *dM, int ldm, double *dR
   // pipeline in ata_kernel (which matters at n >> 4096, where this path runs: the K = 64 updates ran at 17 TFLOP/s at n = 16384).
   static const int gp_env = getenv("NCM_SD_GPU_CHOL_GROUP") != nullptr ? atoi(getenv("NCM_SD_GPU_CHOL_GROUP")) : 0;
   const int GP = gp_env > 0 ? gp_env : (n >= 12288 ? 8 : (n >= 6144 ? 4 : 2));   // measured at n = 16384: 68.0 / 62.2 / 60.1 ms for 2 / 4 / 8
+  // Look-ahead (W = 64 GP columns per group, a multiple of the 128-wide update tile): the update of group g is split into the
+  // head strip -- the W block rows group g + 1 factors -- and the tail.  Panels and head strips run on a highest-priority stream,
+  // the tails (the bulk of the flops) on the context stream, so that the latency-bound panel kernels of group g + 1 execute
+  // while the tail of group g keeps the tensor pipe busy:
+  //     hi :  panels(g)  -> [wait tail(g-1)] head(g) -> panels(g+1) -> ...
+  //     lo :               [wait panels(g)]  tail(g)  -> tail(g+1)  -> ...
+  // ($NCM_SD_GPU_CHOL_LOOKAHEAD=0 keeps everything on one stream.)
+  static const bool la_env = getenv("NCM_SD_GPU_CHOL_LOOKAHEAD") == nullptr || atoi(getenv("NCM_SD_GPU_CHOL_LOOKAHEAD")) != 0;
+  const int W              = GP * NB;
+  const bool lookahead     = la_env && (W % 128 == 0) && n >= 4 * W;
+  cudaStream_t hi = c->stream, lo = c->stream;
+  if (lookahead) {
+    if (c->stream_hi == nullptr) {
+      int least = 0, greatest = 0;
+      NCM_CUDA_OK(c, cudaDeviceGetStreamPriorityRange(&least, &greatest));
+      NCM_CUDA_OK(c, cudaStreamCreateWithPriority(&c->stream_hi, cudaStreamNonBlocking, greatest));
+      NCM_CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_panel, cudaEventDisableTiming));
+      NCM_CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_tail, cudaEventDisableTiming));
+    }
+    hi = c->stream_hi;
+    NCM_CUDA_OK(c, cudaEventRecord(c->ev_tail, lo));   // fork: everything queued on the context stream so far (gather, memset) comes first
+    NCM_CUDA_OK(c, cudaStreamWaitEvent(hi, c->ev_tail, 0));
+  }
   bool done = false;
   for (int kb = 0; kb < nblk && !done; kb += GP) {
     const int k0 = kb * NB;
@@ -405,25 +431,44 @@ int dpotrf_upper_solve(ncm_sd_gpu_ctx *c, int n, double *dM, int ldm, double *dR
         break;
       }
       if (p > 0) {
-        int rc = dsyrk_ata_first_rows64(c, p * NB, n - kp, dM + (size_t) k0 * ldm + kp, ldm, dM + (size_t) kp * ldm + kp, ldm);
+        int rc = dsyrk_ata_first_rows64_on(c, hi, p * NB, n - kp, dM + (size_t) k0 * ldm + kp, ldm, dM + (size_t) kp * ldm + kp, ldm);
         if (rc != NCM_SD_GPU_OK) return rc;
       }
-      chol_diag_kernel<<<1, 256, 0, c->stream>>>(dM, ldm, n, kp, dRhs, dDinv, dInfo);
+      chol_diag_kernel<<<1, 256, 0, hi>>>(dM, ldm, n, kp, dRhs, dDinv, dInfo);
       c->n_launches++;
       const int m = n - kp - NB;
       if (m <= 0) {
         done = true;
         break;
       }
-      chol_panel_kernel<<<(m + 127) / 128, 128, 0, c->stream>>>(dM, ldm, n, kp, dRhs, dDinv);
+      chol_panel_kernel<<<(m + 127) / 128, 128, 0, hi>>>(dM, ldm, n, kp, dRhs, dDinv);
       c->n_launches++;
     }
     if (done) break;
-    const int kg = k0 + GP * NB;
+    const int kg = k0 + W;
     const int mg = n - kg;
     if (mg <= 0) break;
-    int rc = dsyrk_ata_general(c, GP * NB, mg, dM + (size_t) k0 * ldm + kg, ldm, dM + (size_t) kg * ldm + kg, ldm, -1.0, 1.0);
+    const double *dP = dM + (size_t) k0 * ldm + kg;
+    double *dC       = dM + (size_t) kg * ldm + kg;
+    if (!lookahead) {
+      int rc = dsyrk_ata_general(c, W, mg, dP, ldm, dC, ldm, -1.0, 1.0);
+      if (rc != NCM_SD_GPU_OK) return rc;
+      continue;
+    }
+    NCM_CUDA_OK(c, cudaEventRecord(c->ev_panel, hi));
+    NCM_CUDA_OK(c, cudaStreamWaitEvent(lo, c->ev_panel, 0));
+    NCM_CUDA_OK(c, cudaStreamWaitEvent(hi, c->ev_tail, 0));   // tail(g-1) wrote the rows head(g) updates (first group: the fork event)
+    int rc = dsyrk_ata_head_rows_on(c, hi, W, mg, mg < W ? ((mg + 127) / 128) * 128 : W, dP, ldm, dC, ldm);
     if (rc != NCM_SD_GPU_OK) return rc;
+    if (mg > W) {
+      rc = dsyrk_ata_general_on(c, lo, W, mg - W, dP + W, ldm, dC + (size_t) W * ldm + W, ldm, -1.0, 1.0);
+      if (rc != NCM_SD_GPU_OK) return rc;
+    }
+    NCM_CUDA_OK(c, cudaEventRecord(c->ev_tail, lo));
+  }
+  if (lookahead) {   // join: the back substitution (and whatever the caller queues next) follows both streams
+    NCM_CUDA_OK(c, cudaEventRecord(c->ev_panel, hi));
+    NCM_CUDA_OK(c, cudaStreamWaitEvent(lo, c->ev_panel, 0));
   }
   if (dRhs != nullptr) {
     for (int kb = nblk - 1; kb >= 0; --kb) {

@@ -91,6 +91,10 @@ struct ncm_sd_gpu_ctx {
   long long n_launches = 0;
   long long h2d_bytes = 0, d2h_bytes = 0;   // bytes moved over PCIe by this context (ncm_sd_gpu_get_traffic)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // look-ahead Cholesky (chol.cu): a highest-priority stream for the latency-bound panel kernels, run concurrently with the
+  // trailing updates on `stream`; created on first use
+  cudaStream_t stream_hi = nullptr;
+  cudaEvent_t ev_panel = nullptr, ev_tail = nullptr;
 
   int fail(int code, const std::string &msg) {
     err = msg;

@@ -178,7 +178,7 @@ ata_kernel(const double *__restrict__ P, int ldp, int K, int n, double *__restri
 }
 
 template <typename Cfg, bool SUBC>
-cudaError_t ata_launch(cudaStream_t st, const double *dP, int ldp, int K, int n, double *dC, int ldc, double alpha, double beta, bool first_row_only = false) {
+cudaError_t ata_launch(cudaStream_t st, const double *dP, int ldp, int K, int n, double *dC, int ldc, double alpha, double beta, int head_tile_rows = 0) {
   using D = AtaDerived<Cfg>;
   static bool attr_set[NCM_MAX_DEVICES] = {};   // function attributes are per device
   int dev__ = 0;
@@ -190,8 +190,10 @@ cudaError_t ata_launch(cudaStream_t st, const double *dP, int ldp, int K, int n,
     attr_set[dev__] = true;
   }
   const int nt = (n + Cfg::TB - 1) / Cfg::TB;
-  // tiles are enumerated row by row over the upper triangle: the first nt of them are tile row 0
-  ata_kernel<Cfg, SUBC><<<first_row_only ? nt : nt * (nt + 1) / 2, Cfg::THREADS, D::SMEM, st>>>(dP, ldp, K, n, dC, ldc, alpha, beta, nt);
+  // tiles are enumerated row by row over the upper triangle: the first nt of them are tile row 0, the next nt - 1 tile row 1, ...
+  const int hr    = head_tile_rows > nt ? nt : head_tile_rows;
+  const int tiles = hr > 0 ? (hr * (2 * nt - hr + 1)) / 2 : nt * (nt + 1) / 2;
+  ata_kernel<Cfg, SUBC><<<tiles, Cfg::THREADS, D::SMEM, st>>>(dP, ldp, K, n, dC, ldc, alpha, beta, nt);
   return cudaGetLastError();
 }
 
@@ -254,7 +256,13 @@ __global__ void residual_kernel(const double *__restrict__ A, int lda, int nrows
 
 }   // namespace
 
+int dsyrk_ata_general_on(ncm_sd_gpu_ctx *c, cudaStream_t st, int K, int n, const double *dP, int ldp, double *dC, int ldc, double alpha, double beta);
+
 int dsyrk_ata_general(ncm_sd_gpu_ctx *c, int K, int n, const double *dP, int ldp, double *dC, int ldc, double alpha, double beta) {
+  return dsyrk_ata_general_on(c, c->stream, K, n, dP, ldp, dC, ldc, alpha, beta);
+}
+
+int dsyrk_ata_general_on(ncm_sd_gpu_ctx *c, cudaStream_t st, int K, int n, const double *dP, int ldp, double *dC, int ldc, double alpha, double beta) {
   if (n <= 0 || K <= 0) return NCM_SD_GPU_OK;
   if ((ldp & 1) || (ldc & 1) || (((uintptr_t) dP) & 15) || (((uintptr_t) dC) & 15))
     return c->fail(NCM_SD_GPU_EINVAL, "ata: operands must be 16-byte aligned with even leading dimensions");
@@ -264,9 +272,9 @@ int dsyrk_ata_general(ncm_sd_gpu_ctx *c, int K, int n, const double *dP, int ldp
   const bool subc    = (alpha == -1.0 && beta == 1.0);
   cudaError_t e;
   if (small)
-    e = subc ? ata_launch<AtaSmall, true>(c->stream, dP, ldp, K, n, dC, ldc, alpha, beta) : ata_launch<AtaSmall, false>(c->stream, dP, ldp, K, n, dC, ldc, alpha, beta);
+    e = subc ? ata_launch<AtaSmall, true>(st, dP, ldp, K, n, dC, ldc, alpha, beta) : ata_launch<AtaSmall, false>(st, dP, ldp, K, n, dC, ldc, alpha, beta);
   else
-    e = subc ? ata_launch<AtaBig, true>(c->stream, dP, ldp, K, n, dC, ldc, alpha, beta) : ata_launch<AtaBig, false>(c->stream, dP, ldp, K, n, dC, ldc, alpha, beta);
+    e = subc ? ata_launch<AtaBig, true>(st, dP, ldp, K, n, dC, ldc, alpha, beta) : ata_launch<AtaBig, false>(st, dP, ldp, K, n, dC, ldc, alpha, beta);
   NCM_CUDA_OK(c, e);
   c->n_launches++;
   NCM_CUDA_OK(c, cudaGetLastError());
@@ -275,11 +283,27 @@ int dsyrk_ata_general(ncm_sd_gpu_ctx *c, int K, int n, const double *dP, int ldp
 
 // C[0:64, 0:n] -= P[:, 0:64]^T P  (the first 64-row block of the trailing update only): lets the blocked Cholesky factor two
 // 64-wide panels before it touches the rest of the matrix, so that the big update runs with K = 128
-int dsyrk_ata_first_rows64(ncm_sd_gpu_ctx *c, int K, int n, const double *dP, int ldp, double *dC, int ldc) {
+int dsyrk_ata_first_rows64_on(ncm_sd_gpu_ctx *c, cudaStream_t st, int K, int n, const double *dP, int ldp, double *dC, int ldc) {
   if (n <= 0 || K <= 0) return NCM_SD_GPU_OK;
   if ((ldp & 1) || (ldc & 1) || (((uintptr_t) dP) & 15) || (((uintptr_t) dC) & 15))
     return c->fail(NCM_SD_GPU_EINVAL, "ata: operands must be 16-byte aligned with even leading dimensions");
-  NCM_CUDA_OK(c, (ata_launch<AtaSmall, true>(c->stream, dP, ldp, K, n, dC, ldc, -1.0, 1.0, true)));
+  NCM_CUDA_OK(c, (ata_launch<AtaSmall, true>(st, dP, ldp, K, n, dC, ldc, -1.0, 1.0, 1)));
+  c->n_launches++;
+  NCM_CUDA_OK(c, cudaGetLastError());
+  return NCM_SD_GPU_OK;
+}
+
+int dsyrk_ata_first_rows64(ncm_sd_gpu_ctx *c, int K, int n, const double *dP, int ldp, double *dC, int ldc) {
+  return dsyrk_ata_first_rows64_on(c, c->stream, K, n, dP, ldp, dC, ldc);
+}
+
+// C[0:rows, 0:n] -= P[:, 0:rows]^T P with 128 x 128 tiles (rows a multiple of 128): the head strip of a trailing update, i.e. exactly
+// the block rows the next panel group of the look-ahead Cholesky factors
+int dsyrk_ata_head_rows_on(ncm_sd_gpu_ctx *c, cudaStream_t st, int K, int n, int rows, const double *dP, int ldp, double *dC, int ldc) {
+  if (n <= 0 || K <= 0 || rows <= 0) return NCM_SD_GPU_OK;
+  if ((ldp & 1) || (ldc & 1) || (((uintptr_t) dP) & 15) || (((uintptr_t) dC) & 15) || (rows % AtaBig::TB) != 0)
+    return c->fail(NCM_SD_GPU_EINVAL, "ata: operands must be 16-byte aligned with even leading dimensions, head rows a multiple of the tile");
+  NCM_CUDA_OK(c, (ata_launch<AtaBig, true>(st, dP, ldp, K, n, dC, ldc, -1.0, 1.0, rows / AtaBig::TB)));
   c->n_launches++;
   NCM_CUDA_OK(c, cudaGetLastError());
   return NCM_SD_GPU_OK;

@@ -267,6 +267,19 @@ solve_normal_cholesky (orc_nnls *self, const orc_iset *Pset, const double *f)
   if (getenv ("ORC_NNLS_TRACE") != NULL)   /* debugging aid: passive-set size of every factorisation */
     fprintf (stderr, "orc_nnls: chol |P| = %d info = %d\n", self->uncols, info);
 
+  if (getenv ("ORC_NNLS_DUMP") != NULL)    /* debugging aid: append (|P|, indices, solution) of every factorisation to a binary file */
+  {
+    FILE *fp = fopen (getenv ("ORC_NNLS_DUMP"), "ab");
+
+    if (fp != NULL)
+    {
+      fwrite (&Pset->len, sizeof (int), 1, fp);
+      fwrite (Pset->idx, sizeof (int), Pset->len, fp);
+      fwrite (self->x_tmp, sizeof (double), Pset->len, fp);
+      fclose (fp);
+    }
+  }
+
   if (info > 0)
     solve_normal_LU (self, Pset, f);
 }

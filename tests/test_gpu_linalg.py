@@ -79,3 +79,37 @@ def test_dposv_upper(gpu_ctx, n):
     torch.cuda.synchronize()
     assert gpu_ctx.dposv_upper_dev(n, dM.data_ptr(), ld, dB.data_ptr()) == 0
     assert np.array_equal(dB.cpu().numpy(), x)
+
+
+@pytest.mark.parametrize("n", [4500, 6501, 12345])
+def test_dposv_upper_lookahead_path(gpu_ctx, n):
+    """n > 4096: the launch-per-step blocked Cholesky with look-ahead (chol.cu): panel groups of 128 / 256 / 512 columns on a
+    high-priority stream, trailing-update tails on the context stream.  Sizes off every tile multiple; solved twice on the same
+    buffers (stream fork / join must leave nothing in flight)."""
+    import torch
+
+    rs = np.random.default_rng(n)
+    B = rs.standard_normal((n + 10, n))
+    S = B.T @ B + 0.1 * np.eye(n)
+    del B
+    b = rs.standard_normal(n)
+    ld = (n + 7) // 8 * 8
+    dS = torch.from_numpy(np.triu(S)).cuda()
+    dM = torch.full((n, ld), float("nan"), dtype=torch.float64, device="cuda")
+    dM[:, :n] = dS
+    dM[:, :n] += torch.tril(torch.full((n, n), float("nan"), dtype=torch.float64, device="cuda"), -1)   # the lower triangle must never be read
+    dB = torch.from_numpy(b).cuda()
+    torch.cuda.synchronize()
+    assert gpu_ctx.dposv_upper_dev(n, dM.data_ptr(), ld, dB.data_ptr()) == 0
+    x = dB.cpu().numpy()
+    U = torch.triu(dM[:, :n])
+    # residuals instead of a host factorisation at this size: U^T U = S and S x = b
+    R = U.T @ U
+    assert float(torch.max(torch.abs(torch.triu(R) - dS))) < 1e-11 * float(torch.max(torch.abs(dS)))
+    Sfull = torch.from_numpy(S).cuda()
+    assert float(torch.max(torch.abs(Sfull @ dB - torch.from_numpy(b).cuda()))) < 1e-8 * max(1.0, float(np.abs(x).max()) * float(torch.max(torch.abs(dS))))
+    dM[:, :n] = dS
+    dB.copy_(torch.from_numpy(b).cuda())
+    torch.cuda.synchronize()
+    assert gpu_ctx.dposv_upper_dev(n, dM.data_ptr(), ld, dB.data_ptr()) == 0
+    assert np.array_equal(dB.cpu().numpy(), x)
