@@ -22,8 +22,9 @@
 // epoch of the call and never need clearing.  Panel solves and the diagonal factorisation work on 8-row strips: a DMMA
 // sweep with the rows already done, then an 8 x 8 triangular step in registers (no inverses are formed anywhere).
 //
-// Measured (tools/chol_trace.py, n = 2048): 21 us per 64-column phase = factor 8.3 + store/flag 1.5 + panel 5.7 + update 2.5
-// + waits; the 8 x 8 pivot chain (rsqrt -> mul -> fma, ~110 cycles per pivot, one warp) is the floor of the factor step.
+// Measured (tools/chol_trace.py, n = 2048) with three CTA barriers per 8-row strip: 21 us per 64-column phase = factor 11.2
+// + store/flag 1.5 + panel 7.1 + update 3.8 of which the 8 x 8 pivot chain (rsqrt -> mul -> fma, one warp) is about 0.4 us per
+// strip; diag_factor and panel_solve below are therefore warp-level data flow without CTA barriers.
 #include "ctx.h"
 
 namespace {
@@ -109,6 +110,22 @@ __device__ __forceinline__ void trace_ev(const FusedArgs &a, int type, int x, in
     }
   }
 }
+
+#ifdef NCM_FUSED_PROBE   // tools/chol_trace.py --probe: clock64 stamps of every warp inside diag_factor (block k = 0 of a SMALL system, whose
+                        // workers 140 + w are idle and lend their trace regions); compiled out of the library
+__device__ __forceinline__ void probe_ev(const FusedArgs &a, int k, int w, int code) {
+  if (a.trace != nullptr && k == 0 && (threadIdx.x & 31) == 0) {
+    long long *base = a.trace + (size_t) (140 + w) * a.trace_cap * 2;
+    const long long n = base[0];
+    base[2 * (n + 1)]     = clock64();
+    base[2 * (n + 1) + 1] = code;
+    base[0]               = n + 1;
+  }
+}
+#define NCM_PROBE_EV(code) probe_ev(a, k, w, (code))
+#else
+#define NCM_PROBE_EV(code) do { } while (0)
+#endif
 
 __device__ __forceinline__ int row_start(int I, int nbc) { return I * nbc - (I * (I - 1)) / 2; }
 
@@ -241,138 +258,251 @@ __device__ __forceinline__ void diag_store(const FusedArgs &a, int k, const doub
   if (tid < nbk) a.dinv[k0 + tid] = sDinv[tid];
 }
 
+// one warp's share of tile_fetch_async: the whole 64 x 64 tile through the 32 lanes of the calling warp
+__device__ __forceinline__ void tile_fetch_async_warp(const FusedArgs &a, int k, int J, double *sX) {
+  const int lane = threadIdx.x & 31;
+  const int k0 = k * FB, J0 = J * FB;
+  const int nbk = min(FB, a.n - k0);
+#pragma unroll 8
+  for (int q = 0; q < (FB * FB / 2) / 32; ++q) {
+    const int chunk = q * 32 + lane;
+    const int r = chunk >> 5, cc = (chunk & 31) * 2;
+    const int gc = J0 + cc;
+    int bytes    = r < nbk ? (a.n - gc) * 8 : 0;
+    bytes        = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
+    const double *src = bytes > 0 ? a.M + (size_t) (k0 + r) * a.ldm + gc : a.M;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(sX + r * FPITCH + cc)), "l"(src), "r"(bytes) : "memory");
+  }
+}
+
+// 8 x 8 triangular step shared by the diagonal factorisation and the panel solve: the calling lane owns column ci of X and
+// solves its 8 entries of the strip b0 .. b0+7 against the (already final) pivot block of U at (b0, b0)
+__device__ __forceinline__ void strip_column_solve(const double *sU, double *X, const double *sD, int b0, int ci) {
+  double u[8][8], t[8], inv[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+#pragma unroll
+    for (int q = r + 1; q < 8; ++q) u[r][q] = sU[(b0 + r) * FPITCH + b0 + q];
+    t[r]   = X[(b0 + r) * FPITCH + ci];
+    inv[r] = sD[b0 + r];
+  }
+  // column-oriented: as soon as x_s is known every later entry takes its term, so the dependent chain is mul -> fma -> mul ... (15 operations)
+  // instead of the 36 of the row-by-row order; each t[r] still receives its terms in ascending s: same rounding
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    const double xs = t[s] * inv[s];
+    X[(b0 + s) * FPITCH + ci] = xs;
+#pragma unroll
+    for (int r = s + 1; r < 8; ++r) t[r] = fma(-u[s][r], xs, t[r]);
+  }
+}
+
 // ---- diagonal block ---------------------------------------------------------------------------------
+// named CTA barriers (bar.arrive / bar.sync with a thread count): producer-consumer hand-off between warps with the memory
+// ordering of a barrier and without a fence on the producer's path
+__device__ __forceinline__ void bar_sync_n(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void bar_arrive_n(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
 // S (pitch FPITCH) holds the block (upper part valid, identity padding beyond nbk); on return S holds U_kk and
-// sDinv the reciprocal pivots.  Per 8-row strip: DMMA sweep with the rows already factored; warp 0 factors the
-// 8 x 8 pivot block in registers (every lane the same arithmetic: nothing but rsqrt -> mul -> fma on the pivot
-// chain); then one thread per remaining column solves its 8 entries against it.
-// While warp 0 is busy with a pivot block, an otherwise idle lane polls the two flags the spine will need next (want_*:
-// still to be fetched); the tiles are then fetched with cp.async from inside the factorisation, so a worker that is on
-// time never puts an L2 round trip on the chain.
+// sDinv the reciprocal pivots.
+//
+// Data flow over the 8 warps, no CTA barrier inside.  Warp w owns the 8 columns of column block w and keeps its tiles (0, w) ..
+// (w, w) in DMMA accumulator fragments; the block is factored right-looking by 8-row strips:
+//   strip j < w :  fragment (j, w) -> shared memory; wait for pivot block j (barrier P_j); 8 x 8 triangular step, one lane per
+//                  column; wait until the whole strip j is solved (barrier S_j); rank-8 update of the tiles (j+1 .. w, w)
+//   strip j = w :  fragment (w, w) -> shared memory -> every lane loads the 36 entries and factors the 8 x 8 pivot block in
+//                  registers (the same arithmetic in every lane: nothing but rsqrt -> mul -> fma on the pivot chain);
+//                  lane 0 writes it back; arrive on P_w.
+// The next pivot warp (w = j + 1) only ARRIVES on S_j: its own tile (j, j+1) is all its diagonal tile needs, so the chain per
+// strip is  P_j -> triangular step -> 2 DMMA -> fragment round trip -> pivot block  with everything else beside it (the
+// left-looking version with shared-memory flags and fences: 2640 cycles per strip, 1000 of them in fences and sweeps).
+// Warp 0 is free after the first pivot block: it polls the two flags the spine will need next (want_*: still to be
+// fetched) and fetches those tiles with cp.async, so a worker that is on time never puts an L2 round trip on the chain.
 __device__ void diag_factor(const FusedArgs &a, double *S, double *sDinv, int *sBad, int k0, int k, bool &want_panel, bool &want_next, double *sX,
                             double *sC, int *sPoll) {
-  const int tid = threadIdx.x;
-  int pf0 = 0, pf1 = 0;
-#pragma unroll 1
-  for (int kb = 0; kb < FB / 8; ++kb) {
-    const int b0 = 8 * kb;
-    if (kb > 0) {
-      strip_sweep(S, S, b0, kb, FB / 8);
-      __syncthreads();
+  __shared__ int sDone;
+  constexpr int NS = FB / 8;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int lr = lane & 3, lc = lane >> 2;
+  if (tid == 0) {
+    sPoll[0] = 0;
+    sPoll[1] = 0;
+    sBad[3]  = 0x7fffffff;   // lowest failing pivot of this block (several warps may report)
+    sDone    = 0;
+  }
+  __syncthreads();
+  const int bw = 8 * w;
+  double acc[NS][4][2];   // four accumulator pairs per tile in the summation order of the left-looking sweep (see panel_solve)
+#pragma unroll
+  for (int m = 0; m < NS; ++m)
+    if (m <= w) {
+      const double2 v = *reinterpret_cast<const double2 *>(S + (8 * m + lc) * FPITCH + bw + 2 * lr);
+      acc[m][0][0]    = v.x;
+      acc[m][0][1]    = v.y;
+#pragma unroll
+      for (int c = 1; c < 4; ++c) acc[m][c][0] = acc[m][c][1] = 0.0;
     }
-    trace_ev(a, 6, kb, 0);
-    if (tid < 32) {
+  NCM_PROBE_EV(0);
+#pragma unroll
+  for (int j = 0; j < NS; ++j) {
+    const int b0 = 8 * j;
+    if (j < w) {
+      if (j > 0) {
+        const double v0 = (acc[j][0][0] + acc[j][2][0]) + (acc[j][1][0] + acc[j][3][0]);
+        const double v1 = (acc[j][0][1] + acc[j][2][1]) + (acc[j][1][1] + acc[j][3][1]);
+        *reinterpret_cast<double2 *>(S + (b0 + lc) * FPITCH + bw + 2 * lr) = make_double2(v0, v1);
+        __syncwarp();
+      }
+      bar_sync_n(1 + j, 32 * (NS - j));   // P_j
+      NCM_PROBE_EV(300 + j);
+      if (lane < 8) strip_column_solve(S, S, sDinv, b0, bw + lane);
+      __syncwarp();
+      NCM_PROBE_EV(400 + j);
+      if (j + 2 < NS) {                   // S_j has more than one participant
+        if (w == j + 1)
+          bar_arrive_n(1 + NS + j, 32 * (NS - 1 - j));
+        else
+          bar_sync_n(1 + NS + j, 32 * (NS - 1 - j));
+      }
+      const double bx0 = S[(b0 + lr) * FPITCH + bw + lc], bx1 = S[(b0 + 4 + lr) * FPITCH + bw + lc];
+#pragma unroll
+      for (int m = j + 1; m < NS; ++m)
+        if (m <= w) {
+          const double a0 = -S[(b0 + lr) * FPITCH + 8 * m + lc], a1 = -S[(b0 + 4 + lr) * FPITCH + 8 * m + lc];
+          dmma884(acc[m][2 * (j & 1)][0], acc[m][2 * (j & 1)][1], a0, bx0);
+          dmma884(acc[m][2 * (j & 1) + 1][0], acc[m][2 * (j & 1) + 1][1], a1, bx1);
+        }
+      NCM_PROBE_EV(500 + j);
+    } else if (j == w) {
+      if (j > 0) {
+        const double v0 = (acc[j][0][0] + acc[j][2][0]) + (acc[j][1][0] + acc[j][3][0]);
+        const double v1 = (acc[j][0][1] + acc[j][2][1]) + (acc[j][1][1] + acc[j][3][1]);
+        *reinterpret_cast<double2 *>(S + (b0 + lc) * FPITCH + bw + 2 * lr) = make_double2(v0, v1);
+        __syncwarp();
+      }
+      NCM_PROBE_EV(600);
       double dgl[8][8];
 #pragma unroll
       for (int r = 0; r < 8; ++r)
 #pragma unroll
-        for (int q = r; q < 8; ++q) dgl[r][q] = S[(b0 + r) * FPITCH + b0 + q];
+        for (int q = r; q < 8; ++q) dgl[r][q] = S[(bw + r) * FPITCH + bw + q];
       double inv[8];
       int bad = 0;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const double piv = dgl[j][j];
-        if (!(piv > 0.0)) bad = (bad == 0) ? k0 + b0 + j + 1 : bad;   // the factor is garbage (NaN) from here on; info reports it
-        inv[j]    = rsqrt(piv);
-        dgl[j][j] = piv * inv[j];
+      for (int p = 0; p < 8; ++p) {
+        const double piv = dgl[p][p];
+        if (!(piv > 0.0)) bad = (bad == 0) ? k0 + bw + p + 1 : bad;   // the factor is garbage (NaN) from here on; info reports it
+        inv[p]    = rsqrt(piv);
+        dgl[p][p] = piv * inv[p];
 #pragma unroll
-        for (int q = j + 1; q < 8; ++q) dgl[j][q] *= inv[j];
+        for (int q = p + 1; q < 8; ++q) dgl[p][q] *= inv[p];
 #pragma unroll
-        for (int r = j + 1; r < 8; ++r)
+        for (int r = p + 1; r < 8; ++r)
 #pragma unroll
-          for (int q = r; q < 8; ++q) dgl[r][q] = fma(-dgl[j][r], dgl[j][q], dgl[r][q]);
+          for (int q = r; q < 8; ++q) dgl[r][q] = fma(-dgl[p][r], dgl[p][q], dgl[r][q]);
       }
-      if (tid == 0) {
+#ifdef NCM_FUSED_PROBE
+      if (dgl[7][7] == -1.2345) sBad[3] = 1;   // keeps the stamp below after the arithmetic
+      NCM_PROBE_EV(700);
+#endif
+      if (lane == 0) {
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
+          // row r: entries r .. 7; bw + r is even exactly when r is, so the pairs starting at an even column are 16-byte aligned
+          if (r & 1) S[(bw + r) * FPITCH + bw + r] = dgl[r][r];
 #pragma unroll
-          for (int q = r; q < 8; ++q) S[(b0 + r) * FPITCH + b0 + q] = dgl[r][q];
-          sDinv[b0 + r] = inv[r];
+          for (int q = (r + 1) & ~1; q < 8; q += 2)
+            *reinterpret_cast<double2 *>(S + (bw + r) * FPITCH + bw + q) = make_double2(dgl[r][q], dgl[r][q + 1]);
         }
-        if (bad != 0 && *sBad == 0) *sBad = bad;
-      }
-    }
-    if (tid == 224) {
-      // the values loaded one strip ago are consumed now and the next loads are issued: the L2 round trip of a poll
-      // spans a whole strip instead of stretching this stage
-      sPoll[0] = (want_panel && kb > 0) ? (pf0 == a.epoch) : 0;
-      sPoll[1] = (want_next && kb > 0) ? (pf1 == a.epoch) : 0;
-      pf0 = ld_relaxed(a.flagTs + k);
-      pf1 = ld_relaxed(a.flagTd + k + 1);
-    }
-    __syncthreads();
-    if (sPoll[0] != 0 || sPoll[1] != 0) {
-      __threadfence();   // relaxed poll + fence = acquire: the tile data is ordered after the flag that announced it
-      if (sPoll[0] != 0) {
-        tile_fetch_async(a, k, k + 1, sX);
-        want_panel = false;
-      }
-      if (sPoll[1] != 0) {
-        tile_fetch_async(a, k + 1, k + 1, sC);
-        want_next = false;
-      }
-      cp_async_commit();
-    }
-    const int ci = b0 + 8 + tid;
-    if (ci < FB) {
-      double u[8][8], t[8], inv[8];
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-#pragma unroll
-        for (int q = r + 1; q < 8; ++q) u[r][q] = S[(b0 + r) * FPITCH + b0 + q];
-        t[r]   = S[(b0 + r) * FPITCH + ci];
-        inv[r] = sDinv[b0 + r];
+        for (int r = 0; r < 8; r += 2) *reinterpret_cast<double2 *>(sDinv + bw + r) = make_double2(inv[r], inv[r + 1]);
+        if (bad != 0) atomicMin(sBad + 3, bad);
+        if (j == NS - 1) *reinterpret_cast<volatile int *>(&sDone) = 1;
       }
-      double x[8];
-#pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        double tt = t[r];
-#pragma unroll
-        for (int s = 0; s < r; ++s) tt = fma(-u[s][r], x[s], tt);
-        x[r] = tt * inv[r];
-        S[(b0 + r) * FPITCH + ci] = x[r];
-      }
+      __syncwarp();
+      if (j + 1 < NS) bar_arrive_n(1 + j, 32 * (NS - j));   // P_j
+      NCM_PROBE_EV(800);
     }
-    __syncthreads();
-    trace_ev(a, 6, kb, 1);
   }
+  if (w == 0 && (want_panel || want_next)) {
+    bool wp = want_panel, wn = want_next;
+    while ((wp || wn) && *reinterpret_cast<volatile int *>(&sDone) == 0) {
+      int f0 = 0, f1 = 0;
+      if (lane == 0) {
+        f0 = wp ? (ld_relaxed(a.flagTs + k) == a.epoch) : 0;
+        f1 = wn ? (ld_relaxed(a.flagTd + k + 1) == a.epoch) : 0;
+      }
+      f0 = __shfl_sync(0xffffffffu, f0, 0);
+      f1 = __shfl_sync(0xffffffffu, f1, 0);
+      if (f0 != 0 || f1 != 0) {
+        __threadfence();   // relaxed poll + fence = acquire: the tile data is ordered after the flag that announced it
+        if (f0 != 0) {
+          tile_fetch_async_warp(a, k, k + 1, sX);
+          wp = false;
+          if (lane == 0) sPoll[0] = 1;
+        }
+        if (f1 != 0) {
+          tile_fetch_async_warp(a, k + 1, k + 1, sC);
+          wn = false;
+          if (lane == 0) sPoll[1] = 1;
+        }
+        cp_async_commit();
+      }
+    }
+  }
+  __syncthreads();
+  if (sPoll[0] != 0) want_panel = false;
+  if (sPoll[1] != 0) want_next = false;
+  if (tid == 0 && sBad[3] != 0x7fffffff && *sBad == 0) *sBad = sBad[3];
 }
 
 // ---- panel solve in shared memory: sX <- sU^-T sX ----------------------------------------------------------
-// sU: U_kk (pitch FPITCH, identity beyond the valid rows), sD: 1 / U_rr, sX: the tile, solved in place strip by strip.
+// sU: U_kk (pitch FPITCH, identity beyond the valid rows), sD: 1 / U_rr, sX: the tile, solved in place.
+// U_kk is complete, so the 8 column blocks are independent chains: warp w keeps its 64 x 8 column block in DMMA accumulator
+// fragments and works right-looking down the 8 strips -- strip j: fragment -> shared memory, 8 x 8 triangular step (one lane per
+// column), then the rank-8 update of the strips below, the next one first (it is the only one on the chain).  Warp-level
+// synchronisation only, one CTA barrier at the end (the left-looking version with two CTA barriers per strip: 5.3 - 7.1 us per tile).
 __device__ void panel_solve(const FusedArgs &a, const double *sU, double *sX, const double *sD, int width) {
-  const int tid   = threadIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int lr = lane & 3, lc = lane >> 2;
   const int w_end = (width + 7) >> 3;
-#pragma unroll 1
-  for (int blk = 0; blk < FB / 8; ++blk) {
-    const int b0 = 8 * blk;
-    if (blk > 0) {
-      strip_sweep(sU, sX, b0, 0, w_end);
-      __syncthreads();
+  if (w < w_end) {
+    const int ci = 8 * w + lane;
+    // four accumulator pairs per tile, fed exactly as the left-looking DMMA sweep of the earlier versions fed them (rows 16 g + 0..3 ->
+    // c, + 4..7 -> d, + 8..11 -> e, + 12..15 -> f; result (c + e) + (d + f)): the factor stays bit-identical to those versions, on which
+    // the accepted-sequence parity tests were established
+    double acc[FB / 8][4][2];
+#pragma unroll
+    for (int m = 0; m < FB / 8; ++m) {
+      const double2 v = *reinterpret_cast<const double2 *>(sX + (8 * m + lc) * FPITCH + 8 * w + 2 * lr);
+      acc[m][0][0] = v.x;
+      acc[m][0][1] = v.y;
+#pragma unroll
+      for (int c = 1; c < 4; ++c) acc[m][c][0] = acc[m][c][1] = 0.0;
     }
-    trace_ev(a, 7, blk, 0);
-    if (tid < width) {
-      double u[8][8], t[8], inv[8];
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-#pragma unroll
-        for (int q = r + 1; q < 8; ++q) u[r][q] = sU[(b0 + r) * FPITCH + b0 + q];
-        t[r]   = sX[(b0 + r) * FPITCH + tid];
-        inv[r] = sD[b0 + r];
+    for (int j = 0; j < FB / 8; ++j) {
+      const int b0 = 8 * j;
+      if (j > 0) {
+        const double v0 = (acc[j][0][0] + acc[j][2][0]) + (acc[j][1][0] + acc[j][3][0]);
+        const double v1 = (acc[j][0][1] + acc[j][2][1]) + (acc[j][1][1] + acc[j][3][1]);
+        *reinterpret_cast<double2 *>(sX + (b0 + lc) * FPITCH + 8 * w + 2 * lr) = make_double2(v0, v1);
+        __syncwarp();
       }
-      double x[8];
+      if (lane < 8 && ci < width) strip_column_solve(sU, sX, sD, b0, ci);
+      __syncwarp();
+      if (j + 1 < FB / 8) {
+        const double bx0 = sX[(b0 + lr) * FPITCH + 8 * w + lc], bx1 = sX[(b0 + 4 + lr) * FPITCH + 8 * w + lc];
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        double tt = t[r];
-#pragma unroll
-        for (int s = 0; s < r; ++s) tt = fma(-u[s][r], x[s], tt);
-        x[r] = tt * inv[r];
-        sX[(b0 + r) * FPITCH + tid] = x[r];
+        for (int m = j + 1; m < FB / 8; ++m) {
+          const double a0 = -sU[(b0 + lr) * FPITCH + 8 * m + lc], a1 = -sU[(b0 + 4 + lr) * FPITCH + 8 * m + lc];
+          dmma884(acc[m][2 * (j & 1)][0], acc[m][2 * (j & 1)][1], a0, bx0);
+          dmma884(acc[m][2 * (j & 1) + 1][0], acc[m][2 * (j & 1) + 1][1], a1, bx1);
+        }
       }
     }
-    __syncthreads();
-    trace_ev(a, 7, blk, 1);
   }
+  __syncthreads();
 }
 
 // worker: panel block (k, J), J >= k + 2
@@ -604,9 +734,8 @@ __device__ void do_backprod(const FusedArgs &a, int I, int J, double *sx) {
 // S: current diagonal block, sX: panel block (k, k+1), sC: prefetched tile (k+1, k+1)
 __device__ void spine_factor(const FusedArgs &a, double *S, double *sX, double *sC, double *sDinv, int *sBad /* [3]: bad pivot, 2 poll results */) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp >> 2, wn = warp & 3;
+  
   const int lr = lane & 3, lc = lane >> 2;
-  const int rm = wm * 32, cn = wn * 16;
   const int nb = a.nb, nbc = a.nbc;
   if (tid == 0) *sBad = 0;
   {   // tile (0, 0), identity padded
@@ -640,7 +769,9 @@ __device__ void spine_factor(const FusedArgs &a, double *S, double *sX, double *
     cp_async_commit();
     trace_ev(a, 1, k, k);
     diag_factor(a, S, sDinv, sBad, k * FB, k, want_panel, want_next, sX, sC, sBad + 1);
+    trace_ev(a, 6, k, 0);
     diag_store(a, k, S, sDinv);
+    trace_ev(a, 6, k, 1);
     if (tid == 0 && *sBad != 0) atomicCAS(a.info, 0, *sBad);
     post_flag(a, a.flagD + k);
     trace_ev(a, 1 + 8, k, k);
@@ -661,7 +792,9 @@ __device__ void spine_factor(const FusedArgs &a, double *S, double *sX, double *
       trace_ev(a, 2 + 16, k, k + 1);
       const int width = panel_isR ? 1 : min(FB, a.n - (k + 1) * FB);
       panel_solve(a, S, sX, sDinv, width);
+      trace_ev(a, 7, k, 0);
       tile_store(a, k, k + 1, sX);
+      trace_ev(a, 7, k, 1);
       post_flag(a, a.flagP + k * (nb + 1) + k + 1);
       trace_ev(a, 2 + 8, k, k + 1);
     }
@@ -677,38 +810,49 @@ __device__ void spine_factor(const FusedArgs &a, double *S, double *sX, double *
       __syncthreads();
       const int I0 = (k + 1) * FB;
       const int hI = min(FB, a.n - I0);
-      double acc[4][2][2];
+      // only the upper triangle of the diagonal tile is ever read (diag_factor): its 36 8 x 8 sub-tiles are dealt round-robin to the
+      // 8 warps (4 or 5 each, balanced over the four DMMA pipes) instead of 64 sub-tiles in a 4 x 2 block per warp
+      {
+        int tr[5], tc[5];
+        const int nt = warp < 4 ? 5 : 4;   // sub-tile t = warp + 8 i of the row-major enumeration of the upper triangle, t < 36
 #pragma unroll
-      for (int am = 0; am < 4; ++am)
+        for (int i = 0; i < 5; ++i) {
+          int t = warp + 8 * i, r = 0;
 #pragma unroll
-        for (int bn = 0; bn < 2; ++bn) {
-          const double2 v = *reinterpret_cast<const double2 *>(sC + (rm + am * 8 + lc) * FPITCH + cn + bn * 8 + 2 * lr);
-          acc[am][bn][0]  = v.x;
-          acc[am][bn][1]  = v.y;
+          for (int rr = 0; rr < 7; ++rr)
+            if (t >= 8 - rr && r == rr) {
+              t -= 8 - rr;
+              ++r;
+            }
+          tr[i] = r;
+          tc[i] = r + t;
         }
+        double acc[5][2];
 #pragma unroll
-      for (int ks = 0; ks < FB / 4; ++ks) {
-        double af[4], bf[2];
-        const double *pa = sX + (ks * 4 + lr) * FPITCH + rm + lc;
-        const double *pb = sX + (ks * 4 + lr) * FPITCH + cn + lc;
-#pragma unroll
-        for (int am = 0; am < 4; ++am) af[am] = -pa[am * 8];
-#pragma unroll
-        for (int bn = 0; bn < 2; ++bn) bf[bn] = pb[bn * 8];
-#pragma unroll
-        for (int am = 0; am < 4; ++am)
-#pragma unroll
-          for (int bn = 0; bn < 2; ++bn) dmma884(acc[am][bn][0], acc[am][bn][1], af[am], bf[bn]);
-      }
-#pragma unroll
-      for (int am = 0; am < 4; ++am)
-#pragma unroll
-        for (int bn = 0; bn < 2; ++bn)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int ti = rm + am * 8 + lc, tj = cn + bn * 8 + 2 * lr + e;
-            S[ti * FPITCH + tj] = (ti < hI && tj < hI) ? acc[am][bn][e] : (ti == tj ? 1.0 : 0.0);
+        for (int i = 0; i < 5; ++i)
+          if (i < nt) {
+            const double2 v = *reinterpret_cast<const double2 *>(sC + (8 * tr[i] + lc) * FPITCH + 8 * tc[i] + 2 * lr);
+            acc[i][0]       = v.x;
+            acc[i][1]       = v.y;
           }
+#pragma unroll 4
+        for (int ks = 0; ks < FB / 4; ++ks) {
+          const double *prow = sX + (ks * 4 + lr) * FPITCH + lc;
+#pragma unroll
+          for (int i = 0; i < 5; ++i)
+            if (i < nt) dmma884(acc[i][0], acc[i][1], -prow[8 * tr[i]], prow[8 * tc[i]]);
+        }
+        // S <- identity beyond the valid rows, the updated upper triangle elsewhere (the strictly lower sub-tiles are never read)
+#pragma unroll
+        for (int i = 0; i < 5; ++i)
+          if (i < nt) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int ti = 8 * tr[i] + lc, tj = 8 * tc[i] + 2 * lr + e;
+              S[ti * FPITCH + tj] = (ti < hI && tj < hI) ? acc[i][e] : (ti == tj ? 1.0 : 0.0);
+            }
+          }
+      }
       __syncthreads();
       trace_ev(a, 3 + 8, k + 1, k + 1);
     }

@@ -67,10 +67,17 @@ for ts, b, ty, x, y in ev:
     if (ty & 7) in (1, 2, 3) and ((ty & 7) == 1 and x in (10, 11) or (ty & 7) == 2 and x == 10 and y == 11 or (ty & 7) == 3 and x == 11 and y == 11):
         print(names[ty & 7], "start" if ty < 8 else ("ready" if ty & 16 else "end"), x, y, "cta", b, round((ts - t0) / 1e3, 2))
 
+# the spine's own timeline over phases 20 and 21: 6/0 after diag_factor, 6/1 after diag_store, 7/0 after panel_solve, 7/1 after tile_store
+sp = [(ts, ty, x, y) for ts, b, ty, x, y in sorted([e for e in ev if e[1] == 0] + [e for e in fine if e[1] == 0]) if x in (20, 21) or (ty & 7) == 3 and x in (21, 22)]
+if sp:
+    tb = sp[0][0]
+    print("spine:", " ".join(f"{ty}/{x}/{y}@{(ts - tb) / 1e3:.2f}" for ts, ty, x, y in sp))
 # fine-grained: sub-block boundaries inside the diag of k = 10 (cta of diag 10) and the panel (10, 11)
 d10 = [e for e in ev if e[2] == 1 and e[3] == 10][0]
 p10 = [e for e in ev if e[2] == 2 and e[3] == 10 and e[4] == 11][0]
 for nm, ty, start in (("diag10", 6, d10), ("panel10_11", 7, p10)):
     end = [e for e in ev if e[1] == start[1] and e[0] > start[0] and (e[2] & 8) and not (e[2] & 16)][0]
     pts = [(e[0] - start[0]) / 1e3 for e in fine if e[1] == start[1] and e[2] == ty and start[0] <= e[0] <= end[0]]
+    if not pts:
+        continue
     print(nm, "cta", start[1], "total", (end[0] - start[0]) / 1e3, [round(x, 2) for x in pts])
