@@ -83,10 +83,8 @@ __device__ __forceinline__ void wait_flag(const FusedArgs &a, const int *f) {
 // all threads call after their global writes
 __device__ __forceinline__ void post_flag(const FusedArgs &a, int *f) {
   __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    st_release(f, a.epoch);
-  }
+  // st.release.gpu orders the writes of the whole CTA (cumulative over the barrier above) before the flag: no separate fence
+  if (threadIdx.x == 0) st_release(f, a.epoch);
 }
 
 // event record: code = type << 24 | a << 12 | b ; type 1 diag, 2 panel, 3 update, 4 backsolve, 5 backprod; +8 = end, +16 = after the waits
