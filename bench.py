@@ -375,13 +375,13 @@ def run_b200(args):
                 "kernel": "chol_fused_kernel: single-launch Cholesky solve (dposv) of the NNLS passive-set systems, one persistent cooperative "
                           "launch per solve (spine CTA + 147 tile workers, DMMA.8x8x4 updates)",
                 "achieved": chol_ach, "peak": P64, "unit": "TFLOP/s", "frac": chol_ach / P64,
-                # one `ncu --set full` capture of this kernel at n = 2048 (profiles/r01c_ncu_full_chol_fused.txt): dram read + write per launch;
+                # one `ncu --set full` capture of this kernel at n = 2048 (profiles/r01f_ncu_full_chol_fused.txt): dram read + write per launch;
                 # the algorithmic traffic is the upper triangle once (16.8 MB), the factor is written back to L2 only
-                "traffic": 17456640 + 2304,
+                "traffic": 17544192 + 4864,
                 "flops_per_launch": chol_flops / max(nchol, 1), "launches_per_step": nchol / nroof, "ms_per_step": tm["chol"],
                 "ms_per_launch": tm["chol"] / max(nchol / nroof, 1),
                 "note": "latency-bound by construction: n sequential pivots (rsqrt -> mul -> fma, ~110 cycles each) and 3 dependent tile steps per "
-                        "64-column phase, 21 us per phase measured (tools/chol_trace.py); sm__throughput 10 % in the ncu capture.  The throughput kernels "
+                        "64-column phase, 16 - 17 us per phase measured (tools/chol_trace.py); sm__throughput 11 % in the ncu capture.  The throughput kernels "
                         "of the step are listed under `others` with their own fractions.",
                 "peak_source": "FP64 is not in MEASURED_PEAKS.json (bf16 + HBM only); cuBLAS DGEMM 8192^3 measured on this pool, "
                                "profiles/r01_fp64_peaks.jsonl",
