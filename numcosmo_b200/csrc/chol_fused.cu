@@ -403,6 +403,7 @@ __device__ void diag_factor(const FusedArgs &a, double *S, double *sDinv, int *s
       if (dgl[7][7] == -1.2345) sBad[3] = 1;   // keeps the stamp below after the arithmetic
       NCM_PROBE_EV(700);
 #endif
+      __syncwarp();   // every lane has read the tile before lane 0 overwrites it
       if (lane == 0) {
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
@@ -415,7 +416,7 @@ __device__ void diag_factor(const FusedArgs &a, double *S, double *sDinv, int *s
 #pragma unroll
         for (int r = 0; r < 8; r += 2) *reinterpret_cast<double2 *>(sDinv + bw + r) = make_double2(inv[r], inv[r + 1]);
         if (bad != 0) atomicMin(sBad + 3, bad);
-        if (j == NS - 1) *reinterpret_cast<volatile int *>(&sDone) = 1;
+        if (j == NS - 1) atomicExch(&sDone, 1);
       }
       __syncwarp();
       if (j + 1 < NS) bar_arrive_n(1 + j, 32 * (NS - j));   // P_j
@@ -424,14 +425,17 @@ __device__ void diag_factor(const FusedArgs &a, double *S, double *sDinv, int *s
   }
   if (w == 0 && (want_panel || want_next)) {
     bool wp = want_panel, wn = want_next;
-    while ((wp || wn) && *reinterpret_cast<volatile int *>(&sDone) == 0) {
-      int f0 = 0, f1 = 0;
+    for (;;) {
+      int f0 = 0, f1 = 0, done = 0;
       if (lane == 0) {
-        f0 = wp ? (ld_relaxed(a.flagTs + k) == a.epoch) : 0;
-        f1 = wn ? (ld_relaxed(a.flagTd + k + 1) == a.epoch) : 0;
+        done = atomicAdd(&sDone, 0);   // the last pivot block is out: stop polling, the caller takes over
+        f0   = wp ? (ld_relaxed(a.flagTs + k) == a.epoch) : 0;
+        f1   = wn ? (ld_relaxed(a.flagTd + k + 1) == a.epoch) : 0;
       }
-      f0 = __shfl_sync(0xffffffffu, f0, 0);
-      f1 = __shfl_sync(0xffffffffu, f1, 0);
+      done = __shfl_sync(0xffffffffu, done, 0);
+      f0   = __shfl_sync(0xffffffffu, f0, 0);
+      f1   = __shfl_sync(0xffffffffu, f1, 0);
+      if (done != 0 && f0 == 0 && f1 == 0) break;
       if (f0 != 0 || f1 != 0) {
         __threadfence();   // relaxed poll + fence = acquire: the tile data is ordered after the flag that announced it
         if (f0 != 0) {
@@ -446,6 +450,7 @@ __device__ void diag_factor(const FusedArgs &a, double *S, double *sDinv, int *s
         }
         cp_async_commit();
       }
+      if (!(wp || wn)) break;
     }
   }
   __syncthreads();
