@@ -283,6 +283,8 @@ gboolean ncm_fit_esmcmc_walker_apes_get_use_threads (NcmFitESMCMCWalkerAPES *ape
 void ncm_fit_esmcmc_walker_apes_peek_sds (NcmFitESMCMCWalkerAPES *apes, NcmStatsDist **sd0, NcmStatsDist **sd1);
 void ncm_fit_esmcmc_walker_apes_set_local_frac (NcmFitESMCMCWalkerAPES *apes, gdouble local_frac);
 void ncm_fit_esmcmc_walker_apes_set_exploration (NcmFitESMCMCWalkerAPES *apes, guint exploration);
+/* instrumentation of the proposal draws generated ahead of the weights (host/apes.cc): blocks pre-generated, blocks replayed serially */
+void ncm_fit_esmcmc_walker_apes_b200_get_pregen_stats (NcmFitESMCMCWalkerAPES *a, long long *n_blocks, long long *n_fallbacks);
 
 /* The walker vtable entries (ncm_fit_esmcmc_walker.h: setup / step / prob_norm) in array form:
  * theta [nwalkers x nparams] row-major, m2lnL [nwalkers], bounds lb/ub [nparams].

@@ -6,9 +6,18 @@
 //   transition_prob   :819-859   (host: O(d) random-walk mixture on top of the cached density values)
 //   step / prob_norm  :861-919   (step only reads the cache)
 //   run               ncm_fit_esmcmc.c:2136-2148 (jumps), :2151-2232 (run_interval), :2235-2288 (run, ki = 0)
+//
+// Proposal draws ahead of the weights.  The serial stream of a block -- per walker one uniform for the random-walk decision, then either the
+// bounded Gaussian steps of the random walk or {one uniform for kernel_choose, d unit normals, one chi-square} -- does not depend on the
+// interpolation weights; only the kernel index picked by that uniform and the affine map do.  With use_interp the draws of the block are therefore
+// generated on a second host thread WHILE the GPU solves the NNLS (the host thread of prepare_interp mostly waits on the device), and applied
+// afterwards.  The speculation assumes what is true for all but pathological bounds: no proposal falls outside the box (walker_apes.c:735-737
+// would then draw again).  If one does, or if prepare_interp re-prepared on a cut sample (dynamic-range guard), the generator state of the block
+// start is restored and the block is sampled serially, exactly as before: the stream, hence the accepted sequence, is the same either way.
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <thread>
 #include <vector>
 #include "internal.h"
 
@@ -54,6 +63,10 @@ struct _NcmFitESMCMCWalkerAPES {
   std::vector<double> thetastar, m2lnp_star, m2lnp_cur, m2lnL_s0, m2lnL_s1, jumps;
   RandomWalk rw0, rw1;
   double t_sample_ms, t_eval_ms;
+  // draws generated ahead of the weights (one block): random-walk flag, kernel_choose uniform, unit normals, chi-square
+  std::vector<unsigned char> pre_rw;
+  std::vector<double> pre_p, pre_z, pre_chisq;
+  long long n_spec_blocks, n_spec_fallbacks;
 };
 
 namespace {
@@ -155,6 +168,56 @@ double transition_prob(NcmFitESMCMCWalkerAPES *a, const RandomWalk &rw, const do
   return m2lnp_rw - 2.0 * log1p(exp(-0.5 * (m2lnp_sd - m2lnp_rw)));
 }
 
+// the stream of one block, consumed in the order of _ncm_fit_esmcmc_walker_apes_sample (walker_apes.c:716-739) under the assumption that no
+// proposal has to be redrawn; random-walk proposals are complete here (they never depend on the density estimate)
+void pregenerate_block(NcmFitESMCMCWalkerAPES *a, NcmStatsDistKernel *sdk, const RandomWalk &rw, const double *theta, guint ki, guint kf, NcmRNG *rng) {
+  const guint d  = a->nparams;
+  const bool st  = sdk->kind == NCM_SD_GPU_KERNEL_ST;
+  const guint nb = kf - ki;
+  a->pre_rw.assign(nb, 0);
+  a->pre_p.assign(nb, 0.0);
+  a->pre_z.assign((size_t) nb * d, 0.0);
+  a->pre_chisq.assign(nb, 0.0);
+  for (guint k = ki; k < kf; k++) {
+    const guint q = k - ki;
+    if (a->random_walk_prob != 0.0 && ncm_rng_uniform01_pos_gen(rng) < a->random_walk_prob) {
+      a->pre_rw[q] = 1;
+      const double *th = &theta[(size_t) k * d];
+      double *ts       = &a->thetastar[(size_t) k * d];
+      for (guint i = 0; i < d; i++) {
+        double x;
+        do {
+          x = ncm_rng_gaussian_gen(rng, th[i], rw.std[i]);
+        } while ((x < rw.lb[i]) || (x > rw.ub[i]));
+        ts[i] = x;
+      }
+    } else {
+      a->pre_p[q] = ncm_rng_uniform_gen(rng, 0.0, 1.0);
+      for (guint i = 0; i < d; i++) a->pre_z[(size_t) q * d + i] = ncm_rng_ugaussian_gen(rng);
+      if (st) a->pre_chisq[q] = ncm_rng_chisq_gen(rng, sdk->nu);
+    }
+  }
+}
+
+// kernel index and affine map for the pre-drawn proposals; false when one of them leaves the box (the reference would draw again)
+bool apply_pregenerated(NcmFitESMCMCWalkerAPES *a, NcmStatsDist *sd, const double *lb, const double *ub, guint ki, guint kf) {
+  const guint d            = a->nparams;
+  NcmStatsDistKernel *sdk  = ncm_stats_dist_peek_kernel(sd);
+  const double href        = ncm_stats_dist_get_href(sd);
+  GPtrArray *sample        = ncm_stats_dist_peek_sample_array(sd);
+  for (guint k = ki; k < kf; k++) {
+    const guint q = k - ki;
+    double *ts    = &a->thetastar[(size_t) k * d];
+    if (!a->pre_rw[q]) {
+      const guint i = ncm_b200_kernel_choose_p(sd, a->pre_p[q]);
+      NcmVector tsv{ts, d, 1, 1, false};
+      ncm_b200_kernel_sample_from(sdk, ncm_stats_dist_peek_cov_decomp(sd, i), href, (NcmVector *) sample->pdata[i], &tsv, &a->pre_z[(size_t) q * d], a->pre_chisq[q]);
+    }
+    if (!valid_bounds(lb, ub, ts, d)) return false;
+  }
+  return true;
+}
+
 void setup_block(NcmFitESMCMCWalkerAPES *a, int block, const double *lb, const double *ub, const double *theta, const double *m2lnL, guint ki,
                  guint kf, NcmRNG *rng) {
   const guint d          = a->nparams;
@@ -170,18 +233,51 @@ void setup_block(NcmFitESMCMCWalkerAPES *a, int block, const double *lb, const d
     ncm_stats_dist_add_obs(sd, v);
     ncm_vector_free(v);
   }
+  bool speculated = false;
+  NcmRNG rng0;   // generator state at the start of the block's draws
   if (a->use_interp) {
     NcmVector *mv = ncm_vector_new_data_static(s.data(), a->size_2, 1);
-    ncm_stats_dist_prepare_interp(sd, mv);
+    static const bool spec_on = getenv("NCM_B200_APES_PREGEN") == nullptr || atoi(getenv("NCM_B200_APES_PREGEN")) != 0;
+    if (spec_on && ncm_b200_prepare_interp_begin(sd, mv)) {
+      // the kernel (hence the full covariance the random walk scales with) is prepared; the weights are what the GPU works on next
+      prepare_random_walk(a, sd, rw, lb, ub);
+      if (!ncm_b200_error_pending()) {
+        rng0       = *rng;
+        speculated = true;
+        a->n_spec_blocks++;
+        const RandomWalk rw_used = rw;
+        std::thread gen([&]() { pregenerate_block(a, ncm_stats_dist_peek_kernel(sd), rw_used, theta, ki, kf, rng); });
+        ncm_b200_prepare_interp_finish(sd, mv);
+        gen.join();
+        if (!ncm_b200_error_pending()) {
+          prepare_random_walk(a, sd, rw, lb, ub);   // the dynamic-range guard may have re-prepared the object on a cut sample
+          if (rw.std != rw_used.std || ncm_stats_dist_get_n_kernels(sd) != a->size_2) {
+            *rng       = rng0;
+            speculated = false;
+            a->n_spec_fallbacks++;
+          }
+        }
+      } else {
+        ncm_b200_prepare_interp_finish(sd, mv);
+      }
+    } else if (!spec_on) {
+      ncm_stats_dist_prepare_interp(sd, mv);
+    }
     ncm_vector_free(mv);
   } else {
     ncm_stats_dist_prepare(sd);
   }
   if (ncm_b200_error_pending()) return;
-  prepare_random_walk(a, sd, rw, lb, ub);
+  if (!speculated) prepare_random_walk(a, sd, rw, lb, ub);
 
   double t0 = now_ms();
-  for (guint k = ki; k < kf; k++) apes_sample(a, sd, rw, lb, ub, &theta[(size_t) k * d], &a->thetastar[(size_t) k * d], rng);
+  if (speculated && !apply_pregenerated(a, sd, lb, ub, ki, kf)) {
+    *rng       = rng0;   // a proposal left the box: the reference redraws it, which shifts the stream -- replay the block serially
+    speculated = false;
+    a->n_spec_fallbacks++;
+  }
+  if (!speculated)
+    for (guint k = ki; k < kf; k++) apes_sample(a, sd, rw, lb, ub, &theta[(size_t) k * d], &a->thetastar[(size_t) k * d], rng);
   double t1 = now_ms();
   a->t_sample_ms += t1 - t0;
 
@@ -225,6 +321,7 @@ NcmFitESMCMCWalkerAPES *ncm_fit_esmcmc_walker_apes_new_full(guint nwalkers, guin
   a->exploration      = 0;
   a->sd0 = a->sd1 = nullptr;
   a->t_sample_ms = a->t_eval_ms = 0.0;
+  a->n_spec_blocks = a->n_spec_fallbacks = 0;
   set_sys(a);
   return a;
 }
@@ -285,6 +382,11 @@ void ncm_fit_esmcmc_walker_apes_set_local_frac(NcmFitESMCMCWalkerAPES *a, gdoubl
   ncm_stats_dist_vkde_set_local_frac(a->sd1, lf);
 }
 void ncm_fit_esmcmc_walker_apes_set_exploration(NcmFitESMCMCWalkerAPES *a, guint e) { a->exploration = e; }
+// instrumentation: blocks whose draws were generated ahead of the weights, and how many of those had to be replayed serially
+void ncm_fit_esmcmc_walker_apes_b200_get_pregen_stats(NcmFitESMCMCWalkerAPES *a, long long *n_blocks, long long *n_fallbacks) {
+  if (n_blocks) *n_blocks = a->n_spec_blocks;
+  if (n_fallbacks) *n_fallbacks = a->n_spec_fallbacks;
+}
 
 void ncm_fit_esmcmc_walker_apes_setup(NcmFitESMCMCWalkerAPES *a, const gdouble *lb, const gdouble *ub, const gdouble *theta, const gdouble *m2lnL,
                                       guint ki, guint kf, NcmRNG *rng) {

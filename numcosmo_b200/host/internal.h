@@ -134,5 +134,11 @@ double ncm_b200_stats_Qn(std::vector<double> &data);
 bool ncm_b200_cov_robust(int kind, const double *const *rows, int n, int d, double *cov);
 void ncm_b200_jacobi_eig(std::vector<double> &A, int n, std::vector<double> &w, std::vector<double> &V);
 
+// pieces of kernel->sample / kernel_choose / prepare_interp that apes.cc drives separately (proposal draws generated ahead of the weights)
+void ncm_b200_kernel_sample_from(NcmStatsDistKernel *sdk, NcmMatrix *cov_decomp, double href, NcmVector *mu, NcmVector *y, const double *z_raw, double chisq);
+guint ncm_b200_kernel_choose_p(NcmStatsDist *sd, double p);                      // ncm_stats_dist_kernel_choose with the uniform already drawn
+bool ncm_b200_prepare_interp_begin(NcmStatsDist *sd, NcmVector *m2lnp);          // _ncm_stats_dist_prepare + the length check
+void ncm_b200_prepare_interp_finish(NcmStatsDist *sd, NcmVector *m2lnp);         // range guard, IM, NNLS, normalisation
+
 int ncm_b200_default_device();
 bool ncm_b200_host_prepare_kernel();   // debugging / parity switch: run the VKDE prepare_kernel loop on the host

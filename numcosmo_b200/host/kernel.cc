@@ -122,11 +122,23 @@ void ncm_stats_dist_kernel_eval_sum1_gamma_lambda(NcmStatsDistKernel *sdk, NcmVe
 }
 
 // x = mu + s U^T (h z): d normals in index order, then (ST) one chi-square -- the draw order of
-// _kernel_gauss.c:335-355 / _kernel_st.c:388-414
+// _kernel_gauss.c:335-355 / _kernel_st.c:388-414.  The arithmetic lives in ncm_b200_kernel_sample_from (below, after the extern "C"
+// block) so that proposals whose draws were generated ahead of time (apes.cc) go through the very same operations.
 void ncm_stats_dist_kernel_sample(NcmStatsDistKernel *sdk, NcmMatrix *cov_decomp, const gdouble href, NcmVector *mu, NcmVector *y, NcmRNG *rng) {
   const int d = (int) sdk->d;
+  double z[NCM_SD_GPU_MAX_DIM];
+  for (int i = 0; i < d; i++) z[i] = ncm_rng_ugaussian_gen(rng);
+  const double chisq = (sdk->kind == NCM_SD_GPU_KERNEL_ST) ? ncm_rng_chisq_gen(rng, sdk->nu) : 0.0;
+  ncm_b200_kernel_sample_from(sdk, cov_decomp, href, mu, y, z, chisq);
+}
+
+}   // extern "C"
+
+// the affine map of kernel->sample from already drawn unit normals z_raw[d] and (Student-t) chi-square
+void ncm_b200_kernel_sample_from(NcmStatsDistKernel *sdk, NcmMatrix *cov_decomp, double href, NcmVector *mu, NcmVector *y, const double *z_raw, double chisq) {
+  const int d = (int) sdk->d;
   double z[NCM_SD_GPU_MAX_DIM], t[NCM_SD_GPU_MAX_DIM];
-  for (int i = 0; i < d; i++) z[i] = ncm_rng_ugaussian_gen(rng) * href;
+  for (int i = 0; i < d; i++) z[i] = z_raw[i] * href;
   // dtrmv Upper/Trans: t_k = sum_{j <= k} U[j][k] z_j
   const double *U = cov_decomp->data;
   const int ld    = (int) cov_decomp->tda;
@@ -136,8 +148,6 @@ void ncm_stats_dist_kernel_sample(NcmStatsDistKernel *sdk, NcmMatrix *cov_decomp
     t[k] = s;
   }
   double scale = 1.0;
-  if (sdk->kind == NCM_SD_GPU_KERNEL_ST) scale = sqrt(sdk->nu / ncm_rng_chisq_gen(rng, sdk->nu));
+  if (sdk->kind == NCM_SD_GPU_KERNEL_ST) scale = sqrt(sdk->nu / chisq);
   for (int k = 0; k < d; k++) ncm_vector_set(y, k, t[k] * scale + ncm_vector_get(mu, k));
 }
-
-}   // extern "C"

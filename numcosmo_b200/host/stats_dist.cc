@@ -660,12 +660,22 @@ void ncm_stats_dist_prepare(NcmStatsDist *sd) {
 
 // ncm_stats_dist.c:878-1094 (CV_NONE)
 void ncm_stats_dist_prepare_interp(NcmStatsDist *sd, NcmVector *m2lnp) {
+  if (ncm_b200_prepare_interp_begin(sd, m2lnp)) ncm_b200_prepare_interp_finish(sd, m2lnp);
+}
+
+}   // extern "C"
+
+bool ncm_b200_prepare_interp_begin(NcmStatsDist *sd, NcmVector *m2lnp) {
   ncm_b200_error_clear();
-  if (!do_prepare(sd)) return;
+  if (!do_prepare(sd)) return false;
   if (ncm_vector_len(m2lnp) != sd->n_obs) {
     ncm_b200_error("_ncm_stats_dist_prepare_interp: assertion failed (ncm_vector_len (m2lnp) == n_obs): (%u == %u)", ncm_vector_len(m2lnp), sd->n_obs);
-    return;
+    return false;
   }
+  return true;
+}
+
+void ncm_b200_prepare_interp_finish(NcmStatsDist *sd, NcmVector *m2lnp) {
   const double dbl_limit = 2.0;
   const double range_max = -2.0 * dbl_limit * log(DBL_EPSILON);
   sd->min_m2lnp          = INFINITY;
@@ -790,6 +800,8 @@ void ncm_stats_dist_prepare_interp(NcmStatsDist *sd, NcmVector *m2lnp) {
   push_weights(sd);
 }
 
+extern "C" {
+
 static bool check_prepared(NcmStatsDist *sd, const char *where) {
   if (!sd->prepared || sd->gpu == nullptr) {
     ncm_b200_error("%s: object not prepared, call ncm_stats_dist_prepare or ncm_stats_dist_prepare_interp first.", where);
@@ -832,6 +844,15 @@ void ncm_stats_dist_eval_array(NcmStatsDist *sd, NcmMatrix *X, NcmVector *out) {
 
 // ncm_stats_dist.c:1565-1606
 guint ncm_stats_dist_kernel_choose(NcmStatsDist *sd, NcmRNG *rng) {
+  const double p = ncm_rng_uniform_gen(rng, 0.0, 1.0);
+  return ncm_b200_kernel_choose_p(sd, p);
+}
+
+}   // extern "C"
+
+// the cumulative-weight table and the bisection of kernel_choose for a uniform p already drawn.  (In the reference the table is built before the
+// draw; the order is immaterial, the table does not consume the stream.)
+guint ncm_b200_kernel_choose_p(NcmStatsDist *sd, double p) {
   if (!sd->wcum_ready) {
     double cum        = 0.0;
     sd->wcum->data[0] = cum;
@@ -843,7 +864,6 @@ guint ncm_stats_dist_kernel_choose(NcmStatsDist *sd, NcmRNG *rng) {
     for (guint i = 0; i < sd->n_kernels + 1; i++) sd->wcum->data[i] *= s;
     sd->wcum_ready = TRUE;
   }
-  const double p = ncm_rng_uniform_gen(rng, 0.0, 1.0);
   gint ilo = 0, ihi = (gint) sd->n_kernels;
   while (ihi > ilo + 1) {
     const gint mi = (ihi + ilo) / 2;
@@ -854,6 +874,8 @@ guint ncm_stats_dist_kernel_choose(NcmStatsDist *sd, NcmRNG *rng) {
   }
   return (guint) ilo;
 }
+
+extern "C" {
 
 // ncm_stats_dist.c:1618-1627
 void ncm_stats_dist_sample(NcmStatsDist *sd, NcmVector *x, NcmRNG *rng) {

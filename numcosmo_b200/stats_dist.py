@@ -177,6 +177,7 @@ def lib():
             "ncm_fit_esmcmc_walker_apes_set_use_threads": (None, [_vp, i]),
             "ncm_fit_esmcmc_walker_apes_set_local_frac": (None, [_vp, d]),
             "ncm_fit_esmcmc_walker_apes_set_exploration": (None, [_vp, u]),
+            "ncm_fit_esmcmc_walker_apes_b200_get_pregen_stats": (None, [_vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
             "ncm_fit_esmcmc_walker_apes_peek_sds": (None, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
             "ncm_fit_esmcmc_walker_apes_setup": (None, [_vp, _dp, _dp, _dp, _dp, u, u, _vp]),
             "ncm_fit_esmcmc_walker_apes_step": (None, [_vp, _dp, _dp, u]),
@@ -586,6 +587,12 @@ class FitESMCMCWalkerAPES:
 
     def peek_m2lnp_cur(self):
         return np.ctypeslib.as_array(lib().ncm_fit_esmcmc_walker_apes_peek_m2lnp_cur(self._h), shape=(self.nwalkers,)).copy()
+
+    def pregen_stats(self):
+        """(blocks whose proposal draws were generated while the GPU solved the NNLS, blocks that had to be replayed serially)."""
+        a, b = C.c_longlong(), C.c_longlong()
+        lib().ncm_fit_esmcmc_walker_apes_b200_get_pregen_stats(self._h, C.byref(a), C.byref(b))
+        return a.value, b.value
 
     def run(self, target, lb, ub, theta: np.ndarray, m2lnL: np.ndarray, iters: int, rng: RNG, target_args=None, record_accept: bool = True):
         """iters whole-ensemble iterations in place on theta [W x d] / m2lnL [W]; returns (accepted, timers_ms)."""

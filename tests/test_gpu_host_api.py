@@ -139,3 +139,39 @@ def test_apes_identical_accepted_sequence(oracle, target, k_type, d, W):
     assert acc_g.mean() > 0.05, acc_g.mean()
     assert np.max(np.abs(th_g - th_o)) <= 1e-9 * np.abs(th_o).max()
     assert rel_err(ag.peek_m2lnp_star(), ao.peek_m2lnp_star()) < 1e-6
+    # the proposal draws of every block were generated while the GPU solved the NNLS; with wide boxes none is replayed unless the dynamic-range
+    # guard of prepare_interp re-prepared the object on a cut sample (the first Rosenbrock / funnel iterations)
+    n_blocks, n_fallbacks = ag.pregen_stats()
+    assert n_blocks == 2 * iters and (n_fallbacks == 0 if target == "mvnd" else n_fallbacks < n_blocks)
+
+
+@pytest.mark.parametrize("k_type", ["gauss", "st3"])
+def test_apes_tight_bounds_replay_the_block_serially(oracle, k_type):
+    """Proposals that leave the box are drawn again by the reference (walker_apes.c:735-737), which shifts the whole stream: the draws
+    generated ahead of the weights are then discarded and the block is sampled serially from the restored generator state.  A box at
+    about one sigma makes that happen in every block; the accepted sequence must still be the oracle's."""
+    from numcosmo_b200 import stats_dist as S
+
+    kt, ok, nu = {"gauss": (S.FitESMCMCWalkerAPESKType.GAUSS, oracle.KERNEL_GAUSS, 1.0), "st3": (S.FitESMCMCWalkerAPESKType.ST3, oracle.KERNEL_ST, 3.0)}[k_type]
+    d, W, iters = 3, 300, 4
+    mu, cov, X, _ = mvnd_problem(oracle, d, W, seed=91)
+    sig = np.sqrt(np.diag(cov))
+    lb, ub = mu - 1.2 * sig, mu + 1.2 * sig
+    rs = np.random.default_rng(3)
+    theta = X.copy()
+    out = np.any((theta < lb) | (theta > ub), axis=1)     # start inside the box: redraw the outsiders uniformly in it (no coincident points)
+    theta[out] = mu + rs.uniform(-1.1, 1.1, size=(int(out.sum()), d)) * sig
+    theta = np.ascontiguousarray(theta)
+    tgt = oracle.Target(oracle.TARGET_MVND, d, lb, ub, mu=mu, cov=cov)
+    m2lnL0 = np.array([tgt.m2lnL(x) for x in theta])
+    th_o, ml_o = theta.copy(), m2lnL0.copy()
+    acc_o = oracle.APES(W, d, oracle.SD_VKDE, ok, nu, over_smooth=1.0, use_interp=True, use_threads=True).run(tgt, th_o, ml_o, iters, oracle.RNG(5), nthreads=4)
+    th_g, ml_g = theta.copy(), m2lnL0.copy()
+    ag = S.FitESMCMCWalkerAPES(W, d, S.FitESMCMCWalkerAPESMethod.VKDE, kt, 1.0, True)
+    ag.set_use_threads(True)
+    acc_g, _ = ag.run("mvnd", lb, ub, th_g, ml_g, iters, S.RNG(5), target_args=(mu, tgt.U))
+    diff = np.argwhere(acc_o != acc_g)
+    assert diff.size == 0, f"first divergence at (iter, walker) = {diff[0]}"
+    assert np.max(np.abs(th_g - th_o)) <= 1e-9 * np.abs(th_o).max()
+    n_blocks, n_fallbacks = ag.pregen_stats()
+    assert n_blocks == 2 * iters and n_fallbacks >= 1
