@@ -205,17 +205,21 @@ bool apply_pregenerated(NcmFitESMCMCWalkerAPES *a, NcmStatsDist *sd, const doubl
   NcmStatsDistKernel *sdk  = ncm_stats_dist_peek_kernel(sd);
   const double href        = ncm_stats_dist_get_href(sd);
   GPtrArray *sample        = ncm_stats_dist_peek_sample_array(sd);
-  for (guint k = ki; k < kf; k++) {
-    const guint q = k - ki;
+  (void) ncm_b200_kernel_choose_p(sd, 0.0);   // builds the cumulative-weight table once; the loop below only reads it
+  int all_inside = 1;
+  // with the draws in hand the proposals are independent of each other: threads change nothing in the values
+#pragma omp parallel for schedule(static) reduction(&& : all_inside) if (a->use_threads)
+  for (long k = (long) ki; k < (long) kf; k++) {
+    const guint q = (guint) (k - (long) ki);
     double *ts    = &a->thetastar[(size_t) k * d];
     if (!a->pre_rw[q]) {
       const guint i = ncm_b200_kernel_choose_p(sd, a->pre_p[q]);
       NcmVector tsv{ts, d, 1, 1, false};
       ncm_b200_kernel_sample_from(sdk, ncm_stats_dist_peek_cov_decomp(sd, i), href, (NcmVector *) sample->pdata[i], &tsv, &a->pre_z[(size_t) q * d], a->pre_chisq[q]);
     }
-    if (!valid_bounds(lb, ub, ts, d)) return false;
+    all_inside = all_inside && valid_bounds(lb, ub, ts, d);
   }
-  return true;
+  return all_inside != 0;
 }
 
 void setup_block(NcmFitESMCMCWalkerAPES *a, int block, const double *lb, const double *ub, const double *theta, const double *m2lnL, guint ki,
