@@ -904,6 +904,10 @@ def main():
     elif args.workload == "apes_e2e":
         run_apes_e2e(args)
     elif args.workload == "cv":
+        if args.cv == "loo" and args.sweep_n == 65536 and args.dim == 10:
+            # outside KDE-Gauss the CV_LOO objective is a Monte-Carlo integral whose draw count grows like var(p) / mean(p)^2: minutes at d = 10
+            # on either side (ncm_stats_dist.c:606-640); the default LOO line is therefore a small low-dimensional fit
+            args.sweep_n, args.dim = 2048, 3
         if args.sweep_n == 65536:
             args.sweep_n = 8192
         run_cv(args)
