@@ -74,6 +74,35 @@ def ref_kdtree_knn(points, queries, k):
     return idx, dist
 
 
+_REF_NNLS_PATH = os.path.join(_HERE, "_ref", "libnnls_ref.so")        # the reference's vendored Lawson-Hanson NNLS, built by `make ref`
+_ref_nnls = None
+
+
+def ref_nnls_lh(A, f):
+    """min ||A x - f||, x >= 0 by the REFERENCE'S OWN Lawson-Hanson code (numcosmo/external/misc/nnls.c: nnls_c, the solver behind
+    ncm_nnls.c:873-935); returns (x, rnorm, mode) or None when the library was never built.  Column-major (f2c) inside."""
+    global _ref_nnls
+    if _ref_nnls is None:
+        if not os.path.exists(_REF_NNLS_PATH):
+            return None
+        L = C.CDLL(_REF_NNLS_PATH)
+        ip = C.POINTER(C.c_int)
+        L.nnls_c.restype = C.c_int
+        L.nnls_c.argtypes = [_dp, ip, ip, ip, _dp, _dp, _dp, _dp, _dp, ip, ip]
+        _ref_nnls = L
+    A = np.asarray(A, dtype=np.float64)
+    m, n = A.shape
+    a = np.asfortranarray(A).copy(order="F")
+    b = np.ascontiguousarray(f, dtype=np.float64).copy()
+    x, w, zz = np.zeros(n), np.zeros(n), np.zeros(m)
+    index = np.zeros(n, dtype=np.int32)
+    rnorm, mode = C.c_double(), C.c_int()
+    mi, ni = C.c_int(m), C.c_int(n)
+    _ref_nnls.nnls_c(a.ctypes.data_as(_dp), C.byref(mi), C.byref(mi), C.byref(ni), _p(b), _p(x), C.byref(rnorm), _p(w), _p(zz),
+                     index.ctypes.data_as(C.POINTER(C.c_int)), C.byref(mode))
+    return x, rnorm.value, mode.value
+
+
 def knn_brute(points, query, k):
     """The oracle's (squared distance, index)-ordered exact kNN (restatement used by the VKDE prepare_kernel)."""
     pts = np.ascontiguousarray(points, dtype=np.float64)
