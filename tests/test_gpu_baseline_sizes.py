@@ -1,0 +1,148 @@
+"""GPU parity at the BASELINE.json sizes: the CUDA path through the host mirror / C ABI against the CPU
+oracle on the very inputs bench.py builds.
+
+  configs[1]  APES + VKDE-Gauss, 10-D MVND, 4096 walkers, seeds 1 / 1234 (bench.py's make_problem_b200 / S.RNG(1234)):
+              accepted sequence identical to the oracle over 10 iterations.
+  configs[2]  prepare_interp, d = 20, N = 16384 (VKDE-Gauss) and N = 8192 (KDE-Gauss, KDE-ST3, VKDE-ST3): passive set
+              equal, rnorm^2 rel 1e-8, weights to the conditioning-limited bound computed in the test.
+  configs[0]  APES + KDE (Cauchy kernel, the example's default) on 2-D Rosenbrock, 400 walkers, 100 iterations.
+
+Reference behaviour matched: ncm_nnls.c:767-871 (which systems are solved), ncm_stats_dist.c:1087-1093 (normalise + shrink),
+walker_apes.c:742-812, ncm_fit_esmcmc.c:2151-2232.
+"""
+import numpy as np
+import pytest
+
+from helpers import mvnd_problem, rel_err
+
+pytestmark = pytest.mark.gpu
+
+EPS = np.finfo(float).eps
+
+
+def support(w, n, shrink=0.01):
+    """Passive set of the NNLS solution behind normalised + shrunk weights: w_i = (1 - s) x_i / sum x + s / n > s / n  <=>  x_i > 0."""
+    return w > (shrink / n) * (1.0 + 1e-9)
+
+
+def weight_bound(IM, passive):
+    """Conditioning-limited bound on the relative (to the largest) error of NNLS weights obtained through the normal
+    equations: the forward error of a backward-stable solve of M[P,P] x = b[P] is ~ cond_2(M[P,P]) eps, for each of the two
+    implementations (CPU dposv and the device factorisation).  cond_2 = lambda_max / lambda_min by power / inverse iteration
+    on a Cholesky factor (an SVD of a 16384-column matrix would take longer than the test)."""
+    import scipy.linalg as sl
+
+    A = np.ascontiguousarray(IM[:, passive])
+    M = A.T @ A
+    c = sl.cho_factor(M, lower=True, check_finite=False)
+    rs = np.random.default_rng(0)
+    v = rs.standard_normal(M.shape[0])
+    u = v.copy()
+    lmax = lmin_inv = 1.0
+    for _ in range(30):
+        v = M @ (v / np.linalg.norm(v))
+        lmax = np.linalg.norm(v)
+        u = sl.cho_solve(c, u / np.linalg.norm(u), check_finite=False)
+        lmin_inv = np.linalg.norm(u)
+    cond_M = lmax * lmin_inv
+    # the north-star bar (1e-10) wherever the conditioning allows it; never looser than 1e-6 of the largest weight
+    return cond_M, max(1e-10, min(4.0 * cond_M * EPS, 1e-6))
+
+
+def test_configs1_apes_w4096_identical_sequence(oracle):
+    """configs[1] exactly as bench.py builds it."""
+    import bench
+    from numcosmo_b200 import stats_dist as S
+
+    W, d, iters = 4096, 10, 10
+    mu, cov, U_tgt, X, m2lnL = bench.make_problem_b200(S, W, d, seed=1)
+    mu_o, cov_o, tgt, X_o, m2lnL_o = bench.make_problem(W, d, seed=1)
+    assert np.array_equal(X, X_o) and np.array_equal(m2lnL, m2lnL_o)       # the two arms of bench.py read identical bytes
+    lb, ub = np.full(d, -50.0), np.full(d, 50.0)
+    th_o, ml_o = X.copy(), m2lnL.copy()
+    ao = oracle.APES(W, d, oracle.SD_VKDE, oracle.KERNEL_GAUSS, 1.0, over_smooth=1.0, use_interp=True, use_threads=True)
+    acc_o = ao.run(tgt, th_o, ml_o, iters, oracle.RNG(1234), nthreads=oracle.lib().orc_get_max_threads())
+    th_g, ml_g = X.copy(), m2lnL.copy()
+    ag = S.FitESMCMCWalkerAPES(W, d, S.FitESMCMCWalkerAPESMethod.VKDE, S.FitESMCMCWalkerAPESKType.GAUSS, 1.0, True)
+    ag.set_use_threads(True)
+    acc_g, _ = ag.run("mvnd", lb, ub, th_g, ml_g, iters, S.RNG(1234), target_args=(mu, U_tgt))
+    diff = np.argwhere(acc_o != acc_g)
+    assert diff.size == 0, f"first divergence at (iter, walker) = {diff[0]} of {diff.shape[0]}"
+    assert 0.2 < acc_g.mean() < 0.9, acc_g.mean()
+    assert np.max(np.abs(th_g - th_o)) <= 1e-9 * np.abs(th_o).max()
+    assert np.max(np.abs(ml_g - ml_o)) <= 1e-8 * np.abs(ml_o).max()
+    err = rel_err(ag.peek_m2lnp_star(), ao.peek_m2lnp_star())
+    print(f"configs[1]: accept rate {acc_g.mean():.4f}, sequence identical over {iters} iterations, m2lnp* rel err {err:.2e}")
+    assert err < 1e-8
+
+
+PI_CASES = [
+    # sd, kernel, N
+    ("vkde", "gauss", 16384),
+    ("kde", "gauss", 8192),
+    ("kde", "st", 8192),
+    ("vkde", "st", 8192),
+]
+
+
+@pytest.mark.parametrize("sd_s,k_s,N", PI_CASES)
+def test_configs2_prepare_interp_d20(oracle, sd_s, k_s, N):
+    """configs[2]: centres ~ MVND (d = 20, seed 2), m2lnp = exact -2 ln L at the centres, over_smooth = 1."""
+    from numcosmo_b200 import stats_dist as S
+
+    d = 20
+    mu, cov, X, m2lnL = mvnd_problem(oracle, d, N, seed=2)
+    kern = S.StatsDistKernelGauss(d) if k_s == "gauss" else S.StatsDistKernelST(d, 3.0)
+    sd = S.StatsDistKDE(kern, S.StatsDistCV.NONE) if sd_s == "kde" else S.StatsDistVKDE(kern, S.StatsDistCV.NONE)
+    o = oracle.StatsDist(oracle.SD_KDE if sd_s == "kde" else oracle.SD_VKDE, oracle.KERNEL_GAUSS if k_s == "gauss" else oracle.KERNEL_ST, d, 3.0)
+    for x in X:
+        sd.add_obs(x)
+    o.add_obs_matrix(X)
+    o.set_use_threads(True)
+    sd.set_use_threads(True)
+    oracle.lib().orc_set_blas_threads(oracle.lib().orc_get_max_threads())
+    sd.prepare_interp(m2lnL)
+    assert o.prepare_interp(m2lnL) == 0
+    st, so = sd.nnls_stats(), o.nnls_stats()
+    w, wo = sd.peek_weights(), o.peek_weights()
+    pg, po = support(w, N), support(wo, N)
+    assert so["n_lu"] == 0 and so["n_qr"] == 0 and st["n_retry"] == 0, (st, so)
+    assert np.array_equal(pg, po), f"passive sets differ in {np.count_nonzero(pg != po)} of {N} indices ({st} vs {so})"
+    assert st["n_passive"] == so["n_passive"] == int(po.sum())
+    # rnorm^2 = |1 - IM x|^2; an exactly interpolating solution leaves pure rounding, N (64 eps)^2, on either side
+    assert abs(sd.get_rnorm() - o.get_rnorm()) <= 1e-8 * o.get_rnorm() + N * (64 * EPS) ** 2, (sd.get_rnorm(), o.get_rnorm())
+    IM = o.peek_IM()
+    cond_M, bound = weight_bound(IM, po)
+    err = np.max(np.abs(w - wo)) / wo.max()
+    print(f"configs[2] {sd_s}-{k_s} N={N}: |P| = {int(po.sum())}, cond(M[P,P]) = {cond_M:.3e}, weights err/max = {err:.2e} (bound {bound:.2e}), "
+          f"n_chol gpu/oracle = {st['n_chol']}/{so['n_chol']}")
+    assert err <= bound
+    Q = np.vstack([X[:256] + 0.003, mu + 1.5 * (X[256:512] - mu)])
+    e2 = rel_err(sd.eval_m2lnp_array(Q), o.eval_m2lnp_batch(Q, oracle.lib().orc_get_max_threads()))
+    print(f"   downstream m2lnp rel err {e2:.2e}")
+    assert e2 <= max(1e-10, bound)
+
+
+def test_configs0_apes_rosenbrock_cauchy_w400(oracle):
+    """configs[0]: examples/example_apes.py -- APES, method KDE (a VKDE object, walker_apes.c:563-567), Cauchy kernel,
+    2-D Rosenbrock, 400 walkers, over_smooth 1.1, 100 iterations, init N(defaults, 1e2-scaled) as rosenbrock.py:46-49."""
+    from numcosmo_b200 import stats_dist as S
+
+    W, d, iters = 400, 2, 100
+    lb, ub = np.array([-200.0, -400.0]), np.array([200.0, 800.0])
+    tgt = oracle.Target(oracle.TARGET_ROSENBROCK, d, lb, ub)
+    r = oracle.RNG(1234)
+    theta = np.ascontiguousarray(np.array([[r.gaussian(1.0) for _ in range(d)] for _ in range(W)]) * [1.0, 2.0] + [0.5, 1.0])
+    m2lnL0 = np.array([tgt.m2lnL(x) for x in theta])
+    th_o, ml_o = theta.copy(), m2lnL0.copy()
+    ao = oracle.APES(W, d, oracle.SD_VKDE, oracle.KERNEL_ST, 1.0, over_smooth=1.1, use_interp=True, use_threads=True)
+    acc_o = ao.run(tgt, th_o, ml_o, iters, oracle.RNG(4321), nthreads=4)
+    th_g, ml_g = theta.copy(), m2lnL0.copy()
+    ag = S.FitESMCMCWalkerAPES(W, d, S.FitESMCMCWalkerAPESMethod.VKDE, S.FitESMCMCWalkerAPESKType.CAUCHY, 1.1, True)
+    ag.set_use_threads(True)
+    acc_g, _ = ag.run("rosenbrock", lb, ub, th_g, ml_g, iters, S.RNG(4321))
+    diff = np.argwhere(acc_o != acc_g)
+    assert diff.size == 0, f"first divergence at (iter, walker) = {diff[0]} of {diff.shape[0]}"
+    assert acc_g.mean() > 0.05
+    assert np.max(np.abs(th_g - th_o)) <= 1e-9 * np.abs(th_o).max()
+    print(f"configs[0]: accept rate {acc_g.mean():.4f}, sequence identical over {iters} iterations")
