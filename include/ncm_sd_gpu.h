@@ -113,6 +113,11 @@ typedef struct ncm_sd_gpu_nnls_stats
   int n_passive; /* final passive-set size */
   double chol_flops; /* sum over the factorisations of |P|^3 / 3 (algorithmic flops of the Cholesky solves) */
   double syrk_flops; /* nrows * ncols^2 (normal equations) */
+  int n_lowrank;     /* passive-set systems solved by low-rank modification of an earlier factor (lowrank.cu) instead of dposv */
+  int n_lowrank_fallback; /* ... whose refinement correction was too large: solved again by a fresh factorisation */
+  int n_trinv;       /* triangular inverses formed for those solves */
+  int max_lowrank_k; /* largest |D| + |A| served that way */
+  double lowrank_flops;   /* 2 |B|^2 (k + 1) per such solve + |B|^3 / 3 per triangular inverse */
 } ncm_sd_gpu_nnls_stats;
 
 int ncm_sd_gpu_nnls_solve (ncm_sd_gpu_ctx *ctx, double reltol, double *x_out, double *rnorm_out, ncm_sd_gpu_nnls_stats *stats);
@@ -152,6 +157,7 @@ enum
   NCM_SD_GPU_T_H2D,
   NCM_SD_GPU_T_D2H,
   NCM_SD_GPU_T_PREP,      /* VKDE prepare_kernel: kNN + local covariance + Cholesky */
+  NCM_SD_GPU_T_LOWRANK,   /* passive-set solves by low-rank modification: triangular inverse, bordered solve, refinement */
   NCM_SD_GPU_T_LEN
 };
 /* device time (CUDA events on the ctx stream) accumulated per stage, milliseconds, and the
@@ -177,6 +183,10 @@ int ncm_sd_gpu_dpotrf_upper_dev (ncm_sd_gpu_ctx *ctx, int n, double *dM, int ldm
 /* dposv 'U' as ncm_matrix_cholesky_solve calls it (ncm_matrix.c:1199-1210): factor the upper triangle of dM in place and
  * overwrite dRhs [n] with the solution of M x = rhs */
 int ncm_sd_gpu_dposv_upper_dev (ncm_sd_gpu_ctx *ctx, int n, double *dM, int ldm, double *dRhs, int *info_host);
+/* dtrtri 'U' 'N': dW = dU^-1 for an upper-triangular row-major factor (the lower triangle of dU is not read, that of dW is
+ * zeroed); dScratch is n x ld doubles.  Recursive doubling over DMMA GEMMs (csrc/lowrank.cu): the building block that lets
+ * the NNLS solve the passive-set systems after the first (ncm_nnls.c:728-751) without a new dposv each. */
+int ncm_sd_gpu_dtrtri_upper_dev (ncm_sd_gpu_ctx *ctx, int n, const double *dU, int ld, double *dW, double *dScratch);
 
 #ifdef __cplusplus
 }

@@ -238,6 +238,9 @@ gboolean ncm_stats_dist_vkde_get_use_rot_href (NcmStatsDistVKDE *sdvkde);
  * for the first cap of them, (ln over_smooth, objective value or NNLS rnorm) in evaluation order */
 gint ncm_stats_dist_b200_get_cv_trace (NcmStatsDist *sd, gdouble *lnos, gdouble *val, gint cap);
 void ncm_stats_dist_b200_get_nnls_stats (NcmStatsDist *sd, gint *n_chol, gint *n_retry, gint *n_outer, gint *n_passive);
+/* of the last NNLS: systems solved by low-rank modification of an earlier factor instead of a fresh dposv (csrc/lowrank.cu), how many of
+ * those fell back to a fresh factorisation, triangular inverses formed, largest |D| + |A| */
+void ncm_stats_dist_b200_get_nnls_lowrank_stats (NcmStatsDist *sd, gint *n_lowrank, gint *n_fallback, gint *n_trinv, gint *max_k);
 void ncm_stats_dist_b200_get_timers (NcmStatsDist *sd, gdouble *ms7, long long *n_launches, gdouble *host_prepare_kernel_ms);
 void ncm_stats_dist_b200_enable_timers (NcmStatsDist *sd, gboolean on);
 void *ncm_stats_dist_b200_peek_ctx (NcmStatsDist *sd);

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libncm_sd_gpu.so")
 
 KERNEL_GAUSS, KERNEL_ST = 0, 1
 KDE, VKDE = 0, 1
-T_NAMES = ("eval", "IM", "syrk", "chol", "nnls_misc", "h2d", "d2h", "prep")
+T_NAMES = ("eval", "IM", "syrk", "chol", "nnls_misc", "h2d", "d2h", "prep", "lowrank")
 
 OK, EINVAL, ENODEV, ECUDA, ENOTPD, ENCCL, ENOMEM = range(7)
 
@@ -28,7 +28,7 @@ SYMBOLS = (
     "ncm_sd_gpu_compute_IM", "ncm_sd_gpu_nnls_solve", "ncm_sd_gpu_nnls_solve_host", "ncm_sd_gpu_sample_apply", "ncm_sd_gpu_sample_philox",
     "ncm_sd_gpu_comm_unique_id", "ncm_sd_gpu_comm_init", "ncm_sd_gpu_set_row_shard", "ncm_sd_gpu_get_timers", "ncm_sd_gpu_reset_timers",
     "ncm_sd_gpu_enable_timers", "ncm_sd_gpu_get_traffic", "ncm_sd_gpu_dsyrk_ata_dev", "ncm_sd_gpu_dpotrf_upper_dev",
-    "ncm_sd_gpu_vkde_prepare", "ncm_sd_gpu_vkde_finish", "ncm_sd_gpu_dposv_upper_dev", "ncm_sd_gpu_vkde_path", "ncm_sd_gpu_host_alloc", "ncm_sd_gpu_host_free",
+    "ncm_sd_gpu_vkde_prepare", "ncm_sd_gpu_vkde_finish", "ncm_sd_gpu_dposv_upper_dev", "ncm_sd_gpu_dtrtri_upper_dev", "ncm_sd_gpu_vkde_path", "ncm_sd_gpu_host_alloc", "ncm_sd_gpu_host_free",
 )
 
 
@@ -40,7 +40,8 @@ class GpuError(RuntimeError):
 
 class NNLSStats(C.Structure):
     _fields_ = [("n_chol", C.c_int), ("n_retry", C.c_int), ("n_outer", C.c_int), ("n_passive", C.c_int), ("chol_flops", C.c_double),
-                ("syrk_flops", C.c_double)]
+                ("syrk_flops", C.c_double), ("n_lowrank", C.c_int), ("n_lowrank_fallback", C.c_int), ("n_trinv", C.c_int), ("max_lowrank_k", C.c_int),
+                ("lowrank_flops", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -96,6 +97,7 @@ def load():
             "ncm_sd_gpu_dpotrf_upper_dev": (i, [vp, i, vp, i, _ip]),
             "ncm_sd_gpu_dposv_upper_dev": (i, [vp, i, vp, i, vp, _ip]),
             "ncm_sd_gpu_vkde_path": (i, [vp, _ip, _dp]),
+            "ncm_sd_gpu_dtrtri_upper_dev": (i, [vp, i, vp, i, vp, vp]),
         }
         for name, (res, args) in sig.items():
             f = getattr(L, name)
@@ -300,6 +302,9 @@ class Context:
         info = C.c_int()
         self._ck(load().ncm_sd_gpu_dposv_upper_dev(self._h, n, dM_ptr, ldm, dRhs_ptr, C.byref(info)))
         return info.value
+
+    def dtrtri_upper_dev(self, n, dU_ptr, ld, dW_ptr, dScratch_ptr):
+        self._ck(load().ncm_sd_gpu_dtrtri_upper_dev(self._h, n, dU_ptr, ld, dW_ptr, dScratch_ptr))
 
     def dpotrf_upper_dev(self, n, dM_ptr, ldm) -> int:
         info = C.c_int()

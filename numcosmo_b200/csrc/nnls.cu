@@ -12,6 +12,12 @@
 // entries is admitted.  Which systems get solved decides the final passive set, so this
 // logic mirrors the reference decision by decision; only the arithmetic runs on the device.
 //
+// Which systems get solved is the reference's; HOW a system is solved is not always a fresh dposv: once a passive set B has been
+// factorised, the following sets that differ from it by at most min(lowrank_kmax(), |B| / 8) indices are solved by low-rank
+// modification of that factor (lowrank.cu: triangular inverse by recursive doubling, bordered / constrained k x k system, one
+// refinement step on the true residual).  A refinement correction above 1e-7 of the solution falls back to a fresh
+// factorisation.  NCM_SD_GPU_NNLS_REUSE=0 restores one dposv per system.
+//
 // Deviation (documented in DESIGN.md): when a passive-set matrix is not numerically positive
 // definite the reference falls back to LAPACK dsysv and then dgels (ncm_nnls.c:573-638); here the
 // factorisation is retried with a relative diagonal shift (1e-13, 1e-11, 1e-9) and counted in
@@ -166,13 +172,93 @@ struct NnlsWork {
   int *h_idx;      // pinned: n ints
   double diag_mean = 0.0;
   ncm_sd_gpu_nnls_stats *st;
+  // low-rank reuse of the last factorisation (lowrank.cu)
+  bool lr_on = false, base_valid = false, w_valid = false;
+  std::vector<int> baseP;
+  LowrankBufs lb;
+  int ldv = 0;
 };
+
+bool lowrank_enabled() {
+  static const bool on = [] {
+    const char *e = getenv("NCM_SD_GPU_NNLS_REUSE");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return on;
+}
+constexpr int LR_MIN_N = 512;       // below this a fused factorisation (a few 64-column phases) is as cheap as the ~25 launches of an update
+constexpr double LR_MAX_CORR = 1e-7;
+
+// P = (B \ D) u A: solve through the base inverse; returns 1 when the caller has to factorise afresh
+int solve_lowrank(NnlsWork &w, const std::vector<int> &P, bool *done) {
+  ncm_sd_gpu_ctx *c = w.c;
+  *done             = false;
+  const std::vector<int> &B = w.baseP;
+  const int nB = (int) B.size(), np = (int) P.size();
+  int kcap = std::min(lowrank_kmax(), nB / 8);
+  // D = B \ P (positions in B), A = P \ B (global indices): one merge pass over the two ascending lists
+  int *hA = w.h_idx, *hD = w.h_idx + lowrank_kmax() + 8, *hP = hD + lowrank_kmax() + 8;
+  int na = 0, nd = 0;
+  {
+    int i = 0, j = 0;
+    while (i < nB || j < np) {
+      if (j >= np || (i < nB && B[i] < P[j])) {
+        if (nd + na >= kcap) return NCM_SD_GPU_OK;
+        hD[nd++] = i++;
+      } else if (i >= nB || P[j] < B[i]) {
+        if (nd + na >= kcap) return NCM_SD_GPU_OK;
+        hA[na++] = P[j++];
+      } else {
+        ++i;
+        ++j;
+      }
+    }
+  }
+  StageTimer t(c, NCM_SD_GPU_T_LOWRANK);
+  if (!w.w_valid) {
+    int rc = trinv_upper(c, nB, w.dMU, w.lb.W, w.lb.S, w.ldm);
+    if (rc != NCM_SD_GPU_OK) return rc;
+    w.w_valid = true;
+    if (w.st) {
+      w.st->n_trinv++;
+      w.st->lowrank_flops += (double) nB * nB * nB / 3.0;
+    }
+  }
+  std::memcpy(hP, P.data(), sizeof(int) * np);
+  NCM_CUDA_OK(c, ncm_memcpy_async(c, w.lb.idxA, hA, sizeof(int) * (size_t) (2 * (lowrank_kmax() + 8) + np), cudaMemcpyHostToDevice, c->stream));
+  int rc = lowrank_solve(c, w.dM, w.ldm, w.n, w.db, nB, na, nd, np, w.lb, w.ldv, c->nn_tmp);
+  if (rc != NCM_SD_GPU_OK) return rc;
+  NCM_CUDA_OK(c, ncm_memcpy_async(c, w.h_buf, w.lb.out, sizeof(double) * (size_t) (np + 2), cudaMemcpyDeviceToHost, c->stream));
+  NCM_CUDA_OK(c, ncm_memcpy_async(c, w.h_buf + np + 2, w.lb.info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  NCM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  const double mdx = w.h_buf[np], mx = w.h_buf[np + 1];
+  int info;
+  std::memcpy(&info, w.h_buf + np + 2, sizeof(int));
+  if (w.st) {
+    w.st->n_lowrank++;
+    w.st->lowrank_flops += 2.0 * nB * (double) nB * (na + nd + 1);
+    w.st->max_lowrank_k = std::max(w.st->max_lowrank_k, na + nd);
+  }
+  if (info != 0 || !(mdx <= LR_MAX_CORR * mx)) {   // also catches NaN
+    if (w.st) w.st->n_lowrank_fallback++;
+    return NCM_SD_GPU_OK;
+  }
+  *done = true;
+  return NCM_SD_GPU_OK;
+}
 
 // solve M[P,P] x_P = b[P]; result in h_buf[0..np)
 int solve_unconstrained(NnlsWork &w, const std::vector<int> &P) {
   ncm_sd_gpu_ctx *c = w.c;
   const int np      = (int) P.size();
   if (np == 0) return NCM_SD_GPU_OK;
+  if (w.lr_on && w.base_valid && np >= LR_MIN_N) {
+    bool done = false;
+    int rc    = solve_lowrank(w, P, &done);
+    if (rc != NCM_SD_GPU_OK) return rc;
+    if (done) return NCM_SD_GPU_OK;
+  }
+  w.base_valid = false;
   static const double shifts[4] = {0.0, 1.0e-13, 1.0e-11, 1.0e-9};
   for (int attempt = 0; attempt < 4; ++attempt) {
     const double shift = shifts[attempt] * w.diag_mean;
@@ -201,6 +287,13 @@ int solve_unconstrained(NnlsWork &w, const std::vector<int> &P) {
     }
     if (info == 0) {
       NCM_CUDA_OK(c, ncm_memcpy_async(c,w.h_buf, w.drhs, sizeof(double) * np, cudaMemcpyDeviceToHost, c->stream));
+      if (w.lr_on && attempt == 0 && np >= LR_MIN_N) {   // the factor left in dMU becomes the base of the following low-rank solves
+        std::memcpy(w.h_idx, P.data(), sizeof(int) * np);
+        NCM_CUDA_OK(c, ncm_memcpy_async(c, w.lb.idxB, w.h_idx, sizeof(int) * np, cudaMemcpyHostToDevice, c->stream));
+        w.baseP      = P;
+        w.base_valid = true;
+        w.w_valid    = false;
+      }
       NCM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
       return NCM_SD_GPU_OK;
     }
@@ -312,7 +405,7 @@ int nnls_solve_dev(ncm_sd_gpu_ctx *c, int nrows, int ncols, const double *dA, in
   if (!c->M.reserve(mm) || !c->MU.reserve(mm) || !c->nn_b.reserve((size_t) (4 * n + 64) * sizeof(double)) ||
       !c->nn_x.reserve((size_t) (2 * n + 16) * sizeof(double)) || !c->nn_r.reserve((size_t) (2 * nrows + 16) * sizeof(double)) ||
       !c->nn_g.reserve((size_t) (nrows / 8 + n + 64) * sizeof(double)) || !c->nn_idx.reserve((size_t) (n + 16) * sizeof(int)) ||
-      !c->pin_nn.reserve((size_t) (n + 16) * sizeof(double) + (size_t) (n + 16) * sizeof(int)))
+      !c->pin_nn.reserve((size_t) (n + 16) * sizeof(double) + (size_t) (n + 16 + 2 * (lowrank_kmax() + 8)) * sizeof(int)))
     return c->fail(NCM_SD_GPU_ENOMEM, "nnls: out of memory");
 
   NnlsWork w;
@@ -333,6 +426,29 @@ int nnls_solve_dev(ncm_sd_gpu_ctx *c, int nrows, int ncols, const double *dA, in
   w.h_buf  = c->pin_nn.as<double>();
   w.h_idx  = reinterpret_cast<int *>(w.h_buf + (n + 16));
 
+  w.lr_on = lowrank_enabled() && n >= LR_MIN_N && n <= chol_fused_max_n();
+  if (w.lr_on) {
+    const int kmax = lowrank_kmax();
+    w.ldv          = kmax + 8;
+    const size_t nv = (size_t) n + 16;
+    if (!c->lrW.reserve(mm) || !c->lrS.reserve(mm) || !c->lrV.reserve((size_t) n * w.ldv * sizeof(double)) ||
+        !c->lrT.reserve((size_t) n * w.ldv * sizeof(double)) ||
+        !c->lrSmall.reserve(((size_t) w.ldv * w.ldv + (size_t) kmax * (kmax + 1) / 2 + 4 * (size_t) w.ldv + 64) * sizeof(double)) ||
+        !c->lrVec.reserve(11 * nv * sizeof(double)) || !c->lrIdx.reserve((3 * nv + 2 * (size_t) (kmax + 8) + 16) * sizeof(int)))
+      return c->fail(NCM_SD_GPU_ENOMEM, "nnls: out of memory");
+    LowrankBufs &b = w.lb;
+    b.W = c->lrW.as<double>(); b.S = c->lrS.as<double>(); b.V = c->lrV.as<double>(); b.T = c->lrT.as<double>();
+    b.H     = c->lrSmall.as<double>();
+    b.Lg    = b.H + (size_t) w.ldv * w.ldv;
+    b.dinvg = b.Lg + (size_t) kmax * (kmax + 1) / 2;
+    b.z     = b.dinvg + w.ldv;
+    b.rhsz  = b.z + w.ldv;
+    double *v = c->lrVec.as<double>();
+    b.y = v; b.xB = v + nv; b.xfull = v + 2 * nv; b.rfull = v + 3 * nv; b.rB = v + 4 * nv; b.tr = v + 5 * nv; b.dxfull = v + 6 * nv;
+    b.row = v + 7 * nv; b.out = v + 8 * nv; b.stats = nullptr;   // stats follow the np results in `out` (one D2H)
+    int *ix = c->lrIdx.as<int>();
+    b.idxB = ix; b.idxA = ix + nv; b.posD = b.idxA + (kmax + 8); b.idxP = b.posD + (kmax + 8); b.info = b.idxP + nv;
+  }
   int rc;
   {
     StageTimer t(c, NCM_SD_GPU_T_SYRK);

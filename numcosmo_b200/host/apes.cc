@@ -472,7 +472,7 @@ void ncm_b200_esmcmc_run(NcmFitESMCMCWalkerAPES *a, NcmB200M2lnLFunc m2lnL_func,
     timers_ms[0] = h0 + h1;
     timers_ms[1] = g0[NCM_SD_GPU_T_IM] + g1[NCM_SD_GPU_T_IM];
     timers_ms[2] = g0[NCM_SD_GPU_T_SYRK] + g1[NCM_SD_GPU_T_SYRK] + g0[NCM_SD_GPU_T_CHOL] + g1[NCM_SD_GPU_T_CHOL] + g0[NCM_SD_GPU_T_NNLS_MISC] +
-                   g1[NCM_SD_GPU_T_NNLS_MISC];
+                   g1[NCM_SD_GPU_T_NNLS_MISC] + g0[NCM_SD_GPU_T_LOWRANK] + g1[NCM_SD_GPU_T_LOWRANK];
     timers_ms[3] = a->t_sample_ms;
     timers_ms[4] = a->t_eval_ms;
     timers_ms[5] = t_like;

@@ -946,6 +946,13 @@ void ncm_stats_dist_get_Ki(NcmStatsDist *sd, const guint i, NcmVector **y_i, Ncm
     }
 }
 
+void ncm_stats_dist_b200_get_nnls_lowrank_stats(NcmStatsDist *sd, gint *n_lowrank, gint *n_fallback, gint *n_trinv, gint *max_k) {
+  if (n_lowrank) *n_lowrank = sd->nnls_stats.n_lowrank;
+  if (n_fallback) *n_fallback = sd->nnls_stats.n_lowrank_fallback;
+  if (n_trinv) *n_trinv = sd->nnls_stats.n_trinv;
+  if (max_k) *max_k = sd->nnls_stats.max_lowrank_k;
+}
+
 void ncm_stats_dist_b200_get_nnls_stats(NcmStatsDist *sd, gint *n_chol, gint *n_retry, gint *n_outer, gint *n_passive) {
   if (n_chol) *n_chol = sd->nnls_stats.n_chol;
   if (n_retry) *n_retry = sd->nnls_stats.n_retry;

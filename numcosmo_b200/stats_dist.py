@@ -163,6 +163,7 @@ def lib():
             "ncm_stats_dist_vkde_set_use_rot_href": (None, [_vp, i]),
             "ncm_stats_dist_vkde_get_use_rot_href": (i, [_vp]),
             "ncm_stats_dist_b200_get_nnls_stats": (None, [_vp, C.POINTER(i), C.POINTER(i), C.POINTER(i), C.POINTER(i)]),
+            "ncm_stats_dist_b200_get_nnls_lowrank_stats": (None, [_vp, C.POINTER(i), C.POINTER(i), C.POINTER(i), C.POINTER(i)]),
             "ncm_stats_dist_b200_get_cv_trace": (i, [_vp, _dp, _dp, i]),
             "ncm_stats_dist_b200_get_timers": (None, [_vp, _dp, C.POINTER(C.c_longlong), _dp]),
             "ncm_stats_dist_b200_enable_timers": (None, [_vp, i]),
@@ -467,7 +468,10 @@ class StatsDist:
     def nnls_stats(self):
         a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         lib().ncm_stats_dist_b200_get_nnls_stats(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d))
-        return {"n_chol": a.value, "n_retry": b.value, "n_outer": c.value, "n_passive": d.value}
+        out = {"n_chol": a.value, "n_retry": b.value, "n_outer": c.value, "n_passive": d.value}
+        lib().ncm_stats_dist_b200_get_nnls_lowrank_stats(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d))
+        out.update({"n_lowrank": a.value, "n_lowrank_fallback": b.value, "n_trinv": c.value, "max_lowrank_k": d.value})
+        return out
 
     def cv_trace(self):
         """(ln over_smooth, objective or rnorm) of every objective evaluation of the last prepare / prepare_interp
