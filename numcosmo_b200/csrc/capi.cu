@@ -148,7 +148,7 @@ int ncm_sd_gpu_ctx_free(ncm_sd_gpu_ctx *c) {
   if (c->nccl_comm != nullptr && nccl_api().ok) nccl_api().CommDestroy((ncclComm_t) c->nccl_comm);
   DevBuf *bufs[] = {&c->sample, &c->vrec, &c->lnu, &c->cterm, &c->weights, &c->Ufull, &c->zc, &c->zmean, &c->bfrag, &c->kde_U, &c->qX,
                     &c->qOut, &c->qA, &c->part, &c->IM, &c->rowscale, &c->M, &c->MU, &c->nn_b, &c->nn_x, &c->nn_r, &c->nn_g, &c->nn_tmp,
-                    &c->nn_idx, &c->nn_f, &c->chol_flags, &c->chol_part, &c->vrec_mma, &c->dist, &c->lrW, &c->lrS, &c->lrV, &c->lrT, &c->lrSmall, &c->lrVec, &c->lrIdx};
+                    &c->nn_idx, &c->nn_f, &c->chol_flags, &c->chol_part, &c->vrec_mma, &c->dist, &c->lrW, &c->lrWt, &c->lrS, &c->lrV, &c->lrT, &c->lrPart, &c->lrSmall, &c->lrVec, &c->lrIdx};
   for (DevBuf *b : bufs) b->release();
   c->pinX.release();
   c->pinOut.release();
@@ -591,7 +591,7 @@ int ncm_sd_gpu_dtrtri_upper_dev(ncm_sd_gpu_ctx *c, int n, const double *dU, int 
   if (c == nullptr) return NCM_SD_GPU_EINVAL;
   if (n <= 0 || (ld & 7) || ld < n) return c->fail(NCM_SD_GPU_EINVAL, "dtrtri: ld must be a multiple of 8 and >= n");
   cudaSetDevice(c->device);
-  return trinv_upper(c, n, dU, dW, dScratch, ld);
+  return trinv_upper(c, n, dU, dW, dScratch, ld, nullptr);
 }
 
 }   // extern "C"

@@ -75,7 +75,7 @@ struct ncm_sd_gpu_ctx {
   DevBuf rowscale;   // [n_obs]
   DevBuf M, MU, nn_b, nn_x, nn_r, nn_g, nn_tmp, nn_idx, nn_f;
   DevBuf dist;   // VKDE prepare_kernel: squared distances centre x point [n_kernels x n_obs]
-  DevBuf lrW, lrS, lrV, lrT, lrSmall, lrVec, lrIdx;   // low-rank passive-set solves (lowrank.cu): base inverse, scratch, bordered blocks
+  DevBuf lrW, lrWt, lrS, lrV, lrT, lrPart, lrSmall, lrVec, lrIdx;   // low-rank passive-set solves (lowrank.cu): base inverse, scratch, bordered blocks
   DevBuf chol_flags, chol_part;   // single-launch Cholesky (chol_fused.cu): dependency flags, back-substitution contributions
   int chol_epoch = 0;
   long long *chol_trace = nullptr;   // device buffer [n_sm][cap][2] set by ncm_sd_gpu_chol_trace (debugging aid)
@@ -192,15 +192,17 @@ int nnls_solve_dev(ncm_sd_gpu_ctx *c, int nrows, int ncols, const double *dA, in
                    double *rnorm_host, ncm_sd_gpu_nnls_stats *stats);
 // lowrank.cu: passive-set solves by low-rank modification of a base factor
 struct LowrankBufs {
-  double *W, *S;          // n x ldm each: W = U^-1 of the base factor, scratch of the recursive doubling
+  double *W, *Wt, *S;     // n x ldm each: W = U^-1 of the base factor, its transpose, scratch of the recursive doubling
   double *V, *T;          // nB x ldv each: [M_BA | E_D | b_B] and W^T times it
-  double *H;              // ldv x ldv
-  double *Lg, *dinvg;     // packed L J L^T factor of H
-  double *z, *y, *xB, *xfull, *rfull, *rB, *tr, *rhsz, *dxfull, *row, *out, *stats;
-  int *idxB, *idxA, *posD, *idxP, *info;
+  double *part;           // split-K partial sums (lowrank_part_doubles)
+  double *Lg;             // packed L J L^T factor of the k x k system + its inverse diagonal
+  double *z, *z2, *y, *xB, *dxB, *xfull, *rfull, *rB, *tr, *out;
+  int *idxB, *idxA, *posD, *bsel, *psrc, *info;
 };
 int lowrank_kmax();
-int trinv_upper(ncm_sd_gpu_ctx *c, int n, const double *dU, double *dW, double *dS, int ld);
+size_t lowrank_part_doubles(int n, int ldv);
+int symmetrize_upper(ncm_sd_gpu_ctx *c, int n, double *dM, int ld);
+int trinv_upper(ncm_sd_gpu_ctx *c, int n, const double *dU, double *dW, double *dS, int ld, double *dWt);
 int lowrank_solve(ncm_sd_gpu_ctx *c, const double *dM, int ldm, int n, const double *db, int nB, int na, int nd, int np, const LowrankBufs &w, int ldv,
-                  DevBuf &tmp);
+                  bool refine);
 int sample_apply_launch(ncm_sd_gpu_ctx *c, int q, const int *dIdx, const double *dZ, int ldz, const double *dScale, double *dX, int ldx);

@@ -7,20 +7,18 @@
 // P = (B \ D) u A with |D| + |A| <= LR_KMAX is solved through the bordered / constrained system
 //
 //      [ M_BB   M_BA   E_D ] [x_B]   [b_B]          R = [M_BA  E_D],  z = [x_A; mu]
-//      [ M_AB   M_AA    0  ] [x_A] = [b_A]          T = W^T [R  b_B]      (one triangular GEMM, n_B x (k + 1))
+//      [ M_AB   M_AA    0  ] [x_A] = [b_A]          T = W^T [R  b_B]      (one triangular GEMM, n_B x (k + 1), split over K)
 //      [ E_D^T   0      0  ] [mu ]   [ 0 ]          H = T_R^T T_R - diag(M_AA, 0),   H z = T_R^T t_b - [b_A; 0]
 //                                                   x_B = W (t_b - T_R z)
 //
 // (x_D = 0 is enforced by the multipliers mu).  H is k x k, quasi-definite (-Schur complement of the border, +G_DD): it is
-// factorised as L J L^T, J = diag(-I_A, +I_D), without pivoting in shared memory.  One step of iterative refinement on the
-// residual of the TRUE system (b - M x, symmetric product with the stored upper triangle) follows; the size of that
-// correction is returned so that the caller falls back to a fresh factorisation when the base is too ill-conditioned.
+// factorised as L J L^T, J = diag(-I_A, +I_D), without pivoting in shared memory (8-column panels, the right-hand side rides
+// along as one more row so the forward substitution is free).  One step of iterative refinement on the residual of the TRUE
+// system (b - M x, M symmetrised once per NNLS call) follows; the size of that correction is returned so that the caller falls
+// back to a fresh factorisation when the base is too ill-conditioned.
 // Cost per solve: O(n_B^2 k) flops at GEMM rates instead of the n^3/3 latency chain of a factorisation.
 #include <algorithm>
 #include "ctx.h"
-
-int dsyrk_ata_general(ncm_sd_gpu_ctx *c, int K, int n, const double *dP, int ldp, double *dC, int ldc, double alpha, double beta);
-int gemv_t(ncm_sd_gpu_ctx *c, const double *dA, int lda, int nrows, int ncols, const double *dv, double *dOut, DevBuf &tmp);
 
 namespace {
 
@@ -31,7 +29,7 @@ constexpr int GPA = GBK + 4;                    // pitch of the [64][16] A tile 
 constexpr int GPB = GT + 4;                     // pitch of the [16][64] tiles (B, and A when TRANSA)
 constexpr int GSLAB_A = GT * GPA;               // 1280 doubles >= GBK * GPB = 1088
 constexpr int GSLAB_B = GBK * GPB;
-constexpr size_t GEMM_SMEM = (size_t) GSTAGES * (GSLAB_A + GSLAB_B) * sizeof(double);
+constexpr size_t GEMM_SMEM = (size_t) GSTAGES * (GSLAB_A + GSLAB_B) * sizeof(double);   // 56.8 KB: three CTAs per SM
 
 template <bool TRANSA>
 __device__ __forceinline__ void gemm_tile(const double *__restrict__ A, int lda, const double *__restrict__ B, int ldb, double *__restrict__ C, int ldc,
@@ -194,36 +192,91 @@ __global__ void __launch_bounds__(GTHREADS) trinv_step2_kernel(double *__restric
   gemm_tile<false>(W + (size_t) r0 * ld + r0, ld, S + (size_t) r0 * ld + r1, ld, W + (size_t) r0 * ld + r1, ld, s, m2, i0, j0, i0, s, -1.0, smem);
 }
 
-// C = A^T B, A: K x M upper triangular when `upper_a` (k <= i)
-__global__ void __launch_bounds__(GTHREADS) gemm_tn_kernel(const double *__restrict__ A, int lda, const double *__restrict__ B, int ldb, double *__restrict__ C, int ldc,
-                                                           int M, int N, int K, int upper_a) {
+// dst[j][i] = src[i][j] for i <= j (32 x 32 tiles of the upper triangle); in place (dst == src) it symmetrises the matrix
+__global__ void transpose_upper_kernel(const double *src, double *dst, int ld, int n, int nt) {
+  __shared__ double tile[32][33];
+  int t = blockIdx.x, ti = 0;   // linear index -> upper tile (ti <= tj)
+  while (t >= nt - ti) {
+    t -= nt - ti;
+    ++ti;
+  }
+  const int tj = ti + t;
+  const int i0 = ti * 32, j0 = tj * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int gi = i0 + r, gj = j0 + threadIdx.x;
+    tile[r][threadIdx.x] = (gi < n && gj < n && gj >= gi) ? src[(size_t) gi * ld + gj] : 0.0;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int gj = j0 + r, gi = i0 + threadIdx.x;   // writes dst[gj][gi]
+    if (gj < n && gi < n && (gj > gi || (dst != src && gj == gi))) dst[(size_t) gj * ld + gi] = tile[threadIdx.x][r];
+  }
+}
+
+// T partial = W[k-chunk]^T V[k-chunk]: A = W is K x M upper triangular (k <= i), split over K in chunks of KC_T rows
+constexpr int KC_T = 256, KC_H = 128;
+__global__ void __launch_bounds__(GTHREADS) gemm_tn_splitk_kernel(const double *__restrict__ A, int lda, const double *__restrict__ B, int ldb, double *__restrict__ Cpart,
+                                                                  int ldc, size_t cstride, int M, int N, int K) {
   extern __shared__ __align__(16) double smem[];
   const int i0 = blockIdx.y * GT, j0 = blockIdx.x * GT;
-  gemm_tile<true>(A, lda, B, ldb, C, ldc, M, N, i0, j0, 0, upper_a ? min(K, i0 + GT) : K, 1.0, smem);
+  const int k_hi = min(K, i0 + GT), k_lo = blockIdx.z * KC_T;
+  if (k_lo >= k_hi) return;
+  gemm_tile<true>(A, lda, B, ldb, Cpart + (size_t) blockIdx.z * cstride, ldc, M, N, i0, j0, k_lo, min(k_hi, k_lo + KC_T), 1.0, smem);
+}
+// T[i][j] = sum_c Tpart[c][i][j], c < number of K chunks that reach row tile i (fixed order: deterministic)
+__global__ void splitk_reduce_kernel(const double *__restrict__ part, size_t cstride, int ld, int M, int N, int K, double *__restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (j >= N || i >= M) return;
+  const int k_hi = min(K, (i / GT) * GT + GT);
+  const int nc   = (k_hi + KC_T - 1) / KC_T;
+  double s = 0.0;
+  for (int c = 0; c < nc; ++c) s += part[(size_t) c * cstride + (size_t) i * ld + j];
+  out[(size_t) i * ld + j] = s;
+}
+// H partial = T[k-chunk]^T T[k-chunk], upper 64-tiles of the kc x kc result
+__global__ void __launch_bounds__(GTHREADS) syrk_splitk_kernel(const double *__restrict__ T, int ldt, double *__restrict__ Hpart, int ldh, size_t hstride, int kc, int K) {
+  extern __shared__ __align__(16) double smem[];
+  int t = blockIdx.x, ti = 0;
+  const int nt = (kc + GT - 1) / GT;
+  while (t >= nt - ti) {
+    t -= nt - ti;
+    ++ti;
+  }
+  const int tj = ti + t;
+  const int k_lo = blockIdx.y * KC_H;
+  gemm_tile<true>(T, ldt, T, ldt, Hpart + (size_t) blockIdx.y * hstride, ldh, kc, kc, ti * GT, tj * GT, k_lo, min(K, k_lo + KC_H), 1.0, smem);
 }
 
-// ---- index plumbing -----------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double msym(const double *__restrict__ M, int ldm, int a, int b) {
-  return a <= b ? M[(size_t) a * ldm + b] : M[(size_t) b * ldm + a];
+// H0[i][j] = sum_c Hpart[c][i][j] over the upper triangle (j >= i) of the kc x kc matrix, chunks in fixed order
+__global__ void hreduce_kernel(const double *__restrict__ part, size_t hstride, int nhc, int ldh, int kc, double *__restrict__ H0) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (j >= kc || j < i) return;
+  double s0 = 0.0, s1 = 0.0;
+  int c = 0;
+  for (; c + 1 < nhc; c += 2) {
+    s0 += part[(size_t) c * hstride + (size_t) i * ldh + j];
+    s1 += part[(size_t) (c + 1) * hstride + (size_t) i * ldh + j];
+  }
+  if (c < nhc) s0 += part[(size_t) c * hstride + (size_t) i * ldh + j];
+  H0[(size_t) i * ldh + j] = s0 + s1;
 }
 
-// V = [ M[B, A] | E_D | b_B ]   (n_B x (na + nd + 1), row-major, ld = ldv)
-__global__ void lr_gather_V_kernel(const double *__restrict__ M, int ldm, const double *__restrict__ b, const int *__restrict__ idxB, int nB,
+// ---- index plumbing and memory-bound products -----------------------------------------------------------------------------
+// V = [ M[B, A] | E_D | b_B (0 on the rows of D) ]   (n_B x (na + nd + 1), row-major, ld = ldv); M is full symmetric
+__global__ void lr_gather_V_kernel(const double *__restrict__ M, int ldm, const double *__restrict__ b, const int *__restrict__ bsel, const int *__restrict__ idxB, int nB,
                                    const int *__restrict__ idxA, int na, const int *__restrict__ posD, int nd, double *__restrict__ V, int ldv) {
   const int i = blockIdx.x * blockDim.y + threadIdx.y;
   if (i >= nB) return;
   const int gi = idxB[i], kc = na + nd + 1;
+  const double *mrow = M + (size_t) gi * ldm;
   for (int j = threadIdx.x; j < kc; j += blockDim.x) {
     double v;
     if (j < na)
-      v = msym(M, ldm, gi, idxA[j]);
+      v = mrow[idxA[j]];
     else if (j < na + nd)
       v = (posD[j - na] == i) ? 1.0 : 0.0;
-    else {
-      v = b[gi];   // rows in D are constraint rows: their right-hand side is absorbed by the multipliers, so it is dropped (less cancellation)
-      for (int q = 0; q < nd; ++q)
-        if (posD[q] == i) v = 0.0;
-    }
+    else
+      v = bsel[i] >= 0 ? b[gi] : 0.0;   // rows of D are constraint rows: their right-hand side is absorbed by the multipliers
     V[(size_t) i * ldv + j] = v;
   }
 }
@@ -240,85 +293,101 @@ __global__ void lr_y_kernel(const double *__restrict__ T, int ldt, int nB, int k
   if (lane == 0) y[i] = base[(size_t) i * bstride] - s;
 }
 
-// out[i] = sum_{k >= i} A[i][k] v[k]   (upper triangle, warp per row): x = W y, and the row part of the symmetric product
-__global__ void trmv_upper_row_kernel(const double *__restrict__ A, int lda, int n, const double *__restrict__ v, double *__restrict__ out) {
+// out[i] = (base ? base[i] : 0) + sign * sum_{k in range(i)} A[i][k] v[k];  range: UPPER [i, n), LOWER [0, i], FULL [0, n).
+// ROW_WPR warps share a row (64-element chunks dealt round-robin, four chunks in flight per warp), 8 / ROW_WPR rows per CTA:
+// a single warp per row is latency-bound on its 15 KB (measured 11.5 us per product at n = 1900).
+enum { ROW_UPPER = 0, ROW_LOWER = 1, ROW_FULL = 2 };
+constexpr int ROW_WPR = 4;
+template <int MODE>
+__global__ void __launch_bounds__(256) row_dot_kernel(const double *__restrict__ A, int lda, int n, const double *__restrict__ v, const double *__restrict__ base, double sign,
+                                                      double *__restrict__ out) {
+  __shared__ double red[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i    = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (i >= n) return;
-  const double *a = A + (size_t) i * lda;
-  double s0 = 0.0, s1 = 0.0;
-  int k = (i & ~31) + lane;   // aligned start: coalesced 256-byte segments
-  if (k >= i && k < n) s0 = a[k] * v[k];
-  k += 32;
-  for (; k + 32 < n; k += 64) {
-    s0 = fma(a[k], v[k], s0);
-    s1 = fma(a[k + 32], v[k + 32], s1);
-  }
-  for (; k < n; k += 32) s0 = fma(a[k], v[k], s0);
-  double s = s0 + s1;
-  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-  if (lane == 0) out[i] = s;
-}
-
-// part[blk][j] = sum_{r in block, r < j + incl} A[r][j] v[r]   (upper triangle, transposed product; thread per column)
-__global__ void trmv_upper_col_partial_kernel(const double *__restrict__ A, int lda, int n, const double *__restrict__ v, double *__restrict__ part, int rows_per_block,
-                                              int incl) {
-  const int j  = blockIdx.x * blockDim.x + threadIdx.x;
-  const int r0 = blockIdx.y * rows_per_block;
-  if (j >= n) return;
-  const int r1 = min(min(n, r0 + rows_per_block), j + incl);
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  int r = r0;
-  for (; r + 3 < r1; r += 4) {
-    s0 = fma(A[(size_t) r * lda + j], v[r], s0);
-    s1 = fma(A[(size_t) (r + 1) * lda + j], v[r + 1], s1);
-    s2 = fma(A[(size_t) (r + 2) * lda + j], v[r + 2], s2);
-    s3 = fma(A[(size_t) (r + 3) * lda + j], v[r + 3], s3);
-  }
-  for (; r < r1; ++r) s0 = fma(A[(size_t) r * lda + j], v[r], s0);
-  part[(size_t) blockIdx.y * n + j] = (s0 + s1) + (s2 + s3);
-}
-// out[j] = (base ? base[j] : 0) + sign * (sum_p part[p][j] + (extra ? extra[j] : 0))
-__global__ void lr_reduce_kernel(const double *__restrict__ part, int nparts, int n, const double *__restrict__ extra, const double *__restrict__ base, double sign,
-                                 double *__restrict__ out) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
+  const int i    = blockIdx.x * (8 / ROW_WPR) + warp / ROW_WPR, part = warp % ROW_WPR;
   double s = 0.0;
-  for (int p = 0; p < nparts; ++p) s += part[(size_t) p * n + j];
-  if (extra) s += extra[j];
-  out[j] = (base ? base[j] : 0.0) + sign * s;
+  if (i < n) {
+    const double *a = A + (size_t) i * lda;
+    const int lo = MODE == ROW_UPPER ? i : 0, hi = MODE == ROW_LOWER ? i + 1 : n;   // [lo, hi)
+    constexpr int STEP = 64 * ROW_WPR;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0, s5 = 0.0, s6 = 0.0, s7 = 0.0;
+    int k = (lo & ~63) + 64 * part + 2 * lane;   // rows are 16-byte aligned (lda even), v too
+    if (k < lo + 64) {                           // chunk that may straddle lo
+      if (k >= lo && k < hi) s0 = a[k] * v[k];
+      if (k + 1 >= lo && k + 1 < hi) s1 = a[k + 1] * v[k + 1];
+      k += STEP;
+    }
+    for (; k + 3 * STEP + 1 < hi; k += 4 * STEP) {
+      const double2 a0 = *reinterpret_cast<const double2 *>(a + k), a1 = *reinterpret_cast<const double2 *>(a + k + STEP);
+      const double2 a2 = *reinterpret_cast<const double2 *>(a + k + 2 * STEP), a3 = *reinterpret_cast<const double2 *>(a + k + 3 * STEP);
+      const double2 v0 = *reinterpret_cast<const double2 *>(v + k), v1 = *reinterpret_cast<const double2 *>(v + k + STEP);
+      const double2 v2 = *reinterpret_cast<const double2 *>(v + k + 2 * STEP), v3 = *reinterpret_cast<const double2 *>(v + k + 3 * STEP);
+      s0 = fma(a0.x, v0.x, s0);
+      s1 = fma(a0.y, v0.y, s1);
+      s2 = fma(a1.x, v1.x, s2);
+      s3 = fma(a1.y, v1.y, s3);
+      s4 = fma(a2.x, v2.x, s4);
+      s5 = fma(a2.y, v2.y, s5);
+      s6 = fma(a3.x, v3.x, s6);
+      s7 = fma(a3.y, v3.y, s7);
+    }
+    for (; k < hi; k += STEP) {
+      s0 = fma(a[k], v[k], s0);
+      if (k + 1 < hi) s1 = fma(a[k + 1], v[k + 1], s1);
+    }
+    s = ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  }
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  if (i < n && part == 0 && lane == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int q = 0; q < ROW_WPR; ++q) t += red[warp + q];
+    out[i] = (base ? base[i] : 0.0) + sign * t;
+  }
 }
 
-// xfull[B[i]] = xB[i]; then (second launch) the positions in D are forced to 0 and xfull[A[j]] = z[j]
-__global__ void lr_scatter_kernel(double *__restrict__ xfull, const int *__restrict__ idxB, int nB, const double *__restrict__ xB) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < nB) xfull[idxB[i]] = xB[i];
+// part[blk][j] = sum_{r in 16-row block} T[r][j] v[r]   (j < k): the right-hand side T_R^T t_r of the refinement system
+constexpr int TT_ROWS = 16;
+__global__ void __launch_bounds__(256) lr_tTt_partial_kernel(const double *__restrict__ T, int ldt, int nB, int k, const double *__restrict__ v, double *__restrict__ part,
+                                                              int ldp) {
+  const int r0 = blockIdx.x * TT_ROWS, r1 = min(nB, r0 + TT_ROWS);
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    double s0 = 0.0, s1 = 0.0;
+    int r = r0;
+    for (; r + 1 < r1; r += 2) {
+      s0 = fma(T[(size_t) r * ldt + j], v[r], s0);
+      s1 = fma(T[(size_t) (r + 1) * ldt + j], v[r + 1], s1);
+    }
+    if (r < r1) s0 = fma(T[(size_t) r * ldt + j], v[r], s0);
+    part[(size_t) blockIdx.x * ldp + j] = s0 + s1;
+  }
 }
-__global__ void lr_scatter_fix_kernel(double *__restrict__ xfull, const int *__restrict__ idxB, const int *__restrict__ idxA, int na, const double *__restrict__ z,
-                                      const int *__restrict__ posD, int nd) {
+
+// xfull[bsel[i]] = xB[i] for the rows of B that stay, xfull[A[j]] = z[j]   (xfull zeroed before)
+__global__ void lr_scatter_kernel(double *__restrict__ xfull, const int *__restrict__ bsel, int nB, const double *__restrict__ xB, const int *__restrict__ idxA, int na,
+                                  const double *__restrict__ z) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < nd) xfull[idxB[posD[i]]] = 0.0;
+  if (i < nB && bsel[i] >= 0) xfull[bsel[i]] = xB[i];
   if (i < na) xfull[idxA[i]] = z[i];
 }
-__global__ void lr_zero_at_kernel(double *__restrict__ v, const int *__restrict__ pos, int n) {
+// rB[i] = rfull[bsel[i]] (0 on the rows of D)
+__global__ void lr_gather_r_kernel(const double *__restrict__ rfull, const int *__restrict__ bsel, int nB, double *__restrict__ rB) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) v[pos[i]] = 0.0;
+  if (i < nB) rB[i] = bsel[i] >= 0 ? rfull[bsel[i]] : 0.0;
 }
-__global__ void lr_gather_kernel(const double *__restrict__ src, const int *__restrict__ idx, int n, double *__restrict__ dst) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = src[idx[i]];
-}
-// out[j] = x0[P[j]] + dx[P[j]] for the new passive set; stats = {max |dx|, max |x|}   (single CTA)
-__global__ void lr_finalize_kernel(const double *__restrict__ x0, const double *__restrict__ dx, const int *__restrict__ idxP, int np, double *__restrict__ out,
-                                   double *__restrict__ stats) {
+// out[j] = x + dx of the new passive set in its own order: psrc[j] >= 0 -> position in B, else -(1 + position in A);
+// out[np], out[np + 1] = max |dx|, max |x|   (single CTA)
+__global__ void lr_finalize_kernel(const int *__restrict__ psrc, int np, const double *__restrict__ xB, const double *__restrict__ dxB, const double *__restrict__ z1,
+                                   const double *__restrict__ z2, double *__restrict__ out) {
   __shared__ double s_dx[32], s_x[32];
   double mdx = 0.0, mx = 0.0;
   for (int j = threadIdx.x; j < np; j += blockDim.x) {
-    const int g    = idxP[j];
-    const double d = dx ? dx[g] : 0.0, v = x0[g] + d;
-    out[j] = v;
+    const int p    = psrc[j];
+    const double x = p >= 0 ? xB[p] : z1[-1 - p], d = dxB == nullptr ? 0.0 : (p >= 0 ? dxB[p] : z2[-1 - p]);
+    out[j] = x + d;
     mdx    = fmax(mdx, fabs(d));
-    mx     = fmax(mx, fabs(v));
+    mx     = fmax(mx, fabs(x + d));
   }
   for (int off = 16; off > 0; off >>= 1) {
     mdx = fmax(mdx, __shfl_xor_sync(0xffffffffu, mdx, off));
@@ -334,93 +403,224 @@ __global__ void lr_finalize_kernel(const double *__restrict__ x0, const double *
       mdx = fmax(mdx, s_dx[w]);
       mx  = fmax(mx, s_x[w]);
     }
-    stats[0] = mdx;
-    stats[1] = mx;
+    out[np]     = mdx;
+    out[np + 1] = mx;
   }
 }
 
-// ---- the k x k quasi-definite system: H = L J L^T in shared memory, packed lower -----------------------------------------
+// ---- the k x k quasi-definite system: H = L J L^T in shared memory, packed lower, 8-column panels -------------------------
 constexpr int LR_KMAX = 200;
 constexpr int LR_ST = 512;
-constexpr size_t LR_SMALL_SMEM = ((size_t) LR_KMAX * (LR_KMAX + 1) / 2 + 3 * LR_KMAX + 8) * sizeof(double);
+constexpr int LR_PW = 8;
+constexpr int LR_PKR = LR_KMAX + 8;   // row pitch of the column-major panel copies
+// packed lower matrix of order kr = k + 1 (the right-hand side is row k), two panel copies [8][PKR], dinv[k], vec[k], red[8]
+constexpr size_t LR_SMALL_SMEM = ((size_t) (LR_KMAX + 1) * (LR_KMAX + 2) / 2 + 2 * (size_t) LR_PKR * LR_PW + 2 * LR_KMAX + 8 + 80) * sizeof(double);
 
 __device__ __forceinline__ int pidx(int i, int j) { return i * (i + 1) / 2 + j; }   // i >= j
 
-// mode 0: build H = H0[:k,:k] - diag(M_AA, 0) and rhs = H0[:k, k] - [b_A; 0], factor, solve, keep the factor in Lg / dinvg.
-// mode 1: reload the factor, rhs = rhs_in - [rfull_A; 0], solve.                 info: 0 or the 1-based index of a pivot of the wrong sign
-__global__ void __launch_bounds__(LR_ST) lr_small_kernel(int mode, int na, int nd, const double *__restrict__ H0, int ldh, const double *__restrict__ M, int ldm,
-                                                         const int *__restrict__ idxA, const double *__restrict__ b, const double *__restrict__ rhs_in,
-                                                         const double *__restrict__ rfull, double *__restrict__ Lg, double *__restrict__ dinvg, double *__restrict__ z,
-                                                         int *__restrict__ info) {
+// mode 0: H = H0[:k,:k] - diag(M_AA, 0), rhs = H0[:k, k] - [b_A; 0]; factor (rhs as row k: the forward substitution comes with the
+//         factorisation), back-substitute, keep the factor in Lg.
+// mode 1: reload the factor, rhs = sum_p tpart[p] - [rfull_A; 0], blocked forward + back substitution.
+// info: 0 or the 1-based index of a pivot of the wrong sign.
+__global__ void __launch_bounds__(LR_ST) lr_small_kernel(int mode, int na, int nd, const double *__restrict__ H0, int ldh,
+                                                         const double *__restrict__ M, int ldm, const int *__restrict__ idxA, const double *__restrict__ b,
+                                                         const double *__restrict__ tpart, int ldp, int ntp, const double *__restrict__ rfull, double *__restrict__ Lg,
+                                                         double *__restrict__ z, int *__restrict__ info) {
   extern __shared__ __align__(16) double sm[];
   const int k = na + nd, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int npk = k * (k + 1) / 2;
-  double *L = sm, *rhs = sm + (size_t) LR_KMAX * (LR_KMAX + 1) / 2, *dinv = rhs + LR_KMAX, *colj = dinv + LR_KMAX;
+  const int kr = k + 1;
+  const int npk = kr * (kr + 1) / 2;
+  double *L    = sm;
+  double *pan  = sm + (size_t) (LR_KMAX + 1) * (LR_KMAX + 2) / 2;   // [8][PKR]: L[p0 + r][p0 + c] at pan[c * PKR + r]
+  double *pas  = pan + (size_t) LR_PKR * LR_PW;                     // sign-folded copy: J_c L[..][p0 + c]
+  double *dinv = pas + (size_t) LR_PKR * LR_PW;
+  double *vec  = dinv + LR_KMAX;
+  double *red  = vec + LR_KMAX;
+  double *dgs  = red + 8;   // published diagonal block [8][8] + its inverse diagonal [8]
   if (k == 0) return;
   if (mode == 0) {
-    for (int i = warp; i < k; i += LR_ST / 32)
-      for (int j = lane; j <= i; j += 32) {
+    for (int j = warp; j < k; j += LR_ST / 32)          // row j of the upper-stored H0, lanes along it: coalesced
+      for (int i = j + lane; i < kr; i += 32) {
         double v = H0[(size_t) j * ldh + i];
-        if (i < na) v -= M[(size_t) idxA[j] * ldm + idxA[i]];   // idxA ascending: (j, i) is in the stored upper triangle
+        if (i < na) v -= M[(size_t) idxA[j] * ldm + idxA[i]];
+        if (i == k && j < na) v -= b[idxA[j]];
         L[pidx(i, j)] = v;
       }
-    for (int i = tid; i < k; i += LR_ST) rhs[i] = H0[(size_t) i * ldh + k] - (i < na ? b[idxA[i]] : 0.0);
+    if (tid == 0) L[pidx(k, k)] = 0.0;
     __syncthreads();
-    for (int j = 0; j < k; ++j) {
-      const double sgn = j < na ? -1.0 : 1.0;
-      double p         = sgn * L[pidx(j, j)];
-      if (!(p > 0.0)) {
-        if (tid == 0 && *info == 0) *info = j + 1;
-        p = 1.0;
-      }
-      const double ljj = sqrt(p), inv = 1.0 / ljj;
-      for (int i = j + 1 + tid; i < k; i += LR_ST) {
-        const double v = L[pidx(i, j)] * (sgn * inv);
-        L[pidx(i, j)]  = v;
-        colj[i]        = v;
+    for (int p0 = 0; p0 < k; p0 += LR_PW) {
+      const int pw = min(LR_PW, k - p0);
+      // warp 0 factors the pw x pw diagonal block in registers (all lanes redundantly: no communication on the pivot chain) and
+      // publishes it; then every row i >= p0, owned by one thread, is solved against it
+      const int i = p0 + tid;
+      if (warp == 0) {
+        double dg[LR_PW][LR_PW], dv[LR_PW];
+        int bad = 0;
+#pragma unroll
+        for (int r = 0; r < LR_PW; ++r)
+#pragma unroll
+          for (int q = 0; q <= r; ++q) dg[r][q] = (r < pw && q < pw) ? L[pidx(p0 + r, p0 + q)] : (r == q ? 1.0 : 0.0);
+#pragma unroll
+        for (int c = 0; c < LR_PW; ++c) {
+          const double sgc = (p0 + c) < na ? -1.0 : 1.0;
+          double p         = sgc * dg[c][c];
+          if (!(p > 0.0)) {
+            if (c < pw && bad == 0) bad = p0 + c + 1;
+            p = 1.0;
+          }
+          const double inv = rsqrt(p);
+          dg[c][c]         = p * inv;
+          dv[c]            = inv;
+#pragma unroll
+          for (int r = c + 1; r < LR_PW; ++r) dg[r][c] *= sgc * inv;
+#pragma unroll
+          for (int r = c + 1; r < LR_PW; ++r)
+#pragma unroll
+            for (int q = c + 1; q <= r; ++q) dg[r][q] = fma(-sgc * dg[r][c], dg[q][c], dg[r][q]);
+        }
+        if (lane == 0) {
+          if (bad != 0 && *info == 0) *info = bad;
+#pragma unroll
+          for (int r = 0; r < LR_PW; ++r) {
+#pragma unroll
+            for (int q = 0; q <= r; ++q) dgs[r * LR_PW + q] = dg[r][q];
+            dgs[LR_PW * LR_PW + r] = dv[r];
+          }
+        }
       }
       __syncthreads();
-      if (tid == 0) {
-        L[pidx(j, j)] = ljj;
-        dinv[j]       = inv;
+      if (tid < kr - p0) {
+        double row[LR_PW];
+        if (tid < pw) {
+#pragma unroll
+          for (int c = 0; c < LR_PW; ++c) row[c] = c <= tid ? dgs[tid * LR_PW + c] : 0.0;
+          dinv[i] = dgs[LR_PW * LR_PW + tid];
+        } else {
+          double dg[LR_PW][LR_PW], dv[LR_PW];
+#pragma unroll
+          for (int r = 0; r < LR_PW; ++r) {
+#pragma unroll
+            for (int q = 0; q < r; ++q) dg[r][q] = dgs[r * LR_PW + q];
+            dv[r] = dgs[LR_PW * LR_PW + r];
+          }
+#pragma unroll
+          for (int c = 0; c < LR_PW; ++c) row[c] = c < pw ? L[pidx(i, p0 + c)] : 0.0;
+          // row . (L_dd J)^-T : forward over the block columns
+#pragma unroll
+          for (int c = 0; c < LR_PW; ++c) {
+            const double sgc = (p0 + c) < na ? -1.0 : 1.0;
+            row[c] *= sgc * dv[c];
+#pragma unroll
+            for (int q = c + 1; q < LR_PW; ++q) row[q] = fma(-sgc * row[c], dg[q][c], row[q]);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < LR_PW; ++c) {
+          const double sgc = (p0 + c) < na ? -1.0 : 1.0;
+          if (c < pw && (tid >= pw || c <= tid)) L[pidx(i, p0 + c)] = row[c];
+          pan[c * LR_PKR + tid] = c < pw ? row[c] : 0.0;
+          pas[c * LR_PKR + tid] = c < pw ? sgc * row[c] : 0.0;
+        }
       }
-      // trailing update  H[i][l] -= sgn L[i][j] L[l][j],  j < l <= i
-      for (int i = j + 1 + warp; i < k; i += LR_ST / 32) {
-        const double cij = sgn * colj[i];
-        double *row      = L + pidx(i, 0);
-        for (int l = j + 1 + lane; l <= i; l += 32) row[l] = fma(-cij, colj[l], row[l]);
+      __syncthreads();
+      // trailing update: H[i][l] -= sum_c J_c L[i][c] L[l][c],  p0 + pw <= l <= i < kr, l < k
+      const int t0 = p0 + pw;
+      for (int ii = t0 + warp; ii < kr; ii += LR_ST / 32) {
+        double pi[LR_PW];
+#pragma unroll
+        for (int c = 0; c < LR_PW; ++c) pi[c] = pas[c * LR_PKR + (ii - p0)];
+        double *rowp = L + pidx(ii, 0);
+        for (int l = t0 + lane; l <= ii && l < k; l += 32) {
+          double s = rowp[l];
+#pragma unroll
+          for (int c = 0; c < LR_PW; ++c) s = fma(-pi[c], pan[c * LR_PKR + (l - p0)], s);
+          rowp[l] = s;
+        }
       }
       __syncthreads();
     }
     for (int e = tid; e < npk; e += LR_ST) Lg[e] = L[e];
-    for (int i = tid; i < k; i += LR_ST) dinvg[i] = dinv[i];
+    for (int i = tid; i < k; i += LR_ST) {
+      Lg[npk + i] = dinv[i];
+      vec[i]      = L[pidx(k, i)];   // row k = J L^-1 rhs
+    }
+    __syncthreads();
   } else {
     for (int e = tid; e < npk; e += LR_ST) L[e] = Lg[e];
     for (int i = tid; i < k; i += LR_ST) {
-      dinv[i] = dinvg[i];
-      rhs[i]  = rhs_in[i] - (i < na ? rfull[idxA[i]] : 0.0);
+      dinv[i] = Lg[npk + i];
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      int p = 0;
+      for (; p + 3 < ntp; p += 4) {
+        s0 += tpart[(size_t) p * ldp + i];
+        s1 += tpart[(size_t) (p + 1) * ldp + i];
+        s2 += tpart[(size_t) (p + 2) * ldp + i];
+        s3 += tpart[(size_t) (p + 3) * ldp + i];
+      }
+      for (; p < ntp; ++p) s0 += tpart[(size_t) p * ldp + i];
+      vec[i] = ((s0 + s1) + (s2 + s3)) - (i < na ? rfull[idxA[i]] : 0.0);
+    }
+    __syncthreads();
+    // L u = rhs by panels; vec <- v = J u
+    for (int p0 = 0; p0 < k; p0 += LR_PW) {
+      const int pw = min(LR_PW, k - p0), t0 = p0 + pw;
+      if (tid == 0) {
+        double u[LR_PW];
+#pragma unroll
+        for (int c = 0; c < LR_PW; ++c) {
+          double s = c < pw ? vec[p0 + c] : 0.0;
+#pragma unroll
+          for (int q = 0; q < c; ++q)
+            if (c < pw) s = fma(-L[pidx(p0 + c, p0 + q)], u[q], s);
+          u[c] = c < pw ? s * dinv[p0 + c] : 0.0;
+        }
+#pragma unroll
+        for (int c = 0; c < LR_PW; ++c) {
+          pan[c] = u[c];
+          if (c < pw) vec[p0 + c] = (p0 + c) < na ? -u[c] : u[c];
+        }
+      }
+      __syncthreads();
+      for (int i = t0 + tid; i < k; i += LR_ST) {
+        const double *row = L + pidx(i, p0);
+        double s = vec[i];
+#pragma unroll
+        for (int c = 0; c < LR_PW; ++c)
+          if (c < pw) s = fma(-row[c], pan[c], s);
+        vec[i] = s;
+      }
+      __syncthreads();
+    }
+  }
+  // L^T z = v by panels from the last: warp c of the first eight reduces the contributions of the rows below the panel to column p0 + c
+  const int npan = (k + LR_PW - 1) / LR_PW;
+  for (int pb = npan - 1; pb >= 0; --pb) {
+    const int p0 = pb * LR_PW, pw = min(LR_PW, k - p0), t0 = p0 + pw;
+    if (warp < LR_PW) {
+      double s = 0.0;
+      if (warp < pw)
+        for (int i = t0 + lane; i < k; i += 32) s = fma(L[pidx(i, p0 + warp)], vec[i], s);
+      for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+      if (lane == 0) red[warp] = s;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double zc[LR_PW];
+#pragma unroll
+      for (int c = LR_PW - 1; c >= 0; --c) {
+        double s = c < pw ? vec[p0 + c] - red[c] : 0.0;
+#pragma unroll
+        for (int q = c + 1; q < LR_PW; ++q)
+          if (q < pw) s = fma(-L[pidx(p0 + q, p0 + c)], zc[q], s);
+        zc[c] = c < pw ? s * dinv[p0 + c] : 0.0;
+      }
+#pragma unroll
+      for (int c = 0; c < LR_PW; ++c)
+        if (c < pw) vec[p0 + c] = zc[c];
     }
     __syncthreads();
   }
-  if (warp == 0) {
-    // L u = rhs ; v = J u ; L^T z = v
-    for (int j = 0; j < k; ++j) {
-      const double u = rhs[j] * dinv[j];
-      __syncwarp();
-      for (int i = j + 1 + lane; i < k; i += 32) rhs[i] = fma(-L[pidx(i, j)], u, rhs[i]);
-      if (lane == 0) rhs[j] = (j < na) ? -u : u;
-      __syncwarp();
-    }
-    for (int j = k - 1; j >= 0; --j) {
-      const double zz = rhs[j] * dinv[j];
-      __syncwarp();
-      const double *row = L + pidx(j, 0);
-      for (int i = lane; i < j; i += 32) rhs[i] = fma(-row[i], zz, rhs[i]);
-      if (lane == 0) rhs[j] = zz;
-      __syncwarp();
-    }
-    for (int i = lane; i < k; i += 32) z[i] = rhs[i];
-  }
+  for (int i = tid; i < k; i += LR_ST) z[i] = vec[i];
 }
 
 cudaError_t set_smem_attrs() {
@@ -432,7 +632,8 @@ cudaError_t set_smem_attrs() {
   cudaError_t e;
   if ((e = cudaFuncSetAttribute(trinv_step1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) GEMM_SMEM)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(trinv_step2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) GEMM_SMEM)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) GEMM_SMEM)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(gemm_tn_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) GEMM_SMEM)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(syrk_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) GEMM_SMEM)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(lr_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) LR_SMALL_SMEM)) != cudaSuccess) return e;
   done[dev] = true;
   return cudaSuccess;
@@ -441,9 +642,26 @@ cudaError_t set_smem_attrs() {
 }   // namespace
 
 int lowrank_kmax() { return LR_KMAX; }
+// doubles of device scratch lowrank_solve needs for the split-K partial sums of an n_B x ldv product and of the k x k matrix
+size_t lowrank_part_doubles(int n, int ldv) {
+  const size_t tpart = (size_t) ((n + KC_T - 1) / KC_T) * n * ldv;
+  const size_t hpart = (size_t) ((n + KC_H - 1) / KC_H + 1) * ldv * ldv;
+  const size_t ttp   = (size_t) ((n + TT_ROWS - 1) / TT_ROWS) * ldv;
+  return tpart + hpart + ttp;
+}
 
-// W = U^-1 for the upper-triangular factor U (n x n, row-major, ld); S is scratch of the same shape.
-int trinv_upper(ncm_sd_gpu_ctx *c, int n, const double *dU, double *dW, double *dS, int ld) {
+// lower triangle := upper triangle transposed (n x n, row-major, ld)
+int symmetrize_upper(ncm_sd_gpu_ctx *c, int n, double *dM, int ld) {
+  const int nt = (n + 31) / 32;
+  transpose_upper_kernel<<<nt * (nt + 1) / 2, dim3(32, 8), 0, c->stream>>>(dM, dM, ld, n, nt);
+  c->n_launches++;
+  NCM_CUDA_OK(c, cudaGetLastError());
+  return NCM_SD_GPU_OK;
+}
+
+// W = U^-1 for the upper-triangular factor U (n x n, row-major, ld); S is scratch of the same shape.  Wt (optional) receives W^T
+// (lower triangle and diagonal; its upper triangle is not written).
+int trinv_upper(ncm_sd_gpu_ctx *c, int n, const double *dU, double *dW, double *dS, int ld, double *dWt) {
   NCM_CUDA_OK(c, set_smem_attrs());
   NCM_CUDA_OK(c, cudaMemsetAsync(dW, 0, (size_t) n * ld * sizeof(double), c->stream));
   trinv_diag_kernel<<<(n + 63) / 64, 64, 0, c->stream>>>(dU, dW, ld, n);
@@ -455,79 +673,63 @@ int trinv_upper(ncm_sd_gpu_ctx *c, int n, const double *dU, double *dW, double *
     trinv_step2_kernel<<<grid, GTHREADS, GEMM_SMEM, c->stream>>>(dW, dS, ld, n, s);
     c->n_launches += 2;
   }
+  if (dWt != nullptr) {
+    const int nt = (n + 31) / 32;
+    transpose_upper_kernel<<<nt * (nt + 1) / 2, dim3(32, 8), 0, c->stream>>>(dW, dWt, ld, n, nt);
+    c->n_launches++;
+  }
   NCM_CUDA_OK(c, cudaGetLastError());
   return NCM_SD_GPU_OK;
 }
 
-// out = A^T v over the upper triangle of A (rows r <= j, or r < j when !inclusive): two-pass, deterministic
-static int trmv_upper_col(ncm_sd_gpu_ctx *c, const double *dA, int lda, int n, const double *dv, bool inclusive, const double *extra, const double *base, double sign,
-                          double *dOut, DevBuf &tmp) {
-  int nblk = (c->n_sm * 2 * 256 + n - 1) / n;
-  if (nblk > (n + 63) / 64) nblk = (n + 63) / 64;
-  if (nblk < 1) nblk = 1;
-  const int rpb = (n + nblk - 1) / nblk;
-  nblk          = (n + rpb - 1) / rpb;
-  if (!tmp.reserve((size_t) nblk * n * sizeof(double))) return c->fail(NCM_SD_GPU_ENOMEM, "lowrank: out of device memory");
-  dim3 grid((n + 255) / 256, nblk);
-  trmv_upper_col_partial_kernel<<<grid, 256, 0, c->stream>>>(dA, lda, n, dv, tmp.as<double>(), rpb, inclusive ? 1 : 0);
-  lr_reduce_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(tmp.as<double>(), nblk, n, extra, base, sign, dOut);
-  c->n_launches += 2;
-  return NCM_SD_GPU_OK;
-}
-
-// Solve M[P,P] x = b[P] for P = (B \ D) u A through the base inverse W (see the header).  idxB / idxA / posD / idxP are device
-// arrays (ascending); the result (np doubles, in the order of P) and {max |dx|, max |x|} are left in bufs.out / bufs.stats.
+// Solve M[P,P] x = b[P] for P = (B \ D) u A through the base inverse W (see the header).  M is full symmetric.  Device index arrays
+// (all ascending): idxB [nB], idxA [na], posD [nd]; bsel [nB] = idxB[i] or -1 on the rows of D; psrc [np] = position of P[j] in B or
+// -(1 + position in A).  The np results in the order of P, then {max |dx|, max |x|}, are left in bufs.out.
 int lowrank_solve(ncm_sd_gpu_ctx *c, const double *dM, int ldm, int n, const double *db, int nB, int na, int nd, int np, const LowrankBufs &w, int ldv,
-                  DevBuf &tmp) {
+                  bool refine) {
   NCM_CUDA_OK(c, set_smem_attrs());
   const int k = na + nd, kc = k + 1;
   cudaStream_t st = c->stream;
+  const size_t tstride = (size_t) nB * ldv, hstride = (size_t) ldv * ldv;
+  const int ntc = (nB + KC_T - 1) / KC_T, nhc = (nB + KC_H - 1) / KC_H, ntp = (nB + TT_ROWS - 1) / TT_ROWS;
+  double *Tpart = w.part, *Hpart = Tpart + (size_t) ntc * tstride, *H0 = Hpart + (size_t) nhc * hstride, *tTtpart = H0 + hstride;
+  const int ctiles = (kc + GT - 1) / GT, rtiles = (nB + GT - 1) / GT;
   NCM_CUDA_OK(c, cudaMemsetAsync(w.info, 0, sizeof(int), st));
-  {
-    dim3 blk(32, 8);
-    lr_gather_V_kernel<<<(nB + 7) / 8, blk, 0, st>>>(dM, ldm, db, w.idxB, nB, w.idxA, na, w.posD, nd, w.V, ldv);
-  }
-  {
-    dim3 grid((kc + GT - 1) / GT, (nB + GT - 1) / GT);
-    gemm_tn_kernel<<<grid, GTHREADS, GEMM_SMEM, st>>>(w.W, ldm, w.V, ldv, w.T, ldv, nB, kc, nB, 1);
-  }
-  c->n_launches += 2;
-  int rc = dsyrk_ata_general(c, nB, kc, w.T, ldv, w.H, ldv, 1.0, 0.0);
-  if (rc != NCM_SD_GPU_OK) return rc;
+  if (refine) NCM_CUDA_OK(c, cudaMemsetAsync(w.xfull, 0, (size_t) n * sizeof(double), st));
+  lr_gather_V_kernel<<<(nB + 7) / 8, dim3(32, 8), 0, st>>>(dM, ldm, db, w.bsel, w.idxB, nB, w.idxA, na, w.posD, nd, w.V, ldv);
+  gemm_tn_splitk_kernel<<<dim3(ctiles, rtiles, ntc), GTHREADS, GEMM_SMEM, st>>>(w.W, ldm, w.V, ldv, Tpart, ldv, tstride, nB, kc, nB);
+  splitk_reduce_kernel<<<dim3((kc + 63) / 64, nB), 64, 0, st>>>(Tpart, tstride, ldv, nB, kc, nB, w.T);
+  c->n_launches += 3;
   if (k > 0) {
-    lr_small_kernel<<<1, LR_ST, LR_SMALL_SMEM, st>>>(0, na, nd, w.H, ldv, dM, ldm, w.idxA, db, nullptr, nullptr, w.Lg, w.dinvg, w.z, w.info);
-    c->n_launches++;
+    syrk_splitk_kernel<<<dim3(ctiles * (ctiles + 1) / 2, nhc), GTHREADS, GEMM_SMEM, st>>>(w.T, ldv, Hpart, ldv, hstride, kc, nB);
+    hreduce_kernel<<<dim3((kc + 63) / 64, kc), 64, 0, st>>>(Hpart, hstride, nhc, ldv, kc, H0);
+    lr_small_kernel<<<1, LR_ST, LR_SMALL_SMEM, st>>>(0, na, nd, H0, ldv, dM, ldm, w.idxA, db, nullptr, 0, 0, nullptr, w.Lg, w.z, w.info);
+    c->n_launches += 3;
   }
   lr_y_kernel<<<(nB + 7) / 8, 256, 0, st>>>(w.T, ldv, nB, k, w.z, w.T + k, ldv, w.y);
-  trmv_upper_row_kernel<<<(nB + 7) / 8, 256, 0, st>>>(w.W, ldm, nB, w.y, w.xB);
-  NCM_CUDA_OK(c, cudaMemsetAsync(w.xfull, 0, (size_t) n * sizeof(double), st));
-  lr_scatter_kernel<<<(nB + 255) / 256, 256, 0, st>>>(w.xfull, w.idxB, nB, w.xB);
-  if (k > 0) lr_scatter_fix_kernel<<<(std::max(na, nd) + 255) / 256, 256, 0, st>>>(w.xfull, w.idxB, w.idxA, na, w.z, w.posD, nd);
-  c->n_launches += 4;
-
-  // one step of iterative refinement on the true system: r = b - Msym xfull
-  trmv_upper_row_kernel<<<(n + 7) / 8, 256, 0, st>>>(dM, ldm, n, w.xfull, w.row);
-  c->n_launches++;
-  rc = trmv_upper_col(c, dM, ldm, n, w.xfull, false, w.row, db, -1.0, w.rfull, tmp);
-  if (rc != NCM_SD_GPU_OK) return rc;
-  lr_gather_kernel<<<(nB + 255) / 256, 256, 0, st>>>(w.rfull, w.idxB, nB, w.rB);
-  if (nd > 0) lr_zero_at_kernel<<<(nd + 255) / 256, 256, 0, st>>>(w.rB, w.posD, nd);
+  row_dot_kernel<ROW_UPPER><<<(nB * ROW_WPR + 7) / 8, 256, 0, st>>>(w.W, ldm, nB, w.y, nullptr, 1.0, w.xB);
   c->n_launches += 2;
-  rc = trmv_upper_col(c, w.W, ldm, nB, w.rB, true, nullptr, nullptr, 1.0, w.tr, tmp);   // t_r = W^T r_B
-  if (rc != NCM_SD_GPU_OK) return rc;
-  if (k > 0) {
-    rc = gemv_t(c, w.T, ldv, nB, k, w.tr, w.rhsz, tmp);                                   // T_R^T t_r
-    if (rc != NCM_SD_GPU_OK) return rc;
-    lr_small_kernel<<<1, LR_ST, LR_SMALL_SMEM, st>>>(1, na, nd, w.H, ldv, dM, ldm, w.idxA, db, w.rhsz, w.rfull, w.Lg, w.dinvg, w.z, w.info);
+  if (!refine) {   // the base has already shown a negligible correction (see nnls.cu): x is final
+    lr_finalize_kernel<<<1, 1024, 0, st>>>(w.psrc, np, w.xB, nullptr, w.z, nullptr, w.out);
     c->n_launches++;
+    NCM_CUDA_OK(c, cudaGetLastError());
+    return NCM_SD_GPU_OK;
   }
-  lr_y_kernel<<<(nB + 7) / 8, 256, 0, st>>>(w.T, ldv, nB, k, w.z, w.tr, 1, w.y);
-  trmv_upper_row_kernel<<<(nB + 7) / 8, 256, 0, st>>>(w.W, ldm, nB, w.y, w.xB);
-  NCM_CUDA_OK(c, cudaMemsetAsync(w.dxfull, 0, (size_t) n * sizeof(double), st));
-  lr_scatter_kernel<<<(nB + 255) / 256, 256, 0, st>>>(w.dxfull, w.idxB, nB, w.xB);
-  if (k > 0) lr_scatter_fix_kernel<<<(std::max(na, nd) + 255) / 256, 256, 0, st>>>(w.dxfull, w.idxB, w.idxA, na, w.z, w.posD, nd);
-  lr_finalize_kernel<<<1, 1024, 0, st>>>(w.xfull, w.dxfull, w.idxP, np, w.out, w.out + np);
-  c->n_launches += 5;
+  lr_scatter_kernel<<<(std::max(nB, na) + 255) / 256, 256, 0, st>>>(w.xfull, w.bsel, nB, w.xB, w.idxA, na, w.z);
+  // one step of iterative refinement on the true system: r = b - M xfull
+  row_dot_kernel<ROW_FULL><<<(n * ROW_WPR + 7) / 8, 256, 0, st>>>(dM, ldm, n, w.xfull, db, -1.0, w.rfull);
+  lr_gather_r_kernel<<<(nB + 255) / 256, 256, 0, st>>>(w.rfull, w.bsel, nB, w.rB);
+  row_dot_kernel<ROW_LOWER><<<(nB * ROW_WPR + 7) / 8, 256, 0, st>>>(w.Wt, ldm, nB, w.rB, nullptr, 1.0, w.tr);   // t_r = W^T r_B
+  c->n_launches += 4;
+  if (k > 0) {
+    lr_tTt_partial_kernel<<<ntp, 256, 0, st>>>(w.T, ldv, nB, k, w.tr, tTtpart, ldv);
+    lr_small_kernel<<<1, LR_ST, LR_SMALL_SMEM, st>>>(1, na, nd, H0, ldv, dM, ldm, w.idxA, db, tTtpart, ldv, ntp, w.rfull, w.Lg, w.z2, w.info);
+    c->n_launches += 2;
+  }
+  lr_y_kernel<<<(nB + 7) / 8, 256, 0, st>>>(w.T, ldv, nB, k, w.z2, w.tr, 1, w.y);
+  row_dot_kernel<ROW_UPPER><<<(nB * ROW_WPR + 7) / 8, 256, 0, st>>>(w.W, ldm, nB, w.y, nullptr, 1.0, w.dxB);
+  lr_finalize_kernel<<<1, 1024, 0, st>>>(w.psrc, np, w.xB, w.dxB, w.z, w.z2, w.out);
+  c->n_launches += 3;
   NCM_CUDA_OK(c, cudaGetLastError());
   return NCM_SD_GPU_OK;
 }

@@ -173,12 +173,16 @@ struct NnlsWork {
   double diag_mean = 0.0;
   ncm_sd_gpu_nnls_stats *st;
   // low-rank reuse of the last factorisation (lowrank.cu)
-  bool lr_on = false, base_valid = false, w_valid = false;
+  bool lr_on = false, base_valid = false, w_valid = false, base_trusted = false;
   std::vector<int> baseP;
   LowrankBufs lb;
-  int ldv = 0;
+  int ldv = 0, nv = 0;
 };
 
+bool nnls_trace() {   // debugging aid: one stderr line per passive-set system (the oracle prints the same under ORC_NNLS_TRACE)
+  static const bool on = getenv("NCM_SD_GPU_NNLS_TRACE") != nullptr;
+  return on;
+}
 bool lowrank_enabled() {
   static const bool on = [] {
     const char *e = getenv("NCM_SD_GPU_NNLS_REUSE");
@@ -188,6 +192,9 @@ bool lowrank_enabled() {
 }
 constexpr int LR_MIN_N = 512;       // below this a fused factorisation (a few 64-column phases) is as cheap as the ~25 launches of an update
 constexpr double LR_MAX_CORR = 1e-7;
+// a base whose first low-rank solve needed a refinement correction below this is trusted: the later solves from it skip the refinement
+// (its cost is about a third of a solve; the correction measures the conditioning of the base, which does not change between solves)
+constexpr double LR_TRUST_CORR = 1e-12;
 
 // P = (B \ D) u A: solve through the base inverse; returns 1 when the caller has to factorise afresh
 int solve_lowrank(NnlsWork &w, const std::vector<int> &P, bool *done) {
@@ -196,19 +203,25 @@ int solve_lowrank(NnlsWork &w, const std::vector<int> &P, bool *done) {
   const std::vector<int> &B = w.baseP;
   const int nB = (int) B.size(), np = (int) P.size();
   int kcap = std::min(lowrank_kmax(), nB / 8);
-  // D = B \ P (positions in B), A = P \ B (global indices): one merge pass over the two ascending lists
-  int *hA = w.h_idx, *hD = w.h_idx + lowrank_kmax() + 8, *hP = hD + lowrank_kmax() + 8;
+  // D = B \ P (positions in B), A = P \ B (global indices): one merge pass over the two ascending lists; bsel[i] = B[i] or -1 on the rows of D,
+  // psrc[j] = position of P[j] in B or -(1 + position in A)
+  const int kpad = lowrank_kmax() + 8;
+  int *hA = w.h_idx, *hD = hA + kpad, *hSel = hD + kpad, *hSrc = hSel + w.nv;
   int na = 0, nd = 0;
   {
     int i = 0, j = 0;
     while (i < nB || j < np) {
       if (j >= np || (i < nB && B[i] < P[j])) {
         if (nd + na >= kcap) return NCM_SD_GPU_OK;
+        hSel[i] = -1;
         hD[nd++] = i++;
       } else if (i >= nB || P[j] < B[i]) {
         if (nd + na >= kcap) return NCM_SD_GPU_OK;
+        hSrc[j]  = -(1 + na);
         hA[na++] = P[j++];
       } else {
+        hSel[i] = B[i];
+        hSrc[j] = i;
         ++i;
         ++j;
       }
@@ -216,7 +229,7 @@ int solve_lowrank(NnlsWork &w, const std::vector<int> &P, bool *done) {
   }
   StageTimer t(c, NCM_SD_GPU_T_LOWRANK);
   if (!w.w_valid) {
-    int rc = trinv_upper(c, nB, w.dMU, w.lb.W, w.lb.S, w.ldm);
+    int rc = trinv_upper(c, nB, w.dMU, w.lb.W, w.lb.S, w.ldm, w.lb.Wt);
     if (rc != NCM_SD_GPU_OK) return rc;
     w.w_valid = true;
     if (w.st) {
@@ -224,9 +237,9 @@ int solve_lowrank(NnlsWork &w, const std::vector<int> &P, bool *done) {
       w.st->lowrank_flops += (double) nB * nB * nB / 3.0;
     }
   }
-  std::memcpy(hP, P.data(), sizeof(int) * np);
-  NCM_CUDA_OK(c, ncm_memcpy_async(c, w.lb.idxA, hA, sizeof(int) * (size_t) (2 * (lowrank_kmax() + 8) + np), cudaMemcpyHostToDevice, c->stream));
-  int rc = lowrank_solve(c, w.dM, w.ldm, w.n, w.db, nB, na, nd, np, w.lb, w.ldv, c->nn_tmp);
+  NCM_CUDA_OK(c, ncm_memcpy_async(c, w.lb.idxA, hA, sizeof(int) * (size_t) (2 * kpad + 2 * w.nv), cudaMemcpyHostToDevice, c->stream));
+  const bool refine = !w.base_trusted;
+  int rc = lowrank_solve(c, w.dM, w.ldm, w.n, w.db, nB, na, nd, np, w.lb, w.ldv, refine);
   if (rc != NCM_SD_GPU_OK) return rc;
   NCM_CUDA_OK(c, ncm_memcpy_async(c, w.h_buf, w.lb.out, sizeof(double) * (size_t) (np + 2), cudaMemcpyDeviceToHost, c->stream));
   NCM_CUDA_OK(c, ncm_memcpy_async(c, w.h_buf + np + 2, w.lb.info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -239,10 +252,12 @@ int solve_lowrank(NnlsWork &w, const std::vector<int> &P, bool *done) {
     w.st->lowrank_flops += 2.0 * nB * (double) nB * (na + nd + 1);
     w.st->max_lowrank_k = std::max(w.st->max_lowrank_k, na + nd);
   }
+  if (nnls_trace()) fprintf(stderr, "gpu_nnls: lowrank |P| = %d |B| = %d k = %d + %d info = %d corr = %.3e%s\n", np, nB, na, nd, info, mdx / mx, refine ? "" : " (no refinement)");
   if (info != 0 || !(mdx <= LR_MAX_CORR * mx)) {   // also catches NaN
     if (w.st) w.st->n_lowrank_fallback++;
     return NCM_SD_GPU_OK;
   }
+  if (refine && mdx <= LR_TRUST_CORR * mx) w.base_trusted = true;
   *done = true;
   return NCM_SD_GPU_OK;
 }
@@ -285,14 +300,16 @@ int solve_unconstrained(NnlsWork &w, const std::vector<int> &P) {
       w.st->n_chol++;
       w.st->chol_flops += (double) np * np * np / 3.0;
     }
+    if (nnls_trace()) fprintf(stderr, "gpu_nnls: chol |P| = %d info = %d shift = %g\n", np, info, shift);
     if (info == 0) {
       NCM_CUDA_OK(c, ncm_memcpy_async(c,w.h_buf, w.drhs, sizeof(double) * np, cudaMemcpyDeviceToHost, c->stream));
       if (w.lr_on && attempt == 0 && np >= LR_MIN_N) {   // the factor left in dMU becomes the base of the following low-rank solves
         std::memcpy(w.h_idx, P.data(), sizeof(int) * np);
         NCM_CUDA_OK(c, ncm_memcpy_async(c, w.lb.idxB, w.h_idx, sizeof(int) * np, cudaMemcpyHostToDevice, c->stream));
         w.baseP      = P;
-        w.base_valid = true;
-        w.w_valid    = false;
+        w.base_valid   = true;
+        w.w_valid      = false;
+        w.base_trusted = false;
       }
       NCM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
       return NCM_SD_GPU_OK;
@@ -405,7 +422,7 @@ int nnls_solve_dev(ncm_sd_gpu_ctx *c, int nrows, int ncols, const double *dA, in
   if (!c->M.reserve(mm) || !c->MU.reserve(mm) || !c->nn_b.reserve((size_t) (4 * n + 64) * sizeof(double)) ||
       !c->nn_x.reserve((size_t) (2 * n + 16) * sizeof(double)) || !c->nn_r.reserve((size_t) (2 * nrows + 16) * sizeof(double)) ||
       !c->nn_g.reserve((size_t) (nrows / 8 + n + 64) * sizeof(double)) || !c->nn_idx.reserve((size_t) (n + 16) * sizeof(int)) ||
-      !c->pin_nn.reserve((size_t) (n + 16) * sizeof(double) + (size_t) (n + 16 + 2 * (lowrank_kmax() + 8)) * sizeof(int)))
+      !c->pin_nn.reserve((size_t) (n + 16) * sizeof(double) + (size_t) (3 * (n + 32) + 2 * (lowrank_kmax() + 8)) * sizeof(int)))
     return c->fail(NCM_SD_GPU_ENOMEM, "nnls: out of memory");
 
   NnlsWork w;
@@ -428,26 +445,25 @@ int nnls_solve_dev(ncm_sd_gpu_ctx *c, int nrows, int ncols, const double *dA, in
 
   w.lr_on = lowrank_enabled() && n >= LR_MIN_N && n <= chol_fused_max_n();
   if (w.lr_on) {
-    const int kmax = lowrank_kmax();
-    w.ldv          = kmax + 8;
-    const size_t nv = (size_t) n + 16;
-    if (!c->lrW.reserve(mm) || !c->lrS.reserve(mm) || !c->lrV.reserve((size_t) n * w.ldv * sizeof(double)) ||
-        !c->lrT.reserve((size_t) n * w.ldv * sizeof(double)) ||
-        !c->lrSmall.reserve(((size_t) w.ldv * w.ldv + (size_t) kmax * (kmax + 1) / 2 + 4 * (size_t) w.ldv + 64) * sizeof(double)) ||
-        !c->lrVec.reserve(11 * nv * sizeof(double)) || !c->lrIdx.reserve((3 * nv + 2 * (size_t) (kmax + 8) + 16) * sizeof(int)))
+    const int kmax = lowrank_kmax(), kpad = kmax + 8;
+    w.ldv          = kpad;
+    w.nv           = (n + 16 + 7) & ~7;
+    const size_t nv = (size_t) w.nv;
+    if (!c->lrW.reserve(mm) || !c->lrWt.reserve(mm) || !c->lrS.reserve(mm) || !c->lrV.reserve((size_t) n * w.ldv * sizeof(double)) ||
+        !c->lrT.reserve((size_t) n * w.ldv * sizeof(double)) || !c->lrPart.reserve(lowrank_part_doubles(n, w.ldv) * sizeof(double)) ||
+        !c->lrSmall.reserve(((size_t) (kmax + 1) * (kmax + 2) / 2 + 3 * (size_t) kpad + 64) * sizeof(double)) ||
+        !c->lrVec.reserve(9 * nv * sizeof(double)) || !c->lrIdx.reserve((3 * nv + 2 * (size_t) kpad + 16) * sizeof(int)))
       return c->fail(NCM_SD_GPU_ENOMEM, "nnls: out of memory");
     LowrankBufs &b = w.lb;
-    b.W = c->lrW.as<double>(); b.S = c->lrS.as<double>(); b.V = c->lrV.as<double>(); b.T = c->lrT.as<double>();
-    b.H     = c->lrSmall.as<double>();
-    b.Lg    = b.H + (size_t) w.ldv * w.ldv;
-    b.dinvg = b.Lg + (size_t) kmax * (kmax + 1) / 2;
-    b.z     = b.dinvg + w.ldv;
-    b.rhsz  = b.z + w.ldv;
+    b.W = c->lrW.as<double>(); b.Wt = c->lrWt.as<double>(); b.S = c->lrS.as<double>(); b.V = c->lrV.as<double>(); b.T = c->lrT.as<double>();
+    b.part = c->lrPart.as<double>();
+    b.Lg   = c->lrSmall.as<double>();
+    b.z    = b.Lg + ((size_t) (kmax + 1) * (kmax + 2) / 2 + kpad);
+    b.z2   = b.z + kpad;
     double *v = c->lrVec.as<double>();
-    b.y = v; b.xB = v + nv; b.xfull = v + 2 * nv; b.rfull = v + 3 * nv; b.rB = v + 4 * nv; b.tr = v + 5 * nv; b.dxfull = v + 6 * nv;
-    b.row = v + 7 * nv; b.out = v + 8 * nv; b.stats = nullptr;   // stats follow the np results in `out` (one D2H)
-    int *ix = c->lrIdx.as<int>();
-    b.idxB = ix; b.idxA = ix + nv; b.posD = b.idxA + (kmax + 8); b.idxP = b.posD + (kmax + 8); b.info = b.idxP + nv;
+    b.y = v; b.xB = v + nv; b.dxB = v + 2 * nv; b.xfull = v + 3 * nv; b.rfull = v + 4 * nv; b.rB = v + 5 * nv; b.tr = v + 6 * nv; b.out = v + 7 * nv;
+    int *ix = c->lrIdx.as<int>();   // idxA | posD | bsel | psrc are uploaded together; idxB when a base is established
+    b.idxA = ix; b.posD = ix + kpad; b.bsel = b.posD + kpad; b.psrc = b.bsel + nv; b.idxB = b.psrc + nv; b.info = b.idxB + nv;
   }
   int rc;
   {
@@ -457,6 +473,10 @@ int nnls_solve_dev(ncm_sd_gpu_ctx *c, int nrows, int ncols, const double *dA, in
     if (stats) stats->syrk_flops = (double) nrows * n * n;
     rc = allreduce_sum(c, w.dM, (size_t) n * ldm);
     if (rc != NCM_SD_GPU_OK) return rc;
+    if (w.lr_on) {   // the low-rank solves read rows of M[:, A] and take symmetric products: fill the lower triangle once
+      rc = symmetrize_upper(c, n, w.dM, ldm);
+      if (rc != NCM_SD_GPU_OK) return rc;
+    }
   }
   {
     StageTimer t(c, NCM_SD_GPU_T_NNLS_MISC);

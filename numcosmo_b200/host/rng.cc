@@ -69,42 +69,15 @@ double gaussian_polar(NcmRNG *r, double sigma) {
   return sigma * y * sqrt(-2.0 * log(r2) / r2);
 }
 
-// Marsaglia-Tsang ziggurat, 128 levels, rightmost step R (randist/gausszig.c); tables rebuilt from
-// the construction and rounded to the 12 significant digits GSL prints them with.
-constexpr double ZIG_R = 3.44428647676;
-double zig_y[128], zig_w[128];
-unsigned long zig_k[128];
-bool zig_ready = false;
-
-double round12(double v) {
-  char buf[64];
-  snprintf(buf, sizeof(buf), "%.11e", v);
-  return strtod(buf, nullptr);
-}
-
-void zig_build() {
-  double x[129];
-  const double V = ZIG_R * exp(-0.5 * ZIG_R * ZIG_R) + sqrt(M_PI / 2.0) * erfc(ZIG_R / M_SQRT2);
-  x[127]         = ZIG_R;
-  for (int i = 126; i >= 1; i--) {
-    const double y1 = exp(-0.5 * x[i + 1] * x[i + 1]);
-    const double y0 = y1 + V / x[i + 1];
-    x[i]            = (y0 < 1.0) ? sqrt(-2.0 * log(y0)) : 0.0;
-  }
-  x[0] = 0.0;
-  for (int i = 0; i < 128; i++) zig_y[i] = round12(exp(-0.5 * x[i] * x[i]));
-  zig_y[0] = 1.0;
-  for (int i = 0; i < 127; i++) {
-    zig_w[i] = round12(x[i + 1] / 16777216.0);
-    zig_k[i] = (unsigned long) (16777216.0 * x[i] / x[i + 1]);
-  }
-  zig_w[127] = round12(ZIG_R / 16777216.0);
-  zig_k[127] = (unsigned long) (16777216.0 * ZIG_R * exp(-0.5 * ZIG_R * ZIG_R) / V);
-  zig_ready  = true;
-}
+// gsl_ran_gaussian_ziggurat (randist/gausszig.c: Voss' variant of the Marsaglia-Tsang ziggurat, 128 levels).  GSL's three tables are
+// rebuilt from their construction by tools/gen_gausszig_tables.py (the closure condition fixes R = 3.444286476761...; the entries of
+// the GSL source it is pinned on are listed there) and included as the 12-digit literals GSL carries.
+#include "gausszig_tables.h"
+constexpr double ZIG_R = NCM_GAUSSZIG_PARAM_R;
+const double *const zig_y = ncm_gausszig_ytab, *const zig_w = ncm_gausszig_wtab;
+const unsigned long *const zig_k = ncm_gausszig_ktab;
 
 double gaussian_zig(NcmRNG *r, double sigma) {
-  if (!zig_ready) zig_build();
   unsigned long i, j;
   int sign;
   double x, y;

@@ -155,62 +155,14 @@ orc_ran_ugaussian (orc_rng *r)
   return orc_ran_gaussian (r, 1.0);
 }
 
-/* ---- ziggurat (randist/gausszig.c) with regenerated tables ---- */
+/* ---- ziggurat (randist/gausszig.c: Voss' variant, 128 levels).  GSL's tables rebuilt from their construction by
+ * tools/gen_gausszig_tables.py (12-digit literals as in GSL's source; pinned on the entries of the GSL tables listed there) ---- */
 
-#define ZIG_R 3.44428647676
-
-static double zig_ytab[128];
-static unsigned long zig_ktab[128];
-static double zig_wtab[128];
-static int zig_ready = 0;
-
-static double
-round12 (double v)
-{
-  char buf[64];
-
-  snprintf (buf, sizeof (buf), "%.11e", v);
-
-  return strtod (buf, NULL);
-}
-
-static void
-zig_build (void)
-{
-  /* Levels x_0 = 0 < x_1 < ... < x_127 = R; strip i (0..126) lies between heights
-   * y_i = exp(-x_i^2/2) (top) and y_{i+1}; every strip and the base strip (127,
-   * rectangle [0,R] x [0,y_127] plus the tail) has area V. */
-  double x[129];
-  const double V = ZIG_R * exp (-0.5 * ZIG_R * ZIG_R) + sqrt (M_PI / 2.0) * erfc (ZIG_R / M_SQRT2);
-  int i;
-
-  x[127] = ZIG_R;
-
-  for (i = 126; i >= 1; i--)
-  {
-    const double y_ip1 = exp (-0.5 * x[i + 1] * x[i + 1]);
-    const double y_i   = y_ip1 + V / x[i + 1];
-
-    x[i] = (y_i < 1.0) ? sqrt (-2.0 * log (y_i)) : 0.0;
-  }
-
-  x[0] = 0.0;
-
-  for (i = 0; i < 128; i++)
-    zig_ytab[i] = round12 (exp (-0.5 * x[i] * x[i]));
-
-  zig_ytab[0] = 1.0;
-
-  for (i = 0; i < 127; i++)
-  {
-    zig_wtab[i] = round12 (x[i + 1] / 16777216.0);
-    zig_ktab[i] = (unsigned long) (16777216.0 * x[i] / x[i + 1]);
-  }
-
-  zig_wtab[127] = round12 (ZIG_R / 16777216.0);
-  zig_ktab[127] = (unsigned long) (16777216.0 * ZIG_R * exp (-0.5 * ZIG_R * ZIG_R) / V);
-  zig_ready     = 1;
-}
+#include "orc_gausszig_tables.h"
+#define ZIG_R NCM_GAUSSZIG_PARAM_R
+#define zig_ytab ncm_gausszig_ytab
+#define zig_ktab ncm_gausszig_ktab
+#define zig_wtab ncm_gausszig_wtab
 
 double
 orc_ran_gaussian_ziggurat (orc_rng *r, const double sigma)
@@ -218,9 +170,6 @@ orc_ran_gaussian_ziggurat (orc_rng *r, const double sigma)
   unsigned long i, j;
   int sign;
   double x, y;
-
-  if (!zig_ready)
-    zig_build ();
 
   while (1)
   {
