@@ -45,19 +45,27 @@ def parse():
                     choices=["apes_vkde_gauss_mvnd10_w4096", "eval_sweep", "prepare_interp", "apes_e2e", "cv"])
     ap.add_argument("--target", default="funnel", choices=["funnel", "rosenbrock", "mvnd"], help="--workload apes_e2e: configs[3] (funnel) / configs[0] (rosenbrock)")
     ap.add_argument("--over-smooth", type=float, default=None)
-    ap.add_argument("--walkers", type=int, default=4096)
-    ap.add_argument("--dim", type=int, default=10)
+    ap.add_argument("--walkers", type=int, default=None, help="default: 4096 at N = 1 (configs[1]); 32768 for the sharded N > 1 workload (configs[2]/[3] class)")
+    ap.add_argument("--dim", type=int, default=None, help="default: 10 at N = 1; 20 for the sharded N > 1 workload")
     ap.add_argument("--sweep-q", type=int, default=65536)
     ap.add_argument("--sweep-n", type=int, default=65536)
     ap.add_argument("--sd", default="vkde", choices=["kde", "vkde"])
     ap.add_argument("--kernel", default="gauss", choices=["gauss", "st3", "cauchy"])
     ap.add_argument("--cv", default="split", choices=["split", "split_nofit", "loo"], help="--workload cv: the cross-validation mode")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--apes-multi", default="replicas", choices=["replicas", "sharded"],
-                    help="APES workload at N > 1: one independent ensemble per GPU (default, weak scaling) or one ensemble with IM / query rows "
-                         "sharded over the ranks (strong scaling; at 4096 walkers the replicated passive-set Cholesky is 81 %% of the step, so "
-                         "sharding only adds the all-reduce: 11.85 -> 13.06 ms at 2 GPUs, profiles/r01c_bench_2gpu_sharded.log)")
-    return ap.parse_args()
+    ap.add_argument("--apes-multi", default="sharded", choices=["replicas", "sharded"],
+                    help="APES workload at N > 1.  sharded (default): ONE ensemble, interpolation-matrix rows and query rows sharded over the ranks, "
+                         "centres replicated, NCCL all-reduce of the normal equations and all-gather of the densities on the data path (the north-star "
+                         "partitioning, strong scaling), on a configs[2]/[3]-class size (32768 walkers = 16384 centres, d = 20) where sharding can pay.  "
+                         "replicas: one independent ensemble per GPU, no data-path collective (weak scaling; how several chains are run).")
+    a = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    big = world > 1 and a.apes_multi == "sharded" and a.workload == "apes_vkde_gauss_mvnd10_w4096"
+    if a.walkers is None:
+        a.walkers = 32768 if big else 4096
+    if a.dim is None:
+        a.dim = 20 if big else 10
+    return a
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -162,7 +170,7 @@ KT = {"gauss": ("GAUSS", 0, 1.0), "st3": ("ST3", 1, 3.0), "cauchy": ("CAUCHY", 1
 
 
 # ---------------------------------------------------------------------------------------------------
-def cpu_apes(args, W, d, iters, nthreads):
+def cpu_apes(args, W, d, iters, nthreads, warm=True):
     """The reference algorithm on the host cores (oracle port): returns seconds per iteration + stage timers."""
     from oracle import ncm_oracle as O
 
@@ -173,7 +181,8 @@ def cpu_apes(args, W, d, iters, nthreads):
     ap = O.APES(W, d, O.SD_VKDE, okind, nu, over_smooth=1.0, use_interp=True, use_threads=True)
     theta, ml = X.copy(), m2lnL.copy()
     rng = O.RNG(1234)
-    ap.run(tgt, theta, ml, 1, rng, nthreads=nthreads)   # warm-up iteration
+    if warm:
+        ap.run(tgt, theta, ml, 1, rng, nthreads=nthreads)   # warm-up iteration
     t0 = time.perf_counter()
     ap.run(tgt, theta, ml, iters, rng, nthreads=nthreads)
     dt = (time.perf_counter() - t0) / iters
@@ -188,8 +197,11 @@ def run_reference(args):
     ncores = os.cpu_count() or 1
     N = W // 2
     pairs = 6.0 * N * N
-    # warm-up happens inside cpu_apes (1 iteration); args.warmup - 1 further untimed iterations are folded into it
-    dt, timers = cpu_apes(args, W, d, max(1, args.steps), ncores)
+    # warm-up happens inside cpu_apes (1 iteration); args.warmup - 1 further untimed iterations are folded into it.  The sharded N > 1
+    # workload (32768 walkers) costs the CPU about a minute per iteration: its sample is bounded to ONE iteration without warm-up.
+    big = W > 8192
+    iters = 1 if big else max(1, args.steps)
+    dt, timers = cpu_apes(args, W, d, iters, ncores, warm=not big)
     val = pairs / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -198,7 +210,8 @@ def run_reference(args):
                    "note": "CPU oracle port of the reference algorithm (the reference itself cannot be built here: no GLib/GSL/meson)"},
         "walker_steps_per_s": W / dt,
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": ncores, "kind": "port",
-                         "sample": f"{args.steps} full APES iterations at W={W}, d={d} (OpenMP walkers-parallel eval, centre-parallel IM, threaded OpenBLAS NNLS)"},
+                         "sample": f"{iters} full APES iteration(s) at W={W}, d={d}" + (" without warm-up (bounded sample: ~1 min of CPU per iteration)" if big else "") +
+                                   " (OpenMP walkers-parallel eval, centre-parallel IM, threaded OpenBLAS NNLS)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "stage_s_total": {k: float(v) for k, v in timers.items()},
     }
@@ -206,6 +219,99 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------
+def _device_half_steps(torch, capi, sds, ctxs, theta, ml, N, d, steps, warmup, shard, clock_device):
+    """`value`: device-resident half-steps through the C ABI on the contexts behind sd0 / sd1 (centres, packed factors and lnnorms as the
+    last prepare_kernel left them).  shard = (world, rank) when the contexts carry a communicator in auto-shard mode: compute_IM then takes
+    this rank's row block, the NNLS all-reduces the normal equations, the 2N query rows are split and the densities all-gathered."""
+    world, rank = shard
+    gctx, dQ, dOut, dAll, rowscale, hrefs = [], [], [], [], [], []
+    for b in range(2):
+        mlc = ml[N:] if b == 0 else ml[:N]
+        c = ctxs[b]
+        # sd_b's centres are the OTHER half of the ensemble (walker_apes.c:751-811).  Block 1 moved after sd0 was last prepared, so
+        # re-run prepare_kernel on the current positions: centres, factors and m2lnL in the context are then those of a real half-step.
+        sds[b].reset()
+        for xrow in (theta[N:] if b == 0 else theta[:N]):
+            sds[b].add_obs(xrow)
+        sds[b].prepare()
+        c.n_kernels = c.n_obs = N
+        c.d = d
+        f = np.exp(-0.5 * (mlc - mlc.min()))
+        rowscale.append(1.0 / f)
+        blk = theta[:N] if b == 0 else theta[N:]
+        q_all = np.vstack([blk + 1e-3, blk])            # theta*_k and theta_k of the block: 2N query points
+        cap = (2 * N + world - 1) // world
+        q0, q1 = (2 * N * rank) // world, (2 * N * (rank + 1)) // world
+        dQ.append(torch.from_numpy(np.ascontiguousarray(q_all[q0:q1])).cuda())
+        dOut.append(torch.zeros(cap, dtype=torch.float64, device="cuda"))
+        dAll.append(torch.zeros(cap * world, dtype=torch.float64, device="cuda") if world > 1 else None)
+        gctx.append(c)
+        hrefs.append(sds[b].get_href())
+    streams = [torch.cuda.ExternalStream(c.stream) for c in gctx]
+
+    def half_step(b):
+        c = gctx[b]
+        c.compute_IM(rowscale[b])
+        x, rnorm, st = c.nnls_solve()
+        w = (1.0 - 0.01) * x / x.sum() + 0.01 / N
+        c.set_weights(w, hrefs[b])
+        c.eval_m2lnp_dev(dQ[b].shape[0], dQ[b].data_ptr(), d, dOut[b].data_ptr())
+        if world > 1:
+            c.allgather_dev(dOut[b].data_ptr(), dAll[b].data_ptr(), dOut[b].shape[0])
+        return st
+
+    import torch.distributed as dist
+
+    for _ in range(max(warmup, 3)):
+        half_step(0)
+        half_step(1)
+    for c in gctx:
+        c.synchronize()
+        c.reset_timers()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(2 * steps)]
+    with ClockSampler(clock_device) as clk:
+        for it in range(steps):
+            for b in range(2):
+                e0, e1 = ev[2 * it + b]
+                e0.record(streams[b])
+                half_step(b)
+                e1.record(streams[b])
+        for c in gctx:
+            c.synchronize()
+    torch.cuda.synchronize()
+    dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+    if world > 1:
+        t_dev = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+        dist.barrier()
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+        dev_ms = float(t_dev.item())
+    launches = sum(c.get_timers()[1] for c in gctx)
+    # per-stage device time of the step (separate pass with the CUDA-event stage timers on)
+    for c in gctx:
+        c.enable_timers(True)
+        c.reset_timers()
+    nroof = 3
+    agg = {"n_chol": 0, "chol_flops": 0.0, "n_lowrank": 0, "n_trinv": 0, "lowrank_flops": 0.0, "n_lowrank_fallback": 0, "max_lowrank_k": 0}
+    for _ in range(nroof):
+        for b in range(2):
+            st = half_step(b)
+            for k in agg:
+                agg[k] = max(agg[k], st[k]) if k == "max_lowrank_k" else agg[k] + st[k]
+    tm = {k: 0.0 for k in capi.T_NAMES}
+    for c in gctx:
+        t, _ = c.get_timers()
+        for k in tm:
+            tm[k] += t[k] / nroof
+        c.enable_timers(False)
+    for k in agg:
+        if k != "max_lowrank_k":
+            agg[k] = agg[k] / nroof
+    return dev_ms / steps, launches, tm, agg, clk.summary()
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -234,162 +340,112 @@ def run_b200(args):
     sharded = world > 1 and args.apes_multi == "sharded"
     nshard, shard_rank = (world, rank) if sharded else (1, 0)     # ranks one ensemble is split over
     replicas = 1 if sharded or world == 1 else world              # independent ensembles (one per GPU)
+    # sharded: every rank holds the SAME ensemble and draws the SAME generator stream (SPMD); replicas: one ensemble per rank
     mu, cov, U_tgt, X, m2lnL = make_problem_b200(S, W, d, seed=1 + (rank if replicas > 1 else 0))
     ktn, okind, nu = KT[args.kernel]
     lb, ub = np.full(d, -50.0), np.full(d, 50.0)
     peaks = load_peaks()
 
+    def new_apes():
+        ap = S.FitESMCMCWalkerAPES(W, d, S.FitESMCMCWalkerAPESMethod.VKDE, getattr(S.FitESMCMCWalkerAPESKType, ktn), 1.0, True)
+        ap.set_use_threads(True)
+        return ap
+
+    def e2e_run(apes, theta, ml, rng):
+        """end to end through the host API with HOST buffers; returns (seconds per iteration, accept rate, h2d, d2h, launches, stage split)"""
+        apes.run("mvnd", lb, ub, theta, ml, max(args.warmup, 1), rng, target_args=(mu, U_tgt), record_accept=False)
+        sds = apes.peek_sds()
+        ctxs = [capi.Context.borrowed(lib.ncm_stats_dist_b200_peek_ctx(sd._h)) for sd in sds]
+        for c in ctxs:
+            c.reset_timers()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        acc, _ = apes.run("mvnd", lb, ub, theta, ml, args.steps, rng, target_args=(mu, U_tgt), record_accept=True)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / args.steps
+        traffic = [c.get_traffic() for c in ctxs]
+        launches = sum(c.get_timers()[1] for c in ctxs)
+        apes.enable_timers(True)
+        for c in ctxs:
+            c.reset_timers()
+        _, stage = apes.run("mvnd", lb, ub, theta, ml, 2, rng, target_args=(mu, U_tgt), record_accept=False)
+        apes.enable_timers(False)
+        if world > 1:   # the job's rate is set by the slowest rank
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return dt, acc, sum(t[0] for t in traffic) / args.steps, sum(t[1] for t in traffic) / args.steps, launches / args.steps, \
+            {k: v / 2 for k, v in stage.items()}, sds, ctxs
+
+    # ---------------- single-GPU arm of the SAME workload (sharded mode only): the denominator of the strong-scaling speed-up ----------
+    single = None
+    if sharded:
+        ap1 = new_apes()
+        th1, ml1 = X.copy(), m2lnL.copy()
+        dt1, acc1, _, _, _, _, sds1, ctxs1 = e2e_run(ap1, th1, ml1, S.RNG(1234))
+        ms1, _, tm1, agg1, _ = _device_half_steps(torch, capi, sds1, ctxs1, th1, ml1, N, d, args.steps, args.warmup, (1, 0), local_rank)
+        single = {"value": pairs_step / (ms1 * 1e-3), "ms_per_step": ms1, "e2e_value": pairs_step / dt1, "e2e_ms_per_step": dt1 * 1e3,
+                  "step_share_ms": {k: round(v, 4) for k, v in tm1.items()}, "accept_hash": int(np.packbits(acc1).astype(np.uint64).sum()),
+                  "note": "this rank's GPU alone, unsharded, same ensemble and generator seed (all ranks measure it at the same time; rank 0's is reported)"}
+        del ap1, sds1, ctxs1
+        torch.cuda.empty_cache()
+
     # ---------------- e2e: host API, host buffers, whole iteration ----------------
-    apes = S.FitESMCMCWalkerAPES(W, d, S.FitESMCMCWalkerAPESMethod.VKDE, getattr(S.FitESMCMCWalkerAPESKType, ktn), 1.0, True)
-    apes.set_use_threads(True)
+    apes = new_apes()
+    if sharded:
+        apes.comm_init_from_torch()      # one NCCL communicator per NcmStatsDist context, auto-shard on
     theta, ml = X.copy(), m2lnL.copy()
     rng = S.RNG(1234)
-    apes.run("mvnd", lb, ub, theta, ml, max(args.warmup, 1), rng, target_args=(mu, U_tgt), record_accept=False)
-    sds = apes.peek_sds()
-    ctxs = [capi.Context.borrowed(lib.ncm_stats_dist_b200_peek_ctx(sd._h)) for sd in sds]
-    for c in ctxs:
-        c.reset_timers()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    acc, _ = apes.run("mvnd", lb, ub, theta, ml, args.steps, rng, target_args=(mu, U_tgt), record_accept=True)
-    torch.cuda.synchronize()
-    e2e_dt = (time.perf_counter() - t0) / args.steps
-    traffic = [c.get_traffic() for c in ctxs]
-    e2e_launches = sum(c.get_timers()[1] for c in ctxs)
-    h2d_step = sum(t[0] for t in traffic) / args.steps
-    d2h_step = sum(t[1] for t in traffic) / args.steps
+    e2e_dt, acc, h2d_step, d2h_step, e2e_launches, stage, sds, ctxs = e2e_run(apes, theta, ml, rng)
     accept_rate = float(acc.mean())
-    # stage breakdown of the e2e path (separate pass with the per-stage CUDA-event timers on)
-    apes.enable_timers(True)
-    for c in ctxs:
-        c.reset_timers()
-    _, stage = apes.run("mvnd", lb, ub, theta, ml, 2, rng, target_args=(mu, U_tgt), record_accept=False)
-    stage = {k: v / 2 for k, v in stage.items()}
-    apes.enable_timers(False)
+    accept_hash = int(np.packbits(acc).astype(np.uint64).sum())
 
     # ---------------- value: device-resident half-steps through the C ABI ----------------
-    # The two contexts behind sd0 / sd1 hold the state of a real APES iteration (centres, packed factors,
-    # lnnorms of the other half, uploaded by the last prepare_kernel): block b is updated from them.
-    gctx, dQ, dOut, rowscale, hrefs = [], [], [], [], []
-    for b in range(2):
-        mlc = ml[N:] if b == 0 else ml[:N]
-        c = ctxs[b]
-        # sd_b's centres are the OTHER half of the ensemble (walker_apes.c:751-811).  Block 1 moved after sd0 was last prepared, so
-        # re-run prepare_kernel on the current positions: centres, factors and m2lnL in the context are then those of a real half-step.
-        sds[b].reset()
-        for xrow in (theta[N:] if b == 0 else theta[:N]):
-            sds[b].add_obs(xrow)
-        sds[b].prepare()
-        c.n_kernels = c.n_obs = N
-        c.d = d
-        href = sds[b].get_href()
-        if sharded:
-            uid = [capi.comm_unique_id() if rank == 0 else None]
-            dist.broadcast_object_list(uid, src=0)
-            c.comm_init(world, rank, uid[0])
-            r0 = (N * rank) // world
-            r1 = (N * (rank + 1)) // world
-            c.set_row_shard(r0, r1 - r0)
-        f = np.exp(-0.5 * (mlc - mlc.min()))
-        rowscale.append(1.0 / f)
-        blk = theta[:N] if b == 0 else theta[N:]
-        q_all = np.vstack([blk + 1e-3, blk])            # theta*_k and theta_k of the block: 2N query points
-        q0, q1 = (2 * N * shard_rank) // nshard, (2 * N * (shard_rank + 1)) // nshard
-        dQ.append(torch.from_numpy(np.ascontiguousarray(q_all[q0:q1])).cuda())
-        dOut.append(torch.empty(q1 - q0, dtype=torch.float64, device="cuda"))
-        gctx.append(c)
-        hrefs.append(href)
-    streams = [torch.cuda.ExternalStream(c.stream) for c in gctx]
-
-    def half_step(b):
-        c = gctx[b]
-        c.compute_IM(rowscale[b])
-        x, rnorm, st = c.nnls_solve()
-        w = (1.0 - 0.01) * x / x.sum() + 0.01 / N
-        c.set_weights(w, hrefs[b])
-        c.eval_m2lnp_dev(dQ[b].shape[0], dQ[b].data_ptr(), d, dOut[b].data_ptr())
-        return st
-
-    def step():
-        half_step(0)
-        return half_step(1)
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    for c in gctx:
-        c.synchronize()
-        c.reset_timers()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(2 * args.steps)]
-    with ClockSampler(local_rank) as clk:
-        for it in range(args.steps):
-            for b in range(2):
-                e0, e1 = ev[2 * it + b]
-                e0.record(streams[b])
-                st = half_step(b)
-                e1.record(streams[b])
-        for c in gctx:
-            c.synchronize()
-    torch.cuda.synchronize()
-    dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
-    t_dev = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.barrier()
-        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
-    dev_ms = float(t_dev.item())
-    ms_per_step = dev_ms / args.steps
+    ms_per_step, launches, tm, agg, clocks = _device_half_steps(torch, capi, sds, ctxs, theta, ml, N, d, args.steps, args.warmup, (nshard, shard_rank),
+                                                                local_rank)
     value = replicas * pairs_step / (ms_per_step * 1e-3)
-    if world > 1:   # e2e: every rank ran the host-API iteration on its own GPU; the job's rate is set by the slowest rank
-        t_e2e = torch.tensor([e2e_dt], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-        e2e_dt = float(t_e2e.item())
-    launches = sum(c.get_timers()[1] for c in gctx)
 
-    # ---------------- roofline of the dominant kernel (separate pass, per-stage CUDA-event timers on) ----------------
-    for c in gctx:
-        c.enable_timers(True)
-        c.reset_timers()
-    nroof = 3
-    nchol, chol_flops = 0, 0.0
-    for _ in range(nroof):
-        for b in range(2):
-            st = half_step(b)
-            nchol += st["n_chol"]
-            chol_flops += st["chol_flops"]
-    tm = {k: 0.0 for k in capi.T_NAMES}
-    for c in gctx:
-        t, _ = c.get_timers()
-        for k in tm:
-            tm[k] += t[k] / nroof
-        c.enable_timers(False)
+    # ---------------- roofline of the dominant kernel ----------------
     rows_local = N // nshard
-    # dominant component of the step (ncu launch list: chol_diag + chol_panel + ata<Small> + chol_backsolve > 90 % of the
-    # device time): the passive-set Cholesky solves of the NNLS.  Algorithmic flops = sum |P|^3 / 3.
-    chol_ach = chol_flops / nroof / (tm["chol"] * 1e-3) / 1e12
-    syrk_flops = float(rows_local) * N * N                 # n_obs . n_kernels^2, one SYRK launch per half-step
-    syrk_ach = 2.0 * syrk_flops / (tm["syrk"] * 1e-3) / 1e12
     P64 = peaks["fp64_dgemm_tflops"]
-    roofline = {"bound": "tensor",
-                "kernel": "chol_fused_kernel: single-launch Cholesky solve (dposv) of the NNLS passive-set systems, one persistent cooperative "
-                          "launch per solve (spine CTA + 147 tile workers, DMMA.8x8x4 updates)",
-                "achieved": chol_ach, "peak": P64, "unit": "TFLOP/s", "frac": chol_ach / P64,
-                # one `ncu --set full` capture of this kernel at n = 2048 (profiles/r01f_ncu_full_chol_fused.txt): dram read + write per launch;
-                # the algorithmic traffic is the upper triangle once (16.8 MB), the factor is written back to L2 only
-                "traffic": 17544192 + 4864,
-                "flops_per_launch": chol_flops / max(nchol, 1), "launches_per_step": nchol / nroof, "ms_per_step": tm["chol"],
-                "ms_per_launch": tm["chol"] / max(nchol / nroof, 1),
-                "note": "latency-bound by construction: n sequential pivots (rsqrt -> mul -> fma, ~110 cycles each) and 3 dependent tile steps per "
-                        "64-column phase, 16 - 17 us per phase measured (tools/chol_trace.py); sm__throughput 11 % in the ncu capture.  The throughput kernels "
-                        "of the step are listed under `others` with their own fractions.",
+    nchol = max(agg["n_chol"], 1e-9)
+    chol_ach = agg["chol_flops"] / (tm["chol"] * 1e-3) / 1e12 if tm["chol"] > 0 else 0.0
+    syrk_flops = float(rows_local) * N * N                 # n_obs . n_kernels^2 per half-step on this rank, 2 flops each
+    syrk_ach = 2.0 * syrk_flops / (tm["syrk"] * 1e-3) / 1e12
+    lr_ach = agg["lowrank_flops"] / (tm["lowrank"] * 1e-3) / 1e12 if tm["lowrank"] > 0 else 0.0
+    eval_pairs = pairs_step / nshard
+    eval_ach = eval_pairs * (d * d + 2.0 * d + 1.0) / ((tm["eval"] + tm["IM"]) * 1e-3) / 1e12
+    kernels = {
+        "chol": {"kernel": ("chol_fused_kernel: single-launch Cholesky solve (dposv) of the first passive-set system of each NNLS, one persistent cooperative "
+                            "launch (spine CTA + 147 tile workers, DMMA.8x8x4 updates)") if N <= 4096 else
+                           "chol_diag / chol_panel / ata_kernel<AtaBig> / chol_backsolve: blocked right-looking Cholesky solve with look-ahead (chol.cu)",
+                 "achieved": chol_ach, "frac": chol_ach / P64, "ms_per_step": tm["chol"], "launches_per_step": agg["n_chol"],
+                 "flops_per_launch": agg["chol_flops"] / nchol, "ms_per_launch": tm["chol"] / nchol,
+                 # one `ncu --set full` capture at n = 2048 (profiles/r01f_ncu_full_chol_fused.txt): dram read + write per launch
+                 "traffic": 17544192 + 4864 if N <= 4096 else None},
+        "lowrank": {"kernel": "trinv_step1/2 + gemm_tn_splitk + syrk_splitk (DMMA.8x8x4 GEMMs) + lr_small_kernel (k x k L J L^T in shared memory) + row products: "
+                              "passive-set systems after the first solved by low-rank modification of its factor (lowrank.cu)",
+                    "achieved": lr_ach, "frac": lr_ach / P64, "ms_per_step": tm["lowrank"], "solves_per_step": agg["n_lowrank"],
+                    "trinv_per_step": agg["n_trinv"], "fallbacks_per_step": agg["n_lowrank_fallback"], "max_k": agg["max_lowrank_k"],
+                    "flops_model": "|B|^3/3 per triangular inverse + 2 |B|^2 (k + 1) per solve"},
+        "syrk": {"kernel": "ata_kernel<AtaBig> (M = IM^T IM over this rank's %d rows, n = %d, DMMA.8x8x4)" % (rows_local, N), "achieved": syrk_ach,
+                 "frac": syrk_ach / P64, "ms_per_step": tm["syrk"], "ms_per_launch": tm["syrk"] / 2.0},
+        "vkde_eval+IM": {"kernel": "vkde_kernel<%d,0/1>" % d, "pairs_per_s": eval_pairs / ((tm["eval"] + tm["IM"]) * 1e-3), "achieved": eval_ach,
+                         "frac": eval_ach / P64, "ms_per_step": tm["eval"] + tm["IM"]},
+    }
+    dom = max(("chol", "lowrank", "syrk", "vkde_eval+IM"), key=lambda k: kernels[k]["ms_per_step"])
+    roofline = {"bound": "tensor", "kernel": kernels[dom]["kernel"], "achieved": kernels[dom]["achieved"], "peak": P64, "unit": "TFLOP/s",
+                "frac": kernels[dom]["frac"], "traffic": kernels[dom].get("traffic"),
+                "dominant": dom, "ms_per_step": kernels[dom]["ms_per_step"],
+                "note": "dominant stage of the timed step by CUDA-event stage time.  chol: latency-bound by construction (n sequential pivots, 16 - 17 us per "
+                        "64-column phase, tools/chol_trace.py), now ONE factorisation per NNLS instead of 6 (the other passive sets go through `lowrank`); "
+                        "lowrank: GEMM-shaped work at small sizes (|B| ~ 2000, k <= 200) plus one single-CTA k x k factorisation per solve.  "
+                        "Every stage is listed under `others` with its own fraction of the FP64 DGEMM peak.",
                 "peak_source": "FP64 is not in MEASURED_PEAKS.json (bf16 + HBM only); cuBLAS DGEMM 8192^3 measured on this pool, "
                                "profiles/r01_fp64_peaks.jsonl",
-                "others": {"syrk": {"kernel": "ata_kernel<AtaBig> (M = IM^T IM, n = k = %d, DMMA.8x8x4)" % N, "achieved": syrk_ach, "frac": syrk_ach / P64,
-                                    "ms_per_launch": tm["syrk"] / 2.0},
-                           "vkde_eval+IM": {"kernel": "vkde_kernel<10,0/1>", "pairs_per_s": pairs_step / nshard / ((tm["eval"] + tm["IM"]) * 1e-3),
-                                            "achieved": pairs_step / nshard * (d * d + 2.0 * d + 1.0) / ((tm["eval"] + tm["IM"]) * 1e-3) / 1e12,
-                                            "frac": pairs_step / nshard * (d * d + 2.0 * d + 1.0) / ((tm["eval"] + tm["IM"]) * 1e-3) / 1e12 / P64}},
+                "others": {k: v for k, v in kernels.items() if k != dom},
                 "step_share_ms": {k: round(v, 4) for k, v in tm.items()}}
 
     # ---------------- CPU baseline (rank 0, bounded sample) ----------------
@@ -406,22 +462,30 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"APES iteration, VKDE {args.kernel} kernel, {d}-D MVND, {W} walkers (6 N^2 pairs/step, N={N}); " +
-                                   ("one ensemble, IM rows and query rows sharded over ranks, centres replicated" if sharded else
+                                   (f"ONE ensemble over {world} GPUs: interpolation-matrix rows and query rows sharded, centres and factors replicated, "
+                                    "ncclAllReduce of the normal equations + ncclAllGather of the densities on the data path" if sharded else
                                     f"{replicas} independent ensemble(s), one per GPU, no data-path collective"),
                        "multi_gpu": args.apes_multi if world > 1 else "single",
-                       "l2_policy": "each half-step streams a fresh 33.5 MB IM + 2 x 33.5 MB normal matrices; the two half-steps alternate contexts, "
-                                    "so no timed kernel re-reads data left by its previous launch (working set per step > 126 MB L2)"},
+                       "l2_policy": "each half-step streams a fresh IM and two normal-matrix-sized buffers (3 x %.0f MB at N = %d); the two half-steps alternate "
+                                    "contexts, so no timed kernel re-reads data left by its previous launch (working set per step > 126 MB L2)" % (N * N * 8 / 1e6, N)},
             "walker_steps_per_s": replicas * W / (ms_per_step * 1e-3),
             "e2e": {"value": replicas * pairs_step / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": replicas * h2d_step, "d2h_bytes_per_step": replicas * d2h_step,
-                    "ms_per_step": e2e_dt * 1e3, "walker_steps_per_s": replicas * W / e2e_dt, "accept_rate": accept_rate,
-                    "stage_ms_per_step": {k: round(v, 3) for k, v in stage.items()}, "gpu_launches_per_step": e2e_launches / args.steps,
-                    "api": "ncm_b200_esmcmc_run -> ncm_stats_dist_prepare_interp / ncm_stats_dist_eval_m2lnp_array -> C ABI (one GPU per ensemble; "
-                           "with --apes-multi sharded every rank repeats the same host-API iteration, so e2e does not scale there)"},
+                    "ms_per_step": e2e_dt * 1e3, "walker_steps_per_s": replicas * W / e2e_dt, "accept_rate": accept_rate, "accept_hash": accept_hash,
+                    "stage_ms_per_step": {k: round(v, 3) for k, v in stage.items()}, "gpu_launches_per_step": e2e_launches,
+                    "api": "ncm_b200_esmcmc_run -> ncm_stats_dist_prepare_interp / ncm_stats_dist_eval_m2lnp_array -> C ABI" +
+                           (" in multi-rank (SPMD) mode: every rank runs the chain with the same generator seed, the density work behind the calls is "
+                            "sharded (ncm_stats_dist_b200_comm_init); h2d / d2h are this rank's bytes" if sharded else " (one GPU per ensemble)")},
             "gpu_launches": int(launches) * replicas,
-            "clocks": clk.summary(),
+            "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu,
         }
+        if sharded:
+            line["comm"] = {"ms_per_step": tm["comm"], "allreduce_M_bytes_per_half_step": N * ((N + 7) // 8 * 8) * 8,
+                            "what": "ncclAllReduce of M = IM^T IM (once per half-step), of b, A^T r and |r|^2 (per outer NNLS iteration), ncclAllGather of the 2N densities"}
+            line["single_gpu_same_workload"] = single
+            line["strong_scaling_speedup"] = {"value": value / single["value"], "e2e": (pairs_step / e2e_dt) / single["e2e_value"],
+                                              "accepted_sequence_identical_to_single_gpu": accept_hash == single["accept_hash"]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -730,7 +794,8 @@ def run_prepare_interp(args):
 
 # ---------------------------------------------------------------------------------------------------
 def run_apes_e2e(args):
-    """--workload apes_e2e: whole APES iterations through the host API on ONE GPU for the other BASELINE.json chains:
+    """--workload apes_e2e: whole APES iterations through the host API for the other BASELINE.json chains, on one GPU or, under torchrun, in
+    multi-rank (SPMD) mode with the density work sharded over the ranks (e.g. --target funnel --walkers 32768 --dim 30 --gpus 8):
     configs[3] (VKDE Student-t on the 30-D Neal funnel, 32768 walkers: --target funnel --walkers 32768 --dim 30 --kernel cauchy) and
     configs[0] (example_apes.py: 2-D Rosenbrock, 400 walkers, ST kernel: --target rosenbrock --walkers 400 --dim 2 --kernel st3)."""
     import torch
@@ -740,8 +805,18 @@ def run_apes_e2e(args):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; numcosmo_b200 has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
     lib = S.lib()
-    lib.ncm_b200_set_device(0)
+    lib.ncm_b200_set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // world))
+        lib.ncm_b200_set_num_threads(max(1, (os.cpu_count() or 1) // world))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     W, d = args.walkers, args.dim
     N = W // 2
     ktn, okind, nu = KT[args.kernel]
@@ -773,6 +848,8 @@ def run_apes_e2e(args):
     X = np.ascontiguousarray(X)
     apes = S.FitESMCMCWalkerAPES(W, d, S.FitESMCMCWalkerAPESMethod.VKDE, getattr(S.FitESMCMCWalkerAPESKType, ktn), os_, True)
     apes.set_use_threads(True)
+    if world > 1:
+        apes.comm_init_from_torch()
     theta, ml = X.copy(), np.ascontiguousarray(m2lnL)
     rng = S.RNG(4)
     warm = max(1, min(args.warmup, 2))
@@ -784,11 +861,17 @@ def run_apes_e2e(args):
         c.reset_timers()
     torch.cuda.synchronize()
     steps = max(1, args.steps)
-    with ClockSampler(0) as clk:
+    if world > 1:
+        dist.barrier()
+    with ClockSampler(local_rank) as clk:
         t0 = time.perf_counter()
         acc, _ = apes.run(target, lb, ub, theta, ml, steps, rng, target_args=targs, record_accept=True)
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / steps
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
     traffic = [c.get_traffic() for c in ctxs]
     launches = sum(c.get_timers()[1] for c in ctxs)
     apes.enable_timers(True)
@@ -797,16 +880,22 @@ def run_apes_e2e(args):
     nn = [sd.nnls_stats() for sd in sds]
     uses = [c.vkde_path() for c in ctxs]
     pairs_step = 6.0 * N * N
-    line = {"metric": METRIC, "value": pairs_step / dt, "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+    line = {"metric": METRIC, "value": pairs_step / dt, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"APES iteration end to end (host API, host buffers), VKDE {args.kernel} kernel, {d}-D {args.target}, {W} walkers, "
-                                   f"over_smooth {os_} (6 N^2 pairs/step, N={N})"},
+                                   f"over_smooth {os_} (6 N^2 pairs/step, N={N})" +
+                                   (f"; ONE ensemble over {world} GPUs in multi-rank mode (IM rows / query rows sharded, NCCL all-reduce + all-gather)" if world > 1 else ""),
+                       "multi_gpu": "sharded" if world > 1 else "single"},
+            "accept_hash": int(np.packbits(acc).astype(np.uint64).sum()),
             "walker_steps_per_s": W / dt, "accept_rate": float(np.mean(acc)),
             "e2e": {"value": pairs_step / dt, "unit": UNIT, "h2d_bytes_per_step": sum(t[0] for t in traffic) / steps,
                     "d2h_bytes_per_step": sum(t[1] for t in traffic) / steps, "stage_ms_per_step": {k: round(v, 3) for k, v in stage.items()}},
             "vkde_tensor_core_path": [bool(u[0]) for u in uses], "vkde_max_cond": [u[1] for u in uses], "nnls": nn,
             "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": None, "cpu_baseline": None}
-    print(json.dumps(line), flush=True)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -118,6 +118,8 @@ typedef struct ncm_sd_gpu_nnls_stats
   int n_trinv;       /* triangular inverses formed for those solves */
   int max_lowrank_k; /* largest |D| + |A| served that way */
   double lowrank_flops;   /* 2 |B|^2 (k + 1) per such solve + |B|^3 / 3 per triangular inverse */
+  int n_dist_chol;   /* factorisations whose trailing updates were distributed over the ranks (dist_chol.cu) */
+  int reserved_;
 } ncm_sd_gpu_nnls_stats;
 
 int ncm_sd_gpu_nnls_solve (ncm_sd_gpu_ctx *ctx, double reltol, double *x_out, double *rnorm_out, ncm_sd_gpu_nnls_stats *stats);
@@ -145,6 +147,16 @@ int ncm_sd_gpu_comm_unique_id (char id_out[128]);
 int ncm_sd_gpu_comm_init (ncm_sd_gpu_ctx *ctx, int nranks, int rank, const char id[128]);
 /* restrict compute_IM to observation rows [row0, row0 + nrows) on this rank */
 int ncm_sd_gpu_set_row_shard (ncm_sd_gpu_ctx *ctx, int row0, int nrows);
+/* Automatic sharding for SPMD callers (every rank makes the same calls with the same host arrays, as the ranks of a multi-rank
+ * APES run do): with on != 0 and a communicator, compute_IM (IM_host == NULL) takes the row block [n_obs rank / G, n_obs (rank + 1) / G)
+ * of this rank and the NNLS all-reduces the normal equations; eval / eval_m2lnp upload and evaluate this rank's block of the query
+ * rows and ncclAllGather the results on the device, so that every rank receives the complete output.  Centres and factors stay
+ * replicated.  Shards ncm_stats_dist.c:878-1094 (rows of the interpolation matrix) and the per-walker density calls of
+ * walker_apes.c:742-812. */
+int ncm_sd_gpu_set_auto_shard (ncm_sd_gpu_ctx *ctx, int on);
+/* ncclAllGather of `count` doubles per rank on the context stream (device pointers; drecv holds nranks * count): the exchange that
+ * follows a query-sharded ncm_sd_gpu_eval_m2lnp_dev */
+int ncm_sd_gpu_allgather_dev (ncm_sd_gpu_ctx *ctx, const double *dsend, double *drecv, int count);
 
 /* ---- instrumentation ------------------------------------------------------------------------- */
 enum
@@ -158,6 +170,7 @@ enum
   NCM_SD_GPU_T_D2H,
   NCM_SD_GPU_T_PREP,      /* VKDE prepare_kernel: kNN + local covariance + Cholesky */
   NCM_SD_GPU_T_LOWRANK,   /* passive-set solves by low-rank modification: triangular inverse, bordered solve, refinement */
+  NCM_SD_GPU_T_COMM,      /* NCCL collectives on the data path: all-reduce of the normal equations, all-gather of the densities */
   NCM_SD_GPU_T_LEN
 };
 /* device time (CUDA events on the ctx stream) accumulated per stage, milliseconds, and the

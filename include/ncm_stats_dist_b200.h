@@ -237,6 +237,12 @@ gboolean ncm_stats_dist_vkde_get_use_rot_href (NcmStatsDistVKDE *sdvkde);
 /* optimiser trace of the last prepare / prepare_interp under a cross-validation mode: the number of objective evaluations and,
  * for the first cap of them, (ln over_smooth, objective value or NNLS rnorm) in evaluation order */
 gint ncm_stats_dist_b200_get_cv_trace (NcmStatsDist *sd, gdouble *lnos, gdouble *val, gint cap);
+/* Multi-rank (SPMD) mode, one process per GPU: every rank builds the same object, feeds it the same observations and makes the same
+ * calls; after comm_init the rows of the interpolation matrix (ncm_stats_dist.c:878-1094) and the query rows of the batched evaluation
+ * are sharded over the ranks, the NNLS normal equations are all-reduced and the densities all-gathered with NCCL, and every rank
+ * receives the complete, identical results.  id comes from ncm_stats_dist_b200_comm_unique_id on one rank, distributed by the caller. */
+gint ncm_stats_dist_b200_comm_unique_id (gchar id_out[128]);
+gboolean ncm_stats_dist_b200_comm_init (NcmStatsDist *sd, gint nranks, gint rank, const gchar id[128]);
 void ncm_stats_dist_b200_get_nnls_stats (NcmStatsDist *sd, gint *n_chol, gint *n_retry, gint *n_outer, gint *n_passive);
 /* of the last NNLS: systems solved by low-rank modification of an earlier factor instead of a fresh dposv (csrc/lowrank.cu), how many of
  * those fell back to a fresh factorisation, triangular inverses formed, largest |D| + |A| */

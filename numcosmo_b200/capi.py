@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libncm_sd_gpu.so")
 
 KERNEL_GAUSS, KERNEL_ST = 0, 1
 KDE, VKDE = 0, 1
-T_NAMES = ("eval", "IM", "syrk", "chol", "nnls_misc", "h2d", "d2h", "prep", "lowrank")
+T_NAMES = ("eval", "IM", "syrk", "chol", "nnls_misc", "h2d", "d2h", "prep", "lowrank", "comm")
 
 OK, EINVAL, ENODEV, ECUDA, ENOTPD, ENCCL, ENOMEM = range(7)
 
@@ -26,7 +26,7 @@ SYMBOLS = (
     "ncm_sd_gpu_synchronize", "ncm_sd_gpu_set_kernel", "ncm_sd_gpu_upload_kde", "ncm_sd_gpu_upload_vkde", "ncm_sd_gpu_set_weights",
     "ncm_sd_gpu_set_href", "ncm_sd_gpu_get_weights", "ncm_sd_gpu_eval_m2lnp", "ncm_sd_gpu_eval", "ncm_sd_gpu_eval_m2lnp_dev",
     "ncm_sd_gpu_compute_IM", "ncm_sd_gpu_nnls_solve", "ncm_sd_gpu_nnls_solve_host", "ncm_sd_gpu_sample_apply", "ncm_sd_gpu_sample_philox",
-    "ncm_sd_gpu_comm_unique_id", "ncm_sd_gpu_comm_init", "ncm_sd_gpu_set_row_shard", "ncm_sd_gpu_get_timers", "ncm_sd_gpu_reset_timers",
+    "ncm_sd_gpu_comm_unique_id", "ncm_sd_gpu_comm_init", "ncm_sd_gpu_set_row_shard", "ncm_sd_gpu_set_auto_shard", "ncm_sd_gpu_allgather_dev", "ncm_sd_gpu_get_timers", "ncm_sd_gpu_reset_timers",
     "ncm_sd_gpu_enable_timers", "ncm_sd_gpu_get_traffic", "ncm_sd_gpu_dsyrk_ata_dev", "ncm_sd_gpu_dpotrf_upper_dev",
     "ncm_sd_gpu_vkde_prepare", "ncm_sd_gpu_vkde_finish", "ncm_sd_gpu_dposv_upper_dev", "ncm_sd_gpu_dtrtri_upper_dev", "ncm_sd_gpu_vkde_path", "ncm_sd_gpu_host_alloc", "ncm_sd_gpu_host_free",
 )
@@ -41,7 +41,7 @@ class GpuError(RuntimeError):
 class NNLSStats(C.Structure):
     _fields_ = [("n_chol", C.c_int), ("n_retry", C.c_int), ("n_outer", C.c_int), ("n_passive", C.c_int), ("chol_flops", C.c_double),
                 ("syrk_flops", C.c_double), ("n_lowrank", C.c_int), ("n_lowrank_fallback", C.c_int), ("n_trinv", C.c_int), ("max_lowrank_k", C.c_int),
-                ("lowrank_flops", C.c_double)]
+                ("lowrank_flops", C.c_double), ("n_dist_chol", C.c_int), ("reserved_", C.c_int)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -89,6 +89,8 @@ def load():
             "ncm_sd_gpu_comm_unique_id": (i, [C.c_char_p]),
             "ncm_sd_gpu_comm_init": (i, [vp, i, i, C.c_char_p]),
             "ncm_sd_gpu_set_row_shard": (i, [vp, i, i]),
+            "ncm_sd_gpu_set_auto_shard": (i, [vp, i]),
+            "ncm_sd_gpu_allgather_dev": (i, [vp, vp, vp, i]),
             "ncm_sd_gpu_get_timers": (i, [vp, _dp, C.POINTER(ll)]),
             "ncm_sd_gpu_reset_timers": (i, [vp]),
             "ncm_sd_gpu_enable_timers": (i, [vp, i]),
@@ -217,6 +219,12 @@ class Context:
 
     def eval_m2lnp_dev(self, q: int, dX_ptr: int, ldx: int, dOut_ptr: int):
         self._ck(load().ncm_sd_gpu_eval_m2lnp_dev(self._h, q, dX_ptr, ldx, dOut_ptr))
+
+    def set_auto_shard(self, on: bool = True):
+        self._ck(load().ncm_sd_gpu_set_auto_shard(self._h, int(on)))
+
+    def allgather_dev(self, dsend_ptr: int, drecv_ptr: int, count: int):
+        self._ck(load().ncm_sd_gpu_allgather_dev(self._h, dsend_ptr, drecv_ptr, count))
 
     def set_row_shard(self, row0: int, nrows: int):
         self._ck(load().ncm_sd_gpu_set_row_shard(self._h, row0, nrows))

@@ -133,7 +133,7 @@ int ncm_sd_gpu_ctx_new(ncm_sd_gpu_ctx **out, int device) {
   c->device = device;
   c->n_sm   = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&c->ev0) != cudaSuccess ||
-      cudaEventCreate(&c->ev1) != cudaSuccess) {
+      cudaEventCreate(&c->ev1) != cudaSuccess || cudaEventCreate(&c->ev2) != cudaSuccess || cudaEventCreate(&c->ev3) != cudaSuccess) {
     delete c;
     return NCM_SD_GPU_ECUDA;
   }
@@ -148,13 +148,15 @@ int ncm_sd_gpu_ctx_free(ncm_sd_gpu_ctx *c) {
   if (c->nccl_comm != nullptr && nccl_api().ok) nccl_api().CommDestroy((ncclComm_t) c->nccl_comm);
   DevBuf *bufs[] = {&c->sample, &c->vrec, &c->lnu, &c->cterm, &c->weights, &c->Ufull, &c->zc, &c->zmean, &c->bfrag, &c->kde_U, &c->qX,
                     &c->qOut, &c->qA, &c->part, &c->IM, &c->rowscale, &c->M, &c->MU, &c->nn_b, &c->nn_x, &c->nn_r, &c->nn_g, &c->nn_tmp,
-                    &c->nn_idx, &c->nn_f, &c->chol_flags, &c->chol_part, &c->vrec_mma, &c->dist, &c->lrW, &c->lrWt, &c->lrS, &c->lrV, &c->lrT, &c->lrPart, &c->lrSmall, &c->lrVec, &c->lrIdx};
+                    &c->nn_idx, &c->nn_f, &c->chol_flags, &c->chol_part, &c->vrec_mma, &c->dist, &c->lrW, &c->lrWt, &c->lrS, &c->lrV, &c->lrT, &c->lrPart, &c->lrSmall, &c->lrVec, &c->lrIdx, &c->gath, &c->dcPack, &c->dcW, &c->dcStage, &c->dcVec, &c->dcTiles};
   for (DevBuf *b : bufs) b->release();
   c->pinX.release();
   c->pinOut.release();
   c->pin_nn.release();
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
+  cudaEventDestroy(c->ev2);
+  cudaEventDestroy(c->ev3);
   if (c->ev_panel != nullptr) cudaEventDestroy(c->ev_panel);
   if (c->ev_tail != nullptr) cudaEventDestroy(c->ev_tail);
   if (c->stream_hi != nullptr) cudaStreamDestroy(c->stream_hi);
@@ -351,21 +353,41 @@ static int eval_host(ncm_sd_gpu_ctx *c, int q, const double *X, int ldx, double 
   if (q == 0) return NCM_SD_GPU_OK;
   cudaSetDevice(c->device);
   const int d = c->d;
-  if (!c->qX.reserve((size_t) q * d * sizeof(double)) || !c->qOut.reserve((size_t) q * sizeof(double)))
+  // auto-shard: this rank evaluates the query rows [q0, q1) and the blocks are all-gathered (padded to the largest block)
+  const bool shard = c->auto_shard && c->nranks > 1 && q >= c->nranks;
+  const int G = shard ? c->nranks : 1, g = shard ? c->rank : 0;
+  const int q0 = (int) (((long long) q * g) / G), q1 = (int) (((long long) q * (g + 1)) / G), ql = q1 - q0;
+  const int cap = (q + G - 1) / G;
+  if (!c->qX.reserve((size_t) (ql > 0 ? ql : 1) * d * sizeof(double)) || !c->qOut.reserve((size_t) (cap + 8) * sizeof(double)) ||
+      (shard && !c->gath.reserve((size_t) G * cap * sizeof(double))))
     return c->fail(NCM_SD_GPU_ENOMEM, "eval: out of device memory");
-  {
+  if (ql > 0) {
     StageTimer t(c, NCM_SD_GPU_T_H2D);
-    NCM_CUDA_OK(c, ncm_memcpy2d_async(c,c->qX.p, d * sizeof(double), X, ldx * sizeof(double), d * sizeof(double), q, cudaMemcpyHostToDevice, c->stream));
+    NCM_CUDA_OK(c, ncm_memcpy2d_async(c,c->qX.p, d * sizeof(double), X + (size_t) q0 * ldx, ldx * sizeof(double), d * sizeof(double), ql, cudaMemcpyHostToDevice, c->stream));
   }
-  {
+  if (ql > 0) {
     StageTimer t(c, NCM_SD_GPU_T_EVAL);
-    rc = c->type == NCM_SD_GPU_VKDE ? vkde_eval_launch(c, q, c->qX.as<double>(), d, c->qOut.as<double>(), as_density)
-                                    : kde_eval_launch(c, q, c->qX.as<double>(), d, c->qOut.as<double>(), as_density);
+    rc = c->type == NCM_SD_GPU_VKDE ? vkde_eval_launch(c, ql, c->qX.as<double>(), d, c->qOut.as<double>(), as_density)
+                                    : kde_eval_launch(c, ql, c->qX.as<double>(), d, c->qOut.as<double>(), as_density);
     if (rc != NCM_SD_GPU_OK) return rc;
+  }
+  if (shard) {
+    StageTimer t(c, NCM_SD_GPU_T_COMM);
+    NcclApi &api   = nccl_api();
+    ncclResult_t r = api.AllGather(c->qOut.p, c->gath.p, (size_t) cap, ncclDouble, (ncclComm_t) c->nccl_comm, c->stream);
+    if (r != ncclSuccess) return c->fail(NCM_SD_GPU_ENCCL, std::string("ncclAllGather: ") + api.GetErrorString(r));
   }
   {
     StageTimer t(c, NCM_SD_GPU_T_D2H);
-    NCM_CUDA_OK(c, ncm_memcpy_async(c,out, c->qOut.p, (size_t) q * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (shard) {
+      for (int r = 0; r < G; ++r) {
+        const int a = (int) (((long long) q * r) / G), b = (int) (((long long) q * (r + 1)) / G);
+        if (b > a)
+          NCM_CUDA_OK(c, ncm_memcpy_async(c, out + a, c->gath.as<double>() + (size_t) r * cap, (size_t) (b - a) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      }
+    } else {
+      NCM_CUDA_OK(c, ncm_memcpy_async(c,out, c->qOut.p, (size_t) q * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    }
     NCM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
   }
   return NCM_SD_GPU_OK;
@@ -383,10 +405,35 @@ int ncm_sd_gpu_set_row_shard(ncm_sd_gpu_ctx *c, int row0, int nrows) {
   return NCM_SD_GPU_OK;
 }
 
+int ncm_sd_gpu_set_auto_shard(ncm_sd_gpu_ctx *c, int on) {
+  if (c == nullptr) return NCM_SD_GPU_EINVAL;
+  if (on && c->nccl_comm == nullptr) return c->fail(NCM_SD_GPU_EINVAL, "set_auto_shard: ncm_sd_gpu_comm_init first");
+  c->auto_shard = on != 0;
+  c->im_sharded = false;
+  return NCM_SD_GPU_OK;
+}
+
+int ncm_sd_gpu_allgather_dev(ncm_sd_gpu_ctx *c, const double *dsend, double *drecv, int count) {
+  if (c == nullptr) return NCM_SD_GPU_EINVAL;
+  if (c->nccl_comm == nullptr || dsend == nullptr || drecv == nullptr || count < 0) return c->fail(NCM_SD_GPU_EINVAL, "allgather: communicator and buffers required");
+  cudaSetDevice(c->device);
+  StageTimer t(c, NCM_SD_GPU_T_COMM);
+  NcclApi &api   = nccl_api();
+  ncclResult_t r = api.AllGather(dsend, drecv, (size_t) count, ncclDouble, (ncclComm_t) c->nccl_comm, c->stream);
+  if (r != ncclSuccess) return c->fail(NCM_SD_GPU_ENCCL, std::string("ncclAllGather: ") + api.GetErrorString(r));
+  return NCM_SD_GPU_OK;
+}
+
 int ncm_sd_gpu_compute_IM(ncm_sd_gpu_ctx *c, const double *row_scale, double *IM_host) {
   int rc = check_ready(c, false);
   if (rc != NCM_SD_GPU_OK) return rc;
   cudaSetDevice(c->device);
+  if (c->auto_shard && c->nranks > 1) {
+    // whoever wants the matrix on the host (cross-validation modes) gets all rows on every rank; otherwise this rank's row block
+    c->im_sharded = IM_host == nullptr;
+    c->row0       = c->im_sharded ? (int) (((long long) c->n_obs * c->rank) / c->nranks) : 0;
+    c->nrows      = c->im_sharded ? (int) (((long long) c->n_obs * (c->rank + 1)) / c->nranks) - c->row0 : c->n_obs;
+  }
   const int ldim = (c->n_kernels + 7) & ~7;
   if (!c->IM.reserve((size_t) (c->nrows > 0 ? c->nrows : 1) * ldim * sizeof(double)) || !c->rowscale.reserve((size_t) (c->n_obs + 8) * sizeof(double)))
     return c->fail(NCM_SD_GPU_ENOMEM, "compute_IM: out of device memory");
@@ -584,6 +631,9 @@ int ncm_sd_gpu_dposv_upper_dev(ncm_sd_gpu_ctx *c, int n, double *dM, int ldm, do
   if (dRhs == nullptr) return c->fail(NCM_SD_GPU_EINVAL, "dposv: rhs required");
   cudaSetDevice(c->device);
   if (!c->nn_b.reserve((size_t) (n + 64) * sizeof(double)) || !c->nn_idx.reserve(64)) return c->fail(NCM_SD_GPU_ENOMEM, "dposv: out of device memory");
+  // with a communicator and n >= NCM_SD_GPU_DIST_CHOL_MIN_N (8192) every rank must make this call on identical data: the trailing
+  // updates are then distributed over the ranks (dist_chol.cu)
+  if (c->nccl_comm != nullptr && c->nranks > 1 && n >= dist_chol_min_n()) return dpotrf_upper_solve_dist(c, n, dM, ldm, dRhs, info_host);
   return dpotrf_upper_solve_any(c, n, dM, ldm, dRhs, c->nn_b.as<double>(), c->nn_idx.as<int>(), info_host);
 }
 

@@ -85,13 +85,17 @@ struct ncm_sd_gpu_ctx {
   // NCCL
   void *nccl_comm = nullptr;
   int nranks = 1, rank = 0;
+  bool auto_shard = false;   // ncm_sd_gpu_set_auto_shard: compute_IM takes this rank's row block, eval its query block + all-gather
+  bool im_sharded = false;   // the resident IM holds this rank's row block only
+  DevBuf gath;               // all-gather staging [nranks x cap]
+  DevBuf dcPack, dcW, dcStage, dcVec, dcTiles;   // distributed Cholesky (dist_chol.cu): broadcast block, kept inverses, panel staging, tile lists
 
   // timers
   bool timers_on = false;
   double t_ms[NCM_SD_GPU_T_LEN] = {0};
   long long n_launches = 0;
   long long h2d_bytes = 0, d2h_bytes = 0;   // bytes moved over PCIe by this context (ncm_sd_gpu_get_traffic)
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
   // look-ahead Cholesky (chol.cu): a highest-priority stream for the latency-bound panel kernels, run concurrently with the
   // trailing updates on `stream`; created on first use
   cudaStream_t stream_hi = nullptr;
@@ -124,18 +128,24 @@ inline cudaError_t ncm_memcpy2d_async(ncm_sd_gpu_ctx *c, void *dst, size_t dpitc
   return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, kind, s);
 }
 
+// The collectives are timed with their own event pair so that a COMM timer may sit inside another stage's scope (the time is then
+// counted in both; the all-reduce of the normal matrix, the only large one, is kept outside the SYRK scope in nnls.cu).
 struct StageTimer {
   ncm_sd_gpu_ctx *c;
   int stage;
+  cudaEvent_t e0, e1;
   StageTimer(ncm_sd_gpu_ctx *ctx, int st) : c(ctx), stage(st) {
-    if (c->timers_on) cudaEventRecord(c->ev0, c->stream);
+    const bool comm = st == NCM_SD_GPU_T_COMM;
+    e0 = comm ? c->ev2 : c->ev0;
+    e1 = comm ? c->ev3 : c->ev1;
+    if (c->timers_on) cudaEventRecord(e0, c->stream);
   }
   ~StageTimer() {
     if (c->timers_on) {
-      cudaEventRecord(c->ev1, c->stream);
-      cudaEventSynchronize(c->ev1);
+      cudaEventRecord(e1, c->stream);
+      cudaEventSynchronize(e1);
       float ms = 0.f;
-      cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+      cudaEventElapsedTime(&ms, e0, e1);
       c->t_ms[stage] += ms;
     }
   }
@@ -199,6 +209,8 @@ struct LowrankBufs {
   double *z, *z2, *y, *xB, *dxB, *xfull, *rfull, *rB, *tr, *out;
   int *idxB, *idxA, *posD, *bsel, *psrc, *info;
 };
+int dist_chol_min_n();
+int dpotrf_upper_solve_dist(ncm_sd_gpu_ctx *c, int n, double *dM, int ldm, double *dRhs, int *info_host);
 int lowrank_kmax();
 size_t lowrank_part_doubles(int n, int ldv);
 int symmetrize_upper(ncm_sd_gpu_ctx *c, int n, double *dM, int ld);

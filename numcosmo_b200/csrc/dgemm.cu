@@ -48,12 +48,18 @@ __device__ __forceinline__ void tile_from_linear(int t, int nt, int &ti, int &tj
 // cp.async prologue), the A fragments are negated, and the epilogue is stores only.
 template <typename Cfg, bool SUBC>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB)
-ata_kernel(const double *__restrict__ P, int ldp, int K, int n, double *__restrict__ C, int ldc, double alpha, double beta, int nt) {
+ata_kernel(const double *__restrict__ P, int ldp, int K, int n, double *__restrict__ C, int ldc, double alpha, double beta, int nt,
+           const int2 *__restrict__ tiles) {
   using D = AtaDerived<Cfg>;
   constexpr int TB = Cfg::TB, PITCH = D::PITCH, SLAB = D::SLAB, MI = Cfg::MI, NI = Cfg::NI, STAGES = Cfg::STAGES;
   extern __shared__ __align__(16) double smem[];
   int ti, tj;
-  tile_from_linear(blockIdx.x, nt, ti, tj);
+  if (tiles != nullptr) {   // explicit tile list: the column blocks one rank owns in the distributed factorisation (dist_chol.cu)
+    ti = tiles[blockIdx.x].x;
+    tj = tiles[blockIdx.x].y;
+  } else {
+    tile_from_linear(blockIdx.x, nt, ti, tj);
+  }
   const int i0 = ti * TB, j0 = tj * TB;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -193,7 +199,24 @@ cudaError_t ata_launch(cudaStream_t st, const double *dP, int ldp, int K, int n,
   // tiles are enumerated row by row over the upper triangle: the first nt of them are tile row 0, the next nt - 1 tile row 1, ...
   const int hr    = head_tile_rows > nt ? nt : head_tile_rows;
   const int tiles = hr > 0 ? (hr * (2 * nt - hr + 1)) / 2 : nt * (nt + 1) / 2;
-  ata_kernel<Cfg, SUBC><<<tiles, Cfg::THREADS, D::SMEM, st>>>(dP, ldp, K, n, dC, ldc, alpha, beta, nt);
+  ata_kernel<Cfg, SUBC><<<tiles, Cfg::THREADS, D::SMEM, st>>>(dP, ldp, K, n, dC, ldc, alpha, beta, nt, nullptr);
+  return cudaGetLastError();
+}
+
+// C[tile] -= P^T P for an explicit list of 128 x 128 tiles (ti <= tj, tile units)
+cudaError_t ata_launch_tiles(cudaStream_t st, const double *dP, int ldp, int K, int n, double *dC, int ldc, const int2 *dTiles, int ntiles) {
+  using D = AtaDerived<AtaBig>;
+  static bool attr_set[NCM_MAX_DEVICES] = {};
+  int dev__ = 0;
+  cudaGetDevice(&dev__);
+  dev__ = dev__ < 0 || dev__ >= NCM_MAX_DEVICES ? 0 : dev__;
+  if (!attr_set[dev__]) {
+    cudaError_t e = cudaFuncSetAttribute(ata_kernel<AtaBig, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) D::SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set[dev__] = true;
+  }
+  const int nt = (n + AtaBig::TB - 1) / AtaBig::TB;
+  ata_kernel<AtaBig, true><<<ntiles, AtaBig::THREADS, D::SMEM, st>>>(dP, ldp, K, n, dC, ldc, -1.0, 1.0, nt, dTiles);
   return cudaGetLastError();
 }
 
@@ -260,6 +283,16 @@ int dsyrk_ata_general_on(ncm_sd_gpu_ctx *c, cudaStream_t st, int K, int n, const
 
 int dsyrk_ata_general(ncm_sd_gpu_ctx *c, int K, int n, const double *dP, int ldp, double *dC, int ldc, double alpha, double beta) {
   return dsyrk_ata_general_on(c, c->stream, K, n, dP, ldp, dC, ldc, alpha, beta);
+}
+
+// C -= P^T P on the listed upper 128-tiles only (P: K x n row-major, C: n x n)
+int dsyrk_ata_tiles(ncm_sd_gpu_ctx *c, int K, int n, const double *dP, int ldp, double *dC, int ldc, const int *dTiles /* pairs (ti, tj) */, int ntiles) {
+  if (ntiles <= 0 || K <= 0) return NCM_SD_GPU_OK;
+  if ((ldp & 1) || (ldc & 1) || (((uintptr_t) dP) & 15) || (((uintptr_t) dC) & 15))
+    return c->fail(NCM_SD_GPU_EINVAL, "ata: operands must be 16-byte aligned with even leading dimensions");
+  NCM_CUDA_OK(c, ata_launch_tiles(c->stream, dP, ldp, K, n, dC, ldc, reinterpret_cast<const int2 *>(dTiles), ntiles));
+  c->n_launches++;
+  return NCM_SD_GPU_OK;
 }
 
 int dsyrk_ata_general_on(ncm_sd_gpu_ctx *c, cudaStream_t st, int K, int n, const double *dP, int ldp, double *dC, int ldc, double alpha, double beta) {

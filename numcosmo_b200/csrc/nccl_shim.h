@@ -9,6 +9,8 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId *)                                                                    = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int)                                             = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t)              = nullptr;
+  ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t)           = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t)                                                                        = nullptr;
   const char *(*GetErrorString)(ncclResult_t)                                                                    = nullptr;
 };

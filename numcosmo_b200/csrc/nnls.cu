@@ -46,16 +46,20 @@ NcclApi &nccl_api() {
       api.GetUniqueId    = (decltype(api.GetUniqueId)) dlsym(h, "ncclGetUniqueId");
       api.CommInitRank   = (decltype(api.CommInitRank)) dlsym(h, "ncclCommInitRank");
       api.AllReduce      = (decltype(api.AllReduce)) dlsym(h, "ncclAllReduce");
+      api.AllGather      = (decltype(api.AllGather)) dlsym(h, "ncclAllGather");
+      api.Broadcast      = (decltype(api.Broadcast)) dlsym(h, "ncclBroadcast");
       api.CommDestroy    = (decltype(api.CommDestroy)) dlsym(h, "ncclCommDestroy");
       api.GetErrorString = (decltype(api.GetErrorString)) dlsym(h, "ncclGetErrorString");
-      api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.CommDestroy && api.GetErrorString;
+      api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.AllGather && api.Broadcast && api.CommDestroy && api.GetErrorString;
     }
   }
   return api;
 }
 
 static int allreduce_sum(ncm_sd_gpu_ctx *c, double *dbuf, size_t count) {
-  if (c->nranks <= 1) return NCM_SD_GPU_OK;
+  // auto-shard mode with an unsharded IM (someone asked for the whole matrix on the host): every rank holds all rows, nothing to sum
+  if (c->nranks <= 1 || (c->auto_shard && !c->im_sharded)) return NCM_SD_GPU_OK;
+  StageTimer t(c, NCM_SD_GPU_T_COMM);
   NcclApi &api   = nccl_api();
   ncclResult_t r = api.AllReduce(dbuf, dbuf, count, ncclDouble, ncclSum, (ncclComm_t) c->nccl_comm, c->stream);
   if (r != ncclSuccess) return c->fail(NCM_SD_GPU_ENCCL, std::string("ncclAllReduce: ") + api.GetErrorString(r));
@@ -293,8 +297,11 @@ int solve_unconstrained(NnlsWork &w, const std::vector<int> &P) {
     int info = 0;
     {
       StageTimer t(c, NCM_SD_GPU_T_CHOL);
-      int rc = dpotrf_upper_solve_any(c, np, w.dMU, w.ldm, w.drhs, w.ddinv, w.dinfo, &info);
+      // all ranks hold the same all-reduced matrix and take the same decisions: large systems are factorised together (dist_chol.cu)
+      const bool dist = c->nccl_comm != nullptr && c->nranks > 1 && np >= dist_chol_min_n();
+      int rc = dist ? dpotrf_upper_solve_dist(c, np, w.dMU, w.ldm, w.drhs, &info) : dpotrf_upper_solve_any(c, np, w.dMU, w.ldm, w.drhs, w.ddinv, w.dinfo, &info);
       if (rc != NCM_SD_GPU_OK) return rc;
+      if (dist && w.st) w.st->n_dist_chol++;
     }
     if (w.st) {
       w.st->n_chol++;
@@ -471,12 +478,13 @@ int nnls_solve_dev(ncm_sd_gpu_ctx *c, int nrows, int ncols, const double *dA, in
     rc = dsyrk_ata_general(c, nrows, n, dA, lda, w.dM, ldm, 1.0, 0.0);
     if (rc != NCM_SD_GPU_OK) return rc;
     if (stats) stats->syrk_flops = (double) nrows * n * n;
-    rc = allreduce_sum(c, w.dM, (size_t) n * ldm);
+  }
+  rc = allreduce_sum(c, w.dM, (size_t) n * ldm);   // timed as NCM_SD_GPU_T_COMM
+  if (rc != NCM_SD_GPU_OK) return rc;
+  if (w.lr_on) {   // the low-rank solves read rows of M[:, A] and take symmetric products: fill the lower triangle once
+    StageTimer t(c, NCM_SD_GPU_T_NNLS_MISC);
+    rc = symmetrize_upper(c, n, w.dM, ldm);
     if (rc != NCM_SD_GPU_OK) return rc;
-    if (w.lr_on) {   // the low-rank solves read rows of M[:, A] and take symmetric products: fill the lower triangle once
-      rc = symmetrize_upper(c, n, w.dM, ldm);
-      if (rc != NCM_SD_GPU_OK) return rc;
-    }
   }
   {
     StageTimer t(c, NCM_SD_GPU_T_NNLS_MISC);

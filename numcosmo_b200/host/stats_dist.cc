@@ -974,6 +974,17 @@ void ncm_stats_dist_b200_get_timers(NcmStatsDist *sd, gdouble *ms7, long long *n
 void ncm_stats_dist_b200_enable_timers(NcmStatsDist *sd, gboolean on) {
   if (ensure_gpu(sd)) ncm_sd_gpu_enable_timers(sd->gpu, on);
 }
+// Multi-rank (SPMD) mode: every rank of the job makes the same calls on the same host data; behind them the interpolation-matrix rows and
+// the query rows of this object are sharded over the ranks and exchanged with NCCL (ncm_sd_gpu_set_auto_shard).
+gint ncm_stats_dist_b200_comm_unique_id(gchar id_out[128]) { return ncm_sd_gpu_comm_unique_id(id_out); }
+
+gboolean ncm_stats_dist_b200_comm_init(NcmStatsDist *sd, gint nranks, gint rank, const gchar id[128]) {
+  if (!ensure_gpu(sd)) return FALSE;
+  std::lock_guard<std::mutex> lk(g_gpu_mutex);
+  if (!gpu_ok(sd, ncm_sd_gpu_comm_init(sd->gpu, nranks, rank, id), "ncm_stats_dist_b200_comm_init")) return FALSE;
+  return gpu_ok(sd, ncm_sd_gpu_set_auto_shard(sd->gpu, 1), "ncm_stats_dist_b200_comm_init");
+}
+
 void *ncm_stats_dist_b200_peek_ctx(NcmStatsDist *sd) {
   ensure_gpu(sd);
   return sd->gpu;

@@ -164,6 +164,8 @@ def lib():
             "ncm_stats_dist_vkde_get_use_rot_href": (i, [_vp]),
             "ncm_stats_dist_b200_get_nnls_stats": (None, [_vp, C.POINTER(i), C.POINTER(i), C.POINTER(i), C.POINTER(i)]),
             "ncm_stats_dist_b200_get_nnls_lowrank_stats": (None, [_vp, C.POINTER(i), C.POINTER(i), C.POINTER(i), C.POINTER(i)]),
+            "ncm_stats_dist_b200_comm_unique_id": (i, [C.c_char_p]),
+            "ncm_stats_dist_b200_comm_init": (i, [_vp, i, i, C.c_char_p]),
             "ncm_stats_dist_b200_get_cv_trace": (i, [_vp, _dp, _dp, i]),
             "ncm_stats_dist_b200_get_timers": (None, [_vp, _dp, C.POINTER(C.c_longlong), _dp]),
             "ncm_stats_dist_b200_enable_timers": (None, [_vp, i]),
@@ -485,6 +487,21 @@ class StatsDist:
         lib().ncm_stats_dist_b200_enable_timers(self._h, int(on))
         _check()
 
+    def comm_init(self, nranks: int, rank: int, unique_id: bytes):
+        """Multi-rank (SPMD) mode: shard the IM rows / query rows of this object over the ranks (NCCL inside the C ABI)."""
+        assert len(unique_id) == 128
+        lib().ncm_stats_dist_b200_comm_init(self._h, nranks, rank, unique_id)
+        _check()
+
+    def comm_init_from_torch(self, group=None):
+        """comm_init with the NCCL id drawn on rank 0 and broadcast through torch.distributed (any backend)."""
+        import torch.distributed as dist
+
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        uid = [comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0, group=group)
+        self.comm_init(world, rank, uid[0])
+
     def get_timers(self):
         ms = np.zeros(len(capi.T_NAMES))
         n, h = C.c_longlong(), C.c_double()
@@ -537,6 +554,13 @@ class _BorrowedSD(StatsDist):
 TARGET_MVND, TARGET_ROSENBROCK, TARGET_FUNNEL = "mvnd", "rosenbrock", "funnel"
 
 
+def comm_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    if lib().ncm_stats_dist_b200_comm_unique_id(buf) != 0:
+        raise NcmError("ncclGetUniqueId failed (libnccl.so.2 not loadable?)")
+    return buf.raw
+
+
 class FitESMCMCWalkerAPES:
     """Ncm.FitESMCMCWalkerAPES + the accept loop of Ncm.FitESMCMC around it (numcosmo_py/sampling/apes.py)."""
 
@@ -582,6 +606,12 @@ class FitESMCMCWalkerAPES:
     def enable_timers(self, on=True):
         for sd in self.peek_sds():
             sd.enable_timers(on)
+
+    def comm_init_from_torch(self, group=None):
+        """Multi-rank (SPMD) APES: every rank runs the same chain with the same generator seed; the density work of the two NcmStatsDist
+        objects behind the walker is sharded over the ranks (one NCCL communicator each)."""
+        for sd in self.peek_sds():
+            sd.comm_init_from_torch(group)
 
     def peek_thetastar(self):
         return np.ctypeslib.as_array(lib().ncm_fit_esmcmc_walker_apes_peek_thetastar(self._h), shape=(self.nwalkers, self.nparams)).copy()
