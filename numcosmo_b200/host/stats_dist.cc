@@ -607,7 +607,15 @@ gboolean ncm_stats_dist_get_use_threads(NcmStatsDist *sd) { return sd->use_threa
 
 void ncm_stats_dist_kde_set_nearPD_maxiter(NcmStatsDistKDE *sd, const guint maxiter) { sd->nearPD_maxiter = maxiter; }
 guint ncm_stats_dist_kde_get_nearPD_maxiter(NcmStatsDistKDE *sd) { return sd->nearPD_maxiter; }
-void ncm_stats_dist_kde_set_cov_type(NcmStatsDistKDE *sd, NcmStatsDistKDECovType t) { sd->cov_type = t; }
+// ncm_stats_dist_kde.c:784-797: switching to FIXED with a matrix already set factors it here
+void ncm_stats_dist_kde_set_cov_type(NcmStatsDistKDE *sd, NcmStatsDistKDECovType t) {
+  sd->cov_type = t;
+  if (sd->cov_type == NCM_STATS_DIST_KDE_COV_TYPE_FIXED && sd->cov_fixed != nullptr) {
+    memcpy(sd->cov_decomp->data, sd->cov_fixed->data, sizeof(double) * sd->d * sd->d);
+    if (ncm_b200_cholesky_upper(sd->cov_decomp->data, (int) sd->d, (int) sd->d) != 0)
+      ncm_b200_error("ncm_stats_dist_kde_set_cov_fixed: matrix cov_fixed is not positive definite.");
+  }
+}
 NcmStatsDistKDECovType ncm_stats_dist_kde_get_cov_type(NcmStatsDistKDE *sd) { return sd->cov_type; }
 // ncm_stats_dist_kde.c:825-845
 void ncm_stats_dist_kde_set_cov_fixed(NcmStatsDistKDE *sd, NcmMatrix *cov_fixed) {
@@ -702,8 +710,9 @@ void ncm_b200_prepare_interp_finish(NcmStatsDist *sd, NcmVector *m2lnp) {
   }
   if (sd->max_m2lnp - sd->min_m2lnp > range_max) {
     // dynamic-range guard, ncm_stats_dist.c:906-982
-    std::vector<size_t> sort(sd->n_kernels);
-    for (guint i = 0; i < sd->n_kernels; i++) sort[i] = i;
+    // gsl_sort_index runs over the whole vector (n_obs entries, :912-915); the scan below reads the first n_kernels of them
+    std::vector<size_t> sort(sd->n_obs);
+    for (guint i = 0; i < sd->n_obs; i++) sort[i] = i;
     std::stable_sort(sort.begin(), sort.end(), [&](size_t a, size_t b) { return ncm_vector_get(m2lnp, (guint) a) < ncm_vector_get(m2lnp, (guint) b); });
     guint n_cut = 0;
     for (guint i = 0; i < sd->n_kernels; i++) {
@@ -714,9 +723,19 @@ void ncm_b200_prepare_interp_finish(NcmStatsDist *sd, NcmVector *m2lnp) {
     }
     if (n_cut < (guint) (0.5 * sd->n_obs)) {
       ncm_vector_set_all(sd->weights, 0.1 / (sd->n_kernels - n_cut));
-      for (guint i = 0; i < n_cut; i++) ncm_vector_set(sd->weights, (guint) sort[i], 0.9 / n_cut);
+      for (guint i = 0; i < n_cut; i++)
+        if (sort[i] < sd->n_kernels) ncm_vector_set(sd->weights, (guint) sort[i], 0.9 / n_cut);   // held-out observations (CV_SPLIT) carry no weight
       push_weights(sd);
       return;   // returns before the shrink normalisation, as the reference does (:934-946)
+    }
+    // the reference asserts j == n_cut after the copy (:965); with n_obs > n_kernels (CV_SPLIT) the two counts can differ: count first,
+    // fail as the reference does instead of writing past m2lnp_cut
+    guint n_in = 0;
+    for (guint i = 0; i < sd->n_obs; i++)
+      if (ncm_vector_get(m2lnp, i) - sd->min_m2lnp <= range_max) n_in++;
+    if (n_in != n_cut) {
+      ncm_b200_error("_ncm_stats_dist_prepare_interp: assertion failed (j == n_cut): (%u == %u)", n_in, n_cut);
+      return;
     }
     NcmVector *m2lnp_cut = ncm_vector_new(n_cut);
     std::vector<void *> keep;

@@ -1487,13 +1487,15 @@ orc_sd_prepare_interp (orc_sd *sd, const double *m2lnp, int n)
   {
     /* ncm_stats_dist.c:906-982.  gsl_sort_index is a heapsort (not stable); ties are
      * broken here by index, which only matters for exactly equal m2lnp values. */
-    size_t *sort = (size_t *) malloc (sizeof (size_t) * sd->n_kernels);
+    /* The reference sorts the whole vector, ncm_vector_len (m2lnp) = n_obs entries (:912-915; its index array is sized
+     * n_kernels, which under CV_SPLIT, n_obs > n_kernels, it overruns); the scan below reads the first n_kernels. */
+    size_t *sort = (size_t *) malloc (sizeof (size_t) * sd->n_obs);
     int n_cut    = 0;
 
-    for (i = 0; i < sd->n_kernels; i++)
+    for (i = 0; i < sd->n_obs; i++)
       sort[i] = i;
 
-    qsort_r (sort, sd->n_kernels, sizeof (size_t), idx_cmp_ctx, (void *) m2lnp);
+    qsort_r (sort, sd->n_obs, sizeof (size_t), idx_cmp_ctx, (void *) m2lnp);
 
     for (i = 0; i < sd->n_kernels; i++)
     {
@@ -1513,7 +1515,8 @@ orc_sd_prepare_interp (orc_sd *sd, const double *m2lnp, int n)
         sd->weights[i] = 0.1 / (sd->n_kernels - n_cut);
 
       for (i = 0; i < n_cut; i++)
-        sd->weights[sort[i]] = 0.9 / n_cut;
+        if ((int) sort[i] < sd->n_kernels)   /* held-out observations (CV_SPLIT) carry no weight */
+          sd->weights[sort[i]] = 0.9 / n_cut;
 
       free (sort);
 
@@ -1521,9 +1524,23 @@ orc_sd_prepare_interp (orc_sd *sd, const double *m2lnp, int n)
     }
 
     {
-      double *m2lnp_cut = (double *) malloc (sizeof (double) * n_cut);
-      double **cut      = (double **) malloc (sizeof (double *) * n_cut);
-      int j             = 0;
+      double *m2lnp_cut, **cut;
+      int j = 0;
+
+      for (i = 0; i < sd->n_obs; i++)
+        if (m2lnp[i] - sd->min_m2lnp <= range_max)
+          j++;
+
+      if (j != n_cut)   /* g_assert (j == n_cut), :965 */
+      {
+        free (sort);
+
+        return -5;
+      }
+
+      m2lnp_cut = (double *) malloc (sizeof (double) * n_cut);
+      cut       = (double **) malloc (sizeof (double *) * n_cut);
+      j         = 0;
 
       for (i = 0; i < sd->n_obs; i++)
       {

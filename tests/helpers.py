@@ -44,3 +44,53 @@ def upload_from_oracle(ctx, capi, O, sd, sd_type, kernel, nu, X, weights=None):
 def rel_err(a, b):
     a, b = np.asarray(a), np.asarray(b)
     return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))
+
+
+EPS = np.finfo(float).eps
+
+
+def support(w, n, shrink=0.01):
+    """Passive set of the NNLS solution behind normalised + shrunk weights: w_i = (1 - s) x_i / sum x + s / n > s / n  <=>  x_i > 0
+    (ncm_stats_dist.c:1087-1093)."""
+    return w > (shrink / n) * (1.0 + 1e-9)
+
+
+def weight_bound(IM, passive):
+    """Conditioning-limited bound on the relative (to the largest) error of NNLS weights obtained through the normal
+    equations: the forward error of a backward-stable solve of M[P,P] x = b[P] is ~ cond_2(M[P,P]) eps, for each of the two
+    implementations (CPU dposv and the device factorisation).  cond_2 = lambda_max / lambda_min by power / inverse iteration
+    on a Cholesky factor (an SVD of a 16384-column matrix would take longer than the test).  Returns (cond, bound): the
+    north-star bar (1e-10) wherever the conditioning allows it, never looser than 1e-6 of the largest weight."""
+    import scipy.linalg as sl
+
+    A = np.ascontiguousarray(IM[:, passive])
+    M = A.T @ A
+    try:
+        c = sl.cho_factor(M, lower=True, check_finite=False)
+    except np.linalg.LinAlgError:
+        return np.inf, 1e-6
+    rs = np.random.default_rng(0)
+    v = rs.standard_normal(M.shape[0])
+    u = v.copy()
+    lmax = lmin_inv = 1.0
+    for _ in range(30):
+        v = M @ (v / np.linalg.norm(v))
+        lmax = np.linalg.norm(v)
+        u = sl.cho_solve(c, u / np.linalg.norm(u), check_finite=False)
+        lmin_inv = np.linalg.norm(u)
+    cond_M = lmax * lmin_inv
+    return cond_M, max(1e-10, min(4.0 * cond_M * EPS, 1e-6))
+
+
+def assert_weights_parity(w, wo, st, so, IM, shrink=0.01, what=""):
+    """Unconditional parity of the interpolation weights: the two NNLS runs end on the SAME passive set, without
+    any fallback on either side, and the weights agree to the conditioning-limited bound of that set's normal matrix.  Returns the bound."""
+    n = len(wo)
+    assert st["n_retry"] == 0 and so["n_lu"] == 0 and so["n_qr"] == 0, f"{what}: fallback solves taken ({st} vs {so})"
+    pg, po = support(w, n, shrink), support(wo, n, shrink)
+    assert np.array_equal(pg, po), f"{what}: passive sets differ in {np.count_nonzero(pg != po)} of {n} indices ({st} vs {so})"
+    assert st["n_passive"] == so["n_passive"] == int(po.sum()), (what, st, so)
+    cond_M, bound = weight_bound(IM, po)
+    err = np.max(np.abs(w - wo)) / wo.max()
+    assert err <= bound, f"{what}: weights differ by {err:.2e} of the largest (bound {bound:.2e}, cond(M[P,P]) = {cond_M:.2e})"
+    return bound

@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import make_sd, rel_err
+from helpers import make_sd, rel_err, support, weight_bound
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "apes_path_v1.npz")
 
@@ -67,15 +67,26 @@ def test_gpu_matches_golden(gold):
         for x in gold[f"{name}/X"]:
             sd.add_obs(x)
         sd.prepare_interp(gold[f"{name}/m2lnL"])
-        # weights: conditioning-limited -> compare what they produce, and the weights themselves loosely
-        assert rel_err(sd.eval_m2lnp_array(gold[f"{name}/Q"]), gold[f"{name}/m2lnp"]) < 1e-6, name
+        # weights: same passive set as the golden run, weights to the conditioning-limited bound of M[P,P] (computed here from the
+        # row-scaled interpolation matrix of the GPU path), and the densities they produce to the same bound
+        from numcosmo_b200 import capi
+
         w, wg = sd.peek_weights(), gold[f"{name}/weights"]
-        assert np.max(np.abs(w - wg)) < 1e-5 * wg.max(), name
+        st = sd.nnls_stats()
+        assert st["n_retry"] == 0, (name, st)
+        assert np.array_equal(support(w, int(n)), support(wg, int(n))), f"{name}: passive set differs from the golden one"
+        cb = capi.Context.borrowed(S.lib().ncm_stats_dist_b200_peek_ctx(sd._h))
+        cb.n_kernels = cb.n_obs = int(n)
+        cb.d = d
+        m2 = gold[f"{name}/m2lnL"]
+        IMs = cb.compute_IM(np.exp(0.5 * (m2 - m2.min())), fetch=True, nrows=int(n))
+        cond_M, bound = weight_bound(IMs, support(wg, int(n)))
+        err = np.max(np.abs(w - wg)) / wg.max()
+        assert err <= bound, f"{name}: weights differ by {err:.2e} (bound {bound:.2e}, cond {cond_M:.2e})"
+        assert rel_err(sd.eval_m2lnp_array(gold[f"{name}/Q"]), gold[f"{name}/m2lnp"]) <= max(1e-10, bound), name
         # the evaluation proper at the north-star tolerance: same weights on both sides
         sd.prepare()
         ctx_w = gold[f"{name}/weights"]
-        from numcosmo_b200 import capi
-
         c = capi.Context.borrowed(S.lib().ncm_stats_dist_b200_peek_ctx(sd._h))
         c.n_kernels = c.n_obs = int(n)
         c.d = d

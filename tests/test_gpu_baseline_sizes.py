@@ -13,41 +13,9 @@ walker_apes.c:742-812, ncm_fit_esmcmc.c:2151-2232.
 import numpy as np
 import pytest
 
-from helpers import mvnd_problem, rel_err
+from helpers import EPS, mvnd_problem, rel_err, support, weight_bound
 
 pytestmark = pytest.mark.gpu
-
-EPS = np.finfo(float).eps
-
-
-def support(w, n, shrink=0.01):
-    """Passive set of the NNLS solution behind normalised + shrunk weights: w_i = (1 - s) x_i / sum x + s / n > s / n  <=>  x_i > 0."""
-    return w > (shrink / n) * (1.0 + 1e-9)
-
-
-def weight_bound(IM, passive):
-    """Conditioning-limited bound on the relative (to the largest) error of NNLS weights obtained through the normal
-    equations: the forward error of a backward-stable solve of M[P,P] x = b[P] is ~ cond_2(M[P,P]) eps, for each of the two
-    implementations (CPU dposv and the device factorisation).  cond_2 = lambda_max / lambda_min by power / inverse iteration
-    on a Cholesky factor (an SVD of a 16384-column matrix would take longer than the test)."""
-    import scipy.linalg as sl
-
-    A = np.ascontiguousarray(IM[:, passive])
-    M = A.T @ A
-    c = sl.cho_factor(M, lower=True, check_finite=False)
-    rs = np.random.default_rng(0)
-    v = rs.standard_normal(M.shape[0])
-    u = v.copy()
-    lmax = lmin_inv = 1.0
-    for _ in range(30):
-        v = M @ (v / np.linalg.norm(v))
-        lmax = np.linalg.norm(v)
-        u = sl.cho_solve(c, u / np.linalg.norm(u), check_finite=False)
-        lmin_inv = np.linalg.norm(u)
-    cond_M = lmax * lmin_inv
-    # the north-star bar (1e-10) wherever the conditioning allows it; never looser than 1e-6 of the largest weight
-    return cond_M, max(1e-10, min(4.0 * cond_M * EPS, 1e-6))
-
 
 def test_configs1_apes_w4096_identical_sequence(oracle):
     """configs[1] exactly as bench.py builds it."""

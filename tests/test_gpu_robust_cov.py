@@ -4,7 +4,7 @@ sampling -- is the same GPU path as for the sample covariance (ncm_stats_dist_kd
 import numpy as np
 import pytest
 
-from helpers import mvnd_problem, rel_err
+from helpers import assert_weights_parity, mvnd_problem, rel_err, support
 
 pytestmark = pytest.mark.gpu
 
@@ -48,9 +48,14 @@ def test_robust_cov_prepare_interp_eval(oracle, sd_s, k_s, nu, d, n, cov_type):
     w, wo = sd.peek_weights(), o.peek_weights()
     st, so = sd.nnls_stats(), o.nnls_stats()
     Q = np.vstack([X[1:40] + 0.002, mu + 2.0 * (X[41:80] - mu)])
-    if st["n_passive"] == so["n_passive"] and st["n_retry"] == 0:
+    # the factors differ at the 1e-10 level (OGK through Jacobi vs dsyevr), so the two NNLS problems are not bit-identical inputs:
+    # same passive set required, weights to the conditioning-limited bound plus the propagated factor difference
+    bound = assert_weights_parity(w, wo, st, so, o.peek_IM(), what=f"{sd_s}-{k_s} d={d} {cov_type}") if cov_type == "ROBUST_DIAG" else None
+    if bound is not None:
+        assert rel_err(sd.eval_m2lnp_array(Q), o.eval_m2lnp_batch(Q, 4)) <= max(1e-10, bound)
+    else:
+        assert st["n_retry"] == 0 and np.array_equal(support(w, n), support(wo, n)), (st, so)
         assert np.max(np.abs(w - wo)) / wo.max() < 1e-6
-        assert rel_err(sd.eval_m2lnp_array(Q), o.eval_m2lnp_batch(Q, 4)) < 1e-6
     # with the oracle's weights on both sides the densities agree to the kernel-evaluation bar
     o.set_weights(w)
     assert rel_err(sd.eval_m2lnp_array(Q), o.eval_m2lnp_batch(Q, 4)) < 1e-8
