@@ -189,6 +189,21 @@ def cpu_apes(args, W, d, iters, nthreads, warm=True):
     return dt, ap.timers()
 
 
+def apes_config(args, W, d, N, world):
+    """`config` and `scaling` of the APES workload: ONE definition for both arms, so the driver compares like with like."""
+    sharded = world > 1 and args.apes_multi == "sharded"
+    replicas = 1 if sharded or world == 1 else world
+    part = ("single GPU" if world == 1 else
+            f"ONE ensemble over {world} GPUs: interpolation-matrix rows and query rows sharded, centres and factors replicated, ncclAllReduce of the "
+            "normal equations + ncclAllGather of the densities on the data path" if sharded else
+            f"{replicas} independent ensembles, one per GPU, no data-path collective")
+    cfg = {"workload": f"APES iteration, VKDE {args.kernel} kernel, {d}-D MVND, {W} walkers (6 N^2 pairs/step, N={N})",
+           "multi_gpu": "single" if world == 1 else args.apes_multi, "partitioning": part,
+           "l2_policy": "each half-step streams a fresh IM and two normal-matrix-sized buffers (3 x %.0f MB at N = %d); the two half-steps alternate "
+                        "contexts, so no timed kernel re-reads data left by its previous launch (working set per step > 126 MB L2)" % (N * N * 8 / 1e6, N)}
+    return cfg, ("weak" if replicas > 1 else "strong" if world > 1 else "weak")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -203,11 +218,13 @@ def run_reference(args):
     iters = 1 if big else max(1, args.steps)
     dt, timers = cpu_apes(args, W, d, iters, ncores, warm=not big)
     val = pairs / dt
+    cfg, scaling = apes_config(args, W, d, N, args.gpus)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"APES iteration, VKDE {args.kernel} kernel, {d}-D MVND, {W} walkers (6 N^2 pairs/step, N={N})",
-                   "note": "CPU oracle port of the reference algorithm (the reference itself cannot be built here: no GLib/GSL/meson)"},
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": cfg,
+        "note": "CPU oracle port of the reference algorithm on the host cores (the reference itself cannot be built here: no GLib/GSL/meson); "
+                "one ensemble of the arm's size, whatever --gpus says",
         "walker_steps_per_s": W / dt,
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": ncores, "kind": "port",
                          "sample": f"{iters} full APES iteration(s) at W={W}, d={d}" + (" without warm-up (bounded sample: ~1 min of CPU per iteration)" if big else "") +
@@ -460,14 +477,8 @@ def run_b200(args):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"APES iteration, VKDE {args.kernel} kernel, {d}-D MVND, {W} walkers (6 N^2 pairs/step, N={N}); " +
-                                   (f"ONE ensemble over {world} GPUs: interpolation-matrix rows and query rows sharded, centres and factors replicated, "
-                                    "ncclAllReduce of the normal equations + ncclAllGather of the densities on the data path" if sharded else
-                                    f"{replicas} independent ensemble(s), one per GPU, no data-path collective"),
-                       "multi_gpu": args.apes_multi if world > 1 else "single",
-                       "l2_policy": "each half-step streams a fresh IM and two normal-matrix-sized buffers (3 x %.0f MB at N = %d); the two half-steps alternate "
-                                    "contexts, so no timed kernel re-reads data left by its previous launch (working set per step > 126 MB L2)" % (N * N * 8 / 1e6, N)},
+            "higher_is_better": True, "scaling": apes_config(args, W, d, N, world)[1], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": apes_config(args, W, d, N, world)[0],
             "walker_steps_per_s": replicas * W / (ms_per_step * 1e-3),
             "e2e": {"value": replicas * pairs_step / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": replicas * h2d_step, "d2h_bytes_per_step": replicas * d2h_step,
                     "ms_per_step": e2e_dt * 1e3, "walker_steps_per_s": replicas * W / e2e_dt, "accept_rate": accept_rate, "accept_hash": accept_hash,

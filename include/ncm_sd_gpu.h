@@ -108,7 +108,7 @@ int ncm_sd_gpu_compute_IM (ncm_sd_gpu_ctx *ctx, const double *row_scale, double 
 typedef struct ncm_sd_gpu_nnls_stats
 {
   int n_chol;    /* Cholesky factorisations */
-  int n_retry;   /* factorisations that needed the regularised retry */
+  int n_lu;      /* systems dposv found not positive definite, solved by the symmetric-indefinite L D L^T (dsysv, ncm_nnls.c:573-606) */
   int n_outer;   /* accepted outer iterations */
   int n_passive; /* final passive-set size */
   double chol_flops; /* sum over the factorisations of |P|^3 / 3 (algorithmic flops of the Cholesky solves) */
@@ -119,7 +119,7 @@ typedef struct ncm_sd_gpu_nnls_stats
   int max_lowrank_k; /* largest |D| + |A| served that way */
   double lowrank_flops;   /* 2 |B|^2 (k + 1) per such solve + |B|^3 / 3 per triangular inverse */
   int n_dist_chol;   /* factorisations whose trailing updates were distributed over the ranks (dist_chol.cu) */
-  int reserved_;
+  int n_qr;      /* ... whose L D L^T met an exactly singular pivot: least squares by Householder QR (dgels, ncm_nnls.c:608-638) */
 } ncm_sd_gpu_nnls_stats;
 
 int ncm_sd_gpu_nnls_solve (ncm_sd_gpu_ctx *ctx, double reltol, double *x_out, double *rnorm_out, ncm_sd_gpu_nnls_stats *stats);
@@ -200,6 +200,14 @@ int ncm_sd_gpu_dposv_upper_dev (ncm_sd_gpu_ctx *ctx, int n, double *dM, int ldm,
  * zeroed); dScratch is n x ld doubles.  Recursive doubling over DMMA GEMMs (csrc/lowrank.cu): the building block that lets
  * the NNLS solve the passive-set systems after the first (ncm_nnls.c:728-751) without a new dposv each. */
 int ncm_sd_gpu_dtrtri_upper_dev (ncm_sd_gpu_ctx *ctx, int n, const double *dU, int ld, double *dW, double *dScratch);
+/* dsysv 'U' as _ncm_nnls_solve_normal_LU calls it (ncm_nnls.c:573-606 over ncm_lapack.c:798): Bunch-Kaufman L D L^T of the symmetric
+ * (possibly indefinite) matrix in the upper triangle of the row-major dM, then the solve; dM is destroyed, dRhs [n] becomes x.
+ * info_host: 0, or the 1-based index of an exactly singular pivot (nothing solved then, as dsysv).  csrc/ldl_bk.cu */
+int ncm_sd_gpu_dsysv_upper_dev (ncm_sd_gpu_ctx *ctx, int n, double *dM, int ldm, double *dRhs, int *info_host);
+/* dgels 'N' on the columns dIdx [n] (ascending, device) of the row-major dA [m x lda] with right-hand side dF [m], as
+ * _ncm_nnls_solve_normal_QR does (ncm_nnls.c:608-638): Householder QR, dX [n] = least-squares solution.  info_host: 0 or the
+ * 1-based index of an exactly zero diagonal entry of R.  csrc/qr_ls.cu */
+int ncm_sd_gpu_dgels_cols_dev (ncm_sd_gpu_ctx *ctx, int m, int n, const double *dA, int lda, const int *dIdx, const double *dF, double *dX, int *info_host);
 
 #ifdef __cplusplus
 }

@@ -243,7 +243,9 @@ gint ncm_stats_dist_b200_get_cv_trace (NcmStatsDist *sd, gdouble *lnos, gdouble 
  * receives the complete, identical results.  id comes from ncm_stats_dist_b200_comm_unique_id on one rank, distributed by the caller. */
 gint ncm_stats_dist_b200_comm_unique_id (gchar id_out[128]);
 gboolean ncm_stats_dist_b200_comm_init (NcmStatsDist *sd, gint nranks, gint rank, const gchar id[128]);
-void ncm_stats_dist_b200_get_nnls_stats (NcmStatsDist *sd, gint *n_chol, gint *n_retry, gint *n_outer, gint *n_passive);
+void ncm_stats_dist_b200_get_nnls_stats (NcmStatsDist *sd, gint *n_chol, gint *n_lu, gint *n_outer, gint *n_passive);
+/* of the last NNLS: systems that took the reference's fallbacks, dsysv (ncm_nnls.c:573-606) and dgels (:608-638) */
+void ncm_stats_dist_b200_get_nnls_fallback_stats (NcmStatsDist *sd, gint *n_lu, gint *n_qr);
 /* of the last NNLS: systems solved by low-rank modification of an earlier factor instead of a fresh dposv (csrc/lowrank.cu), how many of
  * those fell back to a fresh factorisation, triangular inverses formed, largest |D| + |A| */
 void ncm_stats_dist_b200_get_nnls_lowrank_stats (NcmStatsDist *sd, gint *n_lowrank, gint *n_fallback, gint *n_trinv, gint *max_k);

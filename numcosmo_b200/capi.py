@@ -28,7 +28,7 @@ SYMBOLS = (
     "ncm_sd_gpu_compute_IM", "ncm_sd_gpu_nnls_solve", "ncm_sd_gpu_nnls_solve_host", "ncm_sd_gpu_sample_apply", "ncm_sd_gpu_sample_philox",
     "ncm_sd_gpu_comm_unique_id", "ncm_sd_gpu_comm_init", "ncm_sd_gpu_set_row_shard", "ncm_sd_gpu_set_auto_shard", "ncm_sd_gpu_allgather_dev", "ncm_sd_gpu_get_timers", "ncm_sd_gpu_reset_timers",
     "ncm_sd_gpu_enable_timers", "ncm_sd_gpu_get_traffic", "ncm_sd_gpu_dsyrk_ata_dev", "ncm_sd_gpu_dpotrf_upper_dev",
-    "ncm_sd_gpu_vkde_prepare", "ncm_sd_gpu_vkde_finish", "ncm_sd_gpu_dposv_upper_dev", "ncm_sd_gpu_dtrtri_upper_dev", "ncm_sd_gpu_vkde_path", "ncm_sd_gpu_host_alloc", "ncm_sd_gpu_host_free",
+    "ncm_sd_gpu_vkde_prepare", "ncm_sd_gpu_vkde_finish", "ncm_sd_gpu_dposv_upper_dev", "ncm_sd_gpu_dtrtri_upper_dev", "ncm_sd_gpu_dsysv_upper_dev", "ncm_sd_gpu_dgels_cols_dev", "ncm_sd_gpu_vkde_path", "ncm_sd_gpu_host_alloc", "ncm_sd_gpu_host_free",
 )
 
 
@@ -39,9 +39,9 @@ class GpuError(RuntimeError):
 
 
 class NNLSStats(C.Structure):
-    _fields_ = [("n_chol", C.c_int), ("n_retry", C.c_int), ("n_outer", C.c_int), ("n_passive", C.c_int), ("chol_flops", C.c_double),
+    _fields_ = [("n_chol", C.c_int), ("n_lu", C.c_int), ("n_outer", C.c_int), ("n_passive", C.c_int), ("chol_flops", C.c_double),
                 ("syrk_flops", C.c_double), ("n_lowrank", C.c_int), ("n_lowrank_fallback", C.c_int), ("n_trinv", C.c_int), ("max_lowrank_k", C.c_int),
-                ("lowrank_flops", C.c_double), ("n_dist_chol", C.c_int), ("reserved_", C.c_int)]
+                ("lowrank_flops", C.c_double), ("n_dist_chol", C.c_int), ("n_qr", C.c_int)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -100,6 +100,8 @@ def load():
             "ncm_sd_gpu_dposv_upper_dev": (i, [vp, i, vp, i, vp, _ip]),
             "ncm_sd_gpu_vkde_path": (i, [vp, _ip, _dp]),
             "ncm_sd_gpu_dtrtri_upper_dev": (i, [vp, i, vp, i, vp, vp]),
+            "ncm_sd_gpu_dsysv_upper_dev": (i, [vp, i, vp, i, vp, _ip]),
+            "ncm_sd_gpu_dgels_cols_dev": (i, [vp, i, i, vp, i, vp, vp, vp, _ip]),
         }
         for name, (res, args) in sig.items():
             f = getattr(L, name)
@@ -309,6 +311,16 @@ class Context:
     def dposv_upper_dev(self, n, dM_ptr, ldm, dRhs_ptr) -> int:
         info = C.c_int()
         self._ck(load().ncm_sd_gpu_dposv_upper_dev(self._h, n, dM_ptr, ldm, dRhs_ptr, C.byref(info)))
+        return info.value
+
+    def dsysv_upper_dev(self, n, dM_ptr, ldm, dRhs_ptr) -> int:
+        info = C.c_int()
+        self._ck(load().ncm_sd_gpu_dsysv_upper_dev(self._h, n, dM_ptr, ldm, dRhs_ptr, C.byref(info)))
+        return info.value
+
+    def dgels_cols_dev(self, m, n, dA_ptr, lda, dIdx_ptr, dF_ptr, dX_ptr) -> int:
+        info = C.c_int()
+        self._ck(load().ncm_sd_gpu_dgels_cols_dev(self._h, m, n, dA_ptr, lda, dIdx_ptr, dF_ptr, dX_ptr, C.byref(info)))
         return info.value
 
     def dtrtri_upper_dev(self, n, dU_ptr, ld, dW_ptr, dScratch_ptr):

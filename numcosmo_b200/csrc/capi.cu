@@ -148,7 +148,7 @@ int ncm_sd_gpu_ctx_free(ncm_sd_gpu_ctx *c) {
   if (c->nccl_comm != nullptr && nccl_api().ok) nccl_api().CommDestroy((ncclComm_t) c->nccl_comm);
   DevBuf *bufs[] = {&c->sample, &c->vrec, &c->lnu, &c->cterm, &c->weights, &c->Ufull, &c->zc, &c->zmean, &c->bfrag, &c->kde_U, &c->qX,
                     &c->qOut, &c->qA, &c->part, &c->IM, &c->rowscale, &c->M, &c->MU, &c->nn_b, &c->nn_x, &c->nn_r, &c->nn_g, &c->nn_tmp,
-                    &c->nn_idx, &c->nn_f, &c->chol_flags, &c->chol_part, &c->vrec_mma, &c->dist, &c->lrW, &c->lrWt, &c->lrS, &c->lrV, &c->lrT, &c->lrPart, &c->lrSmall, &c->lrVec, &c->lrIdx, &c->gath, &c->dcPack, &c->dcW, &c->dcStage, &c->dcVec, &c->dcTiles};
+                    &c->nn_idx, &c->nn_f, &c->chol_flags, &c->chol_part, &c->vrec_mma, &c->dist, &c->lrW, &c->lrWt, &c->lrS, &c->lrV, &c->lrT, &c->lrPart, &c->lrSmall, &c->lrVec, &c->lrIdx, &c->gath, &c->dcPack, &c->dcW, &c->dcStage, &c->dcVec, &c->dcTiles, &c->bkWork, &c->qrWork};
   for (DevBuf *b : bufs) b->release();
   c->pinX.release();
   c->pinOut.release();
@@ -635,6 +635,20 @@ int ncm_sd_gpu_dposv_upper_dev(ncm_sd_gpu_ctx *c, int n, double *dM, int ldm, do
   // updates are then distributed over the ranks (dist_chol.cu)
   if (c->nccl_comm != nullptr && c->nranks > 1 && n >= dist_chol_min_n()) return dpotrf_upper_solve_dist(c, n, dM, ldm, dRhs, info_host);
   return dpotrf_upper_solve_any(c, n, dM, ldm, dRhs, c->nn_b.as<double>(), c->nn_idx.as<int>(), info_host);
+}
+
+int ncm_sd_gpu_dsysv_upper_dev(ncm_sd_gpu_ctx *c, int n, double *dM, int ldm, double *dRhs, int *info_host) {
+  if (c == nullptr) return NCM_SD_GPU_EINVAL;
+  if (n <= 0 || dM == nullptr || dRhs == nullptr || ldm < n) return c->fail(NCM_SD_GPU_EINVAL, "dsysv: bad arguments");
+  cudaSetDevice(c->device);
+  return dsysv_upper_solve(c, n, dM, ldm, dRhs, info_host);
+}
+
+int ncm_sd_gpu_dgels_cols_dev(ncm_sd_gpu_ctx *c, int m, int n, const double *dA, int lda, const int *dIdx, const double *dF, double *dX, int *info_host) {
+  if (c == nullptr) return NCM_SD_GPU_EINVAL;
+  if (m <= 0 || n <= 0 || dA == nullptr || dIdx == nullptr || dF == nullptr || dX == nullptr) return c->fail(NCM_SD_GPU_EINVAL, "dgels: bad arguments");
+  cudaSetDevice(c->device);
+  return dgels_cols_solve(c, m, n, dA, lda, dIdx, dF, dX, info_host);
 }
 
 int ncm_sd_gpu_dtrtri_upper_dev(ncm_sd_gpu_ctx *c, int n, const double *dU, int ld, double *dW, double *dScratch) {

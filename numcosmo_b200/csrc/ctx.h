@@ -76,6 +76,7 @@ struct ncm_sd_gpu_ctx {
   DevBuf M, MU, nn_b, nn_x, nn_r, nn_g, nn_tmp, nn_idx, nn_f;
   DevBuf dist;   // VKDE prepare_kernel: squared distances centre x point [n_kernels x n_obs]
   DevBuf lrW, lrWt, lrS, lrV, lrT, lrPart, lrSmall, lrVec, lrIdx;   // low-rank passive-set solves (lowrank.cu): base inverse, scratch, bordered blocks
+  DevBuf bkWork, qrWork;   // fallback solvers of the NNLS (ldl_bk.cu: pivots, info, barrier; qr_ls.cu: gathered columns)
   DevBuf chol_flags, chol_part;   // single-launch Cholesky (chol_fused.cu): dependency flags, back-substitution contributions
   int chol_epoch = 0;
   long long *chol_trace = nullptr;   // device buffer [n_sm][cap][2] set by ncm_sd_gpu_chol_trace (debugging aid)
@@ -209,6 +210,8 @@ struct LowrankBufs {
   double *z, *z2, *y, *xB, *dxB, *xfull, *rfull, *rB, *tr, *out;
   int *idxB, *idxA, *posD, *bsel, *psrc, *info;
 };
+int dsysv_upper_solve(ncm_sd_gpu_ctx *c, int n, double *dS, int lds, double *dRhs, int *info_host);
+int dgels_cols_solve(ncm_sd_gpu_ctx *c, int m, int n, const double *dA, int lda, const int *dIdx, const double *dF, double *dX, int *info_host);
 int dist_chol_min_n();
 int dpotrf_upper_solve_dist(ncm_sd_gpu_ctx *c, int n, double *dM, int ldm, double *dRhs, int *info_host);
 int lowrank_kmax();

@@ -18,10 +18,9 @@
 // refinement step on the true residual).  A refinement correction above 1e-7 of the solution falls back to a fresh
 // factorisation.  NCM_SD_GPU_NNLS_REUSE=0 restores one dposv per system.
 //
-// Deviation (documented in DESIGN.md): when a passive-set matrix is not numerically positive
-// definite the reference falls back to LAPACK dsysv and then dgels (ncm_nnls.c:573-638); here the
-// factorisation is retried with a relative diagonal shift (1e-13, 1e-11, 1e-9) and counted in
-// stats->n_retry.  Such systems are conditioned far beyond the 1e-10 parity bar either way.
+// When dposv reports a non-positive pivot the reference's fallback chain is followed (ncm_nnls.c:573-638, 655-666): the system is
+// solved by the symmetric-indefinite L D L^T (ldl_bk.cu, dsysv) and, if that meets an exactly singular pivot, by Householder least
+// squares on the passive columns (qr_ls.cu, dgels); counted in stats->n_lu / n_qr.
 #include <algorithm>
 #include <cstring>
 #include <dlfcn.h>
@@ -108,19 +107,6 @@ __global__ void sum_parts_kernel(const double *__restrict__ part, int n, double 
   if (threadIdx.x == 0) out[0] = sh[0];
 }
 
-__global__ void diag_mean_kernel(const double *__restrict__ M, int ldm, int n, double *__restrict__ out) {
-  __shared__ double sh[256];
-  double s = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) s += M[(size_t) i * ldm + i];
-  sh[threadIdx.x] = s;
-  __syncthreads();
-  for (int off = 128; off > 0; off >>= 1) {
-    if (threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) out[0] = sh[0] / n;
-}
-
 // GSL sort/subsetind_source.c semantics (first-come wins on ties), as NcmISet uses them
 void sort_smallest_index(std::vector<int> &p, int k, const std::vector<double> &src, int n) {
   p.assign(k, 0);
@@ -174,7 +160,6 @@ struct NnlsWork {
   int *didx, *dinfo;
   double *h_buf;   // pinned: n doubles + 8
   int *h_idx;      // pinned: n ints
-  double diag_mean = 0.0;
   ncm_sd_gpu_nnls_stats *st;
   // low-rank reuse of the last factorisation (lowrank.cu)
   bool lr_on = false, base_valid = false, w_valid = false, base_trusted = false;
@@ -278,52 +263,81 @@ int solve_unconstrained(NnlsWork &w, const std::vector<int> &P) {
     if (done) return NCM_SD_GPU_OK;
   }
   w.base_valid = false;
-  static const double shifts[4] = {0.0, 1.0e-13, 1.0e-11, 1.0e-9};
-  for (int attempt = 0; attempt < 4; ++attempt) {
-    const double shift = shifts[attempt] * w.diag_mean;
-    {
-      StageTimer t(c, NCM_SD_GPU_T_NNLS_MISC);
-      if (np == w.n) {
-        dim3 grid((np + 255) / 256, np);
-        copy_upper_kernel<<<grid, 256, 0, c->stream>>>(w.dM, w.ldm, np, w.dMU, w.ldm, w.db, w.drhs, shift);
-      } else {
-        std::memcpy(w.h_idx, P.data(), sizeof(int) * np);
-        NCM_CUDA_OK(c, ncm_memcpy_async(c,w.didx, w.h_idx, sizeof(int) * np, cudaMemcpyHostToDevice, c->stream));
-        dim3 grid((np + 255) / 256, np);
-        gather_sym_kernel<<<grid, 256, 0, c->stream>>>(w.dM, w.ldm, w.didx, np, w.dMU, w.ldm, w.db, w.drhs, shift);
-      }
-      c->n_launches++;
+  auto gather = [&]() -> int {
+    StageTimer t(c, NCM_SD_GPU_T_NNLS_MISC);
+    if (np == w.n) {
+      dim3 grid((np + 255) / 256, np);
+      copy_upper_kernel<<<grid, 256, 0, c->stream>>>(w.dM, w.ldm, np, w.dMU, w.ldm, w.db, w.drhs, 0.0);
+    } else {
+      std::memcpy(w.h_idx, P.data(), sizeof(int) * np);
+      NCM_CUDA_OK(c, ncm_memcpy_async(c, w.didx, w.h_idx, sizeof(int) * np, cudaMemcpyHostToDevice, c->stream));
+      dim3 grid((np + 255) / 256, np);
+      gather_sym_kernel<<<grid, 256, 0, c->stream>>>(w.dM, w.ldm, w.didx, np, w.dMU, w.ldm, w.db, w.drhs, 0.0);
     }
-    int info = 0;
+    c->n_launches++;
+    return NCM_SD_GPU_OK;
+  };
+  int rc = gather();
+  if (rc != NCM_SD_GPU_OK) return rc;
+  int info = 0;
+  {
+    StageTimer t(c, NCM_SD_GPU_T_CHOL);
+    // all ranks hold the same all-reduced matrix and take the same decisions: large systems are factorised together (dist_chol.cu)
+    const bool dist = c->nccl_comm != nullptr && c->nranks > 1 && np >= dist_chol_min_n();
+    rc = dist ? dpotrf_upper_solve_dist(c, np, w.dMU, w.ldm, w.drhs, &info) : dpotrf_upper_solve_any(c, np, w.dMU, w.ldm, w.drhs, w.ddinv, w.dinfo, &info);
+    if (rc != NCM_SD_GPU_OK) return rc;
+    if (dist && w.st) w.st->n_dist_chol++;
+  }
+  if (w.st) {
+    w.st->n_chol++;
+    w.st->chol_flops += (double) np * np * np / 3.0;
+  }
+  if (nnls_trace()) fprintf(stderr, "gpu_nnls: chol |P| = %d info = %d\n", np, info);
+  if (info == 0) {
+    NCM_CUDA_OK(c, ncm_memcpy_async(c, w.h_buf, w.drhs, sizeof(double) * np, cudaMemcpyDeviceToHost, c->stream));
+    if (w.lr_on && np >= LR_MIN_N) {   // the factor left in dMU becomes the base of the following low-rank solves
+      std::memcpy(w.h_idx, P.data(), sizeof(int) * np);
+      NCM_CUDA_OK(c, ncm_memcpy_async(c, w.lb.idxB, w.h_idx, sizeof(int) * np, cudaMemcpyHostToDevice, c->stream));
+      w.baseP        = P;
+      w.base_valid   = true;
+      w.w_valid      = false;
+      w.base_trusted = false;
+    }
+    NCM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    return NCM_SD_GPU_OK;
+  }
+  // _ncm_nnls_solve_normal_LU, ncm_nnls.c:573-606: the system is gathered again (dposv destroyed it) and solved by dsysv
+  rc = gather();
+  if (rc != NCM_SD_GPU_OK) return rc;
+  int info_lu = 0;
+  {
+    StageTimer t(c, NCM_SD_GPU_T_CHOL);
+    rc = dsysv_upper_solve(c, np, w.dMU, w.ldm, w.drhs, &info_lu);
+    if (rc != NCM_SD_GPU_OK) return rc;
+  }
+  if (w.st) w.st->n_lu++;
+  if (nnls_trace()) fprintf(stderr, "gpu_nnls: lu |P| = %d info = %d\n", np, info_lu);
+  if (info_lu > 0) {
+    // _ncm_nnls_solve_normal_QR, ncm_nnls.c:608-638: least squares on the passive columns of A itself
+    if (c->nranks > 1 && c->im_sharded)
+      return c->fail(NCM_SD_GPU_ENOTPD, "nnls: the passive-set system is exactly singular and the dgels fallback needs the whole matrix on one rank");
+    if (np == w.n) {
+      for (int i = 0; i < np; ++i) w.h_idx[i] = i;
+      NCM_CUDA_OK(c, ncm_memcpy_async(c, w.didx, w.h_idx, sizeof(int) * np, cudaMemcpyHostToDevice, c->stream));
+    }
+    int info_qr = 0;
     {
       StageTimer t(c, NCM_SD_GPU_T_CHOL);
-      // all ranks hold the same all-reduced matrix and take the same decisions: large systems are factorised together (dist_chol.cu)
-      const bool dist = c->nccl_comm != nullptr && c->nranks > 1 && np >= dist_chol_min_n();
-      int rc = dist ? dpotrf_upper_solve_dist(c, np, w.dMU, w.ldm, w.drhs, &info) : dpotrf_upper_solve_any(c, np, w.dMU, w.ldm, w.drhs, w.ddinv, w.dinfo, &info);
+      rc = dgels_cols_solve(c, w.nrows, np, w.dA, w.lda, w.didx, w.dF, w.drhs, &info_qr);
       if (rc != NCM_SD_GPU_OK) return rc;
-      if (dist && w.st) w.st->n_dist_chol++;
     }
-    if (w.st) {
-      w.st->n_chol++;
-      w.st->chol_flops += (double) np * np * np / 3.0;
-    }
-    if (nnls_trace()) fprintf(stderr, "gpu_nnls: chol |P| = %d info = %d shift = %g\n", np, info, shift);
-    if (info == 0) {
-      NCM_CUDA_OK(c, ncm_memcpy_async(c,w.h_buf, w.drhs, sizeof(double) * np, cudaMemcpyDeviceToHost, c->stream));
-      if (w.lr_on && attempt == 0 && np >= LR_MIN_N) {   // the factor left in dMU becomes the base of the following low-rank solves
-        std::memcpy(w.h_idx, P.data(), sizeof(int) * np);
-        NCM_CUDA_OK(c, ncm_memcpy_async(c, w.lb.idxB, w.h_idx, sizeof(int) * np, cudaMemcpyHostToDevice, c->stream));
-        w.baseP      = P;
-        w.base_valid   = true;
-        w.w_valid      = false;
-        w.base_trusted = false;
-      }
-      NCM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
-      return NCM_SD_GPU_OK;
-    }
-    if (w.st) w.st->n_retry++;
+    if (w.st) w.st->n_qr++;
+    if (nnls_trace()) fprintf(stderr, "gpu_nnls: qr |P| = %d info = %d\n", np, info_qr);
+    if (info_qr != 0) return c->fail(NCM_SD_GPU_ENOTPD, "nnls: dgels met an exactly rank-deficient passive set (the reference asserts here, ncm_nnls.c:637)");
   }
-  return c->fail(NCM_SD_GPU_ENOTPD, "nnls: passive-set normal matrix is not positive definite");
+  NCM_CUDA_OK(c, ncm_memcpy_async(c, w.h_buf, w.drhs, sizeof(double) * np, cudaMemcpyDeviceToHost, c->stream));
+  NCM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return NCM_SD_GPU_OK;
 }
 
 // ncm_nnls.c:728-751
@@ -492,11 +506,6 @@ int nnls_solve_dev(ncm_sd_gpu_ctx *c, int nrows, int ncols, const double *dA, in
     if (rc != NCM_SD_GPU_OK) return rc;
     rc = allreduce_sum(c, w.db, n);
     if (rc != NCM_SD_GPU_OK) return rc;
-    diag_mean_kernel<<<1, 256, 0, c->stream>>>(w.dM, ldm, n, w.dscal);
-    c->n_launches++;
-    NCM_CUDA_OK(c, ncm_memcpy_async(c,w.h_buf, w.dscal, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    NCM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
-    w.diag_mean = w.h_buf[0];
   }
 
   std::vector<int> P(n), P_try;

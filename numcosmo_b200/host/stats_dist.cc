@@ -972,9 +972,13 @@ void ncm_stats_dist_b200_get_nnls_lowrank_stats(NcmStatsDist *sd, gint *n_lowran
   if (max_k) *max_k = sd->nnls_stats.max_lowrank_k;
 }
 
-void ncm_stats_dist_b200_get_nnls_stats(NcmStatsDist *sd, gint *n_chol, gint *n_retry, gint *n_outer, gint *n_passive) {
+void ncm_stats_dist_b200_get_nnls_fallback_stats(NcmStatsDist *sd, gint *n_lu, gint *n_qr) {
+  if (n_lu) *n_lu = sd->nnls_stats.n_lu;
+  if (n_qr) *n_qr = sd->nnls_stats.n_qr;
+}
+void ncm_stats_dist_b200_get_nnls_stats(NcmStatsDist *sd, gint *n_chol, gint *n_lu, gint *n_outer, gint *n_passive) {
   if (n_chol) *n_chol = sd->nnls_stats.n_chol;
-  if (n_retry) *n_retry = sd->nnls_stats.n_retry;
+  if (n_lu) *n_lu = sd->nnls_stats.n_lu;
   if (n_outer) *n_outer = sd->nnls_stats.n_outer;
   if (n_passive) *n_passive = sd->nnls_stats.n_passive;
 }

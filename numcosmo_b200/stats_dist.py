@@ -164,6 +164,7 @@ def lib():
             "ncm_stats_dist_vkde_get_use_rot_href": (i, [_vp]),
             "ncm_stats_dist_b200_get_nnls_stats": (None, [_vp, C.POINTER(i), C.POINTER(i), C.POINTER(i), C.POINTER(i)]),
             "ncm_stats_dist_b200_get_nnls_lowrank_stats": (None, [_vp, C.POINTER(i), C.POINTER(i), C.POINTER(i), C.POINTER(i)]),
+            "ncm_stats_dist_b200_get_nnls_fallback_stats": (None, [_vp, C.POINTER(i), C.POINTER(i)]),
             "ncm_stats_dist_b200_comm_unique_id": (i, [C.c_char_p]),
             "ncm_stats_dist_b200_comm_init": (i, [_vp, i, i, C.c_char_p]),
             "ncm_stats_dist_b200_get_cv_trace": (i, [_vp, _dp, _dp, i]),
@@ -470,7 +471,9 @@ class StatsDist:
     def nnls_stats(self):
         a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         lib().ncm_stats_dist_b200_get_nnls_stats(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d))
-        out = {"n_chol": a.value, "n_retry": b.value, "n_outer": c.value, "n_passive": d.value}
+        out = {"n_chol": a.value, "n_lu": b.value, "n_outer": c.value, "n_passive": d.value}
+        lib().ncm_stats_dist_b200_get_nnls_fallback_stats(self._h, C.byref(a), C.byref(b))
+        out["n_qr"] = b.value
         lib().ncm_stats_dist_b200_get_nnls_lowrank_stats(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d))
         out.update({"n_lowrank": a.value, "n_lowrank_fallback": b.value, "n_trinv": c.value, "max_lowrank_k": d.value})
         return out

@@ -73,7 +73,7 @@ def test_gpu_matches_golden(gold):
 
         w, wg = sd.peek_weights(), gold[f"{name}/weights"]
         st = sd.nnls_stats()
-        assert st["n_retry"] == 0, (name, st)
+        assert st["n_lu"] == 0, (name, st)
         assert np.array_equal(support(w, int(n)), support(wg, int(n))), f"{name}: passive set differs from the golden one"
         cb = capi.Context.borrowed(S.lib().ncm_stats_dist_b200_peek_ctx(sd._h))
         cb.n_kernels = cb.n_obs = int(n)

