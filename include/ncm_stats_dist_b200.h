@@ -273,6 +273,7 @@ typedef enum _NcmFitESMCMCWalkerAPESKType
 
 NcmFitESMCMCWalkerAPES *ncm_fit_esmcmc_walker_apes_new (guint nwalkers, guint nparams);
 NcmFitESMCMCWalkerAPES *ncm_fit_esmcmc_walker_apes_new_full (guint nwalkers, guint nparams, NcmFitESMCMCWalkerAPESMethod method, NcmFitESMCMCWalkerAPESKType k_type, gdouble over_smooth, gboolean use_interp);
+NcmFitESMCMCWalkerAPES *ncm_fit_esmcmc_walker_apes_ref (NcmFitESMCMCWalkerAPES *apes);
 void ncm_fit_esmcmc_walker_apes_free (NcmFitESMCMCWalkerAPES *apes);
 void ncm_fit_esmcmc_walker_apes_clear (NcmFitESMCMCWalkerAPES **apes);
 void ncm_fit_esmcmc_walker_apes_set_method (NcmFitESMCMCWalkerAPES *apes, NcmFitESMCMCWalkerAPESMethod method);
@@ -294,6 +295,11 @@ gboolean ncm_fit_esmcmc_walker_apes_get_use_threads (NcmFitESMCMCWalkerAPES *ape
 void ncm_fit_esmcmc_walker_apes_peek_sds (NcmFitESMCMCWalkerAPES *apes, NcmStatsDist **sd0, NcmStatsDist **sd1);
 void ncm_fit_esmcmc_walker_apes_set_local_frac (NcmFitESMCMCWalkerAPES *apes, gdouble local_frac);
 void ncm_fit_esmcmc_walker_apes_set_exploration (NcmFitESMCMCWalkerAPES *apes, guint exploration);
+/* ncm_fit_esmcmc_walker_apes.h:106-108.  The NcmMSet argument of the reference is replaced by what it reads from it: the scales of the
+ * free parameters (ncm_mset_fparam_get_scale (mset, i), i < nparams). */
+void ncm_fit_esmcmc_walker_apes_set_cov_fixed_from_mset (NcmFitESMCMCWalkerAPES *apes, const gdouble *fparam_scales);
+void ncm_fit_esmcmc_walker_apes_set_cov_robust_diag (NcmFitESMCMCWalkerAPES *apes);
+void ncm_fit_esmcmc_walker_apes_set_cov_robust (NcmFitESMCMCWalkerAPES *apes);
 /* instrumentation of the proposal draws generated ahead of the weights (host/apes.cc): blocks pre-generated, blocks replayed serially */
 void ncm_fit_esmcmc_walker_apes_b200_get_pregen_stats (NcmFitESMCMCWalkerAPES *a, long long *n_blocks, long long *n_fallbacks);
 

@@ -590,6 +590,26 @@ int lowrank_solve(ncm_sd_gpu_ctx *c, const double *dM, int ldm, int n, const dou
   const int ctiles = (kc + GT - 1) / GT, rtiles = (nB + GT - 1) / GT;
   NCM_CUDA_OK(c, cudaMemsetAsync(w.info, 0, sizeof(int), st));
   if (refine) NCM_CUDA_OK(c, cudaMemsetAsync(w.xfull, 0, (size_t) n * sizeof(double), st));
+  if (k == 0) {
+    // the base set itself: x_B = W (W^T b_B) -- two triangular matrix-vector products instead of the forward / back substitution
+    // (the fused factorisation then runs without its right-hand side column and its back-substitution phase)
+    lr_gather_r_kernel<<<(nB + 255) / 256, 256, 0, st>>>(db, w.bsel, nB, w.rB);
+    row_dot_kernel<ROW_LOWER><<<(nB * ROW_WPR + 7) / 8, 256, 0, st>>>(w.Wt, ldm, nB, w.rB, nullptr, 1.0, w.y);
+    row_dot_kernel<ROW_UPPER><<<(nB * ROW_WPR + 7) / 8, 256, 0, st>>>(w.W, ldm, nB, w.y, nullptr, 1.0, w.xB);
+    c->n_launches += 3;
+    if (refine) {
+      lr_scatter_kernel<<<(nB + 255) / 256, 256, 0, st>>>(w.xfull, w.bsel, nB, w.xB, w.idxA, 0, w.z);
+      row_dot_kernel<ROW_FULL><<<(n * ROW_WPR + 7) / 8, 256, 0, st>>>(dM, ldm, n, w.xfull, db, -1.0, w.rfull);
+      lr_gather_r_kernel<<<(nB + 255) / 256, 256, 0, st>>>(w.rfull, w.bsel, nB, w.rB);
+      row_dot_kernel<ROW_LOWER><<<(nB * ROW_WPR + 7) / 8, 256, 0, st>>>(w.Wt, ldm, nB, w.rB, nullptr, 1.0, w.tr);
+      row_dot_kernel<ROW_UPPER><<<(nB * ROW_WPR + 7) / 8, 256, 0, st>>>(w.W, ldm, nB, w.tr, nullptr, 1.0, w.dxB);
+      c->n_launches += 5;
+    }
+    lr_finalize_kernel<<<1, 1024, 0, st>>>(w.psrc, np, w.xB, refine ? w.dxB : nullptr, w.z, w.z2, w.out);
+    c->n_launches++;
+    NCM_CUDA_OK(c, cudaGetLastError());
+    return NCM_SD_GPU_OK;
+  }
   lr_gather_V_kernel<<<(nB + 7) / 8, dim3(32, 8), 0, st>>>(dM, ldm, db, w.bsel, w.idxB, nB, w.idxA, na, w.posD, nd, w.V, ldv);
   gemm_tn_splitk_kernel<<<dim3(ctiles, rtiles, ntc), GTHREADS, GEMM_SMEM, st>>>(w.W, ldm, w.V, ldv, Tpart, ldv, tstride, nB, kc, nB);
   splitk_reduce_kernel<<<dim3((kc + 63) / 64, nB), 64, 0, st>>>(Tpart, tstride, ldv, nB, kc, nB, w.T);

@@ -179,6 +179,13 @@ bool lowrank_enabled() {
   }();
   return on;
 }
+bool base_solve_enabled() {   // NCM_SD_GPU_NNLS_BASE_SOLVE=0: the base system keeps its forward / back substitution
+  static const bool on = [] {
+    const char *e = getenv("NCM_SD_GPU_NNLS_BASE_SOLVE");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return on;
+}
 constexpr int LR_MIN_N = 512;       // below this a fused factorisation (a few 64-column phases) is as cheap as the ~25 launches of an update
 constexpr double LR_MAX_CORR = 1e-7;
 // a base whose first low-rank solve needed a refinement correction below this is trusted: the later solves from it skip the refinement
@@ -280,22 +287,27 @@ int solve_unconstrained(NnlsWork &w, const std::vector<int> &P) {
   int rc = gather();
   if (rc != NCM_SD_GPU_OK) return rc;
   int info = 0;
-  {
-    StageTimer t(c, NCM_SD_GPU_T_CHOL);
-    // all ranks hold the same all-reduced matrix and take the same decisions: large systems are factorised together (dist_chol.cu)
-    const bool dist = c->nccl_comm != nullptr && c->nranks > 1 && np >= dist_chol_min_n();
-    rc = dist ? dpotrf_upper_solve_dist(c, np, w.dMU, w.ldm, w.drhs, &info) : dpotrf_upper_solve_any(c, np, w.dMU, w.ldm, w.drhs, w.ddinv, w.dinfo, &info);
-    if (rc != NCM_SD_GPU_OK) return rc;
-    if (dist && w.st) w.st->n_dist_chol++;
-  }
-  if (w.st) {
-    w.st->n_chol++;
-    w.st->chol_flops += (double) np * np * np / 3.0;
-  }
-  if (nnls_trace()) fprintf(stderr, "gpu_nnls: chol |P| = %d info = %d\n", np, info);
-  if (info == 0) {
-    NCM_CUDA_OK(c, ncm_memcpy_async(c, w.h_buf, w.drhs, sizeof(double) * np, cudaMemcpyDeviceToHost, c->stream));
-    if (w.lr_on && np >= LR_MIN_N) {   // the factor left in dMU becomes the base of the following low-rank solves
+  // a set that becomes the base of low-rank solves is only factorised here: its own solution comes from the triangular inverse the
+  // following solves need anyway (x = W W^T b + one refinement step, lowrank.cu), not from a forward / back substitution
+  const bool dist = c->nccl_comm != nullptr && c->nranks > 1 && np >= dist_chol_min_n();
+  const bool as_base = w.lr_on && np >= LR_MIN_N && !dist;
+  for (int pass = 0; pass < 2; ++pass) {
+    const bool factor_only = as_base && pass == 0 && base_solve_enabled();
+    {
+      StageTimer t(c, NCM_SD_GPU_T_CHOL);
+      // all ranks hold the same all-reduced matrix and take the same decisions: large systems are factorised together (dist_chol.cu)
+      rc = dist ? dpotrf_upper_solve_dist(c, np, w.dMU, w.ldm, w.drhs, &info)
+                : dpotrf_upper_solve_any(c, np, w.dMU, w.ldm, factor_only ? nullptr : w.drhs, w.ddinv, w.dinfo, &info);
+      if (rc != NCM_SD_GPU_OK) return rc;
+      if (dist && w.st) w.st->n_dist_chol++;
+    }
+    if (w.st) {
+      w.st->n_chol++;
+      w.st->chol_flops += (double) np * np * np / 3.0;
+    }
+    if (nnls_trace()) fprintf(stderr, "gpu_nnls: chol |P| = %d info = %d%s\n", np, info, factor_only ? " (factor only)" : "");
+    if (info != 0) break;
+    if (as_base) {   // the factor left in dMU becomes the base of the following low-rank solves
       std::memcpy(w.h_idx, P.data(), sizeof(int) * np);
       NCM_CUDA_OK(c, ncm_memcpy_async(c, w.lb.idxB, w.h_idx, sizeof(int) * np, cudaMemcpyHostToDevice, c->stream));
       w.baseP        = P;
@@ -303,9 +315,21 @@ int solve_unconstrained(NnlsWork &w, const std::vector<int> &P) {
       w.w_valid      = false;
       w.base_trusted = false;
     }
-    NCM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
-    return NCM_SD_GPU_OK;
+    if (!factor_only) {
+      NCM_CUDA_OK(c, ncm_memcpy_async(c, w.h_buf, w.drhs, sizeof(double) * np, cudaMemcpyDeviceToHost, c->stream));
+      NCM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+      return NCM_SD_GPU_OK;
+    }
+    bool done = false;
+    rc        = solve_lowrank(w, P, &done);
+    if (rc != NCM_SD_GPU_OK) return rc;
+    if (done) return NCM_SD_GPU_OK;
+    // the inverse of this base is not good enough for its own system: factorise again, this time with the substitutions
+    w.base_valid = false;
+    rc           = gather();
+    if (rc != NCM_SD_GPU_OK) return rc;
   }
+  if (info == 0) return c->fail(NCM_SD_GPU_ECUDA, "nnls: internal error (base solve)");
   // _ncm_nnls_solve_normal_LU, ncm_nnls.c:573-606: the system is gathered again (dposv destroyed it) and solved by dsysv
   rc = gather();
   if (rc != NCM_SD_GPU_OK) return rc;

@@ -67,6 +67,7 @@ struct _NcmFitESMCMCWalkerAPES {
   std::vector<unsigned char> pre_rw;
   std::vector<double> pre_p, pre_z, pre_chisq;
   long long n_spec_blocks, n_spec_fallbacks;
+  int ref = 1;
 };
 
 namespace {
@@ -334,8 +335,13 @@ NcmFitESMCMCWalkerAPES *ncm_fit_esmcmc_walker_apes_new(guint nwalkers, guint npa
   return ncm_fit_esmcmc_walker_apes_new_full(nwalkers, nparams, NCM_FIT_ESMCMC_WALKER_APES_METHOD_VKDE, NCM_FIT_ESMCMC_WALKER_APES_KTYPE_CAUCHY,
                                              1.0, TRUE);
 }
+// ncm_fit_esmcmc_walker_apes.c:1052-1056
+NcmFitESMCMCWalkerAPES *ncm_fit_esmcmc_walker_apes_ref(NcmFitESMCMCWalkerAPES *a) {
+  a->ref++;
+  return a;
+}
 void ncm_fit_esmcmc_walker_apes_free(NcmFitESMCMCWalkerAPES *a) {
-  if (a == nullptr) return;
+  if (a == nullptr || --a->ref > 0) return;
   ncm_stats_dist_clear(&a->sd0);
   ncm_stats_dist_clear(&a->sd1);
   delete a;
@@ -386,6 +392,28 @@ void ncm_fit_esmcmc_walker_apes_set_local_frac(NcmFitESMCMCWalkerAPES *a, gdoubl
   ncm_stats_dist_vkde_set_local_frac(a->sd1, lf);
 }
 void ncm_fit_esmcmc_walker_apes_set_exploration(NcmFitESMCMCWalkerAPES *a, guint e) { a->exploration = e; }
+// ncm_fit_esmcmc_walker_apes.c:1450-1473.  The reference reads nothing from the NcmMSet but the scales of its free parameters
+// (ncm_mset_fparam_get_scale, one per walker dimension): the mirror takes that array.  cov_fixed = diag (scale_i^2) on both halves.
+void ncm_fit_esmcmc_walker_apes_set_cov_fixed_from_mset(NcmFitESMCMCWalkerAPES *a, const gdouble *fparam_scales) {
+  NcmMatrix *cov_fixed = ncm_matrix_new(a->nparams, a->nparams);
+  for (guint i = 0; i < a->nparams; i++)
+    for (guint j = 0; j < a->nparams; j++) ncm_matrix_set(cov_fixed, i, j, i == j ? fparam_scales[i] * fparam_scales[i] : 0.0);
+  ncm_stats_dist_kde_set_cov_type(a->sd0, NCM_STATS_DIST_KDE_COV_TYPE_FIXED);
+  ncm_stats_dist_kde_set_cov_type(a->sd1, NCM_STATS_DIST_KDE_COV_TYPE_FIXED);
+  ncm_stats_dist_kde_set_cov_fixed(a->sd0, cov_fixed);
+  ncm_stats_dist_kde_set_cov_fixed(a->sd1, cov_fixed);
+  ncm_matrix_free(cov_fixed);
+}
+// :1483-1490
+void ncm_fit_esmcmc_walker_apes_set_cov_robust_diag(NcmFitESMCMCWalkerAPES *a) {
+  ncm_stats_dist_kde_set_cov_type(a->sd0, NCM_STATS_DIST_KDE_COV_TYPE_ROBUST_DIAG);
+  ncm_stats_dist_kde_set_cov_type(a->sd1, NCM_STATS_DIST_KDE_COV_TYPE_ROBUST_DIAG);
+}
+// :1500-1507
+void ncm_fit_esmcmc_walker_apes_set_cov_robust(NcmFitESMCMCWalkerAPES *a) {
+  ncm_stats_dist_kde_set_cov_type(a->sd0, NCM_STATS_DIST_KDE_COV_TYPE_ROBUST);
+  ncm_stats_dist_kde_set_cov_type(a->sd1, NCM_STATS_DIST_KDE_COV_TYPE_ROBUST);
+}
 // instrumentation: blocks whose draws were generated ahead of the weights, and how many of those had to be replayed serially
 void ncm_fit_esmcmc_walker_apes_b200_get_pregen_stats(NcmFitESMCMCWalkerAPES *a, long long *n_blocks, long long *n_fallbacks) {
   if (n_blocks) *n_blocks = a->n_spec_blocks;

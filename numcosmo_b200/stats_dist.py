@@ -181,6 +181,10 @@ def lib():
             "ncm_fit_esmcmc_walker_apes_set_use_threads": (None, [_vp, i]),
             "ncm_fit_esmcmc_walker_apes_set_local_frac": (None, [_vp, d]),
             "ncm_fit_esmcmc_walker_apes_set_exploration": (None, [_vp, u]),
+            "ncm_fit_esmcmc_walker_apes_set_cov_fixed_from_mset": (None, [_vp, C.POINTER(C.c_double)]),
+            "ncm_fit_esmcmc_walker_apes_set_cov_robust_diag": (None, [_vp]),
+            "ncm_fit_esmcmc_walker_apes_set_cov_robust": (None, [_vp]),
+            "ncm_fit_esmcmc_walker_apes_ref": (_vp, [_vp]),
             "ncm_fit_esmcmc_walker_apes_b200_get_pregen_stats": (None, [_vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
             "ncm_fit_esmcmc_walker_apes_peek_sds": (None, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
             "ncm_fit_esmcmc_walker_apes_setup": (None, [_vp, _dp, _dp, _dp, _dp, u, u, _vp]),
@@ -592,6 +596,16 @@ class FitESMCMCWalkerAPES:
     def set_local_frac(self, v):
         lib().ncm_fit_esmcmc_walker_apes_set_local_frac(self._h, float(v))
         _check()
+
+    def set_cov_fixed_from_mset(self, fparam_scales):
+        """walker_apes.c:1450-1473; `fparam_scales` = [ncm_mset_fparam_get_scale (mset, i)] (the only thing the reference reads from the mset)."""
+        s = np.ascontiguousarray(fparam_scales, dtype=np.float64)
+        lib().ncm_fit_esmcmc_walker_apes_set_cov_fixed_from_mset(self._h, s.ctypes.data_as(C.POINTER(C.c_double)))
+        _check()
+
+    def set_cov_robust_diag(self): lib().ncm_fit_esmcmc_walker_apes_set_cov_robust_diag(self._h)
+
+    def set_cov_robust(self): lib().ncm_fit_esmcmc_walker_apes_set_cov_robust(self._h)
 
     def peek_sds(self):
         a, b = C.c_void_p(), C.c_void_p()

@@ -258,6 +258,21 @@ orc_apes_new (int nwalkers, int d, int sd_type, int kernel_kind, double nu, doub
   return a;
 }
 
+/* ncm_fit_esmcmc_walker_apes.c:1442-1507: the covariance setters act on both halves; cov_fixed != NULL with ORC_COV_FIXED is
+ * set_cov_fixed_from_mset's diag (scale^2) matrix */
+void
+orc_apes_set_cov_type (orc_apes *a, int cov_type, const double *cov_fixed, int ld)
+{
+  orc_sd_set_cov_type (a->sd0, cov_type);
+  orc_sd_set_cov_type (a->sd1, cov_type);
+
+  if (cov_fixed != NULL)
+  {
+    orc_sd_set_cov_fixed (a->sd0, cov_fixed, ld);
+    orc_sd_set_cov_fixed (a->sd1, cov_fixed, ld);
+  }
+}
+
 void
 orc_apes_free (orc_apes *a)
 {

@@ -99,7 +99,9 @@ def assert_weights_parity(w, wo, st, so, IM, shrink=0.01, what="", rnorm2=None):
         assert st["n_lu"] == 0 and st["n_qr"] == 0, f"{what}: the GPU path left dposv where the oracle did not ({st} vs {so})"
         pg, po = support(w, n, shrink), support(wo, n, shrink)
         assert np.array_equal(pg, po), f"{what}: passive sets differ in {np.count_nonzero(pg != po)} of {n} indices ({st} vs {so})"
-        assert st["n_passive"] == so["n_passive"] == int(po.sum()), (what, st, so)
+        # (a passive x_i that is tiny against sum x leaves w_i == shrink / n in floating point: the support seen through the weights can
+        # be smaller than the passive set, never larger)
+        assert st["n_passive"] == so["n_passive"] and int(po.sum()) <= so["n_passive"], (what, st, so)
         cond_M, bound = weight_bound(IM, po)
         err = np.max(np.abs(w - wo)) / wo.max()
         assert err <= bound, f"{what}: weights differ by {err:.2e} of the largest (bound {bound:.2e}, cond(M[P,P]) = {cond_M:.2e})"
@@ -110,7 +112,7 @@ def assert_weights_parity(w, wo, st, so, IM, shrink=0.01, what="", rnorm2=None):
     dfit = np.linalg.norm(fit_g - fit_o) / np.linalg.norm(fit_o)
     print(f"{what}: fallback regime (oracle {so['n_lu']} lu / {so['n_qr']} qr of {so['n_chol']}, gpu {st['n_lu']} / {st['n_qr']} of {st['n_chol']}): "
           f"|P| {st['n_passive']} vs {so['n_passive']}, fitted values differ by {dfit:.2e}" + (f", rnorm^2 {rnorm2[0]:.6e} vs {rnorm2[1]:.6e}" if rnorm2 else ""))
-    assert dfit <= 1e-3, f"{what}: fitted values at the centres differ by {dfit:.2e}"
-    if rnorm2 is not None:
-        assert abs(np.sqrt(rnorm2[0]) - np.sqrt(rnorm2[1])) <= 1e-4 * np.sqrt(IM.shape[0]), (what, rnorm2)
+    assert dfit <= 1e-2, f"{what}: fitted values at the centres differ by {dfit:.2e}"
+    if rnorm2 is not None:   # the residual norm of the NNLS optimum is unique
+        assert abs(np.sqrt(rnorm2[0]) - np.sqrt(rnorm2[1])) <= 1e-6 * np.sqrt(IM.shape[0]), (what, rnorm2)
     return None

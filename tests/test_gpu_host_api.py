@@ -221,3 +221,39 @@ def test_kde_fixed_covariance_missing_matrix_raises(oracle):
         sd.add_obs(x)
     with pytest.raises(Exception, match="fixed covariance"):
         sd.prepare()
+
+
+@pytest.mark.parametrize("which", ["fixed_from_mset", "robust_diag", "robust"])
+def test_apes_covariance_setters(oracle, which):
+    """ncm_fit_esmcmc_walker_apes_set_cov_fixed_from_mset / _set_cov_robust_diag / _set_cov_robust (walker_apes.h:106-108, .c:1442-1507)
+    (both APES methods build VKDE objects, walker_apes.c:563-572; the type steers the global bandwidth matrix, ncm_stats_dist_kde.c:423-441,
+    and the per-centre estimates, ncm_stats_dist_vkde.c:460-476): same chain as the oracle with the same covariance type on both halves."""
+    from numcosmo_b200 import stats_dist as S
+
+    W, d, iters = 400, 3, 5
+    mu, cov, X, m2lnL = mvnd_problem(oracle, d, W, seed=31)
+    lb, ub = np.full(d, -50.0), np.full(d, 50.0)
+    tgt = oracle.Target(oracle.TARGET_MVND, d, lb, ub, mu=mu, cov=cov)
+    scales = 1.5 * np.sqrt(np.diag(cov))
+    ao = oracle.APES(W, d, oracle.SD_VKDE, oracle.KERNEL_GAUSS, 1.0, use_threads=True, local_frac=0.2)
+    ag = S.FitESMCMCWalkerAPES(W, d, S.FitESMCMCWalkerAPESMethod.VKDE, S.FitESMCMCWalkerAPESKType.GAUSS, 1.0, True)
+    ag.set_local_frac(0.2)
+    ag.set_use_threads(True)
+    if which == "fixed_from_mset":
+        ag.set_cov_fixed_from_mset(scales)
+        ao.set_cov_type(oracle.COV_FIXED, np.diag(scales**2))
+    elif which == "robust_diag":
+        ag.set_cov_robust_diag()
+        ao.set_cov_type(oracle.COV_ROBUST_DIAG)
+    else:
+        ag.set_cov_robust()
+        ao.set_cov_type(oracle.COV_ROBUST)
+    th_o, ml_o, th_g, ml_g = X.copy(), m2lnL.copy(), X.copy(), m2lnL.copy()
+    acc_o = ao.run(tgt, th_o, ml_o, iters, oracle.RNG(5), nthreads=4)
+    acc_g, _ = ag.run("mvnd", lb, ub, th_g, ml_g, iters, S.RNG(5), target_args=(mu, tgt.U))
+    diff = np.argwhere(acc_o != acc_g)
+    assert diff.size == 0, f"{which}: first divergence at (iter, walker) = {diff[0]}"
+    assert 0.05 < acc_g.mean() < 0.95
+    sd0, sd1 = ag.peek_sds()
+    want = {"fixed_from_mset": S.StatsDistKDECovType.FIXED, "robust_diag": S.StatsDistKDECovType.ROBUST_DIAG, "robust": S.StatsDistKDECovType.ROBUST}[which]
+    assert S.lib().ncm_stats_dist_kde_get_cov_type(sd0._h) == int(want) and S.lib().ncm_stats_dist_kde_get_cov_type(sd1._h) == int(want)
