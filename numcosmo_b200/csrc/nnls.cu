@@ -244,13 +244,13 @@ int solve_lowrank(NnlsWork &w, const std::vector<int> &P, bool *done) {
   int info;
   std::memcpy(&info, w.h_buf + np + 2, sizeof(int));
   if (w.st) {
-    w.st->n_lowrank++;
+    if (na + nd > 0) w.st->n_lowrank++;   // the base set's own solve (k = 0) belongs to its factorisation, counted in n_chol
     w.st->lowrank_flops += 2.0 * nB * (double) nB * (na + nd + 1);
     w.st->max_lowrank_k = std::max(w.st->max_lowrank_k, na + nd);
   }
   if (nnls_trace()) fprintf(stderr, "gpu_nnls: lowrank |P| = %d |B| = %d k = %d + %d info = %d corr = %.3e%s\n", np, nB, na, nd, info, mdx / mx, refine ? "" : " (no refinement)");
   if (info != 0 || !(mdx <= LR_MAX_CORR * mx)) {   // also catches NaN
-    if (w.st) w.st->n_lowrank_fallback++;
+    if (w.st && na + nd > 0) w.st->n_lowrank_fallback++;
     return NCM_SD_GPU_OK;
   }
   if (refine && mdx <= LR_TRUST_CORR * mx) w.base_trusted = true;
