@@ -208,6 +208,8 @@ struct LowrankBufs {
   double *part;           // split-K partial sums (lowrank_part_doubles)
   double *Lg;             // packed L J L^T factor of the k x k system + its inverse diagonal
   double *z, *z2, *y, *xB, *dxB, *xfull, *rfull, *rB, *tr, *out;
+  double *tb;             // W^T b_B of the current base (set by its own k = 0 solve)
+  bool tb_valid = false;
   int *idxB, *idxA, *posD, *bsel, *psrc, *info;
 };
 int dsysv_upper_solve(ncm_sd_gpu_ctx *c, int n, double *dS, int lds, double *dRhs, int *info_host);

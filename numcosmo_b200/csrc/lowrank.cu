@@ -167,6 +167,33 @@ __global__ void lr_gather_V_kernel(const double *__restrict__ M, int ldm, const 
   }
 }
 
+// Pure removals (A empty): W^T E_D is a gather of rows of W, no product.  T[i][j] = W[posD[j]][i] for j < k (zero above the diagonal of
+// W), T[i][k] = tb[i] = (W^T b_B)[i], formed once per base.  32 x 32 tiles through shared memory: reads along the rows of W, writes along
+// the rows of T.
+__global__ void lr_gather_T_kernel(const double *__restrict__ W, int ldw, int nB, const int *__restrict__ posD, int k, const double *__restrict__ tb,
+                                   double *__restrict__ T, int ldt) {
+  __shared__ double tile[32][33];
+  const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {   // r: column j of T = row posD[j] of W
+    const int j = j0 + r, i = i0 + threadIdx.x;
+    double v = 0.0;
+    if (i < nB) {
+      if (j < k) {
+        const int pr = posD[j];
+        v = i >= pr ? W[(size_t) pr * ldw + i] : 0.0;
+      } else if (j == k) {
+        v = tb[i];
+      }
+    }
+    tile[r][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int i = i0 + r, j = j0 + threadIdx.x;
+    if (i < nB && j <= k) T[(size_t) i * ldt + j] = tile[threadIdx.x][r];
+  }
+}
+
 // y[i] = base[i * bstride] - sum_j T[i][j] z[j]   (warp per row)
 __global__ void lr_y_kernel(const double *__restrict__ T, int ldt, int nB, int k, const double *__restrict__ z, const double *__restrict__ base, int bstride,
                             double *__restrict__ y) {
@@ -297,12 +324,10 @@ __global__ void lr_finalize_kernel(const int *__restrict__ psrc, int np, const d
 // ---- the k x k quasi-definite system: H = L J L^T in shared memory, packed lower, 8-column panels -------------------------
 constexpr int LR_KMAX = 200;
 constexpr int LR_ST = 512;
-constexpr int LR_PW = 8;              // panel width of the substitutions
-constexpr int LR_FW = 16;             // panel width of the factorisation
+constexpr int LR_PW = 8;
 constexpr int LR_PKR = LR_KMAX + 8;   // row pitch of the column-major panel copies
-// packed lower matrix of order kr = k + 1 (the right-hand side is row k), two panel copies [16][PKR], dinv[k], vec[k], red[8],
-// published diagonal block [16][16] + its inverse diagonal [16]
-constexpr size_t LR_SMALL_SMEM = ((size_t) (LR_KMAX + 1) * (LR_KMAX + 2) / 2 + 2 * (size_t) LR_PKR * LR_FW + 2 * LR_KMAX + 8 + LR_FW * LR_FW + LR_FW) * sizeof(double);
+// packed lower matrix of order kr = k + 1 (the right-hand side is row k), two panel copies [8][PKR], dinv[k], vec[k], red[8]
+constexpr size_t LR_SMALL_SMEM = ((size_t) (LR_KMAX + 1) * (LR_KMAX + 2) / 2 + 2 * (size_t) LR_PKR * LR_PW + 2 * LR_KMAX + 8 + 80) * sizeof(double);
 
 __device__ __forceinline__ int pidx(int i, int j) { return i * (i + 1) / 2 + j; }   // i >= j
 
@@ -319,12 +344,12 @@ __global__ void __launch_bounds__(LR_ST) lr_small_kernel(int mode, int na, int n
   const int kr = k + 1;
   const int npk = kr * (kr + 1) / 2;
   double *L    = sm;
-  double *pan  = sm + (size_t) (LR_KMAX + 1) * (LR_KMAX + 2) / 2;   // [16][PKR]: L[p0 + r][p0 + c] at pan[c * PKR + r]
-  double *pas  = pan + (size_t) LR_PKR * LR_FW;                     // sign-folded copy: J_c L[..][p0 + c]
-  double *dinv = pas + (size_t) LR_PKR * LR_FW;
+  double *pan  = sm + (size_t) (LR_KMAX + 1) * (LR_KMAX + 2) / 2;   // [8][PKR]: L[p0 + r][p0 + c] at pan[c * PKR + r]
+  double *pas  = pan + (size_t) LR_PKR * LR_PW;                     // sign-folded copy: J_c L[..][p0 + c]
+  double *dinv = pas + (size_t) LR_PKR * LR_PW;
   double *vec  = dinv + LR_KMAX;
   double *red  = vec + LR_KMAX;
-  double *dgs  = red + 8;   // published diagonal block [16][16] + its inverse diagonal [16]
+  double *dgs  = red + 8;   // published diagonal block [8][8] + its inverse diagonal [8]
   if (k == 0) return;
   if (mode == 0) {
     for (int j = warp; j < k; j += LR_ST / 32)          // row j of the upper-stored H0, lanes along it: coalesced
@@ -336,67 +361,74 @@ __global__ void __launch_bounds__(LR_ST) lr_small_kernel(int mode, int na, int n
       }
     if (tid == 0) L[pidx(k, k)] = 0.0;
     __syncthreads();
-    for (int p0 = 0; p0 < k; p0 += LR_FW) {
-      const int pw = min(LR_FW, k - p0);
-      // warp 0 factors the pw x pw diagonal block: lane r owns row r in registers, the pivot row travels by shuffles (no shared memory
-      // on the pivot chain); then every row i >= p0, owned by one thread, is solved against the published block
+    for (int p0 = 0; p0 < k; p0 += LR_PW) {
+      const int pw = min(LR_PW, k - p0);
+      // warp 0 factors the pw x pw diagonal block in registers (all lanes redundantly: no communication on the pivot chain) and
+      // publishes it; then every row i >= p0, owned by one thread, is solved against it
       const int i = p0 + tid;
       if (warp == 0) {
-        double d[LR_FW], dvl = 1.0;
+        double dg[LR_PW][LR_PW], dv[LR_PW];
         int bad = 0;
 #pragma unroll
-        for (int q = 0; q < LR_FW; ++q) d[q] = (lane < pw && q <= lane) ? L[pidx(p0 + min(lane, pw - 1), p0 + min(q, pw - 1))] : (q == lane ? 1.0 : 0.0);
-        // (rows / columns beyond pw are an identity block: they factor trivially and touch nothing)
+        for (int r = 0; r < LR_PW; ++r)
 #pragma unroll
-        for (int c = 0; c < LR_FW; ++c) {
+          for (int q = 0; q <= r; ++q) dg[r][q] = (r < pw && q < pw) ? L[pidx(p0 + r, p0 + q)] : (r == q ? 1.0 : 0.0);
+#pragma unroll
+        for (int c = 0; c < LR_PW; ++c) {
           const double sgc = (p0 + c) < na ? -1.0 : 1.0;
-          double p         = sgc * __shfl_sync(0xffffffffu, d[c], c);
-          if (c >= pw) p = 1.0;
+          double p         = sgc * dg[c][c];
           if (!(p > 0.0)) {
-            if (bad == 0) bad = p0 + c + 1;
+            if (c < pw && bad == 0) bad = p0 + c + 1;
             p = 1.0;
           }
           const double inv = rsqrt(p);
-          if (lane == c) {
-            d[c] = p * inv;
-            dvl  = inv;
-          } else if (lane > c) {
-            d[c] *= sgc * inv;
-          }
+          dg[c][c]         = p * inv;
+          dv[c]            = inv;
 #pragma unroll
-          for (int q = c + 1; q < LR_FW; ++q) {
-            const double lqc = __shfl_sync(0xffffffffu, d[c], q);
-            if (lane >= q) d[q] = fma(-sgc * d[c], lqc, d[q]);
-          }
+          for (int r = c + 1; r < LR_PW; ++r) dg[r][c] *= sgc * inv;
+#pragma unroll
+          for (int r = c + 1; r < LR_PW; ++r)
+#pragma unroll
+            for (int q = c + 1; q <= r; ++q) dg[r][q] = fma(-sgc * dg[r][c], dg[q][c], dg[r][q]);
         }
-        if (lane == 0 && bad != 0 && *info == 0) *info = bad;
-        if (lane < LR_FW) {
+        if (lane == 0) {
+          if (bad != 0 && *info == 0) *info = bad;
 #pragma unroll
-          for (int q = 0; q < LR_FW; ++q) dgs[lane * LR_FW + q] = q <= lane ? d[q] : 0.0;
-          dgs[LR_FW * LR_FW + lane] = dvl;
+          for (int r = 0; r < LR_PW; ++r) {
+#pragma unroll
+            for (int q = 0; q <= r; ++q) dgs[r * LR_PW + q] = dg[r][q];
+            dgs[LR_PW * LR_PW + r] = dv[r];
+          }
         }
       }
       __syncthreads();
       if (tid < kr - p0) {
-        double row[LR_FW];
+        double row[LR_PW];
         if (tid < pw) {
 #pragma unroll
-          for (int c = 0; c < LR_FW; ++c) row[c] = c <= tid ? dgs[tid * LR_FW + c] : 0.0;
-          dinv[i] = dgs[LR_FW * LR_FW + tid];
+          for (int c = 0; c < LR_PW; ++c) row[c] = c <= tid ? dgs[tid * LR_PW + c] : 0.0;
+          dinv[i] = dgs[LR_PW * LR_PW + tid];
         } else {
+          double dg[LR_PW][LR_PW], dv[LR_PW];
 #pragma unroll
-          for (int c = 0; c < LR_FW; ++c) row[c] = c < pw ? L[pidx(i, p0 + c)] : 0.0;
+          for (int r = 0; r < LR_PW; ++r) {
+#pragma unroll
+            for (int q = 0; q < r; ++q) dg[r][q] = dgs[r * LR_PW + q];
+            dv[r] = dgs[LR_PW * LR_PW + r];
+          }
+#pragma unroll
+          for (int c = 0; c < LR_PW; ++c) row[c] = c < pw ? L[pidx(i, p0 + c)] : 0.0;
           // row . (L_dd J)^-T : forward over the block columns
 #pragma unroll
-          for (int c = 0; c < LR_FW; ++c) {
+          for (int c = 0; c < LR_PW; ++c) {
             const double sgc = (p0 + c) < na ? -1.0 : 1.0;
-            row[c] *= sgc * dgs[LR_FW * LR_FW + c];
+            row[c] *= sgc * dv[c];
 #pragma unroll
-            for (int q = c + 1; q < LR_FW; ++q) row[q] = fma(-sgc * row[c], dgs[q * LR_FW + c], row[q]);
+            for (int q = c + 1; q < LR_PW; ++q) row[q] = fma(-sgc * row[c], dg[q][c], row[q]);
           }
         }
 #pragma unroll
-        for (int c = 0; c < LR_FW; ++c) {
+        for (int c = 0; c < LR_PW; ++c) {
           const double sgc = (p0 + c) < na ? -1.0 : 1.0;
           if (c < pw && (tid >= pw || c <= tid)) L[pidx(i, p0 + c)] = row[c];
           pan[c * LR_PKR + tid] = c < pw ? row[c] : 0.0;
@@ -404,30 +436,18 @@ __global__ void __launch_bounds__(LR_ST) lr_small_kernel(int mode, int na, int n
         }
       }
       __syncthreads();
-      // trailing update: H[i][l] -= sum_c J_c L[i][c] L[l][c],  p0 + pw <= l <= i < kr, l < k; a warp takes two rows at a time so that
-      // every panel value read serves two products
+      // trailing update: H[i][l] -= sum_c J_c L[i][c] L[l][c],  p0 + pw <= l <= i < kr, l < k
       const int t0 = p0 + pw;
-      for (int ii = t0 + 2 * warp; ii < kr; ii += 2 * (LR_ST / 32)) {
-        const bool two = ii + 1 < kr;
-        double pi0[LR_FW], pi1[LR_FW];
+      for (int ii = t0 + warp; ii < kr; ii += LR_ST / 32) {
+        double pi[LR_PW];
 #pragma unroll
-        for (int c = 0; c < LR_FW; ++c) {
-          pi0[c] = pas[c * LR_PKR + (ii - p0)];
-          pi1[c] = two ? pas[c * LR_PKR + (ii + 1 - p0)] : 0.0;
-        }
-        double *row0 = L + pidx(ii, 0), *row1 = L + pidx(ii + 1, 0);
-        const int lmax = min(two ? ii + 1 : ii, k - 1);
-        for (int l = t0 + lane; l <= lmax; l += 32) {
-          const bool in0 = l <= ii;
-          double s0 = in0 ? row0[l] : 0.0, s1 = two ? row1[l] : 0.0;
+        for (int c = 0; c < LR_PW; ++c) pi[c] = pas[c * LR_PKR + (ii - p0)];
+        double *rowp = L + pidx(ii, 0);
+        for (int l = t0 + lane; l <= ii && l < k; l += 32) {
+          double s = rowp[l];
 #pragma unroll
-          for (int c = 0; c < LR_FW; ++c) {
-            const double pl = pan[c * LR_PKR + (l - p0)];
-            s0 = fma(-pi0[c], pl, s0);
-            s1 = fma(-pi1[c], pl, s1);
-          }
-          if (in0) row0[l] = s0;
-          if (two) row1[l] = s1;
+          for (int c = 0; c < LR_PW; ++c) s = fma(-pi[c], pan[c * LR_PKR + (l - p0)], s);
+          rowp[l] = s;
         }
       }
       __syncthreads();
@@ -601,8 +621,8 @@ int lowrank_solve(ncm_sd_gpu_ctx *c, const double *dM, int ldm, int n, const dou
     // the base set itself: x_B = W (W^T b_B) -- two triangular matrix-vector products instead of the forward / back substitution
     // (the fused factorisation then runs without its right-hand side column and its back-substitution phase)
     lr_gather_r_kernel<<<(nB + 255) / 256, 256, 0, st>>>(db, w.bsel, nB, w.rB);
-    row_dot_kernel<ROW_LOWER><<<(nB * ROW_WPR + 7) / 8, 256, 0, st>>>(w.Wt, ldm, nB, w.rB, nullptr, 1.0, w.y);
-    row_dot_kernel<ROW_UPPER><<<(nB * ROW_WPR + 7) / 8, 256, 0, st>>>(w.W, ldm, nB, w.y, nullptr, 1.0, w.xB);
+    row_dot_kernel<ROW_LOWER><<<(nB * ROW_WPR + 7) / 8, 256, 0, st>>>(w.Wt, ldm, nB, w.rB, nullptr, 1.0, w.tb);   // t_b = W^T b_B: kept for the base's later sets
+    row_dot_kernel<ROW_UPPER><<<(nB * ROW_WPR + 7) / 8, 256, 0, st>>>(w.W, ldm, nB, w.tb, nullptr, 1.0, w.xB);
     c->n_launches += 3;
     if (refine) {
       lr_scatter_kernel<<<(nB + 255) / 256, 256, 0, st>>>(w.xfull, w.bsel, nB, w.xB, w.idxA, 0, w.z);
@@ -617,10 +637,15 @@ int lowrank_solve(ncm_sd_gpu_ctx *c, const double *dM, int ldm, int n, const dou
     NCM_CUDA_OK(c, cudaGetLastError());
     return NCM_SD_GPU_OK;
   }
-  lr_gather_V_kernel<<<(nB + 7) / 8, dim3(32, 8), 0, st>>>(dM, ldm, db, w.bsel, w.idxB, nB, w.idxA, na, w.posD, nd, w.V, ldv);
-  gemm_tn_splitk_kernel<<<dim3(ctiles, rtiles, ntc), GTHREADS, GEMM_SMEM, st>>>(w.W, ldm, w.V, ldv, Tpart, ldv, tstride, nB, kc, nB);
-  splitk_reduce_kernel<<<dim3((kc + 63) / 64, nB), 64, 0, st>>>(Tpart, tstride, ldv, nB, kc, nB, w.T);
-  c->n_launches += 3;
+  if (na == 0 && w.tb_valid) {
+    lr_gather_T_kernel<<<dim3((nB + 31) / 32, (kc + 31) / 32), dim3(32, 8), 0, st>>>(w.W, ldm, nB, w.posD, k, w.tb, w.T, ldv);
+    c->n_launches++;
+  } else {
+    lr_gather_V_kernel<<<(nB + 7) / 8, dim3(32, 8), 0, st>>>(dM, ldm, db, w.bsel, w.idxB, nB, w.idxA, na, w.posD, nd, w.V, ldv);
+    gemm_tn_splitk_kernel<<<dim3(ctiles, rtiles, ntc), GTHREADS, GEMM_SMEM, st>>>(w.W, ldm, w.V, ldv, Tpart, ldv, tstride, nB, kc, nB);
+    splitk_reduce_kernel<<<dim3((kc + 63) / 64, nB), 64, 0, st>>>(Tpart, tstride, ldv, nB, kc, nB, w.T);
+    c->n_launches += 3;
+  }
   if (k > 0) {
     syrk_splitk_kernel<<<dim3(ctiles * (ctiles + 1) / 2, nhc), GTHREADS, GEMM_SMEM, st>>>(w.T, ldv, Hpart, ldv, hstride, kc, nB);
     hreduce_kernel<<<dim3((kc + 63) / 64, kc), 64, 0, st>>>(Hpart, hstride, nhc, ldv, kc, H0);

@@ -237,6 +237,7 @@ int solve_lowrank(NnlsWork &w, const std::vector<int> &P, bool *done) {
   const bool refine = !w.base_trusted;
   int rc = lowrank_solve(c, w.dM, w.ldm, w.n, w.db, nB, na, nd, np, w.lb, w.ldv, refine);
   if (rc != NCM_SD_GPU_OK) return rc;
+  if (na + nd == 0) w.lb.tb_valid = true;   // the base's own solve left t_b = W^T b_B behind: pure removals now need no product with W
   NCM_CUDA_OK(c, ncm_memcpy_async(c, w.h_buf, w.lb.out, sizeof(double) * (size_t) (np + 2), cudaMemcpyDeviceToHost, c->stream));
   NCM_CUDA_OK(c, ncm_memcpy_async(c, w.h_buf + np + 2, w.lb.info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   NCM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
@@ -314,6 +315,7 @@ int solve_unconstrained(NnlsWork &w, const std::vector<int> &P) {
       w.base_valid   = true;
       w.w_valid      = false;
       w.base_trusted = false;
+      w.lb.tb_valid  = false;
     }
     if (!factor_only) {
       NCM_CUDA_OK(c, ncm_memcpy_async(c, w.h_buf, w.drhs, sizeof(double) * np, cudaMemcpyDeviceToHost, c->stream));
@@ -506,7 +508,7 @@ int nnls_solve_dev(ncm_sd_gpu_ctx *c, int nrows, int ncols, const double *dA, in
     b.z    = b.Lg + ((size_t) (kmax + 1) * (kmax + 2) / 2 + kpad);
     b.z2   = b.z + kpad;
     double *v = c->lrVec.as<double>();
-    b.y = v; b.xB = v + nv; b.dxB = v + 2 * nv; b.xfull = v + 3 * nv; b.rfull = v + 4 * nv; b.rB = v + 5 * nv; b.tr = v + 6 * nv; b.out = v + 7 * nv;
+    b.y = v; b.xB = v + nv; b.dxB = v + 2 * nv; b.xfull = v + 3 * nv; b.rfull = v + 4 * nv; b.rB = v + 5 * nv; b.tr = v + 6 * nv; b.out = v + 7 * nv; b.tb = v + 8 * nv;
     int *ix = c->lrIdx.as<int>();   // idxA | posD | bsel | psrc are uploaded together; idxB when a base is established
     b.idxA = ix; b.posD = ix + kpad; b.bsel = b.posD + kpad; b.psrc = b.bsel + nv; b.idxB = b.psrc + nv; b.info = b.idxB + nv;
   }

@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <functional>
 #include <string>
+#include <mutex>
 #include <vector>
 #include "../../include/ncm_sd_gpu.h"
 #include "../../include/ncm_stats_dist_b200.h"
@@ -75,6 +76,7 @@ struct _NcmStatsDistKernel {
 
 struct _NcmStatsDist {
   int ref;
+  std::mutex gpu_mutex;   // serialises the GPU calls of this object (its context, stream and buffers)
   int type;   // NCM_SD_GPU_KDE / VKDE
   NcmStatsDistKernel *kernel;
   guint d;

@@ -25,7 +25,8 @@
 
 namespace {
 
-std::mutex g_gpu_mutex;   // eval may be called concurrently from OpenMP threads (ncm_fit_esmcmc.c:2158)
+// GPU calls of ONE object are serialised by its own mutex (eval may be called concurrently from OpenMP threads, ncm_fit_esmcmc.c:2158);
+// different objects own different contexts and streams and run side by side
 
 double now_ms() {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -251,7 +252,7 @@ bool vkde_build_cov_array(NcmStatsDist *sd) {
     std::vector<int> fail(nk, 0);
     int rc;
     {
-      std::lock_guard<std::mutex> lk(g_gpu_mutex);
+      std::lock_guard<std::mutex> lk(sd->gpu_mutex);
       rc = ncm_sd_gpu_set_kernel(sd->gpu, sd->kernel->kind, sd->kernel->nu, d);
       if (rc == NCM_SD_GPU_OK)
         rc = ncm_sd_gpu_vkde_prepare(sd->gpu, n_obs, nk, sd->sample_matrix.data(), d, sd->invUsample.data(), d, (int) std::min(k, (size_t) n_obs),
@@ -274,7 +275,7 @@ bool vkde_build_cov_array(NcmStatsDist *sd) {
 #pragma omp parallel for if (sd->use_threads)
     for (int i = 0; i < nk; i++) sd->lnnorms[i] = ncm_stats_dist_kernel_get_lnnorm(sd->kernel, sd->cov_array[i]);
     {
-      std::lock_guard<std::mutex> lk(g_gpu_mutex);
+      std::lock_guard<std::mutex> lk(sd->gpu_mutex);
       rc = ncm_sd_gpu_vkde_finish(sd->gpu, sd->lnnorms.data(), (int) fixed_idx.size(), fixed_idx.data(), fixed_U.data());
     }
     if (!gpu_ok(sd, rc, "_ncm_stats_dist_vkde_build_cov_array_kdtree")) return false;
@@ -300,7 +301,7 @@ bool vkde_build_cov_array(NcmStatsDist *sd) {
 bool upload(NcmStatsDist *sd) {
   if (!ensure_gpu(sd)) return false;
   if (sd->type == NCM_SD_GPU_VKDE && sd->resident) return true;   // ncm_sd_gpu_vkde_prepare / _finish left everything in HBM
-  std::lock_guard<std::mutex> lk(g_gpu_mutex);
+  std::lock_guard<std::mutex> lk(sd->gpu_mutex);
   if (!gpu_ok(sd, ncm_sd_gpu_set_kernel(sd->gpu, sd->kernel->kind, sd->kernel->nu, (int) sd->d), "ncm_stats_dist_prepare_kernel")) return false;
   int rc;
   if (sd->type == NCM_SD_GPU_KDE)
@@ -328,7 +329,7 @@ bool prepare_kernel(NcmStatsDist *sd) {
 }
 
 bool push_weights(NcmStatsDist *sd) {
-  std::lock_guard<std::mutex> lk(g_gpu_mutex);
+  std::lock_guard<std::mutex> lk(sd->gpu_mutex);
   return gpu_ok(sd, ncm_sd_gpu_set_weights(sd->gpu, (int) sd->n_kernels, sd->weights->data, sd->href), "ncm_stats_dist_prepare");
 }
 
@@ -350,7 +351,7 @@ double cv_obj_m2lnp(NcmStatsDist *sd, double lnos) {
   std::vector<double> out((size_t) std::max(q, 1));
   if (!push_weights(sd)) return NAN;
   if (q > 0) {
-    std::lock_guard<std::mutex> lk(g_gpu_mutex);
+    std::lock_guard<std::mutex> lk(sd->gpu_mutex);
     if (!gpu_ok(sd, ncm_sd_gpu_eval_m2lnp(sd->gpu, q, &sd->sample_matrix[(size_t) sd->n_kernels * d], d, out.data()), "_ncm_stats_dist_m2lnp")) return NAN;
   }
   double m2lnp = 0.0;
@@ -362,7 +363,7 @@ double cv_obj_m2lnp(NcmStatsDist *sd, double lnos) {
 
 bool cv_IM_to_host(NcmStatsDist *sd, const char *where) {
   sd->IM_host.resize((size_t) sd->n_obs * sd->n_kernels);
-  std::lock_guard<std::mutex> lk(g_gpu_mutex);
+  std::lock_guard<std::mutex> lk(sd->gpu_mutex);
   if (!gpu_ok(sd, ncm_sd_gpu_set_href(sd->gpu, sd->href), where)) return false;
   return gpu_ok(sd, ncm_sd_gpu_compute_IM(sd->gpu, nullptr, sd->IM_host.data()), where);
 }
@@ -439,7 +440,7 @@ double cv_obj_amise(NcmStatsDist *sd, double lnos) {
       ncm_stats_dist_kernel_sample(sd->kernel, ncm_stats_dist_peek_cov_decomp(sd, o_j), sd->href, (NcmVector *) sd->sample[o_j], &x2, rng);
     }
     {
-      std::lock_guard<std::mutex> lk(g_gpu_mutex);
+      std::lock_guard<std::mutex> lk(sd->gpu_mutex);
       ok = gpu_ok(sd, ncm_sd_gpu_eval(sd->gpu, 2 * PAIRS, X->data, d, pv.data()), "_ncm_stats_dist_amise");
     }
     for (int b = 0; b < PAIRS && ok; b++) {
@@ -764,7 +765,7 @@ void ncm_b200_prepare_interp_finish(NcmStatsDist *sd, NcmVector *m2lnp) {
   if (sd->n_kernels > 20000) fprintf(stderr, "_ncm_stats_dist_prepare_interp: very large system n = %u!\n", sd->n_kernels);
   // _ncm_stats_dist_compute_IM_full + NCM_NNLS_SOLVE at the current href; the raw solution lands in sd->weights
   auto IM_nnls = [&](double *rnorm_out) -> bool {
-    std::lock_guard<std::mutex> lk(g_gpu_mutex);
+    std::lock_guard<std::mutex> lk(sd->gpu_mutex);
     // compute_IM needs the bandwidth (weights are irrelevant for IM)
     if (!gpu_ok(sd, ncm_sd_gpu_set_href(sd->gpu, sd->href), "prepare_interp")) return false;
     if (!gpu_ok(sd, ncm_sd_gpu_compute_IM(sd->gpu, inv_f.data(), nullptr), "_ncm_stats_dist_compute_IM_full")) return false;
@@ -799,7 +800,7 @@ void ncm_b200_prepare_interp_finish(NcmStatsDist *sd, NcmVector *m2lnp) {
       sd->href        = sd_href(sd);
       ok              = ok && IM_nnls(&rnorm) && push_weights(sd);
       if (ok) {
-        std::lock_guard<std::mutex> lk(g_gpu_mutex);
+        std::lock_guard<std::mutex> lk(sd->gpu_mutex);
         ok = gpu_ok(sd, ncm_sd_gpu_eval_m2lnp(sd->gpu, (int) sd->n_obs, sd->sample_matrix.data(), (int) sd->d, m2lnpi.data()),
                     "_ncm_stats_dist_prepare_interp_fit_nnls_f");
       }
@@ -848,7 +849,7 @@ gdouble ncm_stats_dist_eval(NcmStatsDist *sd, NcmVector *x) {
   if (!check_prepared(sd, "ncm_stats_dist_eval")) return NAN;
   double xx[NCM_SD_GPU_MAX_DIM], out = NAN;
   for (guint k = 0; k < sd->d; k++) xx[k] = ncm_vector_get(x, k);
-  std::lock_guard<std::mutex> lk(g_gpu_mutex);
+  std::lock_guard<std::mutex> lk(sd->gpu_mutex);
   gpu_ok(sd, ncm_sd_gpu_eval(sd->gpu, 1, xx, (int) sd->d, &out), "ncm_stats_dist_eval");
   return out;
 }
@@ -857,7 +858,7 @@ gdouble ncm_stats_dist_eval_m2lnp(NcmStatsDist *sd, NcmVector *x) {
   if (!check_prepared(sd, "ncm_stats_dist_eval_m2lnp")) return NAN;
   double xx[NCM_SD_GPU_MAX_DIM], out = NAN;
   for (guint k = 0; k < sd->d; k++) xx[k] = ncm_vector_get(x, k);
-  std::lock_guard<std::mutex> lk(g_gpu_mutex);
+  std::lock_guard<std::mutex> lk(sd->gpu_mutex);
   gpu_ok(sd, ncm_sd_gpu_eval_m2lnp(sd->gpu, 1, xx, (int) sd->d, &out), "ncm_stats_dist_eval_m2lnp");
   return out;
 }
@@ -868,7 +869,7 @@ static void eval_array(NcmStatsDist *sd, NcmMatrix *X, NcmVector *out, bool dens
     ncm_b200_error("ncm_stats_dist_eval_m2lnp_array: assertion failed (X is q x d, out has q contiguous entries)");
     return;
   }
-  std::lock_guard<std::mutex> lk(g_gpu_mutex);
+  std::lock_guard<std::mutex> lk(sd->gpu_mutex);
   const int rc = density ? ncm_sd_gpu_eval(sd->gpu, (int) X->nrows, X->data, (int) X->tda, out->data)
                          : ncm_sd_gpu_eval_m2lnp(sd->gpu, (int) X->nrows, X->data, (int) X->tda, out->data);
   gpu_ok(sd, rc, "ncm_stats_dist_eval_m2lnp_array");
@@ -1003,7 +1004,7 @@ gint ncm_stats_dist_b200_comm_unique_id(gchar id_out[128]) { return ncm_sd_gpu_c
 
 gboolean ncm_stats_dist_b200_comm_init(NcmStatsDist *sd, gint nranks, gint rank, const gchar id[128]) {
   if (!ensure_gpu(sd)) return FALSE;
-  std::lock_guard<std::mutex> lk(g_gpu_mutex);
+  std::lock_guard<std::mutex> lk(sd->gpu_mutex);
   if (!gpu_ok(sd, ncm_sd_gpu_comm_init(sd->gpu, nranks, rank, id), "ncm_stats_dist_b200_comm_init")) return FALSE;
   return gpu_ok(sd, ncm_sd_gpu_set_auto_shard(sd->gpu, 1), "ncm_stats_dist_b200_comm_init");
 }

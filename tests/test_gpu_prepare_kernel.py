@@ -69,6 +69,22 @@ def test_vkde_prepare_degenerate_falls_back(oracle):
     sd.prepare()
     out = sd.eval_m2lnp_array(X[:10])
     assert np.all(np.isfinite(out))
+    # the host nearPD runs Higham's iteration over a cyclic-Jacobi eigen-solver where ncm_matrix_nearPD
+    # (ncm_matrix.c:1248-1343) calls dsyevr.  A rank-k covariance (k = 3 of d = 6) has d - k eigenvalues that are zero up to rounding:
+    # which of them come out negative, and hence the repaired values min_pos * eps along those directions, is rounding-driven in the
+    # reference as well.  Stated bound: the repaired covariance U^T U -- everything the estimate determines -- agrees with the oracle's to
+    # 1e-10 of its largest entry; the factor itself and ln |U| are compared only through that product.
+    o = oracle.StatsDist(oracle.SD_VKDE, oracle.KERNEL_GAUSS, d, 3.0)
+    o.add_obs_matrix(X)
+    assert o.prepare() == 0
+    worst = 0.0
+    for i in range(n):
+        Ug, Uo = np.triu(sd.peek_cov_decomp(i)), np.triu(o.peek_cov_decomp(i))
+        Cg, Co = Ug.T @ Ug, Uo.T @ Uo
+        worst = max(worst, np.max(np.abs(Cg - Co)) / np.abs(Co).max())
+        assert np.all(np.isfinite(Ug)) and np.all(np.diag(Ug) > 0.0)
+    print(f"nearPD (Jacobi) vs oracle (dsyevr), {n} rank-3 covariances in d = 6: max |U^T U - ref| / max |ref| = {worst:.2e}")
+    assert worst < 1e-10
 
 
 def test_vkde_prepare_beyond_shared_memory_capacity(oracle, gpu_ctx):
