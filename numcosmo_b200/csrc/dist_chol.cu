@@ -65,6 +65,16 @@ __global__ void __launch_bounds__(GTHREADS) panel_solve_kernel(const double *__r
   gemm_tile<true>(W, DB, M + (size_t) k0 * ldm + j0, ldm, stage_me + (size_t) blockIdx.z * DB * DB, DB, bs, wj, i0, c0, 0, min(bs, i0 + GT), 1.0, smem);
 }
 
+// owner: info slot of the broadcast block <- status of the diagonal factorisation left on the device by the fused kernel
+__global__ void dc_set_info_kernel(const int *__restrict__ fused_info, int k0, double *__restrict__ pk_info) {
+  const int i = fused_info[0];
+  pk_info[0]  = i == 0 ? 0.0 : (double) (k0 + i);
+}
+// every rank: remember the first failing pivot (checked once, after the last step: no host round trip per block column)
+__global__ void dc_acc_info_kernel(const double *__restrict__ pk_info, double *__restrict__ acc) {
+  if (acc[0] == 0.0 && pk_info[0] != 0.0) acc[0] = pk_info[0];
+}
+
 __global__ void axpby_kernel(const double *__restrict__ a, const double *__restrict__ b, double sb, int n, double *__restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = a[i] + sb * b[i];
@@ -149,34 +159,29 @@ int dpotrf_upper_solve_dist(ncm_sd_gpu_ctx *c, int n, double *dM, int ldm, doubl
   const int *dTiles = c->dcTiles.as<int>();
 
   int info_all = 0;
+  double *dInfoAcc = pkInfo + 8;   // inside the 16-double info slot; slot 0 travels with the broadcast, slot 8 accumulates locally
+  NCM_CUDA_OK(c, cudaMemsetAsync(pkInfo, 0, 16 * sizeof(double), st));
+  if (DB > chol_fused_max_n()) return c->fail(NCM_SD_GPU_EINVAL, "dist_chol: block size exceeds the fused factorisation");
   for (int k = 0; k < nb; ++k) {
     const int k0 = k * DB, bs = std::min(DB, n - k0), owner = k % G;
     double *Akk = dM + (size_t) k0 * ldm + k0;
     if (me == owner) {
-      int info = 0;
-      double *dinv_scratch = c->dcVec.as<double>() + 2 * (DB + 16);
-      int *info_scratch    = reinterpret_cast<int *>(dinv_scratch + DB + 16);
-      int rc = dpotrf_upper_solve_any(c, bs, Akk, ldm, nullptr, dinv_scratch, info_scratch, &info);   // synchronises
+      // the fused kernel leaves its status on the device (chol_flags[0]); nothing here waits for the host
+      int rc = dpotrf_upper_solve_fused(c, bs, Akk, ldm, nullptr, nullptr);
       if (rc != NCM_SD_GPU_OK) return rc;
+      dc_set_info_kernel<<<1, 1, 0, st>>>(c->chol_flags.as<int>(), k0, pkInfo);
       pack_upper_kernel<<<dim3((bs + 127) / 128, bs), 128, 0, st>>>(Akk, ldm, pkU, DB, bs, 1);
       rc = trinv_upper(c, bs, pkU, pkW, pkS, DB, nullptr);
       if (rc != NCM_SD_GPU_OK) return rc;
-      const double finfo = info == 0 ? 0.0 : (double) (k0 + info);
-      NCM_CUDA_OK(c, cudaMemcpyAsync(pkInfo, &finfo, sizeof(double), cudaMemcpyHostToDevice, st));
-      NCM_CUDA_OK(c, cudaStreamSynchronize(st));   // finfo is a stack variable
-      c->n_launches++;
+      c->n_launches += 2;
     }
     {
-      ncclResult_t r = api.Broadcast(pkU, pkU, 2 * tile + 16, ncclDouble, owner, (ncclComm_t) c->nccl_comm, st);
+      // {U_kk, W_kk, info}: the first half of the info slot travels, the accumulator in its second half stays local
+      ncclResult_t r = api.Broadcast(pkU, pkU, 2 * tile + 8, ncclDouble, owner, (ncclComm_t) c->nccl_comm, st);
       if (r != ncclSuccess) return c->fail(NCM_SD_GPU_ENCCL, std::string("ncclBroadcast: ") + api.GetErrorString(r));
     }
-    double finfo = 0.0;
-    NCM_CUDA_OK(c, cudaMemcpyAsync(&finfo, pkInfo, sizeof(double), cudaMemcpyDeviceToHost, st));
-    NCM_CUDA_OK(c, cudaStreamSynchronize(st));
-    if (finfo != 0.0) {
-      info_all = (int) finfo;
-      break;
-    }
+    dc_acc_info_kernel<<<1, 1, 0, st>>>(pkInfo, dInfoAcc);
+    c->n_launches++;
     if (me != owner) pack_upper_kernel<<<dim3((bs + 127) / 128, bs), 128, 0, st>>>(pkU, DB, Akk, ldm, bs, 0);
     NCM_CUDA_OK(c, cudaMemcpyAsync(Wall + (size_t) k * tile, pkW, tile * sizeof(double), cudaMemcpyDeviceToDevice, st));
     if (k + 1 >= nb) break;
@@ -201,6 +206,12 @@ int dpotrf_upper_solve_dist(ncm_sd_gpu_ctx *c, int n, double *dM, int ldm, doubl
     }
   }
   NCM_CUDA_OK(c, cudaGetLastError());
+  {
+    double finfo = 0.0;
+    NCM_CUDA_OK(c, cudaMemcpyAsync(&finfo, dInfoAcc, sizeof(double), cudaMemcpyDeviceToHost, st));
+    NCM_CUDA_OK(c, cudaStreamSynchronize(st));
+    info_all = (int) finfo;
+  }
   if (info_host != nullptr) *info_host = info_all;
   if (info_all != 0 || dRhs == nullptr) {
     NCM_CUDA_OK(c, cudaStreamSynchronize(st));
