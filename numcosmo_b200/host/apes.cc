@@ -231,6 +231,9 @@ void setup_block(NcmFitESMCMCWalkerAPES *a, int block, const double *lb, const d
   std::vector<double> &s = block == 0 ? a->m2lnL_s0 : a->m2lnL_s1;
   const guint c0         = block == 0 ? a->size_2 : 0;   // centres come from the OTHER half
 
+  NcmB200ProfScope prof_block("setup_block(total)");
+  NcmB200HostProf *pslot = ncm_b200_prof_on() ? ncm_b200_prof_slot("reset+add_obs") : nullptr;
+  const double tp0 = pslot ? ncm_b200_now_ms() : 0.0;
   ncm_stats_dist_reset(sd);
   for (guint i = 0; i < a->size_2; i++) {
     s[i]         = m2lnL[c0 + i];
@@ -238,12 +241,21 @@ void setup_block(NcmFitESMCMCWalkerAPES *a, int block, const double *lb, const d
     ncm_stats_dist_add_obs(sd, v);
     ncm_vector_free(v);
   }
+  if (pslot) {
+    pslot->ms += ncm_b200_now_ms() - tp0;
+    pslot->calls++;
+  }
   bool speculated = false;
   NcmRNG rng0;   // generator state at the start of the block's draws
   if (a->use_interp) {
     NcmVector *mv = ncm_vector_new_data_static(s.data(), a->size_2, 1);
     static const bool spec_on = getenv("NCM_B200_APES_PREGEN") == nullptr || atoi(getenv("NCM_B200_APES_PREGEN")) != 0;
-    if (spec_on && ncm_b200_prepare_interp_begin(sd, mv)) {
+    bool begun = false;
+    if (spec_on) {
+      NcmB200ProfScope prof("prepare_interp_begin(prepare_kernel)");
+      begun = ncm_b200_prepare_interp_begin(sd, mv);
+    }
+    if (spec_on && begun) {
       // the kernel (hence the full covariance the random walk scales with) is prepared; the weights are what the GPU works on next
       prepare_random_walk(a, sd, rw, lb, ub);
       if (!ncm_b200_error_pending()) {
@@ -252,8 +264,14 @@ void setup_block(NcmFitESMCMCWalkerAPES *a, int block, const double *lb, const d
         a->n_spec_blocks++;
         const RandomWalk rw_used = rw;
         std::thread gen([&]() { pregenerate_block(a, ncm_stats_dist_peek_kernel(sd), rw_used, theta, ki, kf, rng); });
-        ncm_b200_prepare_interp_finish(sd, mv);
-        gen.join();
+        {
+          NcmB200ProfScope prof("prepare_interp_finish");
+          ncm_b200_prepare_interp_finish(sd, mv);
+        }
+        {
+          NcmB200ProfScope prof("join pregenerate thread");
+          gen.join();
+        }
         if (!ncm_b200_error_pending()) {
           prepare_random_walk(a, sd, rw, lb, ub);   // the dynamic-range guard may have re-prepared the object on a cut sample
           if (rw.std != rw_used.std || ncm_stats_dist_get_n_kernels(sd) != a->size_2) {
@@ -292,7 +310,10 @@ void setup_block(NcmFitESMCMCWalkerAPES *a, int block, const double *lb, const d
   NcmVector *out = ncm_vector_new(2 * nb);
   memcpy(ncm_matrix_data(Q), &a->thetastar[(size_t) ki * d], sizeof(double) * nb * d);
   memcpy(ncm_matrix_data(Q) + (size_t) nb * d, &theta[(size_t) ki * d], sizeof(double) * nb * d);
-  ncm_stats_dist_eval_m2lnp_array(sd, Q, out);
+  {
+    NcmB200ProfScope prof("eval_m2lnp_array");
+    ncm_stats_dist_eval_m2lnp_array(sd, Q, out);
+  }
   // per-walker and independent (erf-heavy when the random-walk mixture is on): threads change nothing in the values
 #pragma omp parallel for schedule(static) if (a->use_threads)
   for (long k = (long) ki; k < (long) kf; k++) {

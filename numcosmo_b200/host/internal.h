@@ -11,6 +11,27 @@
 
 // page-locked host array (cudaHostAlloc through the C ABI, plain malloc when no device is usable): the VKDE factor
 // slab comes back from the device every prepare_kernel (118 MB at N = 16384, d = 30) and pageable memory halves that copy
+// NCM_B200_PROFILE_HOST=1: wall-clock of the host-side stages of the end-to-end path, printed at exit (debugging aid)
+struct NcmB200HostProf {
+  const char *name;
+  double ms = 0.0;
+  long long calls = 0;
+};
+NcmB200HostProf *ncm_b200_prof_slot(const char *name);
+bool ncm_b200_prof_on();
+double ncm_b200_now_ms();
+struct NcmB200ProfScope {
+  NcmB200HostProf *s;
+  double t0;
+  explicit NcmB200ProfScope(const char *name) : s(ncm_b200_prof_on() ? ncm_b200_prof_slot(name) : nullptr), t0(s ? ncm_b200_now_ms() : 0.0) {}
+  ~NcmB200ProfScope() {
+    if (s) {
+      s->ms += ncm_b200_now_ms() - t0;
+      s->calls++;
+    }
+  }
+};
+
 struct NcmB200PinnedVec {
   double *p = nullptr;
   size_t n = 0;

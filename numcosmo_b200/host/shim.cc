@@ -285,3 +285,32 @@ void ncm_b200_cholesky_decomp_fallback(double *cov_decomp, const double *cov, in
     }
   }
 }
+
+
+// ---- NCM_B200_PROFILE_HOST ---------------------------------------------------------------------------------------------------
+#include <chrono>
+#include <mutex>
+namespace {
+NcmB200HostProf g_prof[64];
+int g_nprof = 0;
+std::mutex g_prof_mutex;
+void prof_dump() {
+  for (int i = 0; i < g_nprof; i++)
+    fprintf(stderr, "host_prof: %-34s %10.3f ms %8lld calls %9.2f us/call\n", g_prof[i].name, g_prof[i].ms, g_prof[i].calls,
+            g_prof[i].calls ? 1e3 * g_prof[i].ms / g_prof[i].calls : 0.0);
+}
+}   // namespace
+bool ncm_b200_prof_on() {
+  static const bool on = getenv("NCM_B200_PROFILE_HOST") != nullptr;
+  return on;
+}
+double ncm_b200_now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+NcmB200HostProf *ncm_b200_prof_slot(const char *name) {
+  std::lock_guard<std::mutex> lk(g_prof_mutex);
+  for (int i = 0; i < g_nprof; i++)
+    if (g_prof[i].name == name || strcmp(g_prof[i].name, name) == 0) return &g_prof[i];
+  if (g_nprof == 0) atexit(prof_dump);
+  if (g_nprof >= 64) return &g_prof[63];
+  g_prof[g_nprof].name = name;
+  return &g_prof[g_nprof++];
+}

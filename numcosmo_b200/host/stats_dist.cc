@@ -139,6 +139,7 @@ double sd_href(NcmStatsDist *sd) {
 
 // ncm_stats_dist_kde.c:378-490
 bool kde_prepare_kernel(NcmStatsDist *sd) {
+  NcmB200ProfScope prof("kde_prepare_kernel(host cov+whiten)");
   const int d = (int) sd->d;
   StatsVec sv(d);
   for (guint i = 0; i < sd->n_kernels; i++) sv.append(((NcmVector *) sd->sample[i])->data);
@@ -252,6 +253,7 @@ bool vkde_build_cov_array(NcmStatsDist *sd) {
     std::vector<int> fail(nk, 0);
     int rc;
     {
+      NcmB200ProfScope prof("vkde_prepare(ABI)");
       std::lock_guard<std::mutex> lk(sd->gpu_mutex);
       rc = ncm_sd_gpu_set_kernel(sd->gpu, sd->kernel->kind, sd->kernel->nu, d);
       if (rc == NCM_SD_GPU_OK)
@@ -272,9 +274,13 @@ bool vkde_build_cov_array(NcmStatsDist *sd) {
         memcpy(&fixed_U[f * d * d], &sd->cov_slab[(size_t) fixed_idx[f] * d * d], sizeof(double) * d * d);
       }
     }
-#pragma omp parallel for if (sd->use_threads)
-    for (int i = 0; i < nk; i++) sd->lnnorms[i] = ncm_stats_dist_kernel_get_lnnorm(sd->kernel, sd->cov_array[i]);
     {
+      NcmB200ProfScope prof("lnnorms(host)");
+#pragma omp parallel for if (sd->use_threads)
+      for (int i = 0; i < nk; i++) sd->lnnorms[i] = ncm_stats_dist_kernel_get_lnnorm(sd->kernel, sd->cov_array[i]);
+    }
+    {
+      NcmB200ProfScope prof("vkde_finish(ABI)");
       std::lock_guard<std::mutex> lk(sd->gpu_mutex);
       rc = ncm_sd_gpu_vkde_finish(sd->gpu, sd->lnnorms.data(), (int) fixed_idx.size(), fixed_idx.data(), fixed_U.data());
     }
@@ -765,6 +771,7 @@ void ncm_b200_prepare_interp_finish(NcmStatsDist *sd, NcmVector *m2lnp) {
   if (sd->n_kernels > 20000) fprintf(stderr, "_ncm_stats_dist_prepare_interp: very large system n = %u!\n", sd->n_kernels);
   // _ncm_stats_dist_compute_IM_full + NCM_NNLS_SOLVE at the current href; the raw solution lands in sd->weights
   auto IM_nnls = [&](double *rnorm_out) -> bool {
+    NcmB200ProfScope prof("IM+NNLS(ABI)");
     std::lock_guard<std::mutex> lk(sd->gpu_mutex);
     // compute_IM needs the bandwidth (weights are irrelevant for IM)
     if (!gpu_ok(sd, ncm_sd_gpu_set_href(sd->gpu, sd->href), "prepare_interp")) return false;
