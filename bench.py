@@ -60,6 +60,8 @@ def parse():
                          "replicas: one independent ensemble per GPU, no data-path collective (weak scaling; how several chains are run).")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.impl == "reference":   # the reference arm describes the workload of the --gpus N arm it sits next to, torchrun or not
+        world = max(world, a.gpus)
     big = world > 1 and a.apes_multi == "sharded" and a.workload == "apes_vkde_gauss_mvnd10_w4096"
     if a.walkers is None:
         a.walkers = 32768 if big else 4096

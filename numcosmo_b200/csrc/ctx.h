@@ -126,6 +126,8 @@ inline cudaError_t ncm_memcpy2d_async(ncm_sd_gpu_ctx *c, void *dst, size_t dpitc
                                       cudaMemcpyKind kind, cudaStream_t s) {
   if (kind == cudaMemcpyHostToDevice) c->h2d_bytes += (long long) (width * height);
   if (kind == cudaMemcpyDeviceToHost) c->d2h_bytes += (long long) (width * height);
+  // densely packed on both sides (the usual case: ld == d): one linear copy instead of `height` row descriptors
+  if (dpitch == width && spitch == width) return cudaMemcpyAsync(dst, src, width * height, kind, s);
   return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, kind, s);
 }
 

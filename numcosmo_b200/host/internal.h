@@ -23,13 +23,15 @@ double ncm_b200_now_ms();
 struct NcmB200ProfScope {
   NcmB200HostProf *s;
   double t0;
-  explicit NcmB200ProfScope(const char *name) : s(ncm_b200_prof_on() ? ncm_b200_prof_slot(name) : nullptr), t0(s ? ncm_b200_now_ms() : 0.0) {}
-  ~NcmB200ProfScope() {
+  explicit NcmB200ProfScope(const char *name, bool = false) : s(ncm_b200_prof_on() ? ncm_b200_prof_slot(name) : nullptr), t0(s ? ncm_b200_now_ms() : 0.0) {}
+  void stop() {
     if (s) {
       s->ms += ncm_b200_now_ms() - t0;
       s->calls++;
+      s = nullptr;
     }
   }
+  ~NcmB200ProfScope() { stop(); }
 };
 
 struct NcmB200PinnedVec {
@@ -103,6 +105,7 @@ struct _NcmStatsDist {
   guint d;
   // sample_array: GPtrArray of NcmVector (add_obs dups, ncm_stats_dist.c:1681-1686)
   std::vector<void *> sample;
+  std::vector<void *> obs_pool;   // observation copies released by reset, reused by add_obs
   GPtrArray sample_view;
   // properties
   double over_smooth, shrink, split_frac, local_frac;

@@ -197,6 +197,7 @@ bool kde_prepare_kernel(NcmStatsDist *sd) {
 // the raw neighbours accumulated in that order, Cholesky with the nearPD / diagonal fallback.
 bool vkde_build_cov_array(NcmStatsDist *sd) {
   const int d = (int) sd->d, n_obs = (int) sd->n_obs, nk = (int) sd->n_kernels;
+  NcmB200ProfScope prof_pre("vkde_build_cov_array(host setup)", true);
   const double kd = (sd->local_frac * n_obs > 2.0) ? sd->local_frac * n_obs : 2.0;   // GSL_MAX (local_frac * n_obs, 2)
   const size_t k  = (size_t) kd;
   const bool robust = sd->cov_type == NCM_STATS_DIST_KDE_COV_TYPE_ROBUST_DIAG || sd->cov_type == NCM_STATS_DIST_KDE_COV_TYPE_ROBUST;
@@ -248,9 +249,11 @@ bool vkde_build_cov_array(NcmStatsDist *sd) {
   // Device path: kNN + covariance + Cholesky in libncm_sd_gpu, bit-identical to host_centre;
   // only the matrices whose plain Cholesky fails come back to the host for the reference's fallback chain.
   // the robust estimators are sort-bound O(d^2 k log k) work per centre: they stay on the host, OpenMP over the centres
+  prof_pre.stop();
   const bool host_only = ncm_b200_host_prepare_kernel() || robust;
   if (!host_only && n_obs <= 65536 && ensure_gpu(sd)) {
     std::vector<int> fail(nk, 0);
+    NcmB200ProfScope prof_dev("vkde device path(total)");
     int rc;
     {
       NcmB200ProfScope prof("vkde_prepare(ABI)");
@@ -329,8 +332,12 @@ bool prepare_kernel(NcmStatsDist *sd) {
   }
   sd->resident = false;
   if (!kde_prepare_kernel(sd)) return false;
-  if (sd->type == NCM_SD_GPU_VKDE && !vkde_build_cov_array(sd)) return false;
+  {
+    NcmB200ProfScope prof("vkde_build_cov_array(total)");
+    if (sd->type == NCM_SD_GPU_VKDE && !vkde_build_cov_array(sd)) return false;
+  }
   sd->host_prepare_kernel_ms += now_ms() - t0;
+  NcmB200ProfScope prof("upload");
   return upload(sd);
 }
 
@@ -547,6 +554,8 @@ NcmStatsDist *ncm_stats_dist_ref(NcmStatsDist *sd) {
 void ncm_stats_dist_free(NcmStatsDist *sd) {
   if (sd == nullptr || --sd->ref > 0) return;
   ncm_stats_dist_reset(sd);
+  for (void *p : sd->obs_pool) ncm_vector_free((NcmVector *) p);
+  sd->obs_pool.clear();
   clear_cov_array(sd);
   ncm_stats_dist_kernel_free(sd->kernel);
   ncm_matrix_clear(&sd->cov_fixed);
@@ -657,11 +666,26 @@ void ncm_stats_dist_add_obs(NcmStatsDist *sd, NcmVector *y) {
     ncm_b200_error("ncm_stats_dist_add_obs: assertion failed (ncm_vector_len (y) == d)");
     return;
   }
+  // observations are copied (ncm_stats_dist.c:1681-1686); APES resets and refills the object twice per iteration, so the copies released
+  // by the last reset are reused instead of going through the allocator 2 x n_obs times
+  if (!sd->obs_pool.empty()) {
+    NcmVector *v = (NcmVector *) sd->obs_pool.back();
+    sd->obs_pool.pop_back();
+    for (guint i = 0; i < sd->d; i++) v->data[i] = y->data[(size_t) i * y->stride];
+    sd->sample.push_back(v);
+    return;
+  }
   sd->sample.push_back(ncm_vector_dup(y));
 }
 
 void ncm_stats_dist_reset(NcmStatsDist *sd) {
-  for (void *v : sd->sample) ncm_vector_free((NcmVector *) v);
+  for (void *p : sd->sample) {
+    NcmVector *v = (NcmVector *) p;
+    if (v->ref == 1 && v->own && v->len == sd->d && v->stride == 1 && sd->obs_pool.size() < 131072)
+      sd->obs_pool.push_back(v);   // nobody else holds it: keep the storage for the next add_obs
+    else
+      ncm_vector_free(v);
+  }
   sd->sample.clear();
   sd->prepared = false;
 }
