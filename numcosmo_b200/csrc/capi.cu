@@ -159,6 +159,10 @@ int ncm_sd_gpu_ctx_free(ncm_sd_gpu_ctx *c) {
   cudaEventDestroy(c->ev3);
   if (c->ev_panel != nullptr) cudaEventDestroy(c->ev_panel);
   if (c->ev_tail != nullptr) cudaEventDestroy(c->ev_tail);
+  for (cudaEvent_t e : {c->dc_evP, c->dc_evA, c->dc_evD, c->dc_evW, c->dc_evU})
+    if (e != nullptr) cudaEventDestroy(e);
+  if (c->dc_sW != nullptr) cudaStreamDestroy(c->dc_sW);
+  if (c->dc_sP != nullptr) cudaStreamDestroy(c->dc_sP);
   if (c->stream_hi != nullptr) cudaStreamDestroy(c->stream_hi);
   cudaStreamDestroy(c->stream);
   delete c;

@@ -25,6 +25,7 @@
 // Measured (tools/chol_trace.py, n = 2048) with three CTA barriers per 8-row strip: 21 us per 64-column phase = factor 11.2
 // + store/flag 1.5 + panel 7.1 + update 3.8 of which the 8 x 8 pivot chain (rsqrt -> mul -> fma, one warp) is about 0.4 us per
 // strip; diag_factor and panel_solve below are therefore warp-level data flow without CTA barriers.
+#include <algorithm>
 #include "ctx.h"
 
 namespace {
@@ -1025,14 +1026,23 @@ int chol_fused_max_n() { return 4096; }
 // In-place factorisation of the upper triangle of dM (n x n, ld = ldm even, 16-byte aligned rows) and, when
 // dRhs != nullptr, solution of M x = rhs in place.  info_host: 0 or the 1-based index of the first non-positive pivot.
 int dpotrf_upper_solve_fused(ncm_sd_gpu_ctx *c, int n, double *dM, int ldm, double *dRhs, int *info_host) {
+  return dpotrf_upper_solve_fused_on(c, c->stream, c->n_sm, n, dM, ldm, dRhs, info_host);
+}
+
+// The same on stream `st` with at most `max_ctas` CTAs (>= 2: the spine and one worker): a small block factorised next to other work
+// (dist_chol.cu: the next diagonal block while the trailing update of the previous step still owns most SMs) does not have to wait
+// for the whole device to drain, as a cooperative launch of one CTA per SM would.  One fused factorisation per context at a time
+// (the dependency flags are the context's).
+int dpotrf_upper_solve_fused_on(ncm_sd_gpu_ctx *c, cudaStream_t st, int max_ctas, int n, double *dM, int ldm, double *dRhs, int *info_host) {
   if (n <= 0 || n > chol_fused_max_n()) return c->fail(NCM_SD_GPU_EINVAL, "chol_fused: order out of range");
+  const int nctas = std::max(2, std::min(max_ctas, c->n_sm));
   const int nb  = (n + FB - 1) / FB;
   const int nbc = nb + (dRhs != nullptr ? 1 : 0);
   const int nbm = chol_fused_max_n() / FB;
   const size_t n_flags = (size_t) nbm + (size_t) nbm * (nbm + 1) + nbm + (size_t) nbm * nbm + 2 * nbm + 8;
   if (c->chol_flags.cap == 0) {
     if (!c->chol_flags.reserve(n_flags * sizeof(int))) return c->fail(NCM_SD_GPU_ENOMEM, "chol_fused: out of device memory");
-    NCM_CUDA_OK(c, cudaMemsetAsync(c->chol_flags.p, 0, c->chol_flags.cap, c->stream));
+    NCM_CUDA_OK(c, cudaMemsetAsync(c->chol_flags.p, 0, c->chol_flags.cap, st));
     NCM_CUDA_OK(c, cudaFuncSetAttribute(chol_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FUSED_SMEM));
     int per_sm = 0;
     NCM_CUDA_OK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_fused_kernel, FT, FUSED_SMEM));
@@ -1056,14 +1066,23 @@ int dpotrf_upper_solve_fused(ncm_sd_gpu_ctx *c, int n, double *dM, int ldm, doub
   a.epoch = ++c->chol_epoch;
   a.nb = nb; a.nbc = nbc;
   a.trace = c->chol_trace; a.trace_cap = c->chol_trace_cap;
-  NCM_CUDA_OK(c, cudaMemsetAsync(f, 0, 2 * sizeof(int), c->stream));
+  NCM_CUDA_OK(c, cudaMemsetAsync(f, 0, 2 * sizeof(int), st));
   void *params[] = {&a};
-  NCM_CUDA_OK(c, cudaLaunchCooperativeKernel((const void *) chol_fused_kernel, dim3(c->n_sm), dim3(FT), params, FUSED_SMEM, c->stream));
+  if (nctas == c->n_sm) {
+    NCM_CUDA_OK(c, cudaLaunchCooperativeKernel((const void *) chol_fused_kernel, dim3(nctas), dim3(FT), params, FUSED_SMEM, st));
+  } else {
+    // A partial grid next to other kernels: a cooperative launch would wait until all its CTAs fit at once, i.e. (with the update CTAs
+    // of the other stream owning whole SMs) until that kernel has drained.  An ordinary launch places the CTAs as SMs retire; they do
+    // become co-resident -- far fewer CTAs than SMs, and the CTAs they wait behind belong to kernels that terminate -- so the flag
+    // waits inside the kernel cannot deadlock.
+    chol_fused_kernel<<<nctas, FT, FUSED_SMEM, st>>>(a);
+    NCM_CUDA_OK(c, cudaGetLastError());
+  }
   c->n_launches++;
   if (info_host != nullptr) {
     int h[2] = {0, 0};
-    NCM_CUDA_OK(c, ncm_memcpy_async(c, h, f, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    NCM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    NCM_CUDA_OK(c, ncm_memcpy_async(c, h, f, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    NCM_CUDA_OK(c, cudaStreamSynchronize(st));
     if (h[1] != 0) return c->fail(NCM_SD_GPU_ECUDA, "chol_fused: a tile dependency was never satisfied (internal error)");
     *info_host = h[0];
   }

@@ -100,6 +100,9 @@ struct ncm_sd_gpu_ctx {
   // look-ahead Cholesky (chol.cu): a highest-priority stream for the latency-bound panel kernels, run concurrently with the
   // trailing updates on `stream`; created on first use
   cudaStream_t stream_hi = nullptr;
+  // distributed Cholesky (dist_chol.cu): stream of the diagonal-block inversions, events between its three streams
+  cudaStream_t dc_sP = nullptr, dc_sW = nullptr;
+  cudaEvent_t dc_evP = nullptr, dc_evA = nullptr, dc_evD = nullptr, dc_evW = nullptr, dc_evU = nullptr;
   cudaEvent_t ev_panel = nullptr, ev_tail = nullptr;
 
   int fail(int code, const std::string &msg) {
@@ -198,6 +201,7 @@ int update_cterm(ncm_sd_gpu_ctx *c);
 
 int chol_fused_max_n();
 int dpotrf_upper_solve_fused(ncm_sd_gpu_ctx *c, int n, double *dM, int ldm, double *dRhs, int *info_host);
+int dpotrf_upper_solve_fused_on(ncm_sd_gpu_ctx *c, cudaStream_t st, int max_ctas, int n, double *dM, int ldm, double *dRhs, int *info_host);
 int dpotrf_upper_solve_any(ncm_sd_gpu_ctx *c, int n, double *dM, int ldm, double *dRhs, double *dDinv, int *dInfo, int *info_host);
 int dsyrk_ata(ncm_sd_gpu_ctx *c, int nrows, int ncols, const double *dA, int lda, double *dM, int ldm);
 int dpotrf_upper(ncm_sd_gpu_ctx *c, int n, double *dM, int ldm, double *dRhs /* optional, solved in place */, int *info_host);
@@ -222,6 +226,8 @@ int lowrank_kmax();
 size_t lowrank_part_doubles(int n, int ldv);
 int symmetrize_upper(ncm_sd_gpu_ctx *c, int n, double *dM, int ld);
 int trinv_upper(ncm_sd_gpu_ctx *c, int n, const double *dU, double *dW, double *dS, int ld, double *dWt);
+int trinv_upper_on(ncm_sd_gpu_ctx *c, cudaStream_t st, int n, const double *dU, double *dW, double *dS, int ld, double *dWt);
+int dsyrk_ata_tiles_on(ncm_sd_gpu_ctx *c, cudaStream_t st, int K, int n, const double *dP, int ldp, double *dC, int ldc, const int *dTiles, int ntiles);
 int lowrank_solve(ncm_sd_gpu_ctx *c, const double *dM, int ldm, int n, const double *db, int nB, int na, int nd, int np, const LowrankBufs &w, int ldv,
                   bool refine);
 int sample_apply_launch(ncm_sd_gpu_ctx *c, int q, const int *dIdx, const double *dZ, int ldz, const double *dScale, double *dX, int ldx);

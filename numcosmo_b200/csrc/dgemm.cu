@@ -287,10 +287,13 @@ int dsyrk_ata_general(ncm_sd_gpu_ctx *c, int K, int n, const double *dP, int ldp
 
 // C -= P^T P on the listed upper 128-tiles only (P: K x n row-major, C: n x n)
 int dsyrk_ata_tiles(ncm_sd_gpu_ctx *c, int K, int n, const double *dP, int ldp, double *dC, int ldc, const int *dTiles /* pairs (ti, tj) */, int ntiles) {
+  return dsyrk_ata_tiles_on(c, c->stream, K, n, dP, ldp, dC, ldc, dTiles, ntiles);
+}
+int dsyrk_ata_tiles_on(ncm_sd_gpu_ctx *c, cudaStream_t st, int K, int n, const double *dP, int ldp, double *dC, int ldc, const int *dTiles, int ntiles) {
   if (ntiles <= 0 || K <= 0) return NCM_SD_GPU_OK;
   if ((ldp & 1) || (ldc & 1) || (((uintptr_t) dP) & 15) || (((uintptr_t) dC) & 15))
     return c->fail(NCM_SD_GPU_EINVAL, "ata: operands must be 16-byte aligned with even leading dimensions");
-  NCM_CUDA_OK(c, ata_launch_tiles(c->stream, dP, ldp, K, n, dC, ldc, reinterpret_cast<const int2 *>(dTiles), ntiles));
+  NCM_CUDA_OK(c, ata_launch_tiles(st, dP, ldp, K, n, dC, ldc, reinterpret_cast<const int2 *>(dTiles), ntiles));
   c->n_launches++;
   return NCM_SD_GPU_OK;
 }

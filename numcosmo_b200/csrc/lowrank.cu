@@ -582,25 +582,29 @@ int symmetrize_upper(ncm_sd_gpu_ctx *c, int n, double *dM, int ld) {
 
 // W = U^-1 for the upper-triangular factor U (n x n, row-major, ld); S is scratch of the same shape.  Wt (optional) receives W^T
 // (lower triangle and diagonal; its upper triangle is not written).
-int trinv_upper(ncm_sd_gpu_ctx *c, int n, const double *dU, double *dW, double *dS, int ld, double *dWt) {
+int trinv_upper_on(ncm_sd_gpu_ctx *c, cudaStream_t st, int n, const double *dU, double *dW, double *dS, int ld, double *dWt) {
   NCM_CUDA_OK(c, set_smem_attrs());
-  NCM_CUDA_OK(c, cudaMemsetAsync(dW, 0, (size_t) n * ld * sizeof(double), c->stream));
-  trinv_diag_kernel<<<(n + 63) / 64, 64, 0, c->stream>>>(dU, dW, ld, n);
+  NCM_CUDA_OK(c, cudaMemsetAsync(dW, 0, (size_t) n * ld * sizeof(double), st));
+  trinv_diag_kernel<<<(n + 63) / 64, 64, 0, st>>>(dU, dW, ld, n);
   c->n_launches++;
   for (int s = 64; s < n; s *= 2) {
     const int pairs = (n - s + 2 * s - 1) / (2 * s);
     dim3 grid((s + GT - 1) / GT, (s + GT - 1) / GT, pairs);
-    trinv_step1_kernel<<<grid, GTHREADS, GEMM_SMEM, c->stream>>>(dU, dW, dS, ld, n, s);
-    trinv_step2_kernel<<<grid, GTHREADS, GEMM_SMEM, c->stream>>>(dW, dS, ld, n, s);
+    trinv_step1_kernel<<<grid, GTHREADS, GEMM_SMEM, st>>>(dU, dW, dS, ld, n, s);
+    trinv_step2_kernel<<<grid, GTHREADS, GEMM_SMEM, st>>>(dW, dS, ld, n, s);
     c->n_launches += 2;
   }
   if (dWt != nullptr) {
     const int nt = (n + 31) / 32;
-    transpose_upper_kernel<<<nt * (nt + 1) / 2, dim3(32, 8), 0, c->stream>>>(dW, dWt, ld, n, nt);
+    transpose_upper_kernel<<<nt * (nt + 1) / 2, dim3(32, 8), 0, st>>>(dW, dWt, ld, n, nt);
     c->n_launches++;
   }
   NCM_CUDA_OK(c, cudaGetLastError());
   return NCM_SD_GPU_OK;
+}
+
+int trinv_upper(ncm_sd_gpu_ctx *c, int n, const double *dU, double *dW, double *dS, int ld, double *dWt) {
+  return trinv_upper_on(c, c->stream, n, dU, dW, dS, ld, dWt);
 }
 
 // Solve M[P,P] x = b[P] for P = (B \ D) u A through the base inverse W (see the header).  M is full symmetric.  Device index arrays
