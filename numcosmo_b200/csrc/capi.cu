@@ -5,8 +5,6 @@
 #include "ctx.h"
 #include "nccl_shim.h"
 
-int lse_finalize_launch(ncm_sd_gpu_ctx *c, const double *pm, const double *ps, const double *row_add, int q, int n_splits, double shift,
-                        bool as_density, double *dOut);
 int dsyrk_ata_general(ncm_sd_gpu_ctx *c, int K, int n, const double *dP, int ldp, double *dC, int ldc, double alpha, double beta);
 int dpotrf_upper_solve(ncm_sd_gpu_ctx *c, int n, double *dM, int ldm, double *dRhs, double *dDinv, int *dInfo, int *info_host);
 int sample_philox_launch(ncm_sd_gpu_ctx *c, int q, unsigned long long seed, unsigned long long offset, double *dX, int ldx, int *dIdx);
@@ -86,6 +84,25 @@ __global__ void sample_apply_kernel(const double *__restrict__ centres, int ldc,
   }
 }
 
+// clin[i] = exp(cterm[i] - cmax), cmax = max_i cterm[i] (single CTA: two passes over at most a few 10^5 entries); clin[n] = cmax
+__global__ void clin_kernel(const double *__restrict__ cterm, int n, double *__restrict__ clin) {
+  __shared__ double red[32];
+  __shared__ double s_max;
+  double m = NCM_NEG_BIG;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmax(m, cterm[i]);
+  for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int) (blockDim.x >> 5); ++w) m = fmax(m, red[w]);
+    s_max   = m;
+    clin[n] = m;
+  }
+  __syncthreads();
+  const double cm = s_max;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) clin[i] = exp(cterm[i] - cm);   // zero weights (NEG_BIG) -> exactly 0
+}
+
 int check_ready(ncm_sd_gpu_ctx *c, bool need_weights) {
   if (c == nullptr) return NCM_SD_GPU_EINVAL;
   if (c->type < 0 || c->n_kernels <= 0) return c->fail(NCM_SD_GPU_EINVAL, "no centres uploaded");
@@ -95,6 +112,37 @@ int check_ready(ncm_sd_gpu_ctx *c, bool need_weights) {
 
 }   // namespace
 
+bool st_linear_enabled(const ncm_sd_gpu_ctx *c) {
+  static const bool env_on = [] {
+    const char *e = getenv("NCM_SD_GPU_ST_LINEAR");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  const double m = c->nu + c->d;
+  return env_on && c->kind == NCM_SD_GPU_KERNEL_ST && c->nu >= 1.0 && c->nu == floor(c->nu) && m <= 96.0;
+}
+
+void ncm_fill_kp(const ncm_sd_gpu_ctx *c, KernParams &kp, bool eval) {
+  kp.kind   = c->kind;
+  kp.nu     = c->nu;
+  kp.kappa  = -0.5 * (c->nu + c->d);
+  kp.inv_nu = 1.0 / c->nu;
+  kp.m2     = st_linear_enabled(c) ? (int) (c->nu + c->d) : 0;
+  kp.lin    = (eval && kp.m2 > 0 && c->clin_n > 0) ? 1 : 0;
+  kp.cmax   = kp.lin ? c->clin.as<double>() + c->clin_n : nullptr;
+}
+
+// linear-domain weights of the Student-t evaluation from the log-domain ones (dCterm [n_alloc], padding = NEG_BIG)
+int build_clin(ncm_sd_gpu_ctx *c, const double *dCterm, int n_alloc) {
+  c->clin_n = 0;
+  if (!st_linear_enabled(c)) return NCM_SD_GPU_OK;
+  if (!c->clin.reserve((size_t) (n_alloc + 4) * sizeof(double))) return c->fail(NCM_SD_GPU_ENOMEM, "clin: out of device memory");
+  clin_kernel<<<1, 1024, 0, c->stream>>>(dCterm, n_alloc, c->clin.as<double>());
+  c->n_launches++;
+  NCM_CUDA_OK(c, cudaGetLastError());
+  c->clin_n = n_alloc;
+  return NCM_SD_GPU_OK;
+}
+
 int update_cterm(ncm_sd_gpu_ctx *c) {
   if (c->type == NCM_SD_GPU_VKDE) {
     const int n_alloc = c->n_kernels + 2;
@@ -103,7 +151,7 @@ int update_cterm(ncm_sd_gpu_ctx *c) {
                                                              c->cterm.as<double>());
     c->n_launches++;
     NCM_CUDA_OK(c, cudaGetLastError());
-    return NCM_SD_GPU_OK;
+    return build_clin(c, c->cterm.as<double>(), n_alloc);
   }
   return kde_set_weights(c);
 }
@@ -148,7 +196,7 @@ int ncm_sd_gpu_ctx_free(ncm_sd_gpu_ctx *c) {
   if (c->nccl_comm != nullptr && nccl_api().ok) nccl_api().CommDestroy((ncclComm_t) c->nccl_comm);
   DevBuf *bufs[] = {&c->sample, &c->vrec, &c->lnu, &c->cterm, &c->weights, &c->Ufull, &c->zc, &c->zmean, &c->bfrag, &c->kde_U, &c->qX,
                     &c->qOut, &c->qA, &c->part, &c->IM, &c->rowscale, &c->M, &c->MU, &c->nn_b, &c->nn_x, &c->nn_r, &c->nn_g, &c->nn_tmp,
-                    &c->nn_idx, &c->nn_f, &c->chol_flags, &c->chol_part, &c->vrec_mma, &c->dist, &c->lrW, &c->lrWt, &c->lrS, &c->lrV, &c->lrT, &c->lrPart, &c->lrSmall, &c->lrVec, &c->lrIdx, &c->gath, &c->dcPack, &c->dcW, &c->dcStage, &c->dcVec, &c->dcTiles, &c->bkWork, &c->qrWork};
+                    &c->nn_idx, &c->nn_f, &c->chol_flags, &c->chol_part, &c->vrec_mma, &c->dist, &c->lrW, &c->lrWt, &c->lrS, &c->lrV, &c->lrT, &c->lrPart, &c->lrSmall, &c->lrVec, &c->lrIdx, &c->gath, &c->dcPack, &c->dcW, &c->dcStage, &c->dcVec, &c->dcTiles, &c->bkWork, &c->qrWork, &c->clin};
   for (DevBuf *b : bufs) b->release();
   c->pinX.release();
   c->pinOut.release();
@@ -188,6 +236,7 @@ int ncm_sd_gpu_set_kernel(ncm_sd_gpu_ctx *c, int kind, double nu, int d) {
   c->d    = d;
   c->type = -1;
   c->have_weights = false;
+  c->clin_n = 0;
   return NCM_SD_GPU_OK;
 }
 

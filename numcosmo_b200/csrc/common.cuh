@@ -211,12 +211,34 @@ struct KernParams {
   double nu;
   double kappa;    // -(nu + d) / 2
   double inv_nu;
+  int m2;          // ST with integer nu: nu + d, so that Kbar = rsqrt(1 + chi2/nu)^m2 (0: use exp(kappa log1p))
+  int lin;         // ST eval in the linear domain: sum_i exp(c_i - cmax) Kbar_i, no exp / log per pair (needs m2 > 0)
+  const double *cmax;   // device scalar: max_i c_i of the current weights (lin)
 };
+
+// Student-t kernel with an integer number of degrees of freedom: (1 + chi2/nu)^(-(nu + d)/2) = r^(nu + d), r = rsqrt(1 + chi2/nu).
+// One rsqrt and at most 2 log2(m) multiplications (m is uniform over the grid) instead of log1p + exp: relative error <= (m + 1) ulp
+// (4e-15 at m = 35), the same order as the table-based log1p above.  Reference: pow (1 + chi2/nu, kappa), ncm_stats_dist_kernel_st.c:239-243.
+__device__ __forceinline__ double st_pow_u(const KernParams &kp, const double u) {   // u = chi2 / nu >= 0
+  double base = rsqrt(1.0 + u), res = 1.0;
+  for (int e = kp.m2; e != 0; e >>= 1) {
+    if (e & 1) res *= base;
+    base *= base;
+  }
+  return res;
+}
+__device__ __forceinline__ double st_pow_int(const KernParams &kp, const double chi2) { return st_pow_u(kp, fmax(chi2, 0.0) * kp.inv_nu); }
 
 __device__ __forceinline__ double kern_lnK(const KernParams &kp, const double chi2) {
   return kp.kind == 0 ? -0.5 * chi2 : kp.kappa * log1p_nonneg_fast(chi2 * kp.inv_nu);
 }
 // Kbar(chi2) as the reference evaluates it (eval_unnorm): exp(-chi2/2) or pow(1 + chi2/nu, kappa)
 __device__ __forceinline__ double kern_K(const KernParams &kp, const double chi2) {
-  return kp.kind == 0 ? exp_nonpos_fast(-0.5 * chi2) : exp_nonpos_fast(kp.kappa * log1p_nonneg_fast(chi2 * kp.inv_nu));   // kappa < 0
+  if (kp.kind == 0) return exp_nonpos_fast(-0.5 * chi2);
+  if (kp.m2 > 0) return st_pow_int(kp, chi2);
+  return exp_nonpos_fast(kp.kappa * log1p_nonneg_fast(chi2 * kp.inv_nu));   // kappa < 0
 }
+
+// Linear-domain partial of one (query, centre range): the caller stores (m, s) = (cmax, sum) so that the log-sum-exp merge of the
+// splits and lse_finalize apply unchanged (equal m: the sums add).
+__device__ __forceinline__ void lin_push(Lse &a, const KernParams &kp, const double chi2, const double cw) { a.s = fma(cw, st_pow_int(kp, chi2), a.s); }

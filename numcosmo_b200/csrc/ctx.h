@@ -56,6 +56,8 @@ struct ncm_sd_gpu_ctx {
   double vkde_cond = 0.0;     // max_i |L_i|_1 |L_i^-1|_1 of the last pack
   DevBuf lnu;        // [n_kernels] per-kernel lnnorm (VKDE) -- without d ln h
   DevBuf cterm;      // [n_kernels] ln w_i - lnu_i
+  DevBuf clin;       // Student-t linear-domain eval: [n_alloc] exp(cterm_i - cmax), then {cmax} and an int flag (see common.cuh)
+  int clin_n = 0;    // entries of clin (cmax sits at clin[clin_n], the underflow flag at clin[clin_n + 1])
   DevBuf weights;    // [n_kernels]
   DevBuf Ufull;      // VKDE: [n_kernels x d x d] dense factors (sample_apply) ; KDE: [d x d]
 
@@ -198,6 +200,12 @@ int kde_eval_launch(ncm_sd_gpu_ctx *c, int q, const double *dX, int ldx, double 
 int kde_im_launch(ncm_sd_gpu_ctx *c, const double *dRowScale);
 
 int update_cterm(ncm_sd_gpu_ctx *c);
+int lse_finalize_launch(ncm_sd_gpu_ctx *c, const double *pm, const double *ps, const double *row_add, int q, int n_splits, double shift,
+                        bool as_density, double *dOut, int *dFlagOut = nullptr, const int *dOnlyIf = nullptr);
+// Student-t with integer nu: fills kp.m2 / lin / cmax (common.cuh) for the current kernel; clin must have been built by build_clin
+void ncm_fill_kp(const ncm_sd_gpu_ctx *c, KernParams &kp, bool eval);
+int build_clin(ncm_sd_gpu_ctx *c, const double *dCterm, int n_alloc);
+bool st_linear_enabled(const ncm_sd_gpu_ctx *c);
 
 int chol_fused_max_n();
 int dpotrf_upper_solve_fused(ncm_sd_gpu_ctx *c, int n, double *dM, int ldm, double *dRhs, int *info_host);

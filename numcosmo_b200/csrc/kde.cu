@@ -18,8 +18,6 @@
 // (max, sum) pair per row (online log-sum-exp), so nothing but Q doubles per centre-split is written.
 #include "ctx.h"
 
-int lse_finalize_launch(ncm_sd_gpu_ctx *c, const double *pm, const double *ps, const double *row_add, int q, int n_splits, double shift,
-                        bool as_density, double *dOut);
 
 namespace {
 
@@ -143,10 +141,12 @@ struct KdeArgs {
   int ldim;
   double im_scale;       // exp(-(lnnorm + d ln h))
   const double *rowscale;
+  const int *only_if;    // repair pass of the linear-domain Student-t evaluation: return at once unless *only_if != 0
 };
 
 template <int KS, int MODE>   // MODE: 0 Gauss eval, 1 Gauss IM, 2 ST eval, 3 ST IM
 __global__ void __launch_bounds__(KDE_THREADS) kde_kernel(const KdeArgs a) {
+  if (a.only_if != nullptr && *a.only_if == 0) return;
   constexpr int KP    = KS * 4;
   constexpr int STAGE = CHK * KP;          // doubles per stage of B
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -223,7 +223,18 @@ __global__ void __launch_bounds__(KDE_THREADS) kde_kernel(const KdeArgs a) {
       }
     }
 
-    if (MODE == 0 || MODE == 2) {
+    if (MODE == 2 && a.kp.lin) {
+      // linear domain: s += exp(ln w_j - cmax) (1 + chi2/nu)^(-(nu + d)/2), the power by rsqrt and multiplications (common.cuh)
+#pragma unroll
+      for (int ni = 0; ni < NI; ++ni) {
+        const double2 cw = *reinterpret_cast<const double2 *>(ct + ni * 8 + 2 * lr);
+#pragma unroll
+        for (int mi = 0; mi < MI; ++mi) {
+          st[mi].s = fma(cw.x, st_pow_u(a.kp, fmax(acc[mi][ni][0], 0.0)), st[mi].s);
+          st[mi].s = fma(cw.y, st_pow_u(a.kp, fmax(acc[mi][ni][1], 0.0)), st[mi].s);
+        }
+      }
+    } else if (MODE == 0 || MODE == 2) {
       if (MODE == 2) {
         // ln t = kappa log1p(chi2 / nu) + ln w_j
 #pragma unroll
@@ -265,6 +276,9 @@ __global__ void __launch_bounds__(KDE_THREADS) kde_kernel(const KdeArgs a) {
             if (MODE == 1) {
               k0 = exp_nonpos_fast(acc[mi][ni][0]);
               k1 = exp_nonpos_fast(acc[mi][ni][1]);
+            } else if (a.kp.m2 > 0) {
+              k0 = st_pow_u(a.kp, fmax(acc[mi][ni][0], 0.0));
+              k1 = st_pow_u(a.kp, fmax(acc[mi][ni][1], 0.0));
             } else {
               k0 = exp_nonpos_fast(a.kp.kappa * log1p_nonneg_fast(fmax(acc[mi][ni][0], 0.0)));
               k1 = exp_nonpos_fast(a.kp.kappa * log1p_nonneg_fast(fmax(acc[mi][ni][1], 0.0)));
@@ -288,7 +302,7 @@ __global__ void __launch_bounds__(KDE_THREADS) kde_kernel(const KdeArgs a) {
       lse_warp_reduce_xor(st[mi], 4);
       const int row = m0 + mi * 8 + lc;
       if (lr == 0 && row < a.q) {
-        a.part_m[(size_t) blockIdx.y * a.q + row] = st[mi].m;
+        a.part_m[(size_t) blockIdx.y * a.q + row] = (MODE == 2 && a.kp.lin) ? *a.kp.cmax : st[mi].m;
         a.part_s[(size_t) blockIdx.y * a.q + row] = st[mi].s;
       }
     }
@@ -326,12 +340,7 @@ int kde_launch_ks(ncm_sd_gpu_ctx *c, int KS, const KdeArgs &a, int splits) {
   }
 }
 
-void fill_kp(const ncm_sd_gpu_ctx *c, KernParams &kp) {
-  kp.kind   = c->kind;
-  kp.nu     = c->nu;
-  kp.kappa  = -0.5 * (c->nu + c->d);
-  kp.inv_nu = 1.0 / c->nu;
-}
+void fill_kp(const ncm_sd_gpu_ctx *c, KernParams &kp, bool eval = false) { ncm_fill_kp(c, kp, eval); }
 
 int pick_splits(const ncm_sd_gpu_ctx *c, int q_tiles, int n_pad) { return ncm_pick_splits(c->n_sm * 2, q_tiles, n_pad / CHK); }
 
@@ -368,7 +377,7 @@ int kde_set_weights(ncm_sd_gpu_ctx *c) {
                                                           c->bfrag.as<double>(), c->cterm.as<double>());
   c->n_launches++;
   NCM_CUDA_OK(c, cudaGetLastError());
-  return NCM_SD_GPU_OK;
+  return mode == 2 ? build_clin(c, c->cterm.as<double>(), n_pad) : NCM_SD_GPU_OK;
 }
 
 int kde_eval_launch(ncm_sd_gpu_ctx *c, int q, const double *dX, int ldx, double *dOut, bool as_density) {
@@ -389,17 +398,27 @@ int kde_eval_launch(ncm_sd_gpu_ctx *c, int q, const double *dX, int ldx, double 
   c->n_launches++;
   KdeArgs a;
   a.A = dA; a.q = q; a.q_pad = q_pad;
-  a.bfrag = c->bfrag.as<double>(); a.cterm = c->cterm.as<double>();
+  a.bfrag = c->bfrag.as<double>();
   a.n = c->n_kernels; a.n_pad = n_pad; a.per_split = per_split;
-  fill_kp(c, a.kp);
+  fill_kp(c, a.kp, mode == 2);
+  a.cterm = a.kp.lin ? c->clin.as<double>() : c->cterm.as<double>();
   a.mode = mode;
   a.part_m = c->part.as<double>(); a.part_s = a.part_m + (size_t) splits * q;
-  a.IM = nullptr; a.ldim = 0; a.im_scale = 1.0; a.rowscale = nullptr;
+  a.IM = nullptr; a.ldim = 0; a.im_scale = 1.0; a.rowscale = nullptr; a.only_if = nullptr;
+  int *flag = a.kp.lin ? reinterpret_cast<int *>(c->clin.as<double>() + c->clin_n + 1) : nullptr;
+  if (flag != nullptr) NCM_CUDA_OK(c, cudaMemsetAsync(flag, 0, sizeof(int), c->stream));
   int rc = (mode == 0) ? kde_launch_ks<0>(c, KS, a, splits) : kde_launch_ks<2>(c, KS, a, splits);
   if (rc != NCM_SD_GPU_OK) return rc;
   // m2lnp = -2 (gamma + log1p(lambda) - d ln h), gamma already includes -lnnorm (kde.c:679, _kernel_gauss.c:332)
-  return lse_finalize_launch(c, a.part_m, a.part_s, mode == 0 ? dAlpha : nullptr, q, splits, -c->lnnorm - c->d * log(c->href), as_density,
-                             dOut);
+  const double shift = -c->lnnorm - c->d * log(c->href);
+  rc = lse_finalize_launch(c, a.part_m, a.part_s, mode == 0 ? dAlpha : nullptr, q, splits, shift, as_density, dOut, flag, nullptr);
+  if (rc != NCM_SD_GPU_OK || flag == nullptr) return rc;
+  // repair pass in the log domain (see vkde.cu)
+  a.kp.lin = 0;
+  a.cterm = c->cterm.as<double>(); a.only_if = flag;
+  rc = kde_launch_ks<2>(c, KS, a, splits);
+  if (rc != NCM_SD_GPU_OK) return rc;
+  return lse_finalize_launch(c, a.part_m, a.part_s, nullptr, q, splits, shift, as_density, dOut, nullptr, flag);
 }
 
 int kde_im_launch(ncm_sd_gpu_ctx *c, const double *dRowScale) {
@@ -434,5 +453,6 @@ int kde_im_launch(ncm_sd_gpu_ctx *c, const double *dRowScale) {
   a.IM = c->IM.as<double>(); a.ldim = (c->n_kernels + 7) & ~7;
   a.im_scale = exp(-(c->lnnorm + c->d * log(c->href)));   // ncm_stats_dist_kde.c:556
   a.rowscale = dRowScale != nullptr ? dRowScale + c->row0 : nullptr;
+  a.only_if = nullptr;
   return (mode == 1) ? kde_launch_ks<1>(c, KS, a, splits) : kde_launch_ks<3>(c, KS, a, splits);
 }

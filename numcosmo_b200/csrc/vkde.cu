@@ -67,11 +67,13 @@ struct VkdeArgs {
   double *IM;             // [q x ldim]
   int ldim;
   const double *rowscale; // [q] or null
+  const int *only_if;     // when set: the launch is a repair pass and returns at once unless *only_if != 0
 };
 
 template <int DP, int MODE>   // MODE 0: log-sum-exp partials ; MODE 1: IM entries
 __global__ void __launch_bounds__(VkdeCfg<DP>::TQ) vkde_kernel(const VkdeArgs a) {
   using Cfg = VkdeCfg<DP>;
+  if (a.only_if != nullptr && *a.only_if == 0) return;
   constexpr int REC = Cfg::REC, CH = Cfg::CH;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *srec      = reinterpret_cast<double *>(smem_raw);             // [2][CH * REC]
@@ -165,7 +167,10 @@ __global__ void __launch_bounds__(VkdeCfg<DP>::TQ) vkde_kernel(const VkdeArgs a)
       for (int u = 0; u < QPT; ++u) {
         const double c2 = chi2[u] * a.inv_h2;
         if (MODE == 0) {
-          lse_push(acc[u], kern_lnK(a.kp, c2) + cvc);
+          if (a.kp.lin)
+            lin_push(acc[u], a.kp, c2, cvc);   // cvc = exp(ln w_i - lnu_i - cmax)
+          else
+            lse_push(acc[u], kern_lnK(a.kp, c2) + cvc);
         } else {
           if (qv[u]) a.IM[(size_t) qi[u] * a.ldim + (c0 + c)] = kern_K(a.kp, c2) * cvc * rs[u];
         }
@@ -178,7 +183,7 @@ __global__ void __launch_bounds__(VkdeCfg<DP>::TQ) vkde_kernel(const VkdeArgs a)
 #pragma unroll
     for (int u = 0; u < QPT; ++u)
       if (qv[u]) {
-        a.part_m[(size_t) blockIdx.y * a.q + qi[u]] = acc[u].m;
+        a.part_m[(size_t) blockIdx.y * a.q + qi[u]] = a.kp.lin ? *a.kp.cmax : acc[u].m;
         a.part_s[(size_t) blockIdx.y * a.q + qi[u]] = acc[u].s;
       }
   }
@@ -269,32 +274,32 @@ int vkde_pack(ncm_sd_gpu_ctx *c, const double *dU_all) {
 }
 
 // merge the per-split partials:  out = -2 (m + log s + shift)  or  exp(m + log s + shift)
+// flag_out (linear-domain partials): raised when a sum is not safely above the underflow threshold -- the caller's repair pass then
+// recomputes everything in the log domain.  only_if: this launch IS the repair pass.
 __global__ void lse_finalize_kernel(const double *__restrict__ pm, const double *__restrict__ ps, const double *__restrict__ row_add, int q,
-                                    int n_splits, double shift, int as_density, double *__restrict__ out) {
+                                    int n_splits, double shift, int as_density, double *__restrict__ out, int *__restrict__ flag_out,
+                                    const int *__restrict__ only_if) {
+  if (only_if != nullptr && *only_if == 0) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= q) return;
   Lse a;
   a.m = pm[i];
   a.s = ps[i];
   for (int s = 1; s < n_splits; ++s) lse_merge(a, pm[(size_t) s * q + i], ps[(size_t) s * q + i]);
+  if (flag_out != nullptr && !(a.s >= 1.0e-200)) atomicExch(flag_out, 1);   // also NaN
   const double ln = a.m + log(a.s) + shift + (row_add != nullptr ? row_add[i] : 0.0);
   out[i]          = as_density ? exp(ln) : -2.0 * ln;
 }
 
 int lse_finalize_launch(ncm_sd_gpu_ctx *c, const double *pm, const double *ps, const double *row_add, int q, int n_splits, double shift,
-                        bool as_density, double *dOut) {
-  lse_finalize_kernel<<<(q + 255) / 256, 256, 0, c->stream>>>(pm, ps, row_add, q, n_splits, shift, as_density ? 1 : 0, dOut);
+                        bool as_density, double *dOut, int *dFlagOut, const int *dOnlyIf) {
+  lse_finalize_kernel<<<(q + 255) / 256, 256, 0, c->stream>>>(pm, ps, row_add, q, n_splits, shift, as_density ? 1 : 0, dOut, dFlagOut, dOnlyIf);
   c->n_launches++;
   NCM_CUDA_OK(c, cudaGetLastError());
   return NCM_SD_GPU_OK;
 }
 
-static void fill_kp(const ncm_sd_gpu_ctx *c, KernParams &kp) {
-  kp.kind   = c->kind;
-  kp.nu     = c->nu;
-  kp.kappa  = -0.5 * (c->nu + c->d);
-  kp.inv_nu = 1.0 / c->nu;
-}
+static void fill_kp(const ncm_sd_gpu_ctx *c, KernParams &kp, bool eval = false) { ncm_fill_kp(c, kp, eval); }
 
 // choose the number of centre splits so that the grid is about two waves of resident CTAs
 static int pick_splits(const ncm_sd_gpu_ctx *c, int q_tiles, int n, int ch, int ctas_per_sm) {
@@ -313,17 +318,28 @@ int vkde_eval_launch(ncm_sd_gpu_ctx *c, int q, const double *dX, int ldx, double
   if (!c->part.reserve((size_t) 2 * splits * q * sizeof(double))) return c->fail(NCM_SD_GPU_ENOMEM, "vkde_eval: out of device memory");
   VkdeArgs a;
   a.X = dX; a.ldx = ldx; a.q = q; a.d = c->d;
-  a.rec = c->vrec.as<double>(); a.cvec = c->cterm.as<double>();
+  a.rec = c->vrec.as<double>();
   a.n = c->n_kernels; a.per_split = per_split;
   a.inv_h2 = 1.0 / (c->href * c->href);
-  fill_kp(c, a.kp);
+  fill_kp(c, a.kp, true);
+  a.cvec = a.kp.lin ? c->clin.as<double>() : c->cterm.as<double>();
   a.part_m = c->part.as<double>(); a.part_s = a.part_m + (size_t) splits * q;
-  a.IM = nullptr; a.ldim = 0; a.rowscale = nullptr;
+  a.IM = nullptr; a.ldim = 0; a.rowscale = nullptr; a.only_if = nullptr;
+  int *flag = a.kp.lin ? reinterpret_cast<int *>(c->clin.as<double>() + c->clin_n + 1) : nullptr;
+  if (flag != nullptr) NCM_CUDA_OK(c, cudaMemsetAsync(flag, 0, sizeof(int), c->stream));
   int rc = NCM_SD_GPU_OK;
   VKDE_DISPATCH(dp, rc = (launch_t<DP, 0>(c, a, splits)));
   if (rc != NCM_SD_GPU_OK) return rc;
   // m2lnp = -2 (gamma + log1p(lambda) - d ln h), ncm_stats_dist_vkde.c:721
-  return lse_finalize_launch(c, a.part_m, a.part_s, nullptr, q, splits, -c->d * log(c->href), as_density, dOut);
+  rc = lse_finalize_launch(c, a.part_m, a.part_s, nullptr, q, splits, -c->d * log(c->href), as_density, dOut, flag, nullptr);
+  if (rc != NCM_SD_GPU_OK || flag == nullptr) return rc;
+  // repair pass of the linear-domain evaluation: the same launches in the log domain, which return at once unless a sum came out
+  // too close to the underflow threshold (a query absurdly far from every centre)
+  a.kp.lin = 0;
+  a.cvec = c->cterm.as<double>(); a.only_if = flag;
+  VKDE_DISPATCH(dp, rc = (launch_t<DP, 0>(c, a, splits)));
+  if (rc != NCM_SD_GPU_OK) return rc;
+  return lse_finalize_launch(c, a.part_m, a.part_s, nullptr, q, splits, -c->d * log(c->href), as_density, dOut, nullptr, flag);
 }
 
 __global__ void vkde_invnorm_kernel(const double *__restrict__ lnu, int n, double dlnh, double *__restrict__ out) {
@@ -354,6 +370,7 @@ int vkde_im_launch(ncm_sd_gpu_ctx *c, const double *dRowScale) {
   a.part_m = a.part_s = nullptr;
   a.IM = c->IM.as<double>(); a.ldim = (c->n_kernels + 7) & ~7;
   a.rowscale = dRowScale != nullptr ? dRowScale + c->row0 : nullptr;
+  a.only_if = nullptr;
   int rc = NCM_SD_GPU_OK;
   VKDE_DISPATCH(dp, rc = (launch_t<DP, 1>(c, a, splits)));
   return rc;

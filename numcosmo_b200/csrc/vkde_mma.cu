@@ -19,8 +19,6 @@
 #include <cstring>
 #include "ctx.h"
 
-int lse_finalize_launch(ncm_sd_gpu_ctx *c, const double *pm, const double *ps, const double *row_add, int q, int n_splits, double shift,
-                        bool as_density, double *dOut);
 
 namespace {
 
@@ -105,11 +103,13 @@ struct MmaArgs {
   double *IM;
   int ldim;
   const double *rowscale;
+  const int *only_if;   // repair pass of the linear-domain evaluation: return at once unless *only_if != 0
 };
 
 template <int DP, int MODE>
 __global__ void __launch_bounds__(MmaCfg<DP>::WARPS * 32, 2) vkde_mma_kernel(const MmaArgs a) {
   using Cfg = MmaCfg<DP>;
+  if (a.only_if != nullptr && *a.only_if == 0) return;
   constexpr int REC = Cfg::REC, CH = Cfg::CH, NT = Cfg::NT, KS = Cfg::KS, MQ = Cfg::MQ;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *srec   = reinterpret_cast<double *>(smem_raw);   // [2][CH * REC]
@@ -213,7 +213,12 @@ __global__ void __launch_bounds__(MmaCfg<DP>::WARPS * 32, 2) vkde_mma_kernel(con
       for (int mq = 0; mq < MQ; ++mq) {
         const double chi2 = chi[mq] * a.inv_h2;
         if (MODE == 0) {
-          if (cvalid) lse_push(accL[mq], kern_lnK(a.kp, chi2) + cvv);
+          if (cvalid) {
+            if (a.kp.lin)
+              lin_push(accL[mq], a.kp, chi2, cvv);   // cvv = exp(ln w_i - lnu_i - cmax)
+            else
+              lse_push(accL[mq], kern_lnK(a.kp, chi2) + cvv);
+          }
         } else {
           const int qi = q0 + 8 * mq + lc;
           if (cvalid && qi < a.q) a.IM[(size_t) qi * a.ldim + (c0 + cl)] = kern_K(a.kp, chi2) * cvv * rs[mq];
@@ -229,7 +234,7 @@ __global__ void __launch_bounds__(MmaCfg<DP>::WARPS * 32, 2) vkde_mma_kernel(con
       lse_warp_reduce_xor(accL[mq], 4);   // the four centre classes of a query sit in one quad
       const int qi = q0 + 8 * mq + lc;
       if (lr == 0 && qi < a.q) {
-        a.part_m[(size_t) blockIdx.y * a.q + qi] = accL[mq].m;
+        a.part_m[(size_t) blockIdx.y * a.q + qi] = a.kp.lin ? *a.kp.cmax : accL[mq].m;
         a.part_s[(size_t) blockIdx.y * a.q + qi] = accL[mq].s;
       }
     }
@@ -263,12 +268,6 @@ int mma_launch_t(ncm_sd_gpu_ctx *c, const MmaArgs &a, int n_splits) {
 int mma_rec_len(int dp) { return dp + (dp / 8) * (dp / 8 + 1) * 32; }
 int mma_ch(int dp) { return dp <= 16 ? 16 : 8; }
 
-void fill_kp(const ncm_sd_gpu_ctx *c, KernParams &kp) {
-  kp.kind   = c->kind;
-  kp.nu     = c->nu;
-  kp.kappa  = -0.5 * (c->nu + c->d);
-  kp.inv_nu = 1.0 / c->nu;
-}
 
 void splits_for(const ncm_sd_gpu_ctx *c, int q, int n, int ch, int &splits, int &per_split) {
   const int q_tiles = (q + 127) / 128;
@@ -328,16 +327,26 @@ int vkde_mma_eval_launch(ncm_sd_gpu_ctx *c, int q, const double *dX, int ldx, do
   if (!c->part.reserve((size_t) 2 * splits * q * sizeof(double))) return c->fail(NCM_SD_GPU_ENOMEM, "vkde_mma_eval: out of device memory");
   MmaArgs a;
   a.X = dX; a.ldx = ldx; a.q = q; a.d = c->d;
-  a.rec = c->vrec_mma.as<double>(); a.cvec = c->cterm.as<double>();
+  a.rec = c->vrec_mma.as<double>();
   a.n = c->n_kernels; a.per_split = per_split;
   a.inv_h2 = 1.0 / (c->href * c->href);
-  fill_kp(c, a.kp);
+  ncm_fill_kp(c, a.kp, true);
+  a.cvec = a.kp.lin ? c->clin.as<double>() : c->cterm.as<double>();
   a.part_m = c->part.as<double>(); a.part_s = a.part_m + (size_t) splits * q;
-  a.IM = nullptr; a.ldim = 0; a.rowscale = nullptr;
+  a.IM = nullptr; a.ldim = 0; a.rowscale = nullptr; a.only_if = nullptr;
+  int *flag = a.kp.lin ? reinterpret_cast<int *>(c->clin.as<double>() + c->clin_n + 1) : nullptr;
+  if (flag != nullptr) NCM_CUDA_OK(c, cudaMemsetAsync(flag, 0, sizeof(int), c->stream));
   int rc = NCM_SD_GPU_OK;
   MMA_DISPATCH(dp, rc = (mma_launch_t<DP, 0>(c, a, splits)));
   if (rc != NCM_SD_GPU_OK) return rc;
-  return lse_finalize_launch(c, a.part_m, a.part_s, nullptr, q, splits, -c->d * log(c->href), as_density, dOut);
+  rc = lse_finalize_launch(c, a.part_m, a.part_s, nullptr, q, splits, -c->d * log(c->href), as_density, dOut, flag, nullptr);
+  if (rc != NCM_SD_GPU_OK || flag == nullptr) return rc;
+  // repair pass in the log domain (see vkde.cu): returns at once unless a linear-domain sum came out next to the underflow threshold
+  a.kp.lin = 0;
+  a.cvec = c->cterm.as<double>(); a.only_if = flag;
+  MMA_DISPATCH(dp, rc = (mma_launch_t<DP, 0>(c, a, splits)));
+  if (rc != NCM_SD_GPU_OK) return rc;
+  return lse_finalize_launch(c, a.part_m, a.part_s, nullptr, q, splits, -c->d * log(c->href), as_density, dOut, nullptr, flag);
 }
 
 // cvec = 1 / exp(lnu_i + d ln h) prepared by the caller (vkde_im_launch)
@@ -351,7 +360,8 @@ int vkde_mma_im_launch(ncm_sd_gpu_ctx *c, const double *dInvNorm, const double *
   a.rec = c->vrec_mma.as<double>(); a.cvec = dInvNorm;
   a.n = c->n_kernels; a.per_split = per_split;
   a.inv_h2 = 1.0 / (c->href * c->href);
-  fill_kp(c, a.kp);
+  ncm_fill_kp(c, a.kp, false);
+  a.only_if = nullptr;
   a.part_m = a.part_s = nullptr;
   a.IM = c->IM.as<double>(); a.ldim = (c->n_kernels + 7) & ~7;
   a.rowscale = dRowScale != nullptr ? dRowScale + c->row0 : nullptr;

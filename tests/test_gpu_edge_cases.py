@@ -53,6 +53,30 @@ def test_largest_dimension(oracle, gpu_ctx, sd_s, k_s):
     assert rel_err(gpu_ctx.eval_m2lnp(Q), sd.eval_m2lnp_batch(Q, 2)) < TOL
 
 
+@pytest.mark.parametrize("sd_s,d,n", [("kde", 4, 200), ("vkde", 4, 200), ("vkde", 24, 300)])
+@pytest.mark.parametrize("nu", [1.0, 3.0, 2.5])
+def test_student_t_linear_domain_and_its_repair_pass(oracle, gpu_ctx, sd_s, d, n, nu):
+    """Student-t with integer nu: (1 + chi2/nu)^(-(nu + d)/2) as an integer power of rsqrt, summed in the linear domain (csrc/common.cuh
+    st_pow_u / lin_push) -- against the oracle's log-sum-exp of kappa log1p (ncm_stats_dist_kernel_st.c:295-386).  A query so far away
+    that every term underflows in the linear domain (chi2 ~ 1e150) must come out of the log-domain repair pass, finite and equal to the
+    reference; nu = 2.5 (no integer power) keeps the log-domain path throughout.  d = 24: the tensor-core VKDE kernel."""
+    sd, mu, X = _mk(oracle, gpu_ctx, sd_s, "st", d, n, nu=nu, local_frac=0.2)
+    span = np.std(X, axis=0)
+    e0 = np.zeros(d)
+    e0[0] = 1.0
+    Q = np.vstack([X[:50] + 1e-3 * span, mu + 3.0 * (X[50:100] - mu), mu + 1e3 * span])
+    got, exp = gpu_ctx.eval_m2lnp(Q), sd.eval_m2lnp_batch(Q, 2)
+    assert rel_err(got, exp) < TOL
+    dens, dens_o = gpu_ctx.eval(Q[:100]), sd.eval_batch(Q[:100], 2)
+    assert rel_err(dens[dens_o > 1e-290], dens_o[dens_o > 1e-290]) < 1e-9
+    Qfar = np.vstack([Q[:7], mu + 1e75 * span * e0, mu - 1e60 * span])
+    got, exp = gpu_ctx.eval_m2lnp(Qfar), sd.eval_m2lnp_batch(Qfar, 1)
+    assert np.all(np.isfinite(got)), got
+    assert rel_err(got, exp) < TOL
+    # and the next well-behaved batch is served by the fast path again, same answers
+    assert rel_err(gpu_ctx.eval_m2lnp(Q), sd.eval_m2lnp_batch(Q, 2)) < TOL
+
+
 @pytest.mark.parametrize("sd_s,k_s", [("kde", "gauss"), ("kde", "st"), ("vkde", "gauss"), ("vkde", "st")])
 def test_far_and_coincident_queries(oracle, gpu_ctx, sd_s, k_s):
     """Queries on top of a centre (chi2 = 0 for one pair) and hundreds of bandwidths away (every exp underflows
