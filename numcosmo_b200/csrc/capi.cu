@@ -118,7 +118,7 @@ bool st_linear_enabled(const ncm_sd_gpu_ctx *c) {
     return !(e != nullptr && e[0] == '0');
   }();
   const double m = c->nu + c->d;
-  return env_on && c->kind == NCM_SD_GPU_KERNEL_ST && c->nu >= 1.0 && c->nu == floor(c->nu) && m <= 96.0;
+  return env_on && c->kind == NCM_SD_GPU_KERNEL_ST && c->nu >= 1.0 && c->nu == floor(c->nu) && m < 128.0;
 }
 
 void ncm_fill_kp(const ncm_sd_gpu_ctx *c, KernParams &kp, bool eval) {

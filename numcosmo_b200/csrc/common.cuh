@@ -220,12 +220,13 @@ struct KernParams {
 // One rsqrt and at most 2 log2(m) multiplications (m is uniform over the grid) instead of log1p + exp: relative error <= (m + 1) ulp
 // (4e-15 at m = 35), the same order as the table-based log1p above.  Reference: pow (1 + chi2/nu, kappa), ncm_stats_dist_kernel_st.c:239-243.
 __device__ __forceinline__ double st_pow_u(const KernParams &kp, const double u) {   // u = chi2 / nu >= 0
-  double base = rsqrt(1.0 + u), res = 1.0;
-  for (int e = kp.m2; e != 0; e >>= 1) {
-    if (e & 1) res *= base;
-    base *= base;
-  }
-  return res;
+  // straight-line binary powering (m2 < 128): six squarings, the factors picked by the bits of m2 -- selects on a grid-uniform value,
+  // no loop, so that the calls of an unrolled epilogue interleave (a loop per call serialised them: slower than log1p + exp)
+  const double b1 = rsqrt(1.0 + u), b2 = b1 * b1, b4 = b2 * b2, b8 = b4 * b4, b16 = b8 * b8, b32 = b16 * b16, b64 = b32 * b32;
+  const int m = kp.m2;
+  const double lo = ((m & 1) ? b1 : 1.0) * ((m & 2) ? b2 : 1.0), mid = ((m & 4) ? b4 : 1.0) * ((m & 8) ? b8 : 1.0);
+  const double hi = ((m & 16) ? b16 : 1.0) * ((m & 32) ? b32 : 1.0) * ((m & 64) ? b64 : 1.0);
+  return (lo * mid) * hi;
 }
 __device__ __forceinline__ double st_pow_int(const KernParams &kp, const double chi2) { return st_pow_u(kp, fmax(chi2, 0.0) * kp.inv_nu); }
 
