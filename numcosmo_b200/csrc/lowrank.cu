@@ -27,34 +27,39 @@ using namespace ncm_gemm;
 
 // ---- triangular inverse W = U^-1 (upper, row-major) by recursive doubling -----------------------------------------------
 // level 0: the 64 x 64 diagonal blocks, one CTA each (thread t back-substitutes column t)
-__global__ void __launch_bounds__(64) trinv_diag_kernel(const double *__restrict__ U, double *__restrict__ W, int ld, int n) {
-  // upper triangle: U; strictly lower triangle: X = U^-1 transposed (X[i][t] at sU[t][i]); diagonal of X in sDinv
+__global__ void __launch_bounds__(256) trinv_diag_kernel(const double *__restrict__ U, double *__restrict__ W, int ld, int n) {
+  // upper triangle: U; strictly lower triangle: X = U^-1 transposed (X[i][t] at sU[t][i]); diagonal of X in sDinv.
+  // 256 threads move the tile (four rows per pass), the first 64 do the substitutions (thread t: column t of the inverse)
   __shared__ double sU[64][65];
   __shared__ double sDinv[64];
-  const int k0 = blockIdx.x * 64, nb = min(64, n - k0), t = threadIdx.x;
-  for (int r = 0; r < 64; ++r) {
+  const int k0 = blockIdx.x * 64, nb = min(64, n - k0), t = threadIdx.x & 63, ty = threadIdx.x >> 6;
+#pragma unroll 4
+  for (int r = ty; r < 64; r += 4) {
     double v = (r == t) ? 1.0 : 0.0;
     if (r < nb && t < nb && t >= r) v = U[(size_t) (k0 + r) * ld + k0 + t];
     sU[r][t] = v;
   }
   __syncthreads();
-  sDinv[t] = 1.0 / sU[t][t];
+  if (ty == 0) sDinv[t] = 1.0 / sU[t][t];
   __syncthreads();
   const double xtt = sDinv[t];
-  for (int i = 62; i >= 0; --i) {
-    if (i < t) {
-      double s0 = sU[i][t] * xtt, s1 = 0.0;
-      int k = i + 1;
-      for (; k + 1 < t; k += 2) {
-        s0 = fma(sU[i][k], sU[t][k], s0);
-        s1 = fma(sU[i][k + 1], sU[t][k + 1], s1);
+  if (ty == 0) {
+    for (int i = 62; i >= 0; --i) {
+      if (i < t) {
+        double s0 = sU[i][t] * xtt, s1 = 0.0;
+        int k = i + 1;
+        for (; k + 1 < t; k += 2) {
+          s0 = fma(sU[i][k], sU[t][k], s0);
+          s1 = fma(sU[i][k + 1], sU[t][k + 1], s1);
+        }
+        if (k < t) s0 = fma(sU[i][k], sU[t][k], s0);
+        sU[t][i] = -(s0 + s1) * sDinv[i];
       }
-      if (k < t) s0 = fma(sU[i][k], sU[t][k], s0);
-      sU[t][i] = -(s0 + s1) * sDinv[i];
     }
   }
   __syncthreads();
-  for (int r = 0; r < nb; ++r)
+#pragma unroll 4
+  for (int r = ty; r < nb; r += 4)
     if (t < nb) W[(size_t) (k0 + r) * ld + k0 + t] = (t > r) ? sU[t][r] : (t == r ? xtt : 0.0);
 }
 
@@ -585,7 +590,7 @@ int symmetrize_upper(ncm_sd_gpu_ctx *c, int n, double *dM, int ld) {
 int trinv_upper_on(ncm_sd_gpu_ctx *c, cudaStream_t st, int n, const double *dU, double *dW, double *dS, int ld, double *dWt) {
   NCM_CUDA_OK(c, set_smem_attrs());
   NCM_CUDA_OK(c, cudaMemsetAsync(dW, 0, (size_t) n * ld * sizeof(double), st));
-  trinv_diag_kernel<<<(n + 63) / 64, 64, 0, st>>>(dU, dW, ld, n);
+  trinv_diag_kernel<<<(n + 63) / 64, 256, 0, st>>>(dU, dW, ld, n);
   c->n_launches++;
   for (int s = 64; s < n; s *= 2) {
     const int pairs = (n - s + 2 * s - 1) / (2 * s);
