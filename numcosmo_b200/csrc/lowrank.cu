@@ -83,6 +83,27 @@ __global__ void __launch_bounds__(GTHREADS) trinv_step2_kernel(double *__restric
   gemm_tile<false>(W + (size_t) r0 * ld + r0, ld, S + (size_t) r0 * ld + r1, ld, W + (size_t) r0 * ld + r1, ld, s, m2, i0, j0, i0, s, -1.0, smem);
 }
 
+// small levels (s <= 128): both products of a level in ONE launch.  A CTA takes one 64-column strip of a pair's off-diagonal block:
+// it forms its strip of S12 = U12 W22 tile by tile, then W12 = -W11 S12 from that strip alone (no other CTA's tiles are needed), so
+// the two half-empty launches of the level (16 CTAs of work each) become one.
+__global__ void __launch_bounds__(GTHREADS) trinv_step12_kernel(const double *__restrict__ U, double *__restrict__ W, double *__restrict__ S, int ld, int n, int s) {
+  extern __shared__ __align__(16) double smem[];
+  const int r0 = 2 * blockIdx.z * s, r1 = r0 + s;
+  const int m2 = min(s, n - r1);
+  const int j0 = blockIdx.x * GT;
+  if (m2 <= 0 || j0 >= m2) return;
+  for (int i0 = 0; i0 < s; i0 += GT) {
+    gemm_tile<false>(U + (size_t) r0 * ld + r1, ld, W + (size_t) r1 * ld + r1, ld, S + (size_t) r0 * ld + r1, ld, s, m2, i0, j0, 0, min(m2, j0 + GT), 1.0, smem);
+    __syncthreads();   // the staging buffers are reused by the next tile
+  }
+  __threadfence_block();
+  __syncthreads();     // the strip of S12 written above is read back (through L2) below
+  for (int i0 = 0; i0 < s; i0 += GT) {
+    gemm_tile<false>(W + (size_t) r0 * ld + r0, ld, S + (size_t) r0 * ld + r1, ld, W + (size_t) r0 * ld + r1, ld, s, m2, i0, j0, i0, s, -1.0, smem);
+    __syncthreads();
+  }
+}
+
 // dst[j][i] = src[i][j] for i <= j (32 x 32 tiles of the upper triangle); in place (dst == src) it symmetrises the matrix
 __global__ void transpose_upper_kernel(const double *src, double *dst, int ld, int n, int nt) {
   __shared__ double tile[32][33];
@@ -550,6 +571,7 @@ cudaError_t set_smem_attrs() {
   cudaError_t e;
   if ((e = cudaFuncSetAttribute(trinv_step1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) GEMM_SMEM)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(trinv_step2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) GEMM_SMEM)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(trinv_step12_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) GEMM_SMEM)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(gemm_tn_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) GEMM_SMEM)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(syrk_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) GEMM_SMEM)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(lr_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) LR_SMALL_SMEM)) != cudaSuccess) return e;
@@ -594,6 +616,11 @@ int trinv_upper_on(ncm_sd_gpu_ctx *c, cudaStream_t st, int n, const double *dU, 
   c->n_launches++;
   for (int s = 64; s < n; s *= 2) {
     const int pairs = (n - s + 2 * s - 1) / (2 * s);
+    if (s <= 128) {
+      trinv_step12_kernel<<<dim3((s + GT - 1) / GT, 1, pairs), GTHREADS, GEMM_SMEM, st>>>(dU, dW, dS, ld, n, s);
+      c->n_launches++;
+      continue;
+    }
     dim3 grid((s + GT - 1) / GT, (s + GT - 1) / GT, pairs);
     trinv_step1_kernel<<<grid, GTHREADS, GEMM_SMEM, st>>>(dU, dW, dS, ld, n, s);
     trinv_step2_kernel<<<grid, GTHREADS, GEMM_SMEM, st>>>(dW, dS, ld, n, s);
