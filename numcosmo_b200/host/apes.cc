@@ -67,6 +67,7 @@ struct _NcmFitESMCMCWalkerAPES {
   std::vector<unsigned char> pre_rw;
   std::vector<double> pre_p, pre_z, pre_chisq;
   long long n_spec_blocks, n_spec_fallbacks;
+  NcmB200PinnedVec evalQ, evalOut;   // staging of the batched density evaluation of a block
   int ref = 1;
 };
 
@@ -306,8 +307,13 @@ void setup_block(NcmFitESMCMCWalkerAPES *a, int block, const double *lb, const d
 
   // NEW: both density evaluations of _apes_step (walker_apes.c:872-873) for every walker of the block in ONE call
   const guint nb = kf - ki;
-  NcmMatrix *Q   = ncm_matrix_new(2 * nb, d);
-  NcmVector *out = ncm_vector_new(2 * nb);
+  // page-locked staging kept by the walker: the queries go up and the densities come back at PCIe rate, no bounce buffer
+  a->evalQ.resize((size_t) 2 * a->size_2 * d);
+  a->evalOut.resize((size_t) 2 * a->size_2);
+  NcmMatrix Qm, *Q = &Qm;
+  Qm.data = a->evalQ.data(); Qm.nrows = 2 * nb; Qm.ncols = d; Qm.tda = d; Qm.ref = 1; Qm.own = false;
+  NcmVector outv, *out = &outv;
+  outv.data = a->evalOut.data(); outv.len = 2 * nb; outv.stride = 1; outv.ref = 1; outv.own = false;
   memcpy(ncm_matrix_data(Q), &a->thetastar[(size_t) ki * d], sizeof(double) * nb * d);
   memcpy(ncm_matrix_data(Q) + (size_t) nb * d, &theta[(size_t) ki * d], sizeof(double) * nb * d);
   {
@@ -321,8 +327,6 @@ void setup_block(NcmFitESMCMCWalkerAPES *a, int block, const double *lb, const d
     a->m2lnp_star[k] = transition_prob(a, rw, th, ts, ncm_vector_get(out, (guint) (k - ki)));
     a->m2lnp_cur[k]  = transition_prob(a, rw, ts, th, ncm_vector_get(out, (guint) (nb + k - ki)));
   }
-  ncm_matrix_free(Q);
-  ncm_vector_free(out);
   a->t_eval_ms += now_ms() - t1;
 }
 

@@ -49,6 +49,19 @@ struct NcmB200PinnedVec {
     p = nullptr;
     n = 0;
   }
+  void resize(size_t count) {   // contents are unspecified after a change of size
+    if (count == n) return;
+    release();
+    void *q = nullptr;
+    if (count > 0 && ncm_sd_gpu_host_alloc(&q, count * sizeof(double)) == NCM_SD_GPU_OK && q != nullptr) {
+      p = static_cast<double *>(q);
+      pinned = true;
+    } else if (count > 0) {
+      p = static_cast<double *>(malloc(count * sizeof(double)));
+      pinned = false;
+    }
+    n = count;
+  }
   void assign(size_t count, double v) {
     if (count != n) {
       release();
@@ -123,7 +136,7 @@ struct _NcmStatsDist {
   // KDE (NcmStatsDistKDEPrivate)
   NcmMatrix *cov, *cov_decomp;
   double kernel_lnnorm;
-  std::vector<double> sample_matrix, invUsample;   // [n_obs x d]
+  NcmB200PinnedVec sample_matrix, invUsample;     // [n_obs x d], page-locked: uploaded at every prepare_kernel
   // VKDE (NcmStatsDistVKDEPrivate): cov_array as live NcmMatrix objects over one slab
   NcmB200PinnedVec cov_slab;                       // [n_kernels x d x d], page-locked
   std::vector<NcmMatrix *> cov_array;
