@@ -2,6 +2,7 @@
 // sampling.  Everything below runs on the context's CUDA stream; there is no CPU path.
 #include <cstring>
 #include <new>
+#include <algorithm>
 #include "ctx.h"
 #include "nccl_shim.h"
 
@@ -300,9 +301,15 @@ int ncm_sd_gpu_vkde_prepare(ncm_sd_gpu_ctx *c, int n_obs, int n_kernels, const d
     return c->fail(NCM_SD_GPU_EINVAL, "vkde_prepare: bad arguments");
   cudaSetDevice(c->device);
   const int d = c->d;
+  // multi-rank (auto-shard) mode: the kNN search, covariance and factor of a centre do not depend on the other centres, so each rank
+  // prepares a contiguous block of `cap` centres and the factors / failure flags are all-gathered (in place, blocks padded to cap)
+  const bool shard = c->auto_shard && c->nranks > 1 && c->nccl_comm != nullptr && n_kernels >= 8 * c->nranks;
+  const int G = shard ? c->nranks : 1, cap = (n_kernels + G - 1) / G;
+  const int cbeg = shard ? std::min(n_kernels, c->rank * cap) : 0, ncl = shard ? std::max(0, std::min(n_kernels, cbeg + cap) - cbeg) : n_kernels;
+  const size_t n_pad = (size_t) G * cap;
   if (!c->sample.reserve((size_t) n_obs * d * sizeof(double)) || !c->zc.reserve((size_t) n_obs * d * sizeof(double)) ||
-      !c->Ufull.reserve((size_t) n_kernels * d * d * sizeof(double)) || !c->lnu.reserve((size_t) (n_kernels + 8) * sizeof(double)) ||
-      !c->weights.reserve((size_t) (n_kernels + 8) * sizeof(double)) || !c->nn_idx.reserve(((size_t) n_kernels * k + n_kernels + 16) * sizeof(int)))
+      !c->Ufull.reserve(n_pad * d * d * sizeof(double)) || !c->lnu.reserve((size_t) (n_kernels + 8) * sizeof(double)) ||
+      !c->weights.reserve((size_t) (n_kernels + 8) * sizeof(double)) || !c->nn_idx.reserve(((size_t) (ncl > 0 ? ncl : 1) * k + n_pad + 16) * sizeof(int)))
     return c->fail(NCM_SD_GPU_ENOMEM, "vkde_prepare: out of device memory");
   {
     StageTimer t(c, NCM_SD_GPU_T_H2D);
@@ -310,12 +317,19 @@ int ncm_sd_gpu_vkde_prepare(ncm_sd_gpu_ctx *c, int n_obs, int n_kernels, const d
     NCM_CUDA_OK(c, ncm_memcpy2d_async(c, c->zc.p, d * sizeof(double), invUsample, ldz * sizeof(double), d * sizeof(double), n_obs, cudaMemcpyHostToDevice, c->stream));
   }
   int *dNbr  = c->nn_idx.as<int>();
-  int *dFail = dNbr + (size_t) n_kernels * k;
+  int *dFail = dNbr + (size_t) (ncl > 0 ? ncl : 1) * k;   // [n_pad]
   int rc;
-  {
+  if (ncl > 0) {
     StageTimer t(c, NCM_SD_GPU_T_PREP);
-    rc = vkde_prepare_dev(c, n_obs, n_kernels, k, c->zc.as<double>(), c->sample.as<double>(), dNbr, c->Ufull.as<double>(), dFail);
+    rc = vkde_prepare_dev(c, n_obs, ncl, k, c->zc.as<double>(), c->sample.as<double>(), dNbr, c->Ufull.as<double>() + (size_t) cbeg * d * d, dFail + cbeg, cbeg);
     if (rc != NCM_SD_GPU_OK) return rc;
+  }
+  if (shard) {
+    StageTimer t(c, NCM_SD_GPU_T_COMM);
+    NcclApi &api = nccl_api();
+    ncclResult_t r = api.AllGather(c->Ufull.as<double>() + (size_t) c->rank * cap * d * d, c->Ufull.p, (size_t) cap * d * d, ncclDouble, (ncclComm_t) c->nccl_comm, c->stream);
+    if (r == ncclSuccess) r = api.AllGather(dFail + (size_t) c->rank * cap, dFail, (size_t) cap, ncclInt32, (ncclComm_t) c->nccl_comm, c->stream);
+    if (r != ncclSuccess) return c->fail(NCM_SD_GPU_ENCCL, std::string("ncclAllGather: ") + api.GetErrorString(r));
   }
   {
     StageTimer t(c, NCM_SD_GPU_T_D2H);

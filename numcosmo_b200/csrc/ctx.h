@@ -186,7 +186,7 @@ inline int ncm_pick_splits(int slots, int q_tiles, int max_splits) {
 // ---- kernels' host launchers (defined in the .cu files) --------------------------------------------
 int vkde_pad_dim(int d);
 int vkde_pack(ncm_sd_gpu_ctx *c, const double *dU_all /* n x d x d */);
-int vkde_prepare_dev(ncm_sd_gpu_ctx *c, int n_obs, int n_kernels, int k, const double *dZ, const double *dX, int *dNbr, double *dU_all, int *dFail);
+int vkde_prepare_dev(ncm_sd_gpu_ctx *c, int n_obs, int n_kernels, int k, const double *dZ, const double *dX, int *dNbr, double *dU_all, int *dFail, int cbeg = 0);
 int vkde_mma_pad_dim(int d);
 int vkde_mma_pack(ncm_sd_gpu_ctx *c, const double *dU_all, double *cond_max_host);
 int vkde_mma_eval_launch(ncm_sd_gpu_ctx *c, int q, const double *dX, int ldx, double *dOut, bool as_density);

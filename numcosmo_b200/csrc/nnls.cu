@@ -159,6 +159,7 @@ struct NnlsWork {
   double *dM, *dMU, *db, *drhs, *dx, *dr, *dr_try, *dg, *ddinv, *dss, *dscal;
   int *didx, *dinfo;
   double *h_buf;   // pinned: n doubles + 8
+  double *h_g;     // pinned: n doubles (gradient computed along with a residual)
   int *h_idx;      // pinned: n ints
   ncm_sd_gpu_nnls_stats *st;
   // low-rank reuse of the last factorisation (lowrank.cu)
@@ -398,8 +399,10 @@ int solve_feasible(NnlsWork &w, std::vector<int> &P, std::vector<double> &x, int
   }
 }
 
-// rnorm of x (host) -> residual vector left in dr_out
-int compute_residuals(NnlsWork &w, const std::vector<double> &x, double *dr_out, double *rnorm) {
+// rnorm of x (host) -> residual vector left in dr_out.  g_spec != nullptr: the gradient A^T r of that residual is computed in the same
+// submission (ncm_nnls.c:722-726 computes it right after the residuals whenever the step is accepted, which is the rule; when the
+// step is rejected the 20 us of device work are dropped) -- one host round trip instead of two, the very same kernels and values.
+int compute_residuals(NnlsWork &w, const std::vector<double> &x, double *dr_out, double *rnorm, std::vector<double> *g_spec = nullptr) {
   ncm_sd_gpu_ctx *c = w.c;
   StageTimer t(c, NCM_SD_GPU_T_NNLS_MISC);
   std::memcpy(w.h_buf, x.data(), sizeof(double) * w.n);
@@ -412,8 +415,16 @@ int compute_residuals(NnlsWork &w, const std::vector<double> &x, double *dr_out,
   rc = allreduce_sum(c, w.dscal, 1);
   if (rc != NCM_SD_GPU_OK) return rc;
   NCM_CUDA_OK(c, ncm_memcpy_async(c,w.h_buf + w.n, w.dscal, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (g_spec != nullptr) {
+    rc = gemv_t(c, w.dA, w.lda, w.nrows, w.n, dr_out, w.dg, c->nn_tmp);
+    if (rc != NCM_SD_GPU_OK) return rc;
+    rc = allreduce_sum(c, w.dg, w.n);
+    if (rc != NCM_SD_GPU_OK) return rc;
+    NCM_CUDA_OK(c, ncm_memcpy_async(c, w.h_g, w.dg, sizeof(double) * w.n, cudaMemcpyDeviceToHost, c->stream));
+  }
   NCM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
   *rnorm = sqrt(w.h_buf[w.n]);
+  if (g_spec != nullptr) g_spec->assign(w.h_g, w.h_g + w.n);
   return NCM_SD_GPU_OK;
 }
 
@@ -469,7 +480,7 @@ int nnls_solve_dev(ncm_sd_gpu_ctx *c, int nrows, int ncols, const double *dA, in
   if (!c->M.reserve(mm) || !c->MU.reserve(mm) || !c->nn_b.reserve((size_t) (4 * n + 64) * sizeof(double)) ||
       !c->nn_x.reserve((size_t) (2 * n + 16) * sizeof(double)) || !c->nn_r.reserve((size_t) (2 * nrows + 16) * sizeof(double)) ||
       !c->nn_g.reserve((size_t) (nrows / 8 + n + 64) * sizeof(double)) || !c->nn_idx.reserve((size_t) (n + 16) * sizeof(int)) ||
-      !c->pin_nn.reserve((size_t) (n + 16) * sizeof(double) + (size_t) (3 * (n + 32) + 2 * (lowrank_kmax() + 8)) * sizeof(int)))
+      !c->pin_nn.reserve((size_t) (2 * n + 32) * sizeof(double) + (size_t) (3 * (n + 32) + 2 * (lowrank_kmax() + 8)) * sizeof(int)))
     return c->fail(NCM_SD_GPU_ENOMEM, "nnls: out of memory");
 
   NnlsWork w;
@@ -488,7 +499,8 @@ int nnls_solve_dev(ncm_sd_gpu_ctx *c, int nrows, int ncols, const double *dA, in
   w.didx   = c->nn_idx.as<int>();
   w.dinfo  = w.didx + (n + 8);
   w.h_buf  = c->pin_nn.as<double>();
-  w.h_idx  = reinterpret_cast<int *>(w.h_buf + (n + 16));
+  w.h_g    = w.h_buf + (n + 16);
+  w.h_idx  = reinterpret_cast<int *>(w.h_g + (n + 16));
 
   w.lr_on = lowrank_enabled() && n >= LR_MIN_N && n <= chol_fused_max_n();
   if (w.lr_on) {
@@ -539,16 +551,15 @@ int nnls_solve_dev(ncm_sd_gpu_ctx *c, int nrows, int ncols, const double *dA, in
   std::vector<double> x(n, 0.0), x_try(n, 0.0), mgrad;
   double rnorm = 0.0;
 
+  std::vector<double> g_try;
   rc = solve_feasible(w, P, x, n);
   if (rc != NCM_SD_GPU_OK) return rc;
-  rc = compute_residuals(w, x, w.dr, &rnorm);
-  if (rc != NCM_SD_GPU_OK) return rc;
-  rc = compute_mgrad(w, w.dr, mgrad);
+  rc = compute_residuals(w, x, w.dr, &rnorm, &mgrad);
   if (rc != NCM_SD_GPU_OK) return rc;
 
   while (true) {
     double add_frac = 1.0;
-    bool finish     = false;
+    bool finish     = false, have_g = false;
     double lrnorm   = 0.0;
     while (true) {
       P_try           = P;
@@ -560,13 +571,14 @@ int nnls_solve_dev(ncm_sd_gpu_ctx *c, int nrows, int ncols, const double *dA, in
       }
       rc = solve_feasible(w, P_try, x_try, added);
       if (rc != NCM_SD_GPU_OK) return rc;
-      rc = compute_residuals(w, x_try, w.dr_try, &lrnorm);
+      rc = compute_residuals(w, x_try, w.dr_try, &lrnorm, &g_try);
       if (rc != NCM_SD_GPU_OK) return rc;
       if (rnorm - lrnorm > rnorm * reltol) {
         P = P_try;
         x = x_try;
         std::swap(w.dr, w.dr_try);
         rnorm = lrnorm;
+        have_g = true;   // g_try is A^T of the residual just accepted
         if (stats) stats->n_outer++;
         break;
       }
@@ -576,8 +588,12 @@ int nnls_solve_dev(ncm_sd_gpu_ctx *c, int nrows, int ncols, const double *dA, in
       }
     }
     if (finish) break;
-    rc = compute_mgrad(w, w.dr, mgrad);
-    if (rc != NCM_SD_GPU_OK) return rc;
+    if (have_g) {
+      mgrad.swap(g_try);
+    } else {
+      rc = compute_mgrad(w, w.dr, mgrad);
+      if (rc != NCM_SD_GPU_OK) return rc;
+    }
   }
   if (stats) stats->n_passive = (int) P.size();
   std::memcpy(x_host, x.data(), sizeof(double) * n);

@@ -23,7 +23,8 @@ __device__ __forceinline__ bool key_less(double d1, int i1, double d2, int i2) {
 // All squared distances centre x point, D[c][m] = sum_r (z_m[r] - z_c[r])^2 in index order with explicit round-to-nearest
 // operations (kdtree.c:27-38 distance()): 64 x 64 tile per CTA, both point sets staged in shared memory, 4 x 4 pairs per
 // thread.  One pass over the points per 64 centres instead of one per centre (64 GB -> 1 GB of L2 traffic at N = 16384).
-__global__ void __launch_bounds__(256) dist_kernel(const double *__restrict__ Z, int n_obs, int n_kernels, int d, double *__restrict__ D, size_t ldd) {
+// centres cbeg .. cbeg + n_kernels - 1 of Z (a rank's share of the centres in multi-rank mode); row c of D belongs to centre cbeg + c
+__global__ void __launch_bounds__(256) dist_kernel(const double *__restrict__ Z, int n_obs, int cbeg, int n_kernels, int d, double *__restrict__ D, size_t ldd) {
   extern __shared__ __align__(16) unsigned char dist_smem[];
   double *sc = reinterpret_cast<double *>(dist_smem);   // [64][d + 1] centres
   double *sp = sc + 64 * (d + 1);                        // [64][d + 1] points
@@ -31,7 +32,7 @@ __global__ void __launch_bounds__(256) dist_kernel(const double *__restrict__ Z,
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   for (int e = tid; e < 64 * d; e += 256) {
     const int r = e / d, q = e % d;
-    sc[r * (d + 1) + q] = (c0 + r < n_kernels) ? Z[(size_t) (c0 + r) * d + q] : 0.0;
+    sc[r * (d + 1) + q] = (c0 + r < n_kernels) ? Z[(size_t) (cbeg + c0 + r) * d + q] : 0.0;
     sp[r * (d + 1) + q] = (m0 + r < n_obs) ? Z[(size_t) (m0 + r) * d + q] : 0.0;
   }
   __syncthreads();
@@ -71,7 +72,7 @@ __global__ void __launch_bounds__(256) dist_kernel(const double *__restrict__ Z,
 // 46 ms -> a few ms at n_obs = 16384), ordered compaction of the k winners (ties at the threshold are taken in index
 // order, as the (distance, index) ordering of the reference's neighbour list demands), bitonic sort of those k only.
 __global__ void __launch_bounds__(512) knn_kernel(const double *__restrict__ Z, const double *__restrict__ D, size_t ldd, int n_obs, int n_smem, int d,
-                                                  int kpow2, int k, int *__restrict__ nbr) {
+                                                  int kpow2, int k, int *__restrict__ nbr, int cbeg) {
   extern __shared__ __align__(16) unsigned char knn_smem[];
   // distances: a shared-memory copy when it fits (n_smem = n_obs), else the row of the precomputed matrix in global memory
   // (n_smem = 0; the six selection passes and the compaction then stream it from L2)
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(512) knn_kernel(const double *__restrict__ Z, 
     for (int m = tid; m < n_obs; m += nt) ssd[m] = row[m];
     sd = ssd;
   } else {
-    for (int r = tid; r < d; r += nt) st[r] = Z[(size_t) c * d + r];
+    for (int r = tid; r < d; r += nt) st[r] = Z[(size_t) (cbeg + c) * d + r];
     __syncthreads();
     for (int m = tid; m < n_obs; m += nt) {
       // kdtree.c:27-38 distance(): sum of squared differences in index order (point - target), no contraction
@@ -316,7 +317,8 @@ __global__ void __launch_bounds__(256) cov_kernel(const double *__restrict__ X /
 
 // dZ: whitened points [n_obs x d] (device), dX: raw points [n_obs x d] (device).  Outputs on the device:
 // dU_all [n_kernels x d x d], dFail [n_kernels].  Returns NCM_SD_GPU_EINVAL when the shared-memory sort does not fit.
-int vkde_prepare_dev(ncm_sd_gpu_ctx *c, int n_obs, int n_kernels, int k, const double *dZ, const double *dX, int *dNbr, double *dU_all, int *dFail) {
+// centres [cbeg, cbeg + n_kernels) of the sample (dU_all / dFail already point at centre cbeg; dNbr is scratch for n_kernels lists)
+int vkde_prepare_dev(ncm_sd_gpu_ctx *c, int n_obs, int n_kernels, int k, const double *dZ, const double *dX, int *dNbr, double *dU_all, int *dFail, int cbeg) {
   const int d = c->d;
   int kpow2 = 1;
   while (kpow2 < k) kpow2 <<= 1;
@@ -341,14 +343,14 @@ int vkde_prepare_dev(ncm_sd_gpu_ctx *c, int n_obs, int n_kernels, int k, const d
     if (c->dist.reserve((size_t) n_kernels * ldd * sizeof(double))) {
       const size_t smem_dist = (size_t) 2 * 64 * (d + 1) * sizeof(double);
       dim3 dgrid((n_obs + 63) / 64, (n_kernels + 63) / 64);
-      dist_kernel<<<dgrid, 256, smem_dist, c->stream>>>(dZ, n_obs, n_kernels, d, c->dist.as<double>(), ldd);
+      dist_kernel<<<dgrid, 256, smem_dist, c->stream>>>(dZ, n_obs, cbeg, n_kernels, d, c->dist.as<double>(), ldd);
       c->n_launches++;
       dD = c->dist.as<double>();
     }   // else: not enough memory for the matrix, every CTA computes its own distances
   }
   if (n_smem == 0 && dD == nullptr)
     return c->fail(NCM_SD_GPU_ENOMEM, "vkde_prepare: the distance matrix does not fit in device memory and one row does not fit in shared memory");
-  knn_kernel<<<n_kernels, threads, smem_knn, c->stream>>>(dZ, dD, ldd, n_obs, n_smem, d, kpow2, k, dNbr);
+  knn_kernel<<<n_kernels, threads, smem_knn, c->stream>>>(dZ, dD, ldd, n_obs, n_smem, d, kpow2, k, dNbr, cbeg);
   const int wpb = 8;
   const size_t smem_cov = (size_t) wpb * (2 * d + d * d) * sizeof(double);
   const int npair = d * (d - 1) / 2;
