@@ -183,11 +183,13 @@ def cpu_apes(args, W, d, iters, nthreads, warm=True):
     ap = O.APES(W, d, O.SD_VKDE, okind, nu, over_smooth=1.0, use_interp=True, use_threads=True)
     theta, ml = X.copy(), m2lnL.copy()
     rng = O.RNG(1234)
+    accs = []
     if warm:
-        ap.run(tgt, theta, ml, 1, rng, nthreads=nthreads)   # warm-up iteration
+        accs.append(ap.run(tgt, theta, ml, 1, rng, nthreads=nthreads))   # warm-up iteration
     t0 = time.perf_counter()
-    ap.run(tgt, theta, ml, iters, rng, nthreads=nthreads)
+    accs.append(ap.run(tgt, theta, ml, iters, rng, nthreads=nthreads))
     dt = (time.perf_counter() - t0) / iters
+    cpu_apes.last_accepted = np.concatenate(accs, axis=0)   # accepted / rejected of every iteration from the common start, seed 1234
     return dt, ap.timers()
 
 
@@ -372,7 +374,8 @@ def run_b200(args):
 
     def e2e_run(apes, theta, ml, rng):
         """end to end through the host API with HOST buffers; returns (seconds per iteration, accept rate, h2d, d2h, launches, stage split)"""
-        apes.run("mvnd", lb, ub, theta, ml, max(args.warmup, 1), rng, target_args=(mu, U_tgt), record_accept=False)
+        acc_w, _ = apes.run("mvnd", lb, ub, theta, ml, max(args.warmup, 1), rng, target_args=(mu, U_tgt), record_accept=True)
+        e2e_run.acc_warm = acc_w
         sds = apes.peek_sds()
         ctxs = [capi.Context.borrowed(lib.ncm_stats_dist_b200_peek_ctx(sd._h)) for sd in sds]
         for c in ctxs:
@@ -472,9 +475,15 @@ def run_b200(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:   # reported at N = 1 only (the other ranks would sit idle behind it)
         ncores = os.cpu_count() or 1
         cdt, ctm = cpu_apes(args, W, d, 3, ncores)
+        # both arms start from the same ensemble with the same generator seed: their accepted / rejected sequences must be the same
+        acc_cpu = cpu_apes.last_accepted
+        acc_gpu = np.concatenate([e2e_run.acc_warm, acc], axis=0)
+        ncmp = min(len(acc_cpu), len(acc_gpu))
         cpu = {"value": pairs_step / cdt, "unit": UNIT, "cores": ncores, "kind": "port",
                "sample": f"3 full APES iterations at W={W}, d={d} on the host cores (oracle port; 1 warm-up iteration)",
-               "ms_per_step": cdt * 1e3, "walker_steps_per_s": W / cdt}
+               "ms_per_step": cdt * 1e3, "walker_steps_per_s": W / cdt,
+               "accepted_sequence_identical_to_gpu_arm": bool(np.array_equal(np.asarray(acc_cpu[:ncmp]).astype(bool), np.asarray(acc_gpu[:ncmp]).astype(bool))),
+               "iterations_compared": int(ncmp)}
 
     if rank == 0:
         line = {
