@@ -235,7 +235,7 @@ size_t lowrank_part_doubles(int n, int ldv);
 int symmetrize_upper(ncm_sd_gpu_ctx *c, int n, double *dM, int ld);
 int trinv_upper(ncm_sd_gpu_ctx *c, int n, const double *dU, double *dW, double *dS, int ld, double *dWt);
 int trinv_upper_on(ncm_sd_gpu_ctx *c, cudaStream_t st, int n, const double *dU, double *dW, double *dS, int ld, double *dWt);
-int dsyrk_ata_tiles_on(ncm_sd_gpu_ctx *c, cudaStream_t st, int K, int n, const double *dP, int ldp, double *dC, int ldc, const int *dTiles, int ntiles);
+int dsyrk_ata_tiles_on(ncm_sd_gpu_ctx *c, cudaStream_t st, int K, int n, const double *dP, int ldp, double *dC, int ldc, const int *dTiles, int ntiles, int max_ctas = 0);
 int lowrank_solve(ncm_sd_gpu_ctx *c, const double *dM, int ldm, int n, const double *db, int nB, int na, int nd, int np, const LowrankBufs &w, int ldv,
                   bool refine);
 int sample_apply_launch(ncm_sd_gpu_ctx *c, int q, const int *dIdx, const double *dZ, int ldz, const double *dScale, double *dX, int ldx);

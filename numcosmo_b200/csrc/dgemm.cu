@@ -47,19 +47,10 @@ __device__ __forceinline__ void tile_from_linear(int t, int nt, int &ti, int &tj
 // SUBC: C -= P^T P (alpha = -1, beta = 1): C is loaded into the accumulators up front (the loads overlap with the
 // cp.async prologue), the A fragments are negated, and the epilogue is stores only.
 template <typename Cfg, bool SUBC>
-__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB)
-ata_kernel(const double *__restrict__ P, int ldp, int K, int n, double *__restrict__ C, int ldc, double alpha, double beta, int nt,
-           const int2 *__restrict__ tiles) {
+__device__ __forceinline__ void ata_tile(const double *__restrict__ P, int ldp, int K, int n, double *__restrict__ C, int ldc, double alpha, double beta,
+                                         int ti, int tj, double *smem) {
   using D = AtaDerived<Cfg>;
   constexpr int TB = Cfg::TB, PITCH = D::PITCH, SLAB = D::SLAB, MI = Cfg::MI, NI = Cfg::NI, STAGES = Cfg::STAGES;
-  extern __shared__ __align__(16) double smem[];
-  int ti, tj;
-  if (tiles != nullptr) {   // explicit tile list: the column blocks one rank owns in the distributed factorisation (dist_chol.cu)
-    ti = tiles[blockIdx.x].x;
-    tj = tiles[blockIdx.x].y;
-  } else {
-    tile_from_linear(blockIdx.x, nt, ti, tj);
-  }
   const int i0 = ti * TB, j0 = tj * TB;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -184,6 +175,33 @@ ata_kernel(const double *__restrict__ P, int ldp, int K, int n, double *__restri
 }
 
 template <typename Cfg, bool SUBC>
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB)
+ata_kernel(const double *__restrict__ P, int ldp, int K, int n, double *__restrict__ C, int ldc, double alpha, double beta, int nt,
+           const int2 *__restrict__ tiles) {
+  extern __shared__ __align__(16) double smem[];
+  int ti, tj;
+  if (tiles != nullptr) {   // explicit tile list: the column blocks one rank owns in the distributed factorisation (dist_chol.cu)
+    ti = tiles[blockIdx.x].x;
+    tj = tiles[blockIdx.x].y;
+  } else {
+    tile_from_linear(blockIdx.x, nt, ti, tj);
+  }
+  ata_tile<Cfg, SUBC>(P, ldp, K, n, C, ldc, alpha, beta, ti, tj, smem);
+}
+
+// the same over an explicit tile list with FEWER CTAs than tiles (each loops over its share): the trailing update of the distributed
+// factorisation then leaves some SMs to the panel chain of the next step instead of making every one of its kernels wait for a CTA
+// of this one to retire (dist_chol.cu)
+__global__ void __launch_bounds__(AtaBig::THREADS, AtaBig::MINB)
+ata_tiles_persistent_kernel(const double *__restrict__ P, int ldp, int K, int n, double *__restrict__ C, int ldc, const int2 *__restrict__ tiles, int ntiles) {
+  extern __shared__ __align__(16) double smem[];
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    ata_tile<AtaBig, true>(P, ldp, K, n, C, ldc, -1.0, 1.0, tiles[t].x, tiles[t].y, smem);
+    __syncthreads();   // the staging ring is reused by the next tile
+  }
+}
+
+template <typename Cfg, bool SUBC>
 cudaError_t ata_launch(cudaStream_t st, const double *dP, int ldp, int K, int n, double *dC, int ldc, double alpha, double beta, int head_tile_rows = 0) {
   using D = AtaDerived<Cfg>;
   static bool attr_set[NCM_MAX_DEVICES] = {};   // function attributes are per device
@@ -204,7 +222,7 @@ cudaError_t ata_launch(cudaStream_t st, const double *dP, int ldp, int K, int n,
 }
 
 // C[tile] -= P^T P for an explicit list of 128 x 128 tiles (ti <= tj, tile units)
-cudaError_t ata_launch_tiles(cudaStream_t st, const double *dP, int ldp, int K, int n, double *dC, int ldc, const int2 *dTiles, int ntiles) {
+cudaError_t ata_launch_tiles(cudaStream_t st, const double *dP, int ldp, int K, int n, double *dC, int ldc, const int2 *dTiles, int ntiles, int max_ctas) {
   using D = AtaDerived<AtaBig>;
   static bool attr_set[NCM_MAX_DEVICES] = {};
   int dev__ = 0;
@@ -216,6 +234,16 @@ cudaError_t ata_launch_tiles(cudaStream_t st, const double *dP, int ldp, int K, 
     attr_set[dev__] = true;
   }
   const int nt = (n + AtaBig::TB - 1) / AtaBig::TB;
+  if (max_ctas > 0 && max_ctas < ntiles) {
+    static bool attr2_set[NCM_MAX_DEVICES] = {};
+    if (!attr2_set[dev__]) {
+      cudaError_t e = cudaFuncSetAttribute(ata_tiles_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) D::SMEM);
+      if (e != cudaSuccess) return e;
+      attr2_set[dev__] = true;
+    }
+    ata_tiles_persistent_kernel<<<max_ctas, AtaBig::THREADS, D::SMEM, st>>>(dP, ldp, K, n, dC, ldc, dTiles, ntiles);
+    return cudaGetLastError();
+  }
   ata_kernel<AtaBig, true><<<ntiles, AtaBig::THREADS, D::SMEM, st>>>(dP, ldp, K, n, dC, ldc, -1.0, 1.0, nt, dTiles);
   return cudaGetLastError();
 }
@@ -287,13 +315,14 @@ int dsyrk_ata_general(ncm_sd_gpu_ctx *c, int K, int n, const double *dP, int ldp
 
 // C -= P^T P on the listed upper 128-tiles only (P: K x n row-major, C: n x n)
 int dsyrk_ata_tiles(ncm_sd_gpu_ctx *c, int K, int n, const double *dP, int ldp, double *dC, int ldc, const int *dTiles /* pairs (ti, tj) */, int ntiles) {
-  return dsyrk_ata_tiles_on(c, c->stream, K, n, dP, ldp, dC, ldc, dTiles, ntiles);
+  return dsyrk_ata_tiles_on(c, c->stream, K, n, dP, ldp, dC, ldc, dTiles, ntiles, 0);
 }
-int dsyrk_ata_tiles_on(ncm_sd_gpu_ctx *c, cudaStream_t st, int K, int n, const double *dP, int ldp, double *dC, int ldc, const int *dTiles, int ntiles) {
+// max_ctas > 0: at most that many CTAs, each looping over its share of the tiles
+int dsyrk_ata_tiles_on(ncm_sd_gpu_ctx *c, cudaStream_t st, int K, int n, const double *dP, int ldp, double *dC, int ldc, const int *dTiles, int ntiles, int max_ctas) {
   if (ntiles <= 0 || K <= 0) return NCM_SD_GPU_OK;
   if ((ldp & 1) || (ldc & 1) || (((uintptr_t) dP) & 15) || (((uintptr_t) dC) & 15))
     return c->fail(NCM_SD_GPU_EINVAL, "ata: operands must be 16-byte aligned with even leading dimensions");
-  NCM_CUDA_OK(c, ata_launch_tiles(st, dP, ldp, K, n, dC, ldc, reinterpret_cast<const int2 *>(dTiles), ntiles));
+  NCM_CUDA_OK(c, ata_launch_tiles(st, dP, ldp, K, n, dC, ldc, reinterpret_cast<const int2 *>(dTiles), ntiles, max_ctas));
   c->n_launches++;
   return NCM_SD_GPU_OK;
 }

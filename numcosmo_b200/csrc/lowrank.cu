@@ -463,17 +463,31 @@ __global__ void __launch_bounds__(LR_ST) lr_small_kernel(int mode, int na, int n
       }
       __syncthreads();
       // trailing update: H[i][l] -= sum_c J_c L[i][c] L[l][c],  p0 + pw <= l <= i < kr, l < k
+      // (a warp takes two rows at a time and splits every dot product in two: the eight dependent FMAs of one element were the
+      // longest chain of the kernel -- ncu r02f: a third of its stall samples sat on them)
       const int t0 = p0 + pw;
-      for (int ii = t0 + warp; ii < kr; ii += LR_ST / 32) {
-        double pi[LR_PW];
+      for (int ii = t0 + 2 * warp; ii < kr; ii += 2 * (LR_ST / 32)) {
+        const bool two = ii + 1 < kr;
+        double pi0[LR_PW], pi1[LR_PW];
 #pragma unroll
-        for (int c = 0; c < LR_PW; ++c) pi[c] = pas[c * LR_PKR + (ii - p0)];
-        double *rowp = L + pidx(ii, 0);
-        for (int l = t0 + lane; l <= ii && l < k; l += 32) {
-          double s = rowp[l];
+        for (int c = 0; c < LR_PW; ++c) {
+          pi0[c] = pas[c * LR_PKR + (ii - p0)];
+          pi1[c] = two ? pas[c * LR_PKR + (ii + 1 - p0)] : 0.0;
+        }
+        double *row0 = L + pidx(ii, 0), *row1 = L + pidx(ii + 1, 0);
+        const int lmax = min(two ? ii + 1 : ii, k - 1);
+        for (int l = t0 + lane; l <= lmax; l += 32) {
+          double a0 = 0.0, b0 = 0.0, a1 = 0.0, b1 = 0.0;
 #pragma unroll
-          for (int c = 0; c < LR_PW; ++c) s = fma(-pi[c], pan[c * LR_PKR + (l - p0)], s);
-          rowp[l] = s;
+          for (int c = 0; c < LR_PW; c += 2) {
+            const double pl0 = pan[c * LR_PKR + (l - p0)], pl1 = pan[(c + 1) * LR_PKR + (l - p0)];
+            a0 = fma(pi0[c], pl0, a0);
+            b0 = fma(pi0[c + 1], pl1, b0);
+            a1 = fma(pi1[c], pl0, a1);
+            b1 = fma(pi1[c + 1], pl1, b1);
+          }
+          if (l <= ii) row0[l] -= a0 + b0;
+          if (two) row1[l] -= a1 + b1;
         }
       }
       __syncthreads();
