@@ -243,8 +243,9 @@ int dpotrf_upper_solve_dist(ncm_sd_gpu_ctx *c, int n, double *dM, int ldm, doubl
   }
   static const bool la_on = getenv("NCM_SD_GPU_DIST_CHOL_LOOKAHEAD") == nullptr || atoi(getenv("NCM_SD_GPU_DIST_CHOL_LOOKAHEAD")) != 0;
   static const int reserve_env = getenv("NCM_SD_GPU_DIST_CHOL_RESERVE") != nullptr ? atoi(getenv("NCM_SD_GPU_DIST_CHOL_RESERVE")) : -1;
-  // SMs kept free of update CTAs for the panel chain: only where the update of a step is shorter than the chain (six ranks and more)
-  const int reserve = !la_on ? 0 : (reserve_env >= 0 ? std::min(reserve_env, c->n_sm - 16) : (G >= 6 ? 64 : 0));
+  // SMs kept free of update CTAs for the panel chain (experiment knob, off by default: at 8 GPUs 64 reserved SMs changed nothing --
+  // 52.4 against 52.1 ms for two factorisations of order 16384 -- and 96 cost 12 ms: the chain is not waiting for SMs)
+  const int reserve = !la_on ? 0 : (reserve_env >= 0 ? std::min(reserve_env, c->n_sm - 16) : 0);
   cudaStream_t sP = la_on ? c->dc_sP : sU, sW = la_on ? c->dc_sW : sU;   // =0: everything in order on the context stream (A/B switch)
   static bool attr_set[NCM_MAX_DEVICES] = {};
   {
@@ -332,8 +333,7 @@ int dpotrf_upper_solve_dist(ncm_sd_gpu_ctx *c, int n, double *dM, int ldm, doubl
     }
     NCM_CUDA_OK(c, cudaEventRecord(c->dc_evA, sU));
     if (nB > 0) {
-      // the bulk of the update: with many ranks it is short against the chain of the next panel, and it leaves `reserve` SMs to
-      // that chain (whose kernels would otherwise each wait ~80 us for a 128 x 128 update CTA to retire before they get an SM)
+      // the bulk of the update (optionally on fewer CTAs than SMs, see `reserve` above)
       int rc = dsyrk_ata_tiles_on(c, sU, bs, n, dM + (size_t) k0 * ldm, ldm, dM, ldm, dTiles + 2 * offB[k], nB, reserve > 0 ? c->n_sm - reserve : 0);
       if (rc != NCM_SD_GPU_OK) return rc;
     }
