@@ -120,6 +120,8 @@ typedef struct ncm_sd_gpu_nnls_stats
   double lowrank_flops;   /* 2 |B|^2 (k + 1) per such solve + |B|^3 / 3 per triangular inverse */
   int n_dist_chol;   /* factorisations whose trailing updates were distributed over the ranks (dist_chol.cu) */
   int n_qr;      /* ... whose L D L^T met an exactly singular pivot: least squares by Householder QR (dgels, ncm_nnls.c:608-638) */
+  int n_lowrank_nested; /* low-rank solves whose removed set contained the previous one: the k x k factor was extended, not rebuilt */
+  int reserved_;
 } ncm_sd_gpu_nnls_stats;
 
 int ncm_sd_gpu_nnls_solve (ncm_sd_gpu_ctx *ctx, double reltol, double *x_out, double *rnorm_out, ncm_sd_gpu_nnls_stats *stats);

@@ -41,7 +41,7 @@ class GpuError(RuntimeError):
 class NNLSStats(C.Structure):
     _fields_ = [("n_chol", C.c_int), ("n_lu", C.c_int), ("n_outer", C.c_int), ("n_passive", C.c_int), ("chol_flops", C.c_double),
                 ("syrk_flops", C.c_double), ("n_lowrank", C.c_int), ("n_lowrank_fallback", C.c_int), ("n_trinv", C.c_int), ("max_lowrank_k", C.c_int),
-                ("lowrank_flops", C.c_double), ("n_dist_chol", C.c_int), ("n_qr", C.c_int)]
+                ("lowrank_flops", C.c_double), ("n_dist_chol", C.c_int), ("n_qr", C.c_int), ("n_lowrank_nested", C.c_int), ("reserved_", C.c_int)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

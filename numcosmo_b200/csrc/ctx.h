@@ -237,5 +237,5 @@ int trinv_upper(ncm_sd_gpu_ctx *c, int n, const double *dU, double *dW, double *
 int trinv_upper_on(ncm_sd_gpu_ctx *c, cudaStream_t st, int n, const double *dU, double *dW, double *dS, int ld, double *dWt);
 int dsyrk_ata_tiles_on(ncm_sd_gpu_ctx *c, cudaStream_t st, int K, int n, const double *dP, int ldp, double *dC, int ldc, const int *dTiles, int ntiles, int max_ctas = 0);
 int lowrank_solve(ncm_sd_gpu_ctx *c, const double *dM, int ldm, int n, const double *db, int nB, int na, int nd, int np, const LowrankBufs &w, int ldv,
-                  bool refine);
+                  bool refine, int kold = 0);
 int sample_apply_launch(ncm_sd_gpu_ctx *c, int q, const int *dIdx, const double *dZ, int ldz, const double *dScale, double *dX, int ldx);

@@ -359,9 +359,14 @@ __device__ __forceinline__ int pidx(int i, int j) { return i * (i + 1) / 2 + j; 
 
 // mode 0: H = H0[:k,:k] - diag(M_AA, 0), rhs = H0[:k, k] - [b_A; 0]; factor (rhs as row k: the forward substitution comes with the
 //         factorisation), back-substitute, keep the factor in Lg.
+//         kold > 0 (a multiple of 8, only with na = 0): the leading kold x kold block of H is the one factorised by the previous call
+//         (the removed set only grew and the new members were appended): its factor is reloaded from Lg and only the rows below it
+//         are eliminated -- the old panels cost a publish and a few row solves instead of a diagonal factorisation and an update
+//         of everything behind them.
 // mode 1: reload the factor, rhs = sum_p tpart[p] - [rfull_A; 0], blocked forward + back substitution.
 // info: 0 or the 1-based index of a pivot of the wrong sign.
-__global__ void __launch_bounds__(LR_ST) lr_small_kernel(int mode, int na, int nd, const double *__restrict__ H0, int ldh,
+constexpr int LR_NPK_MAX = (LR_KMAX + 1) * (LR_KMAX + 2) / 2;   // Lg: packed factor [LR_NPK_MAX], then the inverse diagonal at a FIXED offset
+__global__ void __launch_bounds__(LR_ST) lr_small_kernel(int mode, int kold, int na, int nd, const double *__restrict__ H0, int ldh,
                                                          const double *__restrict__ M, int ldm, const int *__restrict__ idxA, const double *__restrict__ b,
                                                          const double *__restrict__ tpart, int ldp, int ntp, const double *__restrict__ rfull, double *__restrict__ Lg,
                                                          double *__restrict__ z, int *__restrict__ info) {
@@ -378,8 +383,10 @@ __global__ void __launch_bounds__(LR_ST) lr_small_kernel(int mode, int na, int n
   double *dgs  = red + 8;   // published diagonal block [8][8] + its inverse diagonal [8]
   if (k == 0) return;
   if (mode == 0) {
+    for (int e = tid; e < pidx(kold, 0); e += LR_ST) L[e] = Lg[e];   // rows < kold: the factor of the previous, nested system
+    for (int i = tid; i < kold; i += LR_ST) dinv[i] = Lg[LR_NPK_MAX + i];
     for (int j = warp; j < k; j += LR_ST / 32)          // row j of the upper-stored H0, lanes along it: coalesced
-      for (int i = j + lane; i < kr; i += 32) {
+      for (int i = max(j, kold) + lane; i < kr; i += 32) {
         double v = H0[(size_t) j * ldh + i];
         if (i < na) v -= M[(size_t) idxA[j] * ldm + idxA[i]];
         if (i == k && j < na) v -= b[idxA[j]];
@@ -392,7 +399,14 @@ __global__ void __launch_bounds__(LR_ST) lr_small_kernel(int mode, int na, int n
       // warp 0 factors the pw x pw diagonal block in registers (all lanes redundantly: no communication on the pivot chain) and
       // publishes it; then every row i >= p0, owned by one thread, is solved against it
       const int i = p0 + tid;
-      if (warp == 0) {
+      const bool old_panel = p0 + LR_PW <= kold;   // already factorised: publish it, solve the new rows against it
+      if (warp == 0 && old_panel) {
+        if (lane < LR_PW) {
+#pragma unroll
+          for (int q = 0; q < LR_PW; ++q) dgs[lane * LR_PW + q] = q <= lane ? L[pidx(p0 + lane, p0 + q)] : 0.0;
+          dgs[LR_PW * LR_PW + lane] = dinv[p0 + lane];
+        }
+      } else if (warp == 0) {
         double dg[LR_PW][LR_PW], dv[LR_PW];
         int bad = 0;
 #pragma unroll
@@ -430,7 +444,11 @@ __global__ void __launch_bounds__(LR_ST) lr_small_kernel(int mode, int na, int n
       __syncthreads();
       if (tid < kr - p0) {
         double row[LR_PW];
-        if (tid < pw) {
+        const bool old_row = i < kold;   // its entries in this (old) panel are final
+        if (old_row) {
+#pragma unroll
+          for (int c = 0; c < LR_PW; ++c) row[c] = (tid >= pw || c <= tid) ? L[pidx(i, p0 + c)] : 0.0;
+        } else if (tid < pw) {
 #pragma unroll
           for (int c = 0; c < LR_PW; ++c) row[c] = c <= tid ? dgs[tid * LR_PW + c] : 0.0;
           dinv[i] = dgs[LR_PW * LR_PW + tid];
@@ -456,7 +474,7 @@ __global__ void __launch_bounds__(LR_ST) lr_small_kernel(int mode, int na, int n
 #pragma unroll
         for (int c = 0; c < LR_PW; ++c) {
           const double sgc = (p0 + c) < na ? -1.0 : 1.0;
-          if (c < pw && (tid >= pw || c <= tid)) L[pidx(i, p0 + c)] = row[c];
+          if (!old_row && c < pw && (tid >= pw || c <= tid)) L[pidx(i, p0 + c)] = row[c];
           pan[c * LR_PKR + tid] = c < pw ? row[c] : 0.0;
           pas[c * LR_PKR + tid] = c < pw ? sgc * row[c] : 0.0;
         }
@@ -465,8 +483,8 @@ __global__ void __launch_bounds__(LR_ST) lr_small_kernel(int mode, int na, int n
       // trailing update: H[i][l] -= sum_c J_c L[i][c] L[l][c],  p0 + pw <= l <= i < kr, l < k
       // (a warp takes two rows at a time and splits every dot product in two: the eight dependent FMAs of one element were the
       // longest chain of the kernel -- ncu r02f: a third of its stall samples sat on them)
-      const int t0 = p0 + pw;
-      for (int ii = t0 + 2 * warp; ii < kr; ii += 2 * (LR_ST / 32)) {
+      const int t0 = p0 + pw, u0 = max(t0, old_panel ? kold : 0);   // behind an old panel only the new rows change
+      for (int ii = u0 + 2 * warp; ii < kr; ii += 2 * (LR_ST / 32)) {
         const bool two = ii + 1 < kr;
         double pi0[LR_PW], pi1[LR_PW];
 #pragma unroll
@@ -494,14 +512,14 @@ __global__ void __launch_bounds__(LR_ST) lr_small_kernel(int mode, int na, int n
     }
     for (int e = tid; e < npk; e += LR_ST) Lg[e] = L[e];
     for (int i = tid; i < k; i += LR_ST) {
-      Lg[npk + i] = dinv[i];
+      Lg[LR_NPK_MAX + i] = dinv[i];
       vec[i]      = L[pidx(k, i)];   // row k = J L^-1 rhs
     }
     __syncthreads();
   } else {
     for (int e = tid; e < npk; e += LR_ST) L[e] = Lg[e];
     for (int i = tid; i < k; i += LR_ST) {
-      dinv[i] = Lg[npk + i];
+      dinv[i] = Lg[LR_NPK_MAX + i];
       double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
       int p = 0;
       for (; p + 3 < ntp; p += 4) {
@@ -656,8 +674,9 @@ int trinv_upper(ncm_sd_gpu_ctx *c, int n, const double *dU, double *dW, double *
 // Solve M[P,P] x = b[P] for P = (B \ D) u A through the base inverse W (see the header).  M is full symmetric.  Device index arrays
 // (all ascending): idxB [nB], idxA [na], posD [nd]; bsel [nB] = idxB[i] or -1 on the rows of D; psrc [np] = position of P[j] in B or
 // -(1 + position in A).  The np results in the order of P, then {max |dx|, max |x|}, are left in bufs.out.
+// kold: the first kold entries of posD are, in this order, the whole removed set of the previous solve from this base (0: unrelated).
 int lowrank_solve(ncm_sd_gpu_ctx *c, const double *dM, int ldm, int n, const double *db, int nB, int na, int nd, int np, const LowrankBufs &w, int ldv,
-                  bool refine) {
+                  bool refine, int kold) {
   NCM_CUDA_OK(c, set_smem_attrs());
   const int k = na + nd, kc = k + 1;
   cudaStream_t st = c->stream;
@@ -699,7 +718,7 @@ int lowrank_solve(ncm_sd_gpu_ctx *c, const double *dM, int ldm, int n, const dou
   if (k > 0) {
     syrk_splitk_kernel<<<dim3(ctiles * (ctiles + 1) / 2, nhc), GTHREADS, GEMM_SMEM, st>>>(w.T, ldv, Hpart, ldv, hstride, kc, nB);
     hreduce_kernel<<<dim3((kc + 63) / 64, kc), 64, 0, st>>>(Hpart, hstride, nhc, ldv, kc, H0);
-    lr_small_kernel<<<1, LR_ST, LR_SMALL_SMEM, st>>>(0, na, nd, H0, ldv, dM, ldm, w.idxA, db, nullptr, 0, 0, nullptr, w.Lg, w.z, w.info);
+    lr_small_kernel<<<1, LR_ST, LR_SMALL_SMEM, st>>>(0, na == 0 ? (kold & ~7) : 0, na, nd, H0, ldv, dM, ldm, w.idxA, db, nullptr, 0, 0, nullptr, w.Lg, w.z, w.info);
     c->n_launches += 3;
   }
   lr_y_kernel<<<(nB + 7) / 8, 256, 0, st>>>(w.T, ldv, nB, k, w.z, w.T + k, ldv, w.y);
@@ -719,7 +738,7 @@ int lowrank_solve(ncm_sd_gpu_ctx *c, const double *dM, int ldm, int n, const dou
   c->n_launches += 4;
   if (k > 0) {
     lr_tTt_partial_kernel<<<ntp, 256, 0, st>>>(w.T, ldv, nB, k, w.tr, tTtpart, ldv);
-    lr_small_kernel<<<1, LR_ST, LR_SMALL_SMEM, st>>>(1, na, nd, H0, ldv, dM, ldm, w.idxA, db, tTtpart, ldv, ntp, w.rfull, w.Lg, w.z2, w.info);
+    lr_small_kernel<<<1, LR_ST, LR_SMALL_SMEM, st>>>(1, 0, na, nd, H0, ldv, dM, ldm, w.idxA, db, tTtpart, ldv, ntp, w.rfull, w.Lg, w.z2, w.info);
     c->n_launches += 2;
   }
   lr_y_kernel<<<(nB + 7) / 8, 256, 0, st>>>(w.T, ldv, nB, k, w.z2, w.tr, 1, w.y);

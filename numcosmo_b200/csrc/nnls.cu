@@ -165,6 +165,8 @@ struct NnlsWork {
   // low-rank reuse of the last factorisation (lowrank.cu)
   bool lr_on = false, base_valid = false, w_valid = false, base_trusted = false;
   std::vector<int> baseP;
+  std::vector<int> prevD, ordD;   // removed set (positions in the base, device order) whose k x k factor is resident; scratch
+  std::vector<char> markB;
   LowrankBufs lb;
   int ldv = 0, nv = 0;
 };
@@ -224,6 +226,29 @@ int solve_lowrank(NnlsWork &w, const std::vector<int> &P, bool *done) {
       }
     }
   }
+  // nested growth of the removed set (the rule inside ncm_nnls.c:728-751: every pass only removes): keep the previous members first, in
+  // their previous order, and append the new ones -- the k x k factor of the previous solve is then the leading block of this one's
+  int kold = 0;
+  if (na == 0 && !w.prevD.empty() && (int) w.prevD.size() <= nd) {
+    std::vector<char> &mark = w.markB;
+    mark.assign(nB, 0);
+    for (int q = 0; q < nd; ++q) mark[hD[q]] = 1;
+    bool nested = true;
+    for (int p : w.prevD)
+      if (!mark[p]) {
+        nested = false;
+        break;
+      }
+    if (nested) {
+      for (int p : w.prevD) mark[p] = 2;
+      std::vector<int> &ord = w.ordD;
+      ord.assign(w.prevD.begin(), w.prevD.end());
+      for (int q = 0; q < nd; ++q)
+        if (mark[hD[q]] == 1) ord.push_back(hD[q]);
+      std::memcpy(hD, ord.data(), sizeof(int) * nd);
+      kold = (int) w.prevD.size();
+    }
+  }
   StageTimer t(c, NCM_SD_GPU_T_LOWRANK);
   if (!w.w_valid) {
     int rc = trinv_upper(c, nB, w.dMU, w.lb.W, w.lb.S, w.ldm, w.lb.Wt);
@@ -236,8 +261,9 @@ int solve_lowrank(NnlsWork &w, const std::vector<int> &P, bool *done) {
   }
   NCM_CUDA_OK(c, ncm_memcpy_async(c, w.lb.idxA, hA, sizeof(int) * (size_t) (2 * kpad + 2 * w.nv), cudaMemcpyHostToDevice, c->stream));
   const bool refine = !w.base_trusted;
-  int rc = lowrank_solve(c, w.dM, w.ldm, w.n, w.db, nB, na, nd, np, w.lb, w.ldv, refine);
+  int rc = lowrank_solve(c, w.dM, w.ldm, w.n, w.db, nB, na, nd, np, w.lb, w.ldv, refine, kold);
   if (rc != NCM_SD_GPU_OK) return rc;
+  w.prevD.clear();   // valid again only once this solve's factor is known to be good (below)
   if (na + nd == 0) w.lb.tb_valid = true;   // the base's own solve left t_b = W^T b_B behind: pure removals now need no product with W
   NCM_CUDA_OK(c, ncm_memcpy_async(c, w.h_buf, w.lb.out, sizeof(double) * (size_t) (np + 2), cudaMemcpyDeviceToHost, c->stream));
   NCM_CUDA_OK(c, ncm_memcpy_async(c, w.h_buf + np + 2, w.lb.info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -256,6 +282,8 @@ int solve_lowrank(NnlsWork &w, const std::vector<int> &P, bool *done) {
     return NCM_SD_GPU_OK;
   }
   if (refine && mdx <= LR_TRUST_CORR * mx) w.base_trusted = true;
+  if (na == 0 && nd > 0) w.prevD.assign(hD, hD + nd);   // the factor left on the device belongs to this removed set, in this order
+  if (w.st && kold > 0) w.st->n_lowrank_nested++;
   *done = true;
   return NCM_SD_GPU_OK;
 }
@@ -317,6 +345,7 @@ int solve_unconstrained(NnlsWork &w, const std::vector<int> &P) {
       w.w_valid      = false;
       w.base_trusted = false;
       w.lb.tb_valid  = false;
+      w.prevD.clear();
     }
     if (!factor_only) {
       NCM_CUDA_OK(c, ncm_memcpy_async(c, w.h_buf, w.drhs, sizeof(double) * np, cudaMemcpyDeviceToHost, c->stream));
