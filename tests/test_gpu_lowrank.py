@@ -75,6 +75,7 @@ def test_kernel_gram_weights_with_reuse(oracle, gpu_ctx, sd_s, k_s, d, n, same_p
     w_o = sd.peek_weights()
     w = (1.0 - 0.01) * x / x.sum() + 0.01 / n
     print(f"{sd_s}-{k_s} d={d} n={n}: gpu {st}, oracle {so}")
+    assert 0 <= st["n_lowrank_nested"] <= st["n_lowrank"]   # solves whose k x k factor was extended from the previous, nested one
     assert so["n_lu"] == 0 and st["n_lu"] == 0
     assert np.array_equal(x > 0, w_o > (0.01 / n) * (1 + 1e-9))
     if same_path:
