@@ -29,38 +29,44 @@ using namespace ncm_gemm;
 // level 0: the 64 x 64 diagonal blocks, one CTA each (thread t back-substitutes column t)
 __global__ void __launch_bounds__(256) trinv_diag_kernel(const double *__restrict__ U, double *__restrict__ W, int ld, int n) {
   // upper triangle: U; strictly lower triangle: X = U^-1 transposed (X[i][t] at sU[t][i]); diagonal of X in sDinv.
-  // 256 threads move the tile (four rows per pass), the first 64 do the substitutions (thread t: column t of the inverse)
+  // Column t of the inverse is back-substituted by FOUR adjacent lanes (each a quarter of every dot product, two shuffles to add
+  // them up): the columns are independent, so a warp only synchronises with itself; 256 threads also move the tile.
   __shared__ double sU[64][65];
   __shared__ double sDinv[64];
-  const int k0 = blockIdx.x * 64, nb = min(64, n - k0), t = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int k0 = blockIdx.x * 64, nb = min(64, n - k0);
+  {
+    const int t = threadIdx.x & 63, ty = threadIdx.x >> 6;
 #pragma unroll 4
-  for (int r = ty; r < 64; r += 4) {
-    double v = (r == t) ? 1.0 : 0.0;
-    if (r < nb && t < nb && t >= r) v = U[(size_t) (k0 + r) * ld + k0 + t];
-    sU[r][t] = v;
-  }
-  __syncthreads();
-  if (ty == 0) sDinv[t] = 1.0 / sU[t][t];
-  __syncthreads();
-  const double xtt = sDinv[t];
-  if (ty == 0) {
-    for (int i = 62; i >= 0; --i) {
-      if (i < t) {
-        double s0 = sU[i][t] * xtt, s1 = 0.0;
-        int k = i + 1;
-        for (; k + 1 < t; k += 2) {
-          s0 = fma(sU[i][k], sU[t][k], s0);
-          s1 = fma(sU[i][k + 1], sU[t][k + 1], s1);
-        }
-        if (k < t) s0 = fma(sU[i][k], sU[t][k], s0);
-        sU[t][i] = -(s0 + s1) * sDinv[i];
-      }
+    for (int r = ty; r < 64; r += 4) {
+      double v = (r == t) ? 1.0 : 0.0;
+      if (r < nb && t < nb && t >= r) v = U[(size_t) (k0 + r) * ld + k0 + t];
+      sU[r][t] = v;
     }
   }
   __syncthreads();
+  if (threadIdx.x < 64) sDinv[threadIdx.x] = 1.0 / sU[threadIdx.x][threadIdx.x];
+  __syncthreads();
+  const int t = threadIdx.x >> 2, part = threadIdx.x & 3;
+  const double xtt = sDinv[t];
+  for (int i = 62; i >= 0; --i) {
+    // all four lanes of a column take the same branch; the columns of one warp (8 of them) may differ: shuffles under the full mask
+    double s = 0.0;
+    if (i < t) {
+      for (int k = i + 1 + part; k < t; k += 4) s = fma(sU[i][k], sU[t][k], s);
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if (i < t && part == 0) sU[t][i] = -(fma(sU[i][t], xtt, s)) * sDinv[i];
+    __syncwarp();
+  }
+  __syncthreads();
+  {
+    const int tc = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    const double xd = sDinv[tc];
 #pragma unroll 4
-  for (int r = ty; r < nb; r += 4)
-    if (t < nb) W[(size_t) (k0 + r) * ld + k0 + t] = (t > r) ? sU[t][r] : (t == r ? xtt : 0.0);
+    for (int r = ty; r < nb; r += 4)
+      if (tc < nb) W[(size_t) (k0 + r) * ld + k0 + tc] = (tc > r) ? sU[tc][r] : (tc == r ? xd : 0.0);
+  }
 }
 
 // level s: for every pair of adjacent s-blocks (r0 = 2 p s, r1 = r0 + s)  S12 = U12 W22 ;  W12 = - W11 S12
