@@ -142,9 +142,14 @@ int ncm_sd_gpu_sample_philox (ncm_sd_gpu_ctx *ctx, int q, unsigned long long see
                               double *X_out, int ldx, int *kidx_out);
 
 /* ---- multi-GPU ------------------------------------------------------------------------------
- * One process per GPU.  Query rows and IM row blocks are sharded by the caller (each rank
- * uploads the same centres and its own rows); the only exchange is the all-reduce of the NNLS
- * normal equations (M = IM^T IM, b = IM^T 1) and of A^T r / |r|^2 per outer iteration. */
+ * One process per GPU, centres and factors replicated.  Either the caller shards by hand
+ * (ncm_sd_gpu_set_row_shard: this rank's IM row block; its own query rows) or, in SPMD callers,
+ * ncm_sd_gpu_set_auto_shard does it behind unchanged calls.  The exchanges, all NCCL on the context's
+ * streams: all-reduce of the NNLS normal equations (M = IM^T IM, b = IM^T 1) and of A^T r / |r|^2 per
+ * outer iteration; all-gather of the densities of a sharded evaluation; all-gather of the factors of a
+ * sharded ncm_sd_gpu_vkde_prepare; broadcast / all-gather of the panels of the distributed Cholesky that
+ * ncm_sd_gpu_nnls_solve uses for passive sets of NCM_SD_GPU_DIST_CHOL_MIN_N (8192) indices and more
+ * (replaces ncm_matrix_cholesky_solve, ncm_matrix.c:1199-1210, as called from ncm_nnls.c:655-666). */
 int ncm_sd_gpu_comm_unique_id (char id_out[128]);
 int ncm_sd_gpu_comm_init (ncm_sd_gpu_ctx *ctx, int nranks, int rank, const char id[128]);
 /* restrict compute_IM to observation rows [row0, row0 + nrows) on this rank */
@@ -152,8 +157,8 @@ int ncm_sd_gpu_set_row_shard (ncm_sd_gpu_ctx *ctx, int row0, int nrows);
 /* Automatic sharding for SPMD callers (every rank makes the same calls with the same host arrays, as the ranks of a multi-rank
  * APES run do): with on != 0 and a communicator, compute_IM (IM_host == NULL) takes the row block [n_obs rank / G, n_obs (rank + 1) / G)
  * of this rank and the NNLS all-reduces the normal equations; eval / eval_m2lnp upload and evaluate this rank's block of the query
- * rows and ncclAllGather the results on the device, so that every rank receives the complete output.  Centres and factors stay
- * replicated.  Shards ncm_stats_dist.c:878-1094 (rows of the interpolation matrix) and the per-walker density calls of
+ * rows and ncclAllGather the results on the device, so that every rank receives the complete output; ncm_sd_gpu_vkde_prepare builds the
+ * factors of a contiguous block of centres per rank and all-gathers them.  Centres and factors stay replicated.  Shards ncm_stats_dist.c:878-1094 (rows of the interpolation matrix) and the per-walker density calls of
  * walker_apes.c:742-812. */
 int ncm_sd_gpu_set_auto_shard (ncm_sd_gpu_ctx *ctx, int on);
 /* ncclAllGather of `count` doubles per rank on the context stream (device pointers; drecv holds nranks * count): the exchange that
