@@ -174,6 +174,7 @@ __device__ void bk_factor_solve(Acc A, int n, double *b, int *ipiv, int *info_ou
       __syncthreads();
       const double bk = b[k];
       for (int i = k + 1 + tid; i < n; i += BK_T) b[i] = fma(-A(i, k), bk, b[i]);
+      __syncthreads();   // every warp has read b[k] before it is overwritten (racecheck, r02y)
       if (tid == 0) b[k] = bk * (1.0 / A(k, k));   // dscal (1 / A(k,k))
       __syncthreads();
       k += 1;
@@ -187,6 +188,7 @@ __device__ void bk_factor_solve(Acc A, int n, double *b, int *ipiv, int *info_ou
       __syncthreads();
       const double bk = b[k], bk1 = b[k + 1];
       for (int i = k + 2 + tid; i < n; i += BK_T) b[i] = fma(-A(i, k + 1), bk1, fma(-A(i, k), bk, b[i]));
+      __syncthreads();   // b[k], b[k + 1] are read by every warp above
       if (tid == 0) {
         const double akm1k = A(k + 1, k), akm1 = A(k, k) / akm1k, ak = A(k + 1, k + 1) / akm1k, denom = akm1 * ak - 1.0;
         const double bkm1 = bk / akm1k, bkk = bk1 / akm1k;
