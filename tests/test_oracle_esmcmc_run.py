@@ -1,0 +1,136 @@
+"""The reference's end-to-end test of the APES walker, restated for the CPU oracle: tests/c/ncm/fit/test_ncm_fit_esmcmc.c.
+
+  new_apes (:129-274)   a random MVND posterior of dimension 1 - 3 (ncm_data_gauss_cov_mvnd_new_full (dim, 2e-2, 5e-2, 30, 1, 2)),
+                        100 dim walkers started from a Gaussian with the Fisher covariance at the best fit, over_smooth set to 1.01,
+                        walker = APES default (VKDE, Cauchy, interpolation) or new_full (VKDE | KDE, Cauchy | ST3 | Gauss, 1.0, TRUE)
+  run      (:433-510)   dim * [15000, 20000) / nrun_div iterations (nrun_div = 1000 for the APES cases), burn-in trimmed, then
+                        - ncm_fit_esmcmc_validate: -2 ln L recomputed on the chain agrees with the stored one
+                        - variances of the chain against the posterior's: ncm_matrix_cmp_diag (cat, data, 0) < 0.25
+                        - correlations against the posterior's: ncm_matrix_cmp (cor_cat, cor_data, 1) < 0.25
+                        retried with twice the iterations (up to 15 times) while the two bars are not met; the Gauss kernel cases are
+                        skipped by the reference ("APES-Move:*:Gauss walker not supported", :443-448) and are not asserted here either.
+
+The ensemble loop is the oracle's (orc_apes_run follows ncm_fit_esmcmc.c:2235-2288); the reference draws dim / seeds from g_test_rand_*,
+here they are swept.  Note that the reference's set_sys builds NcmStatsDistVKDE objects for METHOD_KDE as well
+(ncm_fit_esmcmc_walker_apes.c:563-572), so its cases 3 / 4 repeat 0 / 1; the oracle's "kde" arm below runs the true KDE class through the
+same ensemble loop, which the reference's suite never does.  This pins the WHOLE oracle path (prepare_kernel, interpolation matrix, NNLS weights, proposal draws, acceptance)
+on the one property the reference's own suite demands of it: the chain samples the posterior."""
+import numpy as np
+import pytest
+
+from helpers import mvnd_problem
+
+TOL = 2.5e-1                     # TEST_NCM_FIT_ESMCMC_TOL, :430
+MAX_TRIES = 15                   # :438
+CASES = [("vkde", 1.0), ("vkde", 3.0), ("kde", 1.0), ("kde", 3.0)]     # cases 0/3 (Cauchy), 1/4 (ST3); 2/5 (Gauss) skipped as in the reference
+
+
+def _cmp(a, b, scale):           # ncm_matrix_cmp, ncm_matrix.c:914-940
+    return np.max(np.abs((a - b) / (scale + b)))
+
+
+def _cov2cor(c):
+    s = np.sqrt(np.diag(c))
+    return c / np.outer(s, s)
+
+
+@pytest.mark.parametrize("d", [1, 2, 3])
+@pytest.mark.parametrize("sd_s,nu", CASES)
+def test_esmcmc_run_recovers_posterior_covariance(oracle, sd_s, nu, d):
+    O = oracle
+    W = 100 * d
+    seed = 1000 * d + int(10 * nu) + (7 if sd_s == "kde" else 0)
+    mu, cov, X, m2lnL = mvnd_problem(O, d, W, seed=seed)            # initial ensemble ~ N (best fit, Fisher covariance)
+    tgt = O.Target(O.TARGET_MVND, d, np.full(d, -50.0), np.full(d, 50.0), mu=mu, cov=cov)
+    ap = O.APES(W, d, O.SD_KDE if sd_s == "kde" else O.SD_VKDE, O.KERNEL_ST, nu, over_smooth=1.01, use_interp=True, use_threads=False)
+    rng = O.RNG(seed + 1)
+    th, ml = X.copy(), np.array([tgt.m2lnL(x) for x in X])
+    run = d * 17
+    chain, nacc, ntot = [], 0, 0
+    ok = False
+    for _ in range(MAX_TRIES):
+        for _ in range(run):
+            acc = ap.run(tgt, th, ml, 1, rng, nthreads=1)
+            nacc += int(acc.sum())
+            ntot += W
+            chain.append(th.copy())
+        # validate (:468): the stored -2 ln L is the target's at the stored point
+        assert np.allclose(ml, [tgt.m2lnL(x) for x in th], rtol=1e-13, atol=1e-13)
+        C = np.concatenate(chain[len(chain) // 5:])                 # burn-in: first fifth dropped
+        cat = np.atleast_2d(np.cov(C.T))
+        ok = _cmp(np.diag(cat), np.diag(cov), 0.0) < TOL and _cmp(_cov2cor(cat), _cov2cor(cov), 1.0) < TOL
+        if ok:
+            break
+        run *= 2
+    print(f"{sd_s} nu={nu} d={d}: {len(chain)} iterations, acceptance {nacc / ntot:.3f}, "
+          f"var {_cmp(np.diag(cat), np.diag(cov), 0.0):.3f}, cor {_cmp(_cov2cor(cat), _cov2cor(cov), 1.0):.3f}")
+    assert ok
+    assert np.max(np.abs(C.mean(axis=0) - mu) / np.sqrt(np.diag(cov))) < 0.25
+    assert nacc / ntot > 0.2                                        # an independence sampler with a fitted proposal: far from stuck
+
+
+@pytest.mark.parametrize("sd_s,nu", CASES)
+def test_esmcmc_run_forgets_a_displaced_start(oracle, sd_s, nu):
+    """Harder than the reference's start (which already samples the posterior): the initial ensemble is displaced by two standard
+    deviations and three times too wide.  The same two bars must be met after burn-in -- the property that makes the walker usable,
+    and the one a wrong weight solve or a wrong proposal density in the acceptance ratio would break."""
+    O = oracle
+    d, W = 2, 200
+    seed = 77 + int(10 * nu) + (7 if sd_s == "kde" else 0)
+    mu, cov, X, _ = mvnd_problem(O, d, W, seed=seed)
+    X = np.ascontiguousarray(mu + 2.0 * np.sqrt(np.diag(cov)) + 3.0 * (X - mu))
+    tgt = O.Target(O.TARGET_MVND, d, np.full(d, -50.0), np.full(d, 50.0), mu=mu, cov=cov)
+    ap = O.APES(W, d, O.SD_KDE if sd_s == "kde" else O.SD_VKDE, O.KERNEL_ST, nu, over_smooth=1.01, use_interp=True, use_threads=False)
+    rng = O.RNG(seed + 1)
+    th, ml = X.copy(), np.array([tgt.m2lnL(x) for x in X])
+    chain = []
+    for _ in range(120):
+        ap.run(tgt, th, ml, 1, rng, nthreads=1)
+        chain.append(th.copy())
+    C = np.concatenate(chain[40:])
+    cat = np.cov(C.T)
+    v, c = _cmp(np.diag(cat), np.diag(cov), 0.0), _cmp(_cov2cor(cat), _cov2cor(cov), 1.0)
+    print(f"{sd_s} nu={nu}: displaced start, var {v:.3f}, cor {c:.3f}, mean {np.max(np.abs(C.mean(axis=0) - mu) / np.sqrt(np.diag(cov))):.3f} sigma")
+    assert v < TOL and c < TOL
+    assert np.max(np.abs(C.mean(axis=0) - mu) / np.sqrt(np.diag(cov))) < 0.25
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("d", [2, 3])
+@pytest.mark.parametrize("method,k_type", [("VKDE", "CAUCHY"), ("VKDE", "ST3"), ("KDE", "CAUCHY"), ("KDE", "ST3")])
+def test_gpu_esmcmc_run_recovers_posterior_covariance(oracle, method, k_type, d):
+    """The same test through the product (host mirror of NcmFitESMCMCWalkerAPES over the CUDA library): cases 0, 1, 3, 4 of
+    test_ncm_fit_esmcmc.c:155-183, including the reference's retry rule.  The oracle is used for the problem set-up only."""
+    from numcosmo_b200 import stats_dist as S
+
+    W = 100 * d
+    seed = 500 * d + len(method) + len(k_type)
+    mu, cov, X, _ = mvnd_problem(oracle, d, W, seed=seed)
+    lb, ub = np.full(d, -50.0), np.full(d, 50.0)
+    U = np.ascontiguousarray(np.linalg.cholesky(cov).T)
+    ap = S.FitESMCMCWalkerAPES.new_full(W, d, getattr(S.FitESMCMCWalkerAPESMethod, method), getattr(S.FitESMCMCWalkerAPESKType, k_type), 1.0, True)
+    ap.set_over_smooth(1.01)                                        # :202-203
+    rng = S.RNG(seed + 1)
+    th = X.copy()
+    z = np.linalg.solve(U.T, (th - mu).T)
+    ml = np.ascontiguousarray(np.einsum("ij,ij->j", z, z))
+    run = d * 17
+    chain, nacc, ntot, ok = [], 0, 0, False
+    for _ in range(MAX_TRIES):
+        for _ in range(run):
+            acc, _t = ap.run("mvnd", lb, ub, th, ml, 1, rng, target_args=(mu, U))
+            nacc += int(acc.sum())
+            ntot += W
+            chain.append(th.copy())
+        z = np.linalg.solve(U.T, (th - mu).T)
+        assert np.allclose(ml, np.einsum("ij,ij->j", z, z), rtol=1e-9, atol=1e-9)      # validate, :468
+        C = np.concatenate(chain[len(chain) // 5:])
+        cat = np.cov(C.T)
+        v, c = _cmp(np.diag(cat), np.diag(cov), 0.0), _cmp(_cov2cor(cat), _cov2cor(cov), 1.0)
+        ok = v < TOL and c < TOL
+        if ok or len(chain) > 2000:
+            break
+        run *= 2
+    print(f"gpu {method} {k_type} d={d}: {len(chain)} iterations, acceptance {nacc / ntot:.3f}, var {v:.3f}, cor {c:.3f}")
+    assert ok
+    assert nacc / ntot > 0.2
