@@ -72,6 +72,39 @@ def test_row_range_partition():
         shard.row_range(10, 2, 2)
 
 
+def test_spmd_partitions_of_the_c_abi():
+    """The two partitions of the multi-rank (auto-shard) mode of the C ABI, restated: capi.cu eval_host / compute_IM take the row block
+    [n r / G, n (r + 1) / G) and all-gather blocks padded to cap = ceil (n / G); ncm_sd_gpu_vkde_prepare takes the centre block
+    [min (n, r cap), min (n, (r + 1) cap)) and all-gathers IN PLACE at offset r cap.  Both must tile 0..n exactly, fit their padded
+    slots, and -- for the in-place gather -- put every non-empty block at its global position."""
+    sys.path.insert(0, ROOT)
+    from numcosmo_b200 import shard
+
+    for n in (1, 7, 8, 63, 64, 65, 2048, 16384, 65537):
+        for G in (1, 2, 3, 4, 8):
+            cap = (n + G - 1) // G
+            # query / IM rows
+            gath = np.full(G * cap, np.nan)
+            for r in range(G):
+                a, b = (n * r) // G, (n * (r + 1)) // G
+                assert (a, b) == shard.row_range(n, r, G) and 0 <= b - a <= cap
+                gath[r * cap:r * cap + (b - a)] = np.arange(a, b)                # what rank r contributes to the padded all-gather
+            out = np.concatenate([gath[r * cap:r * cap + shard.row_range(n, r, G)[1] - shard.row_range(n, r, G)[0]] for r in range(G)])
+            assert np.array_equal(out, np.arange(n))
+            # VKDE prepare_kernel centres: contiguous cap-blocks, gathered in place
+            buf = np.full(G * cap, np.nan)
+            edges = []
+            for r in range(G):
+                cbeg = min(n, r * cap)
+                ncl = max(0, min(n, cbeg + cap) - cbeg)
+                edges.append((cbeg, cbeg + ncl))
+                assert ncl == 0 or cbeg == r * cap                                 # a non-empty block already sits at its gather offset
+                buf[r * cap:r * cap + ncl] = np.arange(cbeg, cbeg + ncl)
+            assert edges[0][0] == 0 and max(e[1] for e in edges) == n
+            assert all(edges[i][1] == edges[i + 1][0] or edges[i + 1][0] == edges[i + 1][1] == n for i in range(G - 1))
+            assert np.array_equal(buf[:n], np.arange(n))
+
+
 def test_sharded_path_world2_gloo():
     import torch.multiprocessing as mp
 
