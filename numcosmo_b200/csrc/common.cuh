@@ -217,8 +217,8 @@ struct KernParams {
 };
 
 // Student-t kernel with an integer number of degrees of freedom: (1 + chi2/nu)^(-(nu + d)/2) = r^(nu + d), r = rsqrt(1 + chi2/nu).
-// One rsqrt and at most 2 log2(m) multiplications (m is uniform over the grid) instead of log1p + exp: relative error <= (m + 1) ulp
-// (4e-15 at m = 35), the same order as the table-based log1p above.  Reference: pow (1 + chi2/nu, kappa), ncm_stats_dist_kernel_st.c:239-243.
+// One rsqrt and at most 2 log2(m) multiplications (m is uniform over the grid) instead of log1p + exp: relative error about 2 m x 2^-52
+// with a 1-ulp rsqrt (1.6e-14 at m = 35; tests/test_st_integer_power_rule.py), the same order as the table-based log1p above.  Reference: pow (1 + chi2/nu, kappa), ncm_stats_dist_kernel_st.c:239-243.
 __device__ __forceinline__ double st_pow_u(const KernParams &kp, const double u) {   // u = chi2 / nu >= 0
   // straight-line binary powering (m2 < 128): six squarings, the factors picked by the bits of m2 -- selects on a grid-uniform value,
   // no loop, so that the calls of an unrolled epilogue interleave (a loop per call serialised them: slower than log1p + exp)

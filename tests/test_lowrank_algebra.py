@@ -97,3 +97,35 @@ def test_append_only_extension_of_the_small_factor():
     xr = np.zeros(n)
     xr[P] = np.linalg.solve(M[np.ix_(P, P)], b[P])
     assert np.max(np.abs(x - xr)) <= 1e-9 * np.abs(xr).max()
+
+
+def trinv_recursive_doubling(U, blk):
+    """lowrank.cu trinv_upper_on: level 0 inverts the blk x blk diagonal blocks (trinv_diag_kernel, 64 on the device); level s = blk,
+    2 blk, ... takes every pair of adjacent s-blocks (r0 = 2 p s, r1 = r0 + s, the second one min (s, n - r1) wide, absent when
+    r1 >= n) and fills  W12 = - W11 (U12 W22)  (trinv_step1 / step2, or step12 in one launch for s <= 128)."""
+    n = U.shape[0]
+    W = np.zeros_like(U)
+    for k0 in range(0, n, blk):
+        k1 = min(k0 + blk, n)
+        W[k0:k1, k0:k1] = np.linalg.solve(U[k0:k1, k0:k1], np.eye(k1 - k0))
+    s = blk
+    while s < n:
+        for r0 in range(0, n, 2 * s):
+            r1 = r0 + s
+            m2 = min(s, n - r1)
+            if m2 <= 0:
+                continue
+            S12 = U[r0:r1, r1:r1 + m2] @ W[r1:r1 + m2, r1:r1 + m2]
+            W[r0:r1, r1:r1 + m2] = -W[r0:r1, r0:r1] @ S12
+        s *= 2
+    return W
+
+
+@pytest.mark.parametrize("n,blk", [(1, 4), (4, 4), (5, 4), (8, 4), (9, 4), (13, 4), (64, 8), (100, 8), (129, 16), (200, 64)])
+def test_triangular_inverse_by_recursive_doubling(n, blk):
+    rs = np.random.default_rng(n)
+    B = rs.standard_normal((n + 5, n))
+    U = np.linalg.cholesky(B.T @ B + 0.5 * np.eye(n)).T
+    W = trinv_recursive_doubling(U, blk)
+    assert np.array_equal(W, np.triu(W))
+    assert np.max(np.abs(W @ U - np.eye(n))) <= 1e-12 * np.linalg.cond(U)
