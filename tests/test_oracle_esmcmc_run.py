@@ -134,3 +134,23 @@ def test_gpu_esmcmc_run_recovers_posterior_covariance(oracle, method, k_type, d)
     print(f"gpu {method} {k_type} d={d}: {len(chain)} iterations, acceptance {nacc / ntot:.3f}, var {v:.3f}, cor {c:.3f}")
     assert ok
     assert nacc / ntot > 0.2
+
+
+@pytest.mark.parametrize("sd_s,nu", CASES)
+def test_serial_and_threaded_runs_draw_the_same_sequence(oracle, sd_s, nu):
+    """The pattern of test_ncm_fit_esmcmc.c:888-971 (parity/serial_vs_threaded: fixed seed, dim 2, 60 walkers, 5 iterations, every catalog
+    entry compared with ==), which the reference runs on the Stretch walker, applied to APES on the oracle: use_threads changes who
+    evaluates a point, not what is computed, so positions, -2 ln L and accept flags must be identical bit for bit."""
+    O = oracle
+    d, W, iters = 2, 60, 5
+    mu, cov, X, _ = mvnd_problem(O, d, W, seed=20260721 % 100000, sigma=(1.0e-2, 2.0e-2), cor_level=0.3, mu_range=(-1.0, 1.0))
+    tgt = O.Target(O.TARGET_MVND, d, np.full(d, -50.0), np.full(d, 50.0), mu=mu, cov=cov)
+    ml0 = np.array([tgt.m2lnL(x) for x in X])
+    runs = []
+    for use_threads, nthreads in ((False, 1), (True, 4)):
+        ap = O.APES(W, d, O.SD_KDE if sd_s == "kde" else O.SD_VKDE, O.KERNEL_ST, nu, use_interp=True, use_threads=use_threads, local_frac=0.1)
+        th, ml = X.copy(), ml0.copy()
+        acc = ap.run(tgt, th, ml, iters, O.RNG(20260721), nthreads=nthreads)
+        runs.append((th, ml, np.asarray(acc).copy()))
+    assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[0][1], runs[1][1]) and np.array_equal(runs[0][2], runs[1][2])
+    assert runs[0][2].any()
