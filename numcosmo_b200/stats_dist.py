@@ -590,6 +590,7 @@ class FitESMCMCWalkerAPES:
     def set_shrink(self, v): lib().ncm_fit_esmcmc_walker_apes_set_shrink(self._h, float(v))
     def set_random_walk_prob(self, v): lib().ncm_fit_esmcmc_walker_apes_set_random_walk_prob(self._h, float(v))
     def set_random_walk_scale(self, v): lib().ncm_fit_esmcmc_walker_apes_set_random_walk_scale(self._h, float(v))
+    def set_exploration(self, n): lib().ncm_fit_esmcmc_walker_apes_set_exploration(self._h, int(n))
     def use_interp(self, v): lib().ncm_fit_esmcmc_walker_apes_use_interp(self._h, int(v))
     def set_use_threads(self, v): lib().ncm_fit_esmcmc_walker_apes_set_use_threads(self._h, int(v))
 

@@ -182,6 +182,7 @@ typedef struct orc_apes orc_apes;
 orc_apes *orc_apes_new (int nwalkers, int d, int method_vkde_obj, int kernel_kind, double nu, double over_smooth, int use_interp, double shrink, double random_walk_prob, double local_frac, int use_threads);
 void orc_apes_free (orc_apes *a);
 void orc_apes_set_cov_type (orc_apes *a, int cov_type, const double *cov_fixed, int ld);
+void orc_apes_set_exploration (orc_apes *a, unsigned int exploration);
 /* theta [nwalkers x d] and m2lnL [nwalkers] are updated in place; accepted[nwalkers*iters] receives the accept flags
  * in walker order per iteration.  Follows ncm_fit_esmcmc.c:2235-2288 + walker_apes.c:742-919. */
 void orc_apes_run (orc_apes *a, const orc_target *t, double *theta, double *m2lnL, int iters, orc_rng *rng, unsigned char *accepted, int nthreads);

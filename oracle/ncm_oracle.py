@@ -221,6 +221,7 @@ def lib():
             "orc_apes_new": (vp, [i, i, i, i, d, d, i, d, d, d, i]),
             "orc_apes_free": (None, [vp]),
             "orc_apes_set_cov_type": (None, [vp, i, _dp, i]),
+            "orc_apes_set_exploration": (None, [vp, C.c_uint]),
             "orc_apes_run": (None, [vp, vp, _dp, _dp, i, vp, C.POINTER(C.c_ubyte), i]),
             "orc_apes_get_timers": (None, [vp, _dp]),
             "orc_apes_peek_thetastar": (_dp, [vp]),
@@ -566,6 +567,9 @@ class APES:
     def set_cov_type(self, cov_type, cov_fixed=None):
         cf = np.ascontiguousarray(cov_fixed, dtype=np.float64) if cov_fixed is not None else None
         lib().orc_apes_set_cov_type(self._h, int(cov_type), _p(cf) if cf is not None else None, self.d)
+
+    def set_exploration(self, n):
+        lib().orc_apes_set_exploration(self._h, int(n))
 
     def timers(self):
         t = np.zeros(6)

@@ -210,6 +210,7 @@ typedef struct orc_apes_rw
 struct orc_apes
 {
   int size, size_2, nparams;
+  unsigned int exploration; /* walker_apes.c:142, 182: setup calls left in which the proposal density is left out of the acceptance */
   orc_sd *sd0, *sd1;
   double *thetastar, *m2lnp_star, *m2lnp_cur, *m2lnL_s0, *m2lnL_s1, *jumps;
   orc_apes_rw rw0, rw1;
@@ -260,6 +261,13 @@ orc_apes_new (int nwalkers, int d, int sd_type, int kernel_kind, double nu, doub
 
 /* ncm_fit_esmcmc_walker_apes.c:1442-1507: the covariance setters act on both halves; cov_fixed != NULL with ORC_COV_FIXED is
  * set_cov_fixed_from_mset's diag (scale^2) matrix */
+/* ncm_fit_esmcmc_walker_apes.c:1523-1528 */
+void
+orc_apes_set_exploration (orc_apes *a, unsigned int exploration)
+{
+  a->exploration = exploration;
+}
+
 void
 orc_apes_set_cov_type (orc_apes *a, int cov_type, const double *cov_fixed, int ld)
 {
@@ -492,7 +500,8 @@ apes_run_block (orc_apes *a, const orc_target *t, double *theta, double *m2lnL, 
 
       if (isfinite (m2lnL_star))
       {
-        const double lnq   = -0.5 * (a->m2lnp_cur[k] - a->m2lnp_star[k]);
+        /* _ncm_fit_esmcmc_walker_apes_prob_norm, walker_apes.c:908-919: 0 while exploring */
+        const double lnq   = a->exploration ? 0.0 : -0.5 * (a->m2lnp_cur[k] - a->m2lnp_star[k]);
         const double m2lnq = -2.0 * lnq;
         const double m2lnp = m2lnL_star - m2lnL[k] + m2lnq;
 
@@ -534,9 +543,14 @@ orc_apes_run (orc_apes *a, const orc_target *t, double *theta, double *m2lnL, in
     for (k = 0; k < a->size; k++)
       a->jumps[k] = orc_rng_uniform (rng);
 
+    /* every setup call counts the exploration phase down once it has drawn its proposals (walker_apes.c:815-816) */
     apes_setup_block (a, t, theta, m2lnL, 0, rng);
+    if (a->exploration > 0)
+      a->exploration--;
     apes_run_block (a, t, theta, m2lnL, 0, acc, nthreads);
     apes_setup_block (a, t, theta, m2lnL, 1, rng);
+    if (a->exploration > 0)
+      a->exploration--;
     apes_run_block (a, t, theta, m2lnL, 1, acc, nthreads);
   }
 }

@@ -154,3 +154,98 @@ def test_serial_and_threaded_runs_draw_the_same_sequence(oracle, sd_s, nu):
         runs.append((th, ml, np.asarray(acc).copy()))
     assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[0][1], runs[1][1]) and np.array_equal(runs[0][2], runs[1][2])
     assert runs[0][2].any()
+
+
+def _var_m2lnL_run(run_iter, W, iters, burn):
+    vals = []
+    for it in range(iters):
+        ml = run_iter()
+        if it >= burn:
+            vals.append(ml.copy())
+    return float(np.var(np.concatenate(vals), ddof=1))
+
+
+@pytest.mark.parametrize("exploration", [0, 10])
+@pytest.mark.parametrize("d", [1, 2, 3])
+@pytest.mark.parametrize("sd_s,nu", CASES)
+def test_variance_of_m2lnL_after_burnin_and_exploration(oracle, sd_s, nu, d, exploration):
+    """run/burnin (:563-614) and run/exploration (:617-655): 100 iterations -- the first with the proposal density left out of the
+    acceptance for `exploration` setup calls (two per iteration, ncm_fit_esmcmc_walker_apes.c:815-816, 901-919) -- then
+    var (-2 ln L) over the trimmed catalog equals 2 dim (a chi-square with dim degrees of freedom) within 0.6."""
+    O = oracle
+    W = 100 * d
+    seed = 300 * d + int(10 * nu) + (7 if sd_s == "kde" else 0) + exploration
+    mu, cov, X, _ = mvnd_problem(O, d, W, seed=seed)
+    tgt = O.Target(O.TARGET_MVND, d, np.full(d, -50.0), np.full(d, 50.0), mu=mu, cov=cov)
+    ap = O.APES(W, d, O.SD_KDE if sd_s == "kde" else O.SD_VKDE, O.KERNEL_ST, nu, over_smooth=1.01, use_interp=True, use_threads=False)
+    ap.set_exploration(exploration)
+    rng = O.RNG(seed + 1)
+    th, ml = X.copy(), np.array([tgt.m2lnL(x) for x in X])
+
+    def one():
+        ap.run(tgt, th, ml, 1, rng, nthreads=1)
+        return ml
+
+    v = _var_m2lnL_run(one, W, 100, 20)
+    print(f"{sd_s} nu={nu} d={d} exploration={exploration}: var(-2 ln L) = {v:.3f} (2 dim = {2 * d})")
+    assert abs(v / (2.0 * d) - 1.0) < 0.6
+
+
+def test_exploration_leaves_the_proposal_density_out_for_that_many_setups(oracle):
+    """While exploring, acceptance is min (1, L*/L).  The counter is decremented at the END of every setup call (one per half-ensemble,
+    ncm_fit_esmcmc_walker_apes.c:815-816), i.e. before the acceptance of that half reads it (:901-919): `exploration` = n leaves the
+    proposal density out of n - 1 half-steps.  With n = 3 the whole first iteration accepts every proposal that improves the
+    likelihood; with n = 2 only its first half does."""
+    O = oracle
+    d, W = 2, 200
+    mu, cov, X, _ = mvnd_problem(O, d, W, seed=5)
+    tgt = O.Target(O.TARGET_MVND, d, np.full(d, -50.0), np.full(d, 50.0), mu=mu, cov=cov)
+    ml0 = np.array([tgt.m2lnL(x) for x in X])
+    ap = O.APES(W, d, O.SD_VKDE, O.KERNEL_ST, 1.0, use_interp=True, use_threads=False)
+    ap.set_exploration(3)                                           # both halves of the first iteration
+    th, ml, rng = X.copy(), ml0.copy(), O.RNG(9)
+    before = ml.copy()
+    acc = ap.run(tgt, th, ml, 1, rng, nthreads=1)[0].astype(bool)
+    star = np.array([tgt.m2lnL(x) for x in ap.peek_thetastar()])
+    assert np.all(acc[star <= before])                              # an improving proposal is always taken while exploring
+    # without exploration the same stream takes a different decision somewhere (the proposal density matters)
+    ap2 = O.APES(W, d, O.SD_VKDE, O.KERNEL_ST, 1.0, use_interp=True, use_threads=False)
+    th2, ml2 = X.copy(), ml0.copy()
+    acc2 = ap2.run(tgt, th2, ml2, 1, O.RNG(9), nthreads=1)[0].astype(bool)
+    assert np.array_equal(ap2.peek_thetastar()[: W // 2], ap.peek_thetastar()[: W // 2])   # first half: same proposals, drawn before any decision
+    assert not np.array_equal(acc, acc2)
+    # n = 2: the first half explores, the second does not -- from there on the run IS the ordinary one only if the first halves agreed,
+    # so compare the decisions of the first half with the exploring run and check that the second half's differ from it somewhere
+    ap3 = O.APES(W, d, O.SD_VKDE, O.KERNEL_ST, 1.0, use_interp=True, use_threads=False)
+    ap3.set_exploration(2)
+    th3, ml3 = X.copy(), ml0.copy()
+    acc3 = ap3.run(tgt, th3, ml3, 1, O.RNG(9), nthreads=1)[0].astype(bool)
+    assert np.array_equal(acc3[: W // 2], acc[: W // 2])
+    star3 = np.array([tgt.m2lnL(x) for x in ap3.peek_thetastar()])
+    assert not np.all(acc3[W // 2:][star3[W // 2:] <= before[W // 2:]])            # an improving proposal refused: the density is back
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("exploration", [3, 10])
+def test_gpu_exploration_phase_follows_the_oracle(oracle, exploration):
+    """ncm_fit_esmcmc_walker_apes_set_exploration through the product: same generator stream, same accepted sequence and positions as
+    the oracle across the exploring half-steps and the return to the ordinary acceptance."""
+    from numcosmo_b200 import stats_dist as S
+
+    d, W, iters = 3, 300, 7
+    mu, cov, X, _ = mvnd_problem(oracle, d, W, seed=321)
+    lb, ub = np.full(d, -50.0), np.full(d, 50.0)
+    tgt = oracle.Target(oracle.TARGET_MVND, d, lb, ub, mu=mu, cov=cov)
+    ml0 = np.array([tgt.m2lnL(x) for x in X])
+    ao = oracle.APES(W, d, oracle.SD_VKDE, oracle.KERNEL_ST, 3.0, over_smooth=1.0, use_interp=True, use_threads=True)
+    ao.set_exploration(exploration)
+    th_o, ml_o = X.copy(), ml0.copy()
+    acc_o = ao.run(tgt, th_o, ml_o, iters, oracle.RNG(77), nthreads=4)
+    ag = S.FitESMCMCWalkerAPES(W, d, S.FitESMCMCWalkerAPESMethod.VKDE, S.FitESMCMCWalkerAPESKType.ST3, 1.0, True)
+    ag.set_use_threads(True)
+    ag.set_exploration(exploration)
+    th_g, ml_g = X.copy(), ml0.copy()
+    acc_g, _ = ag.run("mvnd", lb, ub, th_g, ml_g, iters, S.RNG(77), target_args=(mu, tgt.U))
+    diff = np.argwhere(np.asarray(acc_o) != np.asarray(acc_g))
+    assert diff.size == 0, f"first divergence at (iter, walker) = {diff[0]}"
+    assert np.max(np.abs(th_g - th_o)) <= 1e-9 * np.abs(th_o).max()
