@@ -390,9 +390,28 @@ void ncm_fit_esmcmc_walker_apes_set_over_smooth(NcmFitESMCMCWalkerAPES *a, const
   ncm_stats_dist_set_over_smooth(a->sd0, os);   // forwarded immediately (walker_apes.c:1162-1166)
   ncm_stats_dist_set_over_smooth(a->sd1, os);
 }
-void ncm_fit_esmcmc_walker_apes_set_shrink(NcmFitESMCMCWalkerAPES *a, const gdouble s) { a->shrink = s; }   // only stored (:1178-1187)
-void ncm_fit_esmcmc_walker_apes_set_random_walk_prob(NcmFitESMCMCWalkerAPES *a, const gdouble p) { a->random_walk_prob = p; }
-void ncm_fit_esmcmc_walker_apes_set_random_walk_scale(NcmFitESMCMCWalkerAPES *a, const gdouble s) { a->random_walk_scale = s; }
+// range checks and messages of walker_apes.c:1178-1227; shrink is only stored (the objects got theirs in set_sys)
+void ncm_fit_esmcmc_walker_apes_set_shrink(NcmFitESMCMCWalkerAPES *a, const gdouble s) {
+  if ((s < 0.0) || (s > 1.0)) {
+    ncm_b200_error("ncm_fit_esmcmc_walker_apes_set_shrink: invalid shrink `%f'.", s);
+    return;
+  }
+  a->shrink = s;
+}
+void ncm_fit_esmcmc_walker_apes_set_random_walk_prob(NcmFitESMCMCWalkerAPES *a, const gdouble p) {
+  if ((p < 0.0) || (p > 1.0)) {
+    ncm_b200_error("ncm_fit_esmcmc_walker_apes_set_random_walk_prob: invalid probability `%f'.", p);
+    return;
+  }
+  a->random_walk_prob = p;
+}
+void ncm_fit_esmcmc_walker_apes_set_random_walk_scale(NcmFitESMCMCWalkerAPES *a, const gdouble s) {
+  if (s <= 0.0) {
+    ncm_b200_error("ncm_fit_esmcmc_walker_apes_set_random_walk_scale: invalid scale `%f'.", s);
+    return;
+  }
+  a->random_walk_scale = s;
+}
 NcmFitESMCMCWalkerAPESMethod ncm_fit_esmcmc_walker_apes_get_method(NcmFitESMCMCWalkerAPES *a) { return a->method; }
 NcmFitESMCMCWalkerAPESKType ncm_fit_esmcmc_walker_apes_get_k_type(NcmFitESMCMCWalkerAPES *a) { return a->k_type; }
 gdouble ncm_fit_esmcmc_walker_apes_get_over_smooth(NcmFitESMCMCWalkerAPES *a) { return a->over_smooth; }

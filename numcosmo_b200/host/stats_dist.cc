@@ -604,15 +604,27 @@ gdouble ncm_stats_dist_get_href(NcmStatsDist *sd) { return sd_href(sd); }
 
 void ncm_stats_dist_set_over_smooth(NcmStatsDist *sd, const gdouble os) { sd->over_smooth = os; }
 gdouble ncm_stats_dist_get_over_smooth(NcmStatsDist *sd) { return sd->over_smooth; }
+// the function's own asserts (ncm_stats_dist.c:1307-1308); the narrower [0.10, 0.95] is the range of the GObject property (:430-434)
 void ncm_stats_dist_set_split_frac(NcmStatsDist *sd, const gdouble f) {
-  if (!(f >= 0.1 && f <= 0.95)) {
-    ncm_b200_error("ncm_stats_dist_set_split_frac: assertion failed (0.1 <= split_frac <= 0.95)");
+  if (!(f >= 0.01)) {
+    ncm_b200_error("ncm_stats_dist_set_split_frac: assertion failed (split_frac >= 0.01): (%g >= 0.01)", f);
+    return;
+  }
+  if (!(f <= 1.0)) {
+    ncm_b200_error("ncm_stats_dist_set_split_frac: assertion failed (split_frac <= 1.0): (%g <= 1.0)", f);
     return;
   }
   sd->split_frac = f;
 }
 gdouble ncm_stats_dist_get_split_frac(NcmStatsDist *sd) { return sd->split_frac; }
-void ncm_stats_dist_set_shrink(NcmStatsDist *sd, const gdouble s) { sd->shrink = s; }
+// ncm_stats_dist.c:1342-1343
+void ncm_stats_dist_set_shrink(NcmStatsDist *sd, const gdouble s) {
+  if (!(s >= 0.0 && s <= 1.0)) {
+    ncm_b200_error("ncm_stats_dist_set_shrink: assertion failed (0.0 <= shrink <= 1.0): (%g)", s);
+    return;
+  }
+  sd->shrink = s;
+}
 gdouble ncm_stats_dist_get_shrink(NcmStatsDist *sd) { return sd->shrink; }
 void ncm_stats_dist_set_print_fit(NcmStatsDist *sd, const gboolean p) { sd->print_fit = p; }
 gboolean ncm_stats_dist_get_print_fit(NcmStatsDist *sd) { return sd->print_fit; }

@@ -177,6 +177,14 @@ def lib():
             "ncm_fit_esmcmc_walker_apes_set_shrink": (None, [_vp, d]),
             "ncm_fit_esmcmc_walker_apes_set_random_walk_prob": (None, [_vp, d]),
             "ncm_fit_esmcmc_walker_apes_set_random_walk_scale": (None, [_vp, d]),
+            "ncm_fit_esmcmc_walker_apes_get_method": (i, [_vp]),
+            "ncm_fit_esmcmc_walker_apes_get_k_type": (i, [_vp]),
+            "ncm_fit_esmcmc_walker_apes_get_over_smooth": (d, [_vp]),
+            "ncm_fit_esmcmc_walker_apes_get_shrink": (d, [_vp]),
+            "ncm_fit_esmcmc_walker_apes_get_random_walk_prob": (d, [_vp]),
+            "ncm_fit_esmcmc_walker_apes_get_random_walk_scale": (d, [_vp]),
+            "ncm_fit_esmcmc_walker_apes_interp": (i, [_vp]),
+            "ncm_fit_esmcmc_walker_apes_get_use_threads": (i, [_vp]),
             "ncm_fit_esmcmc_walker_apes_use_interp": (None, [_vp, i]),
             "ncm_fit_esmcmc_walker_apes_set_use_threads": (None, [_vp, i]),
             "ncm_fit_esmcmc_walker_apes_set_local_frac": (None, [_vp, d]),
@@ -375,7 +383,10 @@ class StatsDist:
     def get_href(self): return lib().ncm_stats_dist_get_href(self._h)
     def set_over_smooth(self, v): lib().ncm_stats_dist_set_over_smooth(self._h, float(v))
     def get_over_smooth(self): return lib().ncm_stats_dist_get_over_smooth(self._h)
-    def set_shrink(self, v): lib().ncm_stats_dist_set_shrink(self._h, float(v))
+    def set_shrink(self, v):
+        lib().ncm_stats_dist_set_shrink(self._h, float(v))
+        _check()
+
     def get_shrink(self): return lib().ncm_stats_dist_get_shrink(self._h)
     def set_cv_type(self, v): lib().ncm_stats_dist_set_cv_type(self._h, int(v))
     def get_cv_type(self): return StatsDistCV(lib().ncm_stats_dist_get_cv_type(self._h))
@@ -587,10 +598,28 @@ class FitESMCMCWalkerAPES:
             self._h = None
 
     def set_over_smooth(self, v): lib().ncm_fit_esmcmc_walker_apes_set_over_smooth(self._h, float(v))
-    def set_shrink(self, v): lib().ncm_fit_esmcmc_walker_apes_set_shrink(self._h, float(v))
-    def set_random_walk_prob(self, v): lib().ncm_fit_esmcmc_walker_apes_set_random_walk_prob(self._h, float(v))
-    def set_random_walk_scale(self, v): lib().ncm_fit_esmcmc_walker_apes_set_random_walk_scale(self._h, float(v))
+
+    def set_shrink(self, v):
+        lib().ncm_fit_esmcmc_walker_apes_set_shrink(self._h, float(v))
+        _check()
+
+    def set_random_walk_prob(self, v):
+        lib().ncm_fit_esmcmc_walker_apes_set_random_walk_prob(self._h, float(v))
+        _check()
+
+    def set_random_walk_scale(self, v):
+        lib().ncm_fit_esmcmc_walker_apes_set_random_walk_scale(self._h, float(v))
+        _check()
+
     def set_exploration(self, n): lib().ncm_fit_esmcmc_walker_apes_set_exploration(self._h, int(n))
+    def get_method(self): return FitESMCMCWalkerAPESMethod(lib().ncm_fit_esmcmc_walker_apes_get_method(self._h))
+    def get_k_type(self): return FitESMCMCWalkerAPESKType(lib().ncm_fit_esmcmc_walker_apes_get_k_type(self._h))
+    def get_over_smooth(self): return lib().ncm_fit_esmcmc_walker_apes_get_over_smooth(self._h)
+    def get_shrink(self): return lib().ncm_fit_esmcmc_walker_apes_get_shrink(self._h)
+    def get_random_walk_prob(self): return lib().ncm_fit_esmcmc_walker_apes_get_random_walk_prob(self._h)
+    def get_random_walk_scale(self): return lib().ncm_fit_esmcmc_walker_apes_get_random_walk_scale(self._h)
+    def interp(self): return bool(lib().ncm_fit_esmcmc_walker_apes_interp(self._h))
+    def get_use_threads(self): return bool(lib().ncm_fit_esmcmc_walker_apes_get_use_threads(self._h))
     def use_interp(self, v): lib().ncm_fit_esmcmc_walker_apes_use_interp(self._h, int(v))
     def set_use_threads(self, v): lib().ncm_fit_esmcmc_walker_apes_set_use_threads(self._h, int(v))
 

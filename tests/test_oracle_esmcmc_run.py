@@ -249,3 +249,70 @@ def test_gpu_exploration_phase_follows_the_oracle(oracle, exploration):
     diff = np.argwhere(np.asarray(acc_o) != np.asarray(acc_g))
     assert diff.size == 0, f"first divergence at (iter, walker) = {diff[0]}"
     assert np.max(np.abs(th_g - th_o)) <= 1e-9 * np.abs(th_o).max()
+
+
+VARIANTS = [("no_interp", dict(use_interp=False)), ("random_walk_half", dict(random_walk_prob=0.5)), ("no_random_walk", dict(random_walk_prob=0.0)),
+            ("shrink_10pc", dict(shrink=0.1))]
+
+
+@pytest.mark.parametrize("name,kw", VARIANTS)
+@pytest.mark.parametrize("sd_s,nu", CASES)
+def test_walker_options_still_sample_the_posterior(oracle, sd_s, nu, name, kw):
+    """The options of the walker that change the proposal -- uniform weights instead of the interpolated ones (use_interp FALSE: prepare,
+    not prepare_interp, walker_apes.c:789-802), the random-walk mixture (random_walk_prob, :700-737, whose density enters the transition
+    probability :822-860), the shrink floor of the weights -- must leave the chain's law alone: same two bars as the run test."""
+    O = oracle
+    d, W = 2, 200
+    seed = 900 + int(10 * nu) + (7 if sd_s == "kde" else 0) + len(name)
+    mu, cov, X, _ = mvnd_problem(O, d, W, seed=seed)
+    tgt = O.Target(O.TARGET_MVND, d, np.full(d, -50.0), np.full(d, 50.0), mu=mu, cov=cov)
+    args = dict(over_smooth=1.01, use_interp=True, use_threads=False)
+    args.update(kw)
+    ap = O.APES(W, d, O.SD_KDE if sd_s == "kde" else O.SD_VKDE, O.KERNEL_ST, nu, **args)
+    rng = O.RNG(seed + 1)
+    th, ml = X.copy(), np.array([tgt.m2lnL(x) for x in X])
+    chain, run, ok = [], 40, False
+    for _ in range(6):
+        for _ in range(run):
+            ap.run(tgt, th, ml, 1, rng, nthreads=1)
+            chain.append(th.copy())
+        C = np.concatenate(chain[len(chain) // 5:])
+        cat = np.cov(C.T)
+        v, c = _cmp(np.diag(cat), np.diag(cov), 0.0), _cmp(_cov2cor(cat), _cov2cor(cov), 1.0)
+        ok = v < TOL and c < TOL
+        if ok:
+            break
+        run *= 2
+    print(f"{sd_s} nu={nu} {name}: {len(chain)} iterations, var {v:.3f}, cor {c:.3f}")
+    assert ok
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,kw", VARIANTS[:3])
+def test_gpu_walker_options_follow_the_oracle(oracle, name, kw):
+    """The same options through the product's setters: identical accepted sequence and positions as the oracle.  (The shrink setter
+    of the walker only stores its value once the object is constructed, walker_apes.c:1178-1187 -- the objects got theirs in set_sys
+    -- so there is nothing to follow for it.)"""
+    from numcosmo_b200 import stats_dist as S
+
+    d, W, iters = 3, 300, 5
+    mu, cov, X, _ = mvnd_problem(oracle, d, W, seed=123 + len(name))
+    lb, ub = np.full(d, -50.0), np.full(d, 50.0)
+    tgt = oracle.Target(oracle.TARGET_MVND, d, lb, ub, mu=mu, cov=cov)
+    ml0 = np.array([tgt.m2lnL(x) for x in X])
+    args = dict(over_smooth=1.0, use_interp=True, use_threads=True)
+    args.update(kw)
+    ao = oracle.APES(W, d, oracle.SD_VKDE, oracle.KERNEL_ST, 3.0, **args)
+    th_o, ml_o = X.copy(), ml0.copy()
+    acc_o = ao.run(tgt, th_o, ml_o, iters, oracle.RNG(55), nthreads=4)
+    ag = S.FitESMCMCWalkerAPES(W, d, S.FitESMCMCWalkerAPESMethod.VKDE, S.FitESMCMCWalkerAPESKType.ST3, 1.0, True)
+    ag.set_use_threads(True)
+    if "use_interp" in kw:
+        ag.use_interp(kw["use_interp"])
+    if "random_walk_prob" in kw:
+        ag.set_random_walk_prob(kw["random_walk_prob"])
+    th_g, ml_g = X.copy(), ml0.copy()
+    acc_g, _ = ag.run("mvnd", lb, ub, th_g, ml_g, iters, S.RNG(55), target_args=(mu, tgt.U))
+    diff = np.argwhere(np.asarray(acc_o) != np.asarray(acc_g))
+    assert diff.size == 0, f"{name}: first divergence at (iter, walker) = {diff[0]}"
+    assert np.max(np.abs(th_g - th_o)) <= 1e-9 * np.abs(th_o).max()
