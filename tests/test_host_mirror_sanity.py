@@ -93,3 +93,40 @@ def test_apes_vkde_needs_enough_walkers_per_block(S):
         S.FitESMCMCWalkerAPES.new_full(40, 2, M.VKDE, K.CAUCHY, 1.0, True)
     S.FitESMCMCWalkerAPES.new_full(40, 2, M.KDE, K.CAUCHY, 1.0, True)
     S.FitESMCMCWalkerAPES.new_full(80, 2, M.VKDE, K.CAUCHY, 1.0, True)
+
+
+def test_precondition_failures_before_any_device_call(S):
+    """g_assert / g_error sites of the classes that are decided on the host: they must fire here exactly as on a GPU box (no device is
+    touched before them), with the reference's messages."""
+    d = 3
+    kern = S.StatsDistKernelGauss(d)
+    sd = S.StatsDistKDE(kern, S.StatsDistCV.NONE)
+    with pytest.raises(S.NcmError, match=r"ncm_vector_len \(y\) == d"):                  # ncm_stats_dist.c add_obs
+        sd.add_obs(np.zeros(d + 1))
+    for i in range(d):
+        sd.add_obs(np.arange(float(d)) + i)
+    with pytest.raises(S.NcmError, match="the sample is too small"):                     # ncm_stats_dist.c:748-749, n_obs <= d
+        sd.prepare()
+    with pytest.raises(S.NcmError, match="cov_fixed"):                                   # ncm_stats_dist_kde.c:831-832
+        sd.set_cov_fixed(np.eye(d + 1))
+    sd.set_cov_type(S.StatsDistKDECovType.FIXED)
+    with pytest.raises(S.NcmError, match="not positive definite"):                       # :843
+        sd.set_cov_fixed(np.diag([1.0, -1.0, 1.0]))
+    sd.set_cov_fixed(np.eye(d))
+    v = S.StatsDistVKDE(kern, S.StatsDistCV.NONE)
+    for bad in (0.0009, 1.01):                                                           # ncm_stats_dist_vkde.c:808-809
+        with pytest.raises(S.NcmError, match="local_frac"):
+            v.set_local_frac(bad)
+    v.set_local_frac(0.001)
+    v.set_local_frac(1.0)
+    assert v.get_local_frac() == 1.0
+    v.set_local_frac(0.05)
+    rs = np.random.default_rng(0)
+    for _ in range(30):
+        v.add_obs(rs.standard_normal(d))
+    with pytest.raises(S.NcmError, match="Too few observations"):                        # :505-510, local_frac n_obs = 1.5 < 2
+        v.prepare()
+    with pytest.raises(S.NcmError, match="outside"):                                     # the one limit of this implementation: d <= 32
+        S.StatsDistKernelGauss(33)
+    with pytest.raises(S.NcmError, match="outside"):
+        S.StatsDistKernelST(0, 3.0)
