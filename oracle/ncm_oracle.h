@@ -188,6 +188,7 @@ void orc_apes_set_exploration (orc_apes *a, unsigned int exploration);
 void orc_apes_run (orc_apes *a, const orc_target *t, double *theta, double *m2lnL, int iters, orc_rng *rng, unsigned char *accepted, int nthreads);
 /* stage timers accumulated over run: [0] prepare_kernel [1] IM [2] NNLS [3] sample [4] eval [5] likelihood+accept */
 void orc_apes_get_timers (const orc_apes *a, double *t6);
+void orc_apes_get_fallback_counts (const orc_apes *a, long *n3);
 const double *orc_apes_peek_thetastar (const orc_apes *a);
 const double *orc_apes_peek_m2lnp_star (const orc_apes *a);
 const double *orc_apes_peek_m2lnp_cur (const orc_apes *a);

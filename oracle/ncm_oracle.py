@@ -222,6 +222,7 @@ def lib():
             "orc_apes_free": (None, [vp]),
             "orc_apes_set_cov_type": (None, [vp, i, _dp, i]),
             "orc_apes_set_exploration": (None, [vp, C.c_uint]),
+            "orc_apes_get_fallback_counts": (None, [vp, C.POINTER(C.c_long)]),
             "orc_apes_run": (None, [vp, vp, _dp, _dp, i, vp, C.POINTER(C.c_ubyte), i]),
             "orc_apes_get_timers": (None, [vp, _dp]),
             "orc_apes_peek_thetastar": (_dp, [vp]),
@@ -570,6 +571,12 @@ class APES:
 
     def set_exploration(self, n):
         lib().orc_apes_set_exploration(self._h, int(n))
+
+    def fallback_counts(self):
+        """(prepare_interp calls, dsysv fallbacks, dgels fallbacks) of the NNLS since the object was made."""
+        n = (C.c_long * 3)()
+        lib().orc_apes_get_fallback_counts(self._h, n)
+        return int(n[0]), int(n[1]), int(n[2])
 
     def timers(self):
         t = np.zeros(6)

@@ -210,6 +210,7 @@ typedef struct orc_apes_rw
 struct orc_apes
 {
   int size, size_2, nparams;
+  long n_lu_total, n_qr_total, n_nnls_total; /* instrumentation for the tests: NNLS solves of the run and how many left dposv */
   unsigned int exploration; /* walker_apes.c:142, 182: setup calls left in which the proposal density is left out of the acceptance */
   orc_sd *sd0, *sd1;
   double *thetastar, *m2lnp_star, *m2lnp_cur, *m2lnL_s0, *m2lnL_s1, *jumps;
@@ -440,7 +441,15 @@ apes_setup_block (orc_apes *a, const orc_target *t, double *theta, double *m2lnL
   }
 
   if (a->use_interp)
+  {
+    orc_nnls_stats st;
+
     orc_sd_prepare_interp (sd, m2lnL_s, a->size_2);
+    orc_sd_get_nnls_stats (sd, &st);
+    a->n_nnls_total++;
+    a->n_lu_total += st.n_lu;
+    a->n_qr_total += st.n_qr;
+  }
   else
     orc_sd_prepare (sd);
 
@@ -553,6 +562,15 @@ orc_apes_run (orc_apes *a, const orc_target *t, double *theta, double *m2lnL, in
       a->exploration--;
     apes_run_block (a, t, theta, m2lnL, 1, acc, nthreads);
   }
+}
+
+/* test instrumentation: {prepare_interp calls, dsysv fallbacks, dgels fallbacks} since the object was made */
+void
+orc_apes_get_fallback_counts (const orc_apes *a, long *n3)
+{
+  n3[0] = a->n_nnls_total;
+  n3[1] = a->n_lu_total;
+  n3[2] = a->n_qr_total;
 }
 
 void

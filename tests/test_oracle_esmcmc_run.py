@@ -241,6 +241,7 @@ def test_gpu_exploration_phase_follows_the_oracle(oracle, exploration):
     ao.set_exploration(exploration)
     th_o, ml_o = X.copy(), ml0.copy()
     acc_o = ao.run(tgt, th_o, ml_o, iters, oracle.RNG(77), nthreads=4)
+    assert ao.fallback_counts()[1:] == (0, 0)                      # every weight solve stayed in dposv: the bit-level regime
     ag = S.FitESMCMCWalkerAPES(W, d, S.FitESMCMCWalkerAPESMethod.VKDE, S.FitESMCMCWalkerAPESKType.ST3, 1.0, True)
     ag.set_use_threads(True)
     ag.set_exploration(exploration)
@@ -305,6 +306,7 @@ def test_gpu_walker_options_follow_the_oracle(oracle, name, kw):
     ao = oracle.APES(W, d, oracle.SD_VKDE, oracle.KERNEL_ST, 3.0, **args)
     th_o, ml_o = X.copy(), ml0.copy()
     acc_o = ao.run(tgt, th_o, ml_o, iters, oracle.RNG(55), nthreads=4)
+    assert ao.fallback_counts()[1:] == (0, 0)                      # every weight solve stayed in dposv: the bit-level regime
     ag = S.FitESMCMCWalkerAPES(W, d, S.FitESMCMCWalkerAPESMethod.VKDE, S.FitESMCMCWalkerAPESKType.ST3, 1.0, True)
     ag.set_use_threads(True)
     if "use_interp" in kw:
