@@ -54,6 +54,8 @@ struct RandomWalk {
 
 struct _NcmFitESMCMCWalkerAPES {
   guint size, size_2, nparams;
+  guint a_size = 0, a_nparams = 0;   // the configuration the objects below were built for (walker_apes.c:515-523)
+  int a_mk = -1;
   NcmFitESMCMCWalkerAPESMethod method;
   NcmFitESMCMCWalkerAPESKType k_type;
   double over_smooth, shrink, random_walk_prob, random_walk_scale, local_frac;
@@ -73,7 +75,27 @@ struct _NcmFitESMCMCWalkerAPES {
 
 namespace {
 
+// _ncm_fit_esmcmc_walker_apes_vkde_check_sizes (walker_apes.c:489-507): reads the local fraction the OBJECTS hold
+void vkde_check_sizes(NcmFitESMCMCWalkerAPES *a) {
+  for (NcmStatsDist *sd : {a->sd0, a->sd1}) {
+    const guint cov_estimates = (guint) (ncm_stats_dist_vkde_get_local_frac(sd) * a->size_2);
+    if (cov_estimates < 2) {
+      ncm_b200_error("Number of walkers per block (%d) is too low for the current dimension (%d).\n\tToo few points (%d) to estimate local covariances.",
+                     a->size_2, a->nparams, cov_estimates);
+      return;
+    }
+  }
+}
+
+// _ncm_fit_esmcmc_walker_apes_set_sys (walker_apes.c:509-598): the objects are rebuilt only when size, dimension, method or kernel
+// type changed; fresh objects start from their own defaults (local_frac 0.05, covariance type SAMPLE) and receive the walker's
+// over_smooth, shrink and use_threads
 void set_sys(NcmFitESMCMCWalkerAPES *a) {
+  const int mk = (int) a->method * 1000 + (int) a->k_type;
+  if (a->size == a->a_size && a->nparams == a->a_nparams && mk == a->a_mk) return;
+  a->a_size    = a->size;
+  a->a_nparams = a->nparams;
+  a->a_mk      = mk;
   ncm_stats_dist_clear(&a->sd0);
   ncm_stats_dist_clear(&a->sd1);
   if (a->size % 2 != 0) {
@@ -97,18 +119,12 @@ void set_sys(NcmFitESMCMCWalkerAPES *a) {
   // METHOD_KDE and METHOD_VKDE both construct NcmStatsDistVKDE (walker_apes.c:563-572)
   a->sd0 = ncm_stats_dist_vkde_new(kernel, NCM_STATS_DIST_CV_NONE);
   a->sd1 = ncm_stats_dist_vkde_new(kernel, NCM_STATS_DIST_CV_NONE);
-  if (a->method == NCM_FIT_ESMCMC_WALKER_APES_METHOD_VKDE) {
-    const guint cov_estimates = (guint) (a->local_frac * a->size_2);
-    if (cov_estimates < 2)
-      ncm_b200_error("Number of walkers per block (%d) is too low for the current dimension (%d).\n\tToo few points (%d) to estimate local covariances.",
-                     a->size_2, a->nparams, cov_estimates);
-  }
+  if (a->method == NCM_FIT_ESMCMC_WALKER_APES_METHOD_VKDE) vkde_check_sizes(a);
   ncm_stats_dist_kernel_free(kernel);
   for (NcmStatsDist *sd : {a->sd0, a->sd1}) {
     ncm_stats_dist_set_over_smooth(sd, a->over_smooth);
     ncm_stats_dist_set_shrink(sd, a->shrink);
     ncm_stats_dist_set_use_threads(sd, a->use_threads);
-    ncm_stats_dist_vkde_set_local_frac(sd, a->local_frac);
   }
 }
 
@@ -377,11 +393,20 @@ void ncm_fit_esmcmc_walker_apes_clear(NcmFitESMCMCWalkerAPES **a) {
     *a = nullptr;
   }
 }
+// walker_apes.c:1110-1144 (the second message is the reference's own, copy-and-paste of the first included)
 void ncm_fit_esmcmc_walker_apes_set_method(NcmFitESMCMCWalkerAPES *a, NcmFitESMCMCWalkerAPESMethod m) {
+  if ((guint) m >= (guint) NCM_FIT_ESMCMC_WALKER_APES_METHOD_LEN) {
+    ncm_b200_error("ncm_fit_esmcmc_walker_apes_set_method: invalid method `%d'.", (int) m);
+    return;
+  }
   a->method = m;
   set_sys(a);
 }
 void ncm_fit_esmcmc_walker_apes_set_k_type(NcmFitESMCMCWalkerAPES *a, NcmFitESMCMCWalkerAPESKType k) {
+  if ((guint) k >= (guint) NCM_FIT_ESMCMC_WALKER_APES_KTYPE_LEN) {
+    ncm_b200_error("ncm_fit_esmcmc_walker_apes_set_method: invalid method `%d'.", (int) k);
+    return;
+  }
   a->k_type = k;
   set_sys(a);
 }
@@ -430,10 +455,17 @@ void ncm_fit_esmcmc_walker_apes_peek_sds(NcmFitESMCMCWalkerAPES *a, NcmStatsDist
   *sd0 = a->sd0;
   *sd1 = a->sd1;
 }
+// walker_apes.c:1428-1439: VKDE method only, forwarded to both objects (which keep it until set_sys rebuilds them), sizes re-checked
 void ncm_fit_esmcmc_walker_apes_set_local_frac(NcmFitESMCMCWalkerAPES *a, gdouble lf) {
-  a->local_frac = lf;
+  if (a->method != NCM_FIT_ESMCMC_WALKER_APES_METHOD_VKDE) {
+    ncm_b200_error("ncm_fit_esmcmc_walker_apes_set_local_frac: cannot set local fraction for a non-VKDE method.");
+    return;
+  }
   ncm_stats_dist_vkde_set_local_frac(a->sd0, lf);
+  if (ncm_stats_dist_vkde_get_local_frac(a->sd0) != lf) return;   // refused by the object's own range assert (reported there)
   ncm_stats_dist_vkde_set_local_frac(a->sd1, lf);
+  a->local_frac = lf;
+  vkde_check_sizes(a);
 }
 void ncm_fit_esmcmc_walker_apes_set_exploration(NcmFitESMCMCWalkerAPES *a, guint e) { a->exploration = e; }
 // ncm_fit_esmcmc_walker_apes.c:1450-1473.  The reference reads nothing from the NcmMSet but the scales of its free parameters

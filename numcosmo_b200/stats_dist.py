@@ -177,6 +177,8 @@ def lib():
             "ncm_fit_esmcmc_walker_apes_set_shrink": (None, [_vp, d]),
             "ncm_fit_esmcmc_walker_apes_set_random_walk_prob": (None, [_vp, d]),
             "ncm_fit_esmcmc_walker_apes_set_random_walk_scale": (None, [_vp, d]),
+            "ncm_fit_esmcmc_walker_apes_set_method": (None, [_vp, i]),
+            "ncm_fit_esmcmc_walker_apes_set_k_type": (None, [_vp, i]),
             "ncm_fit_esmcmc_walker_apes_get_method": (i, [_vp]),
             "ncm_fit_esmcmc_walker_apes_get_k_type": (i, [_vp]),
             "ncm_fit_esmcmc_walker_apes_get_over_smooth": (d, [_vp]),
@@ -561,7 +563,7 @@ class StatsDistVKDE(StatsDistKDE):
     def get_use_rot_href(self): return bool(lib().ncm_stats_dist_vkde_get_use_rot_href(self._h))
 
 
-class _BorrowedSD(StatsDist):
+class _BorrowedSD(StatsDistVKDE):   # the walker builds NcmStatsDistVKDE objects for both methods (walker_apes.c:563-572)
     def __init__(self, handle, dim):
         self._h = handle
         self.dim = dim
@@ -612,6 +614,15 @@ class FitESMCMCWalkerAPES:
         _check()
 
     def set_exploration(self, n): lib().ncm_fit_esmcmc_walker_apes_set_exploration(self._h, int(n))
+
+    def set_method(self, m):
+        lib().ncm_fit_esmcmc_walker_apes_set_method(self._h, int(m))
+        _check()
+
+    def set_k_type(self, k):
+        lib().ncm_fit_esmcmc_walker_apes_set_k_type(self._h, int(k))
+        _check()
+
     def get_method(self): return FitESMCMCWalkerAPESMethod(lib().ncm_fit_esmcmc_walker_apes_get_method(self._h))
     def get_k_type(self): return FitESMCMCWalkerAPESKType(lib().ncm_fit_esmcmc_walker_apes_get_k_type(self._h))
     def get_over_smooth(self): return lib().ncm_fit_esmcmc_walker_apes_get_over_smooth(self._h)

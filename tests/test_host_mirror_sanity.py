@@ -130,3 +130,38 @@ def test_precondition_failures_before_any_device_call(S):
         S.StatsDistKernelGauss(33)
     with pytest.raises(S.NcmError, match="outside"):
         S.StatsDistKernelST(0, 3.0)
+
+
+def test_apes_set_sys_rebuilds_only_on_a_changed_configuration(S):
+    """_ncm_fit_esmcmc_walker_apes_set_sys (walker_apes.c:509-598): the two objects are rebuilt when size, dimension, method or kernel
+    type change -- and then start from their own defaults again, the walker holds no local fraction of its own -- and are left alone
+    otherwise; set_local_frac is a VKDE-method call that re-checks the block size (:1428-1439); the enum setters refuse values past
+    their _LEN (:1110-1144)."""
+    M, K = S.FitESMCMCWalkerAPESMethod, S.FitESMCMCWalkerAPESKType
+    ap = S.FitESMCMCWalkerAPES.new_full(200, 2, M.VKDE, K.CAUCHY, 1.3, True)
+    ap.set_local_frac(0.2)
+    sd0, sd1 = ap.peek_sds()
+    assert sd0.get_local_frac() == 0.2 and sd1.get_local_frac() == 0.2
+    # same configuration: nothing is rebuilt, the objects keep what they were given
+    ap.set_method(M.VKDE)
+    ap.set_k_type(K.CAUCHY)
+    sd0, sd1 = ap.peek_sds()
+    assert sd0.get_local_frac() == 0.2 and sd0.get_over_smooth() == 1.3
+    # a new kernel type: fresh objects, the local fraction is the class default again, over_smooth is the walker's
+    ap.set_k_type(K.ST3)
+    sd0, sd1 = ap.peek_sds()
+    assert sd0.get_local_frac() == 0.05 and sd1.get_local_frac() == 0.05 and sd0.get_over_smooth() == 1.3
+    assert ap.get_k_type() == K.ST3
+    # too small a fraction for the block: 0.01 * 100 = 1 < 2
+    with pytest.raises(S.NcmError, match="too low"):
+        ap.set_local_frac(0.01)
+    with pytest.raises(S.NcmError, match="local_frac"):                                  # the object's own range assert, nothing forwarded
+        ap.set_local_frac(2.0)
+    ap.set_method(M.KDE)
+    with pytest.raises(S.NcmError, match="non-VKDE"):
+        ap.set_local_frac(0.2)
+    with pytest.raises(S.NcmError, match="invalid method"):
+        ap.set_method(2)
+    with pytest.raises(S.NcmError, match="invalid method"):
+        ap.set_k_type(3)
+    assert ap.get_method() == M.KDE and ap.get_k_type() == K.ST3
