@@ -450,7 +450,13 @@ void ncm_fit_esmcmc_walker_apes_set_use_threads(NcmFitESMCMCWalkerAPES *a, gbool
   ncm_stats_dist_set_use_threads(a->sd0, u);
   ncm_stats_dist_set_use_threads(a->sd1, u);
 }
-gboolean ncm_fit_esmcmc_walker_apes_get_use_threads(NcmFitESMCMCWalkerAPES *a) { return a->use_threads; }
+// walker_apes.c:1378-1391: the two objects must agree with the walker (someone may have reached them through peek_sds)
+gboolean ncm_fit_esmcmc_walker_apes_get_use_threads(NcmFitESMCMCWalkerAPES *a) {
+  const gboolean u0 = ncm_stats_dist_get_use_threads(a->sd0), u1 = ncm_stats_dist_get_use_threads(a->sd1);
+  if (!a->use_threads != !u0) ncm_b200_error("ncm_fit_esmcmc_walker_apes_get_use_threads: assertion failed (self->use_threads == use_threads0)");
+  if (!u0 != !u1) ncm_b200_error("ncm_fit_esmcmc_walker_apes_get_use_threads: assertion failed (use_threads0 == use_threads1)");
+  return u0;
+}
 void ncm_fit_esmcmc_walker_apes_peek_sds(NcmFitESMCMCWalkerAPES *a, NcmStatsDist **sd0, NcmStatsDist **sd1) {
   *sd0 = a->sd0;
   *sd1 = a->sd1;

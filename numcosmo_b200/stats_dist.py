@@ -630,7 +630,11 @@ class FitESMCMCWalkerAPES:
     def get_random_walk_prob(self): return lib().ncm_fit_esmcmc_walker_apes_get_random_walk_prob(self._h)
     def get_random_walk_scale(self): return lib().ncm_fit_esmcmc_walker_apes_get_random_walk_scale(self._h)
     def interp(self): return bool(lib().ncm_fit_esmcmc_walker_apes_interp(self._h))
-    def get_use_threads(self): return bool(lib().ncm_fit_esmcmc_walker_apes_get_use_threads(self._h))
+    def get_use_threads(self):
+        r = bool(lib().ncm_fit_esmcmc_walker_apes_get_use_threads(self._h))
+        _check()
+        return r
+
     def use_interp(self, v): lib().ncm_fit_esmcmc_walker_apes_use_interp(self._h, int(v))
     def set_use_threads(self, v): lib().ncm_fit_esmcmc_walker_apes_set_use_threads(self._h, int(v))
 

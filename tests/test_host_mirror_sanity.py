@@ -68,7 +68,11 @@ def test_apes_constructors_and_setters(S, case):
     ap.use_interp(False)
     assert not ap.interp()
     ap.set_use_threads(True)
-    assert ap.get_use_threads()
+    assert ap.get_use_threads() and sd0.get_use_threads() and sd1.get_use_threads()     # forwarded (:1349-1361)
+    sd1.set_use_threads(False)
+    with pytest.raises(S.NcmError, match="use_threads0 == use_threads1"):               # the getter's own asserts (:1378-1391)
+        ap.get_use_threads()
+    sd1.set_use_threads(True)
     # range checks, :1178-1227
     for bad in (-0.1, 1.1):
         with pytest.raises(S.NcmError, match="invalid shrink"):
